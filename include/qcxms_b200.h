@@ -1,0 +1,126 @@
+/* qcxms_b200 -- C ABI of the B200-native QCxMS production-trajectory hot path.
+ *
+ * Every entry point takes plain pointers and sizes; all arrays are HOST memory owned by
+ * the caller (the library keeps device buffers behind opaque handles and copies in/out).
+ * Array layout: xyz/gradient/velo are [nat][3] C row-major == Fortran (3,nat) column-major,
+ * so the reference's arrays can be passed unchanged through iso_c_binding.
+ * Units as in the reference: bohr, Eh, Eh/bohr, electron masses, atomic time units, K.
+ *
+ * Return value of every function: 0 on success, non-zero on a library-level failure
+ * (no CUDA device, bad argument, unsupported element).  Per-calculation status follows
+ * the reference's convention and is returned through `stat`.
+ */
+#ifndef QCXMS_B200_H
+#define QCXMS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* method selector ids, reference src/tblite.f90:34-40 */
+#define QCXMS_B200_GFN1 1
+#define QCXMS_B200_GFN2 2
+#define QCXMS_B200_IPEA1 11
+/* stat values, reference src/tblite.f90:55-58 */
+#define QCXMS_B200_STAT_OK 0
+#define QCXMS_B200_STAT_FATAL (-1)
+#define QCXMS_B200_STAT_UNKNOWN_METHOD 5
+
+/* library-level error codes */
+#define QCXMS_B200_ERR_ARG 1
+#define QCXMS_B200_ERR_CUDA 2
+#define QCXMS_B200_ERR_UNSUPPORTED 3
+
+/* ---------------------------------------------------------------------------------------
+ * Replaces  subroutine get_xtb_egrad(num, xyz, charge, multiplicity, method, etemp,
+ *                                    output_file, qat, energy, gradient, stat, spec_calc)
+ * reference src/tblite.f90:65-66 (called from egrad src/iniqm.f90:625,644, iniqm :188,195,
+ * eqm :393,409).  Cold-start SCC with accuracy 1.0 exactly like the reference; output_file /
+ * spec_calc side effects are handled by the Fortran shim.
+ */
+int qcxms_b200_egrad(int nat, const int32_t *num, const double *xyz, int charge, int multiplicity,
+                     int method_id, double etemp_kelvin, double *qat, double *energy, double *gradient,
+                     int32_t *stat);
+
+/* Batched form: nsys geometries of ONE composition evaluated as one ensemble (one CTA each).
+ * xyz [nsys][nat][3]; qat [nsys][nat]; energy [nsys]; gradient [nsys][nat][3]; stat [nsys];
+ * niter [nsys] (number of SCC cycles) may be NULL. */
+int qcxms_b200_egrad_batch(int nsys, int nat, const int32_t *num, const double *xyz, int charge,
+                           int multiplicity, int method_id, double etemp_kelvin, double *qat, double *energy,
+                           double *gradient, int32_t *stat, int32_t *niter);
+
+/* ---------------------------------------------------------------------------------------
+ * Small routines of the path exposed 1:1 for parity tests (device implementations).
+ * fragment_structure(nat, oz, xyz, rcut, at1=1, at2=0, frag): reference src/fragments.f90:93-182
+ * (integer result must be bit-identical to the reference for identical coordinates). */
+int qcxms_b200_fragment_structure(int nsys, int nat, const int32_t *num, const double *xyz, double rcut,
+                                  int32_t *frag /* [nsys][nat] */);
+
+/* ---------------------------------------------------------------------------------------
+ * Ensemble of trajectories: replaces "one qcxms --prod process per TMP.<n> directory"
+ * (reference bin/pqcxms:88-98) and the md() loop (reference src/md.f90:34-708) for it > 0.
+ */
+typedef struct qcxms_b200_ensemble qcxms_b200_ensemble_t;
+
+typedef struct {
+    int32_t method_id;   /* QCXMS_B200_GFN2 ... */
+    int32_t mchrg;       /* molecular charge of every trajectory (reference: mchrg) */
+    int32_t nfragexit;   /* reference default 3 (2 for isec > 1), src/main.F90:2252 */
+    int32_t exit_rules;  /* 1: reference EI exit rules (md.f90:623-679); 0: run exactly nmax steps */
+    int32_t nmax;        /* maximum number of MD steps (reference nmax = tmax/tstep) */
+    int32_t isec;        /* index of the (secondary) run, reference isec; affects the error exit */
+    double tstep;        /* MD time step in atomic units (reference tstep after *fstoau) */
+    double etemp_in;     /* electronic temperature; < 0: reference setetemp() rule (5000 K + ...) */
+    double ieetemp;      /* reference common1 ieetemp (default 0) */
+    double ax;           /* reference common1 ax (0 for xtb) */
+} qcxms_b200_md_config_t;
+
+typedef struct {
+    int32_t mdok;        /* reference mdok */
+    int32_t fragstate;   /* reference fragstate: 0 undefined, 1 normal, 2 nfrag=2 constant */
+    int32_t nstep;       /* MD steps done */
+    int32_t nfrag;       /* fragments at exit */
+    int32_t status;      /* 0 running, 1 finished, 2 failed (egrad failure at start) */
+    int32_t scc_iter_total; /* total SCC cycles spent (for the roofline accounting) */
+    double Tav, Epav, Ekav, aTlast, dtime, ttime;
+    double Epot, Ekin;   /* last values */
+} qcxms_b200_md_result_t;
+
+/* device: CUDA device ordinal.  num [nat] atomic numbers, mass [nat] in electron masses. */
+int qcxms_b200_ensemble_create(const qcxms_b200_md_config_t *cfg, int ntraj, int nat, const int32_t *num,
+                               const double *mass, int device, qcxms_b200_ensemble_t **out);
+int qcxms_b200_ensemble_destroy(qcxms_b200_ensemble_t *h);
+
+/* initial conditions of one trajectory = contents of start.xyz + qcxms.start
+ * (reference src/utility.f90:379-422 rdstart): xyz, velo [nat][3], velof [nat], eimp (Eh), tadd (a.u.) */
+int qcxms_b200_ensemble_set_trajectory(qcxms_b200_ensemble_t *h, int itrj, const double *xyz, const double *velo,
+                                       const double *velof, double eimp, double tadd);
+/* bulk variant: arrays carry a leading [ntraj] axis (reference run_settings layout, src/settings.f90:9-25) */
+int qcxms_b200_ensemble_set_all(qcxms_b200_ensemble_t *h, const double *xyz, const double *velo,
+                                const double *velof, const double *eimp, const double *tadd);
+
+/* md(): initial egrad + MD loop until every trajectory has exited (or max_steps more steps were
+ * taken per trajectory when max_steps > 0).  Returns the number of trajectory-MD-steps executed
+ * in *steps_done (may be NULL). */
+int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_steps, int64_t *steps_done);
+
+int qcxms_b200_ensemble_get_result(qcxms_b200_ensemble_t *h, int itrj, double *xyz, double *velo, double *grad,
+                                   int32_t *list, double *achrg, double *axyz, qcxms_b200_md_result_t *res);
+
+/* device time (ms, CUDA events on the launching stream) and kernel launch count of the last run_md */
+int qcxms_b200_ensemble_last_timing(qcxms_b200_ensemble_t *h, double *kernel_ms, int64_t *launches,
+                                    int64_t *scc_iterations);
+
+/* Fragment-mass histogram of the finished trajectories of this ensemble (bins = nominal integer m/z of
+ * every fragment, weight 1 per fragment); this is what one ncclAllReduce(sum) combines across GPUs in
+ * place of concatenating every TMP.n/qcxms.res (reference bin/pqcxms:101-103).  Returns the device pointer as well so
+ * the caller can hand it to NCCL without a host round trip (may be NULL). */
+int qcxms_b200_ensemble_histogram(qcxms_b200_ensemble_t *h, int nbins, double *bins_host, void **bins_device);
+
+const char *qcxms_b200_last_error(void);
+const char *qcxms_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

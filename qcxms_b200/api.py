@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference interface of the hot path, on top of the C ABI.
+
+Names follow the reference: get_xtb_egrad (src/tblite.f90:65), the method selectors gfn1_xtb /
+gfn2_xtb / ipea1_xtb (src/tblite.f90:34-40), md() results (src/md.f90:34-39), fragment_structure
+(src/fragments.f90:93).  All heavy lifting happens in libqcxms_b200.so (hand-written sm_100a CUDA);
+this module only marshals numpy arrays through ctypes.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqcxms_b200.so")
+_LIB = None
+
+# method selectors (reference src/tblite.f90:34-40)
+gfn1_xtb, gfn2_xtb, ipea1_xtb = 1, 2, 11
+
+FSTOAU = 41.3413733365614       # reference src/xtb_mctc_convert.f90:55
+AUTOEV = 27.21138505
+AMUTOAU = 1.660539040e-27 * (1.0 / 9.10938356e-31)
+KB = 3.166808578545117e-06
+
+
+class MdConfig(C.Structure):
+    """qcxms_b200_md_config_t"""
+    _fields_ = [("method_id", C.c_int32), ("mchrg", C.c_int32), ("nfragexit", C.c_int32), ("exit_rules", C.c_int32),
+                ("nmax", C.c_int32), ("isec", C.c_int32), ("tstep", C.c_double), ("etemp_in", C.c_double),
+                ("ieetemp", C.c_double), ("ax", C.c_double)]
+
+
+class MdResult(C.Structure):
+    """qcxms_b200_md_result_t"""
+    _fields_ = [("mdok", C.c_int32), ("fragstate", C.c_int32), ("nstep", C.c_int32), ("nfrag", C.c_int32),
+                ("status", C.c_int32), ("scc_iter_total", C.c_int32)] + \
+        [(k, C.c_double) for k in ("Tav", "Epav", "Ekav", "aTlast", "dtime", "ttime", "Epot", "Ekin")]
+
+
+EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_egrad_batch", "qcxms_b200_fragment_structure", "qcxms_b200_ensemble_create",
+           "qcxms_b200_ensemble_destroy", "qcxms_b200_ensemble_set_trajectory", "qcxms_b200_ensemble_set_all",
+           "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_last_timing",
+           "qcxms_b200_ensemble_histogram", "qcxms_b200_last_error", "qcxms_b200_version"]
+
+
+def lib():
+    """Load libqcxms_b200.so; fails loudly when the CUDA extension has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("qcxms_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                               "there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        L.qcxms_b200_egrad.argtypes = [C.c_int, ip, dp, C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, dp, ip]
+        L.qcxms_b200_egrad_batch.argtypes = [C.c_int, C.c_int, ip, dp, C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, dp, ip, ip]
+        L.qcxms_b200_fragment_structure.argtypes = [C.c_int, C.c_int, ip, dp, C.c_double, ip]
+        L.qcxms_b200_ensemble_create.argtypes = [C.POINTER(MdConfig), C.c_int, C.c_int, ip, dp, C.c_int, C.POINTER(C.c_void_p)]
+        L.qcxms_b200_ensemble_destroy.argtypes = [C.c_void_p]
+        L.qcxms_b200_ensemble_set_trajectory.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, C.c_double, C.c_double]
+        L.qcxms_b200_ensemble_set_all.argtypes = [C.c_void_p, dp, dp, dp, dp, dp]
+        L.qcxms_b200_ensemble_run_md.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        L.qcxms_b200_ensemble_get_result.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, ip, dp, dp, C.POINTER(MdResult)]
+        L.qcxms_b200_ensemble_last_timing.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.qcxms_b200_ensemble_histogram.argtypes = [C.c_void_p, C.c_int, dp, C.POINTER(C.c_void_p)]
+        L.qcxms_b200_last_error.restype = C.c_char_p
+        L.qcxms_b200_version.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _check(rc):
+    if rc:
+        raise RuntimeError("qcxms_b200 error %d: %s" % (rc, lib().qcxms_b200_last_error().decode()))
+
+
+def version():
+    return lib().qcxms_b200_version().decode()
+
+
+def get_xtb_egrad(num, xyz, charge, multiplicity, method, etemp):
+    """get_xtb_egrad(num, xyz, charge, multiplicity, method, etemp, ...) -> qat, energy, gradient, stat
+    (reference src/tblite.f90:65-66; output_file / spec_calc are host-side concerns of the Fortran shim)."""
+    num = np.ascontiguousarray(num, dtype=np.int32)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(len(num), 3)
+    qat, grad = np.zeros(len(num)), np.zeros((len(num), 3))
+    e, stat = C.c_double(0.0), C.c_int32(0)
+    _check(lib().qcxms_b200_egrad(len(num), _ip(num), _dp(xyz), int(charge), int(multiplicity), int(method), float(etemp),
+                                  _dp(qat), C.byref(e), _dp(grad), C.byref(stat)))
+    return qat, e.value, grad, stat.value
+
+
+def egrad_batch(num, xyz, charge, multiplicity, method, etemp):
+    """Batched get_xtb_egrad over xyz[nsys, nat, 3] -> dict(qat, energy, gradient, stat, niter)."""
+    num = np.ascontiguousarray(num, dtype=np.int32)
+    nat = len(num)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, nat, 3)
+    nsys = xyz.shape[0]
+    qat, grad, e = np.zeros((nsys, nat)), np.zeros((nsys, nat, 3)), np.zeros(nsys)
+    stat, niter = np.zeros(nsys, dtype=np.int32), np.zeros(nsys, dtype=np.int32)
+    _check(lib().qcxms_b200_egrad_batch(nsys, nat, _ip(num), _dp(xyz), int(charge), int(multiplicity), int(method), float(etemp),
+                                        _dp(qat), _dp(e), _dp(grad), _ip(stat), _ip(niter)))
+    return dict(qat=qat, energy=e, gradient=grad, stat=stat, niter=niter)
+
+
+def fragment_structure(num, xyz, rcut=3.0):
+    """fragment_structure(nat, oz, xyz, rcut, 1, 0, frag) for xyz[nsys, nat, 3] -> frag[nsys, nat] (int32)."""
+    num = np.ascontiguousarray(num, dtype=np.int32)
+    nat = len(num)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, nat, 3)
+    frag = np.zeros((xyz.shape[0], nat), dtype=np.int32)
+    _check(lib().qcxms_b200_fragment_structure(xyz.shape[0], nat, _ip(num), _dp(xyz), float(rcut), _ip(frag)))
+    return frag
+
+
+class Ensemble:
+    """A batch of EI trajectories of one molecule: the replacement for one `qcxms --prod` process per
+    TMPQCXMS/TMP.<n> directory (reference bin/pqcxms:88-98) running md() (reference src/md.f90:34)."""
+
+    def __init__(self, num, mass, ntraj, mchrg=1, tstep_fs=0.5, nmax=10000, nfragexit=3, exit_rules=True, method=gfn2_xtb,
+                 etemp=-1.0, ieetemp=0.0, ax=0.0, isec=1, device=0):
+        self.num = np.ascontiguousarray(num, dtype=np.int32)
+        self.nat = len(self.num)
+        self.ntraj = int(ntraj)
+        self.mass = np.ascontiguousarray(mass, dtype=np.float64)
+        self.cfg = MdConfig(int(method), int(mchrg), int(nfragexit), int(bool(exit_rules)), int(nmax), int(isec),
+                            float(tstep_fs) * FSTOAU, float(etemp), float(ieetemp), float(ax))
+        self._h = C.c_void_p()
+        _check(lib().qcxms_b200_ensemble_create(C.byref(self.cfg), self.ntraj, self.nat, _ip(self.num), _dp(self.mass), int(device),
+                                                C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().qcxms_b200_ensemble_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_trajectory(self, itrj, xyz, velo, velof, eimp, tadd):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64); velo = np.ascontiguousarray(velo, dtype=np.float64)
+        velof = np.ascontiguousarray(velof, dtype=np.float64)
+        _check(lib().qcxms_b200_ensemble_set_trajectory(self._h, int(itrj), _dp(xyz), _dp(velo), _dp(velof), float(eimp), float(tadd)))
+
+    def set_all(self, xyz, velo, velof, eimp, tadd):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (xyz, velo, velof, eimp, tadd)]
+        assert a[0].size == self.ntraj * self.nat * 3 and a[3].size == self.ntraj
+        _check(lib().qcxms_b200_ensemble_set_all(self._h, *[_dp(v) for v in a]))
+
+    def run_md(self, max_steps=0):
+        """Runs md() for every trajectory; returns the number of trajectory-MD-steps executed."""
+        n = C.c_int64(0)
+        _check(lib().qcxms_b200_ensemble_run_md(self._h, int(max_steps), C.byref(n)))
+        return n.value
+
+    def result(self, itrj):
+        nat = self.nat
+        out = dict(xyz=np.zeros((nat, 3)), velo=np.zeros((nat, 3)), grad=np.zeros((nat, 3)), list=np.zeros(nat, dtype=np.int32),
+                   achrg=np.zeros(nat), axyz=np.zeros((nat, 3)))
+        res = MdResult()
+        _check(lib().qcxms_b200_ensemble_get_result(self._h, int(itrj), _dp(out["xyz"]), _dp(out["velo"]), _dp(out["grad"]),
+                                                    _ip(out["list"]), _dp(out["achrg"]), _dp(out["axyz"]), C.byref(res)))
+        for k, _ in MdResult._fields_:
+            out[k] = getattr(res, k)
+        return out
+
+    def last_timing(self):
+        ms, launches, scc = C.c_double(0), C.c_int64(0), C.c_int64(0)
+        _check(lib().qcxms_b200_ensemble_last_timing(self._h, C.byref(ms), C.byref(launches), C.byref(scc)))
+        return dict(kernel_ms=ms.value, launches=launches.value, scc_iterations=scc.value)
+
+    def histogram(self, nbins=512):
+        bins = np.zeros(nbins)
+        dev = C.c_void_p()
+        _check(lib().qcxms_b200_ensemble_histogram(self._h, int(nbins), _dp(bins), C.byref(dev)))
+        return bins, dev.value
+
+
+def load_molecule(name):
+    """Benchmark/test input geometries (bohr): the reference's share/examples molecules + caffeine."""
+    with open(os.path.join(_HERE, "data", "molecules.json")) as f:
+        m = json.load(f)[name]
+    return np.array(m["num"], dtype=np.int32), np.array(m["xyz"], dtype=np.float64), int(m["charge"])

@@ -1,0 +1,609 @@
+// C ABI of qcxms_b200 (include/qcxms_b200.h) and the ensemble kernels.
+//
+// Kernels are persistent: a grid of (resident CTAs per SM x SM count) CTAs pulls trajectories from an
+// atomic work queue; one CTA owns one trajectory at a time and keeps the SCC matrices in shared memory
+// and the integral slab in its private, L2-resident global scratch.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/qcxms_b200.h"
+#include "qx_host_model.h"
+#include "qx_md.cuh"
+
+using namespace qx;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_OK(expr)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (expr);                                                                          \
+        if (e__ != cudaSuccess) return fail(QCXMS_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(QX_NT) k_egrad_batch(DevModel m, ScratchLayout L, double *scratch, const double *xyz, double kt, int nsys,
+                                                       int *queue, double *energy, double *grad, double *qat, int *stat, int *niter) {
+    extern __shared__ double smem[];
+    __shared__ int s_next;
+    Sm s;
+    carve(m, smem, s);
+    double *my = scratch + (size_t)blockIdx.x * L.total;
+    const int nat = m.nat;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
+        __syncthreads();
+        const int t = s_next;
+        if (t >= nsys) break;
+        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.xyz[i] = xyz[(size_t)t * 3 * nat + i];
+        __syncthreads();
+        EgradOut o;
+        egrad_cta(m, s, my, L, kt, o);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) grad[(size_t)t * 3 * nat + i] = s.grad[i];
+        for (int i = threadIdx.x; i < nat; i += QX_NT) qat[(size_t)t * nat + i] = s.qat[i];
+        if (threadIdx.x == 0) {
+            energy[t] = o.energy;
+            stat[t] = o.stat == 0 ? 0 : -1;
+            if (niter) niter[t] = o.niter;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(QX_NT) k_fragments(DevModel m, const double *xyz, double rcut, int nsys, int *frag, unsigned char *conn, int *stack) {
+    const int nat = m.nat;
+    for (int t = blockIdx.x; t < nsys; t += gridDim.x)
+        md_fragments(m, xyz + (size_t)t * 3 * nat, rcut, conn + (size_t)blockIdx.x * nat * nat, frag + (size_t)t * nat, stack + (size_t)blockIdx.x * nat);
+}
+
+// one egrad + sanity gate for trajectory t; returns Epot (0 on failure, like the reference's checkqc)
+__device__ inline double md_egrad(const DevModel &m, Sm &s, double *my, const ScratchLayout &L, const MdConfig &cfg, const MdState &st, int t, double etemp) {
+    const int nat = m.nat;
+    EgradOut o;
+    egrad_cta(m, s, my, L, etemp * QC_KTOAU, o);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool ok = o.stat != -2 && md_checkqc(m, o.energy, s.grad, s.qat, cfg.mchrg);
+        s.red[48] = ok ? o.energy : 0.0;
+        st.scc_total[t] += o.niter;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) st.grad[(size_t)t * 3 * nat + i] = s.grad[i];
+    for (int i = threadIdx.x; i < nat; i += QX_NT) st.achrg[(size_t)t * nat + i] = s.qat[i];
+    return s.red[48];
+}
+
+// md(): everything before the loop (reference src/md.f90:155-283)
+__global__ void __launch_bounds__(QX_NT) k_md_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int *queue) {
+    extern __shared__ double smem[];
+    __shared__ int s_next;
+    Sm s;
+    carve(m, smem, s);
+    double *my = scratch + (size_t)blockIdx.x * L.total;
+    const int nat = m.nat;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
+        __syncthreads();
+        const int t = s_next;
+        if (t >= ntraj) break;
+        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.xyz[i] = st.xyz[(size_t)t * 3 * nat + i];
+        __syncthreads();
+        const double eimp = st.eimp[t];
+        const double etemp = cfg.etemp_in < 0.0 ? md_setetemp(cfg, 1, eimp) : cfg.etemp_in;
+        const double epot = md_egrad(m, s, my, L, cfg, st, t, etemp);
+        if (threadIdx.x == 0) {
+            const double ekin = md_ekinet_seq(nat, st.velo + (size_t)t * 3 * nat, m.mass, 0.0, nullptr);
+            const double tadd = st.tadd[t];
+            st.ekin[t] = ekin; st.ekinstart[t] = ekin; st.epot[t] = epot; st.etemp[t] = etemp;
+            st.Tav[t] = 0; st.Epav[t] = 0; st.Ekav[t] = 0; st.Edum[t] = 0; st.aTlast[t] = 0; st.dtime[t] = 0; st.ttime[t] = 0;
+            st.nstep[t] = 0; st.kdump[t] = 50; st.fconst[t] = 0; st.morestep[t] = 0; st.nfrag[t] = 1;
+            st.fragstate[t] = 0; st.mdok[t] = 0;
+            st.nadd[t] = (int)((tadd + cfg.tstep) / cfg.tstep - 1.0);
+            st.fadd[t] = cfg.tstep / (tadd + cfg.tstep);
+            st.status[t] = epot == 0.0 ? TRJ_FAILED : TRJ_RUNNING;
+        }
+        for (int i = threadIdx.x; i < nat; i += QX_NT) { st.avchrg[(size_t)t * nat + i] = 0.0; st.list[(size_t)t * nat + i] = 1; }
+        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) st.avxyz[(size_t)t * 3 * nat + i] = 0.0;
+    }
+}
+
+// up to `chunk` MD steps (reference src/md.f90:285-682) for every running trajectory
+__global__ void __launch_bounds__(QX_NT) k_md_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int chunk,
+                                                    int step_limit, int *queue, unsigned long long *steps_done) {
+    extern __shared__ double smem[];
+    __shared__ int s_next, s_flag;
+    Sm s;
+    carve(m, smem, s);
+    double *my = scratch + (size_t)blockIdx.x * L.total;
+    const int nat = m.nat;
+    const double fstoau = QC_FSTOAU, kB = QC_KB;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
+        __syncthreads();
+        const int t = s_next;
+        if (t >= ntraj) break;
+        if (st.status[t] != TRJ_RUNNING) continue;
+        double *xyz = st.xyz + (size_t)t * 3 * nat, *velo = st.velo + (size_t)t * 3 * nat, *grad = st.grad + (size_t)t * 3 * nat;
+        double *achrg = st.achrg + (size_t)t * nat, *avchrg = st.avchrg + (size_t)t * nat, *avxyz = st.avxyz + (size_t)t * 3 * nat;
+        const double *velof = st.velof + (size_t)t * nat;
+        int *list = st.list + (size_t)t * nat;
+        // scalar state, kept redundantly in every thread
+        int nstep = st.nstep[t], kdump = st.kdump[t], fconst = st.fconst[t], morestep = st.morestep[t], nfrag = st.nfrag[t];
+        int fragstate = 0, mdok = 0, status = TRJ_RUNNING;
+        const int nadd = st.nadd[t];
+        const double fadd = st.fadd[t], eimp = st.eimp[t], ekinstart = st.ekinstart[t];
+        double epot = st.epot[t], ekin = st.ekin[t], etemp = st.etemp[t], Tav = st.Tav[t], Epav = st.Epav[t], Ekav = st.Ekav[t], Edum = st.Edum[t];
+        double aTlast = st.aTlast[t], dtime = st.dtime[t], ttime = st.ttime[t];
+        const int max_steps = step_limit > 0 && step_limit < cfg.nmax ? step_limit : cfg.nmax;
+        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.xyz[i] = xyz[i];
+        __syncthreads();
+        int done = 0;
+        for (int it = 0; it < chunk && status == TRJ_RUNNING; ++it) {
+            nstep += 1;
+            const double T = ekin / (0.5 * 3 * nat * kB);
+            Tav += T; Epav += epot; Ekav += ekin;
+            double Eav;
+            if (nstep > nadd) { Edum += epot + ekin; Eav = Edum / (double)(float)(nstep - nadd); }
+            else Eav = epot + ekin;
+            const double Eerror = Eav - epot - ekin;
+            const bool err1 = epot == 0.0, err2 = fabs(Eerror) > (double)0.1f;
+            if (err1 || (err2 && cfg.exit_rules)) {
+                mdok = ((nfrag > 1 && nfrag <= 4) || cfg.isec > 1) ? 1 : 0;
+                status = TRJ_FINISHED;
+                break;
+            }
+            if (kdump > 50 - 1) {
+                kdump = 0;
+                aTlast = 0.0;
+                for (int i = threadIdx.x; i < nat; i += QX_NT) avchrg[i] = 0.0;
+                for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) avxyz[i] = 0.0;
+            }
+            for (int i = threadIdx.x; i < nat; i += QX_NT) avchrg[i] += achrg[i];
+            for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) avxyz[i] += s.xyz[i];
+            aTlast += T;
+            // leapfrog (reference md.f90:749-773); kinetic-energy terms summed in the reference order
+            for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) {
+                const double mass = m.mass[i / 3];
+                const double vold = velo[i];
+                const double vnew = __dsub_rn(vold, __ddiv_rn(__dmul_rn(cfg.tstep, grad[i]), mass));
+                const double vavg = __dmul_rn(0.5, __dadd_rn(vold, vnew));
+                const double x = __dadd_rn(s.xyz[i], __dmul_rn(cfg.tstep, vnew));
+                velo[i] = vnew;
+                s.xyz[i] = x;
+                xyz[i] = x;
+                s.vdp[i] = __dmul_rn(0.5, __dmul_rn(__dmul_rn(mass, vavg), vavg));
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double ke = 0.0;
+                for (int i = 0; i < 3 * nat; ++i) ke = __dadd_rn(ke, s.vdp[i]);
+                s.red[49] = ke;
+            }
+            __syncthreads();
+            ekin = s.red[49];
+            ttime += cfg.tstep / fstoau;
+            epot = md_egrad(m, s, my, L, cfg, st, t, etemp);
+            done += 1;
+            kdump += 1;
+            if (nfrag == 1) morestep = 0;
+            if (nfrag > 1 && dtime < 1e-6) dtime = ttime / 1000.0;
+            // IEE heating while the ion is intact
+            if (nstep <= nadd && nfrag == 1) {
+                if (!md_impactscale(m, velo, velof, eimp, fadd * nstep, ekinstart, &s_flag)) { status = TRJ_FAILED; break; }
+            }
+            if (cfg.etemp_in < 0.0) {
+                const double dum = eimp - eimp * (double)(float)nstep / (double)(float)nadd;
+                etemp = md_setetemp(cfg, nfrag, dum);
+            }
+            md_fragments(m, s.xyz, 3.0, (unsigned char *)(my + L.taskout), list, (int *)(my + L.taskout) + (nat * nat + 3) / 4 + 4);
+            if (threadIdx.x == 0) s_flag = md_nfrag(m, list);
+            __syncthreads();
+            nfrag = s_flag;
+            if (cfg.exit_rules) {
+                if (nfrag > 6) { status = TRJ_FINISHED; break; }
+                if (nfrag > cfg.nfragexit) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
+                fconst = nfrag >= 2 ? fconst + 1 : 0;
+                if (fconst > 1000) { fragstate = 2; mdok = 1; status = TRJ_FINISHED; break; }
+                if (nfrag >= cfg.nfragexit) {
+                    morestep += 1;
+                    if (morestep > 250) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
+                }
+            }
+            if (nstep >= max_steps) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            st.nstep[t] = nstep; st.kdump[t] = kdump; st.fconst[t] = fconst; st.morestep[t] = morestep; st.nfrag[t] = nfrag;
+            st.epot[t] = epot; st.ekin[t] = ekin; st.etemp[t] = etemp; st.Tav[t] = Tav; st.Epav[t] = Epav; st.Ekav[t] = Ekav; st.Edum[t] = Edum;
+            st.aTlast[t] = aTlast; st.dtime[t] = dtime; st.ttime[t] = ttime;
+            if (status != TRJ_RUNNING) { st.status[t] = status; st.fragstate[t] = fragstate; st.mdok[t] = mdok; }
+            atomicAdd(steps_done, (unsigned long long)done);
+        }
+    }
+}
+
+__global__ void k_histogram(DevModel m, MdState st, int ntraj, int nbins, double *bins) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntraj || st.status[t] != TRJ_FINISHED || !st.mdok[t]) return;
+    const int *list = st.list + (size_t)t * m.nat;
+    for (int f = 1; f <= 10; ++f) {
+        double mass = 0.0;
+        for (int i = 0; i < m.nat; ++i)
+            if (list[i] == f) mass += m.mass[i];
+        if (mass > 0.0) {
+            int bin = (int)llrint(mass * QC_AUTOAMU);
+            if (bin >= 0 && bin < nbins) atomicAdd(&bins[bin], 1.0);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+struct Context {
+    HostModel hm;
+    ScratchLayout L{};
+    int ncta = 0, device = 0;
+    size_t smem = 0;
+    double *d_scratch = nullptr;
+    int *d_queue = nullptr;
+    std::vector<int32_t> key;
+};
+
+static int context_init(Context &c, int nat, const int32_t *num, const double *mass, int charge, int multiplicity, int device, int nwork) {
+    CUDA_OK(cudaSetDevice(device));
+    std::string why = build_host_model(c.hm, nat, num, mass, charge, multiplicity);
+    if (!why.empty()) return fail(QCXMS_B200_ERR_UNSUPPORTED, why);
+    CUDA_OK(upload_model(c.hm));
+    c.L = make_layout(c.hm);
+    c.device = device;
+    c.smem = smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld) * sizeof(double) + 64;
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (c.smem > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(QCXMS_B200_ERR_UNSUPPORTED, "basis too large for the shared-memory SCC kernel (nao = " + std::to_string(c.hm.nao) + ")");
+    CUDA_OK(cudaFuncSetAttribute(k_egrad_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    CUDA_OK(cudaFuncSetAttribute(k_md_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    CUDA_OK(cudaFuncSetAttribute(k_md_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    int per_sm = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_chunk, QX_NT, c.smem));
+    if (per_sm < 1) per_sm = 1;
+    c.ncta = per_sm * prop.multiProcessorCount;
+    if (nwork > 0 && c.ncta > nwork) c.ncta = nwork;
+    CUDA_OK(cudaMalloc(&c.d_scratch, c.L.total * sizeof(double) * (size_t)c.ncta));
+    CUDA_OK(cudaMalloc(&c.d_queue, sizeof(int)));
+    return 0;
+}
+
+static void context_free(Context &c) {
+    if (c.d_scratch) cudaFree(c.d_scratch);
+    if (c.d_queue) cudaFree(c.d_queue);
+    if (c.hm.d_blob) cudaFree(c.hm.d_blob);
+    c.d_scratch = nullptr; c.d_queue = nullptr; c.hm.d_blob = nullptr;
+}
+
+extern "C" int qcxms_b200_egrad_batch(int nsys, int nat, const int32_t *num, const double *xyz, int charge, int multiplicity, int method_id,
+                                      double etemp, double *qat, double *energy, double *gradient, int32_t *stat, int32_t *niter) {
+    if (nsys < 1 || nat < 1 || !num || !xyz || !qat || !energy || !gradient || !stat) return fail(QCXMS_B200_ERR_ARG, "null or empty argument");
+    if (method_id != QCXMS_B200_GFN2) {
+        // reference: unknown method -> stat = 5, outputs untouched (src/tblite.f90:114-120).  GFN1/IPEA1 are not built yet.
+        for (int i = 0; i < nsys; ++i) stat[i] = QCXMS_B200_STAT_UNKNOWN_METHOD;
+        return 0;
+    }
+    // cache the model of the last composition: the reference calls this entry point once per MD step
+    static std::mutex mtx;
+    static Context ctx;
+    std::lock_guard<std::mutex> lock(mtx);
+    std::vector<int32_t> key(num, num + nat);
+    key.push_back(charge); key.push_back(multiplicity); key.push_back(nsys > 1 ? 1 << 20 : 1);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (key != ctx.key || ctx.device != dev) {
+        context_free(ctx);
+        ctx.key.clear();
+        int rc = context_init(ctx, nat, num, nullptr, charge, multiplicity, dev, nsys > 1 ? 0 : 1);
+        if (rc) { context_free(ctx); return rc; }
+        ctx.key = key;
+    }
+    const size_t n3 = (size_t)nsys * nat * 3;
+    double *d_xyz = nullptr, *d_e = nullptr, *d_g = nullptr, *d_q = nullptr;
+    int *d_stat = nullptr, *d_nit = nullptr;
+    CUDA_OK(cudaMalloc(&d_xyz, n3 * sizeof(double)));
+    CUDA_OK(cudaMalloc(&d_g, n3 * sizeof(double)));
+    CUDA_OK(cudaMalloc(&d_q, (size_t)nsys * nat * sizeof(double)));
+    CUDA_OK(cudaMalloc(&d_e, nsys * sizeof(double)));
+    CUDA_OK(cudaMalloc(&d_stat, nsys * sizeof(int)));
+    CUDA_OK(cudaMalloc(&d_nit, nsys * sizeof(int)));
+    CUDA_OK(cudaMemcpy(d_xyz, xyz, n3 * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemset(ctx.d_queue, 0, sizeof(int)));
+    int grid = ctx.ncta < nsys ? ctx.ncta : nsys;
+    k_egrad_batch<<<grid, QX_NT, ctx.smem>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, d_xyz, etemp * QC_KTOAU, nsys, ctx.d_queue, d_e, d_g, d_q, d_stat, d_nit);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(energy, d_e, nsys * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(gradient, d_g, n3 * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(qat, d_q, (size_t)nsys * nat * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(stat, d_stat, nsys * sizeof(int), cudaMemcpyDeviceToHost));
+    if (niter) CUDA_OK(cudaMemcpy(niter, d_nit, nsys * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_xyz); cudaFree(d_g); cudaFree(d_q); cudaFree(d_e); cudaFree(d_stat); cudaFree(d_nit);
+    return 0;
+}
+
+extern "C" int qcxms_b200_egrad(int nat, const int32_t *num, const double *xyz, int charge, int multiplicity, int method_id, double etemp,
+                                double *qat, double *energy, double *gradient, int32_t *stat) {
+    return qcxms_b200_egrad_batch(1, nat, num, xyz, charge, multiplicity, method_id, etemp, qat, energy, gradient, stat, nullptr);
+}
+
+extern "C" int qcxms_b200_fragment_structure(int nsys, int nat, const int32_t *num, const double *xyz, double rcut, int32_t *frag) {
+    if (nsys < 1 || nat < 1 || !num || !xyz || !frag) return fail(QCXMS_B200_ERR_ARG, "null or empty argument");
+    // only the radii table is needed: build a minimal model
+    std::vector<double> qcrad(nat), mass(nat);
+    for (int i = 0; i < nat; ++i) {
+        if (num[i] < 1 || num[i] > ELEM_MAXZ) return fail(QCXMS_B200_ERR_ARG, "bad atomic number");
+        qcrad[i] = QC_AATOAU * QCXMS_RAD_AA[num[i]];
+        mass[i] = ATOMIC_MASS_AMU[num[i]] * QC_AMUTOAU;
+    }
+    DevModel m{};
+    m.nat = nat;
+    double *d_rad, *d_xyz;
+    int *d_frag, *d_stack;
+    unsigned char *d_conn;
+    int grid = nsys < 1024 ? nsys : 1024;
+    CUDA_OK(cudaMalloc(&d_rad, nat * sizeof(double)));
+    CUDA_OK(cudaMalloc(&d_xyz, (size_t)nsys * nat * 3 * sizeof(double)));
+    CUDA_OK(cudaMalloc(&d_frag, (size_t)nsys * nat * sizeof(int)));
+    CUDA_OK(cudaMalloc(&d_stack, (size_t)grid * nat * sizeof(int)));
+    CUDA_OK(cudaMalloc(&d_conn, (size_t)grid * nat * nat));
+    CUDA_OK(cudaMemcpy(d_rad, qcrad.data(), nat * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_xyz, xyz, (size_t)nsys * nat * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    m.at_qcrad = d_rad;
+    k_fragments<<<grid, QX_NT>>>(m, d_xyz, rcut, nsys, d_frag, d_conn, d_stack);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpy(frag, d_frag, (size_t)nsys * nat * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_rad); cudaFree(d_xyz); cudaFree(d_frag); cudaFree(d_stack); cudaFree(d_conn);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ ensemble
+struct qcxms_b200_ensemble {
+    Context ctx;
+    MdConfig cfg{};
+    MdState st{};
+    int ntraj = 0;
+    std::vector<void *> allocs;
+    unsigned long long *d_steps = nullptr;
+    double *d_bins = nullptr;
+    int nbins = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool initialised = false;
+    double last_ms = 0.0;
+    int64_t launches = 0, scc_iters = 0;
+};
+
+template <class T>
+static cudaError_t ens_alloc(qcxms_b200_ensemble *h, T **p, size_t n) {
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e == cudaSuccess) {
+        h->allocs.push_back(*p);
+        e = cudaMemset(*p, 0, n * sizeof(T));
+    }
+    return e;
+}
+
+extern "C" int qcxms_b200_ensemble_create(const qcxms_b200_md_config_t *cfg, int ntraj, int nat, const int32_t *num, const double *mass, int device,
+                                          qcxms_b200_ensemble_t **out) {
+    if (!cfg || !num || !out || ntraj < 1 || nat < 1) return fail(QCXMS_B200_ERR_ARG, "null or empty argument");
+    if (cfg->method_id != QCXMS_B200_GFN2) return fail(QCXMS_B200_ERR_UNSUPPORTED, "only GFN2-xTB (method id 2) is implemented");
+    auto *h = new qcxms_b200_ensemble();
+    // multiplicity as the reference's getspin() would pass it (src/utility.f90:449-464); tblite discards it anyway
+    int zsum = 0;
+    for (int i = 0; i < nat; ++i) zsum += num[i];
+    int j = zsum - std::abs(cfg->mchrg);
+    int mult = j < 1 ? -1 : 1 + j % 2;
+    int rc = context_init(h->ctx, nat, num, mass, cfg->mchrg, mult, device, ntraj);
+    if (rc) { context_free(h->ctx); delete h; return rc; }
+    h->ntraj = ntraj;
+    h->cfg.mchrg = cfg->mchrg; h->cfg.nfragexit = cfg->nfragexit; h->cfg.exit_rules = cfg->exit_rules; h->cfg.nmax = cfg->nmax; h->cfg.isec = cfg->isec;
+    h->cfg.tstep = cfg->tstep; h->cfg.etemp_in = cfg->etemp_in; h->cfg.ieetemp = cfg->ieetemp; h->cfg.ax = cfg->ax;
+    const size_t n1 = (size_t)ntraj * nat, n3 = n1 * 3, nt = ntraj;
+    MdState &s = h->st;
+    cudaError_t e = cudaSuccess;
+#define EA(field, n) if (e == cudaSuccess) e = ens_alloc(h, &s.field, n)
+    EA(xyz, n3); EA(velo, n3); EA(grad, n3); EA(achrg, n1); EA(velof, n1); EA(avchrg, n1); EA(avxyz, n3);
+    EA(eimp, nt); EA(tadd, nt); EA(epot, nt); EA(ekin, nt); EA(ekinstart, nt); EA(etemp, nt); EA(Tav, nt); EA(Epav, nt); EA(Ekav, nt); EA(Edum, nt);
+    EA(aTlast, nt); EA(dtime, nt); EA(ttime, nt); EA(fadd, nt);
+    EA(nstep, nt); EA(kdump, nt); EA(fconst, nt); EA(morestep, nt); EA(nfrag, nt); EA(status, nt); EA(fragstate, nt); EA(mdok, nt); EA(nadd, nt);
+    EA(list, n1); EA(scc_total, nt);
+#undef EA
+    if (e == cudaSuccess) e = ens_alloc(h, &h->d_steps, 1);
+    if (e == cudaSuccess) e = cudaStreamCreate(&h->stream);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e != cudaSuccess) {
+        std::string msg = cudaGetErrorString(e);
+        qcxms_b200_ensemble_destroy(h);
+        return fail(QCXMS_B200_ERR_CUDA, "ensemble allocation: " + msg);
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int qcxms_b200_ensemble_destroy(qcxms_b200_ensemble_t *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->ctx.device);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->d_bins) cudaFree(h->d_bins);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    context_free(h->ctx);
+    delete h;
+    return 0;
+}
+
+extern "C" int qcxms_b200_ensemble_set_trajectory(qcxms_b200_ensemble_t *h, int itrj, const double *xyz, const double *velo, const double *velof,
+                                                  double eimp, double tadd) {
+    if (!h || itrj < 0 || itrj >= h->ntraj || !xyz || !velo || !velof) return fail(QCXMS_B200_ERR_ARG, "bad trajectory index or null array");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    const size_t nat = h->ctx.hm.nat;
+    CUDA_OK(cudaMemcpy(h->st.xyz + itrj * nat * 3, xyz, nat * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->st.velo + itrj * nat * 3, velo, nat * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->st.velof + itrj * nat, velof, nat * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->st.eimp + itrj, &eimp, sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->st.tadd + itrj, &tadd, sizeof(double), cudaMemcpyHostToDevice));
+    h->initialised = false;
+    return 0;
+}
+
+extern "C" int qcxms_b200_ensemble_set_all(qcxms_b200_ensemble_t *h, const double *xyz, const double *velo, const double *velof, const double *eimp,
+                                           const double *tadd) {
+    if (!h || !xyz || !velo || !velof || !eimp || !tadd) return fail(QCXMS_B200_ERR_ARG, "null array");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    const size_t n1 = (size_t)h->ntraj * h->ctx.hm.nat;
+    CUDA_OK(cudaMemcpyAsync(h->st.xyz, xyz, n1 * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->st.velo, velo, n1 * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->st.velof, velof, n1 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->st.eimp, eimp, h->ntraj * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->st.tadd, tadd, h->ntraj * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->initialised = false;
+    return 0;
+}
+
+extern "C" int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_steps, int64_t *steps_done) {
+    if (!h) return fail(QCXMS_B200_ERR_ARG, "null handle");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    Context &c = h->ctx;
+    const int grid = c.ncta < h->ntraj ? c.ncta : h->ntraj;
+    h->launches = 0;
+    CUDA_OK(cudaMemsetAsync(h->d_steps, 0, sizeof(unsigned long long), h->stream));
+    CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+    int base_step = 0;
+    if (!h->initialised) {
+        CUDA_OK(cudaMemsetAsync(c.d_queue, 0, sizeof(int), h->stream));
+        k_md_init<<<grid, QX_NT, c.smem, h->stream>>>(c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, c.d_queue);
+        CUDA_OK(cudaGetLastError());
+        h->launches += 1;
+        h->initialised = true;
+    } else {
+        // continue: the step limit is relative to the steps already taken (all trajectories advance in lockstep chunks)
+        std::vector<int> ns(h->ntraj);
+        CUDA_OK(cudaMemcpyAsync(ns.data(), h->st.nstep, h->ntraj * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        for (int v : ns) base_step = v > base_step ? v : base_step;
+    }
+    const int limit = max_steps > 0 ? base_step + max_steps : 0;
+    const int total = max_steps > 0 ? max_steps : h->cfg.nmax;
+    const int chunk = 64;
+    std::vector<int> status(h->ntraj);
+    for (int done = 0; done < total; done += chunk) {
+        const int this_chunk = total - done < chunk ? total - done : chunk;
+        CUDA_OK(cudaMemsetAsync(c.d_queue, 0, sizeof(int), h->stream));
+        k_md_chunk<<<grid, QX_NT, c.smem, h->stream>>>(c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, this_chunk, limit, c.d_queue, h->d_steps);
+        CUDA_OK(cudaGetLastError());
+        h->launches += 1;
+        // poll for completion every few chunks (cheap: ntraj ints)
+        if ((done / chunk) % 4 == 3 || done + chunk >= total) {
+            CUDA_OK(cudaMemcpyAsync(status.data(), h->st.status, h->ntraj * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_OK(cudaStreamSynchronize(h->stream));
+            bool any = false;
+            for (int v : status) any = any || v == TRJ_RUNNING;
+            if (!any) break;
+        }
+    }
+    CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    unsigned long long steps = 0;
+    CUDA_OK(cudaMemcpy(&steps, h->d_steps, sizeof(steps), cudaMemcpyDeviceToHost));
+    if (steps_done) *steps_done = (int64_t)steps;
+    std::vector<int> scc(h->ntraj);
+    CUDA_OK(cudaMemcpy(scc.data(), h->st.scc_total, h->ntraj * sizeof(int), cudaMemcpyDeviceToHost));
+    h->scc_iters = 0;
+    for (int v : scc) h->scc_iters += v;
+    return 0;
+}
+
+extern "C" int qcxms_b200_ensemble_get_result(qcxms_b200_ensemble_t *h, int itrj, double *xyz, double *velo, double *grad, int32_t *list, double *achrg,
+                                              double *axyz, qcxms_b200_md_result_t *res) {
+    if (!h || itrj < 0 || itrj >= h->ntraj) return fail(QCXMS_B200_ERR_ARG, "bad trajectory index");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    const size_t nat = h->ctx.hm.nat, t = itrj;
+    const MdState &s = h->st;
+    int nstep, kdump;
+    CUDA_OK(cudaMemcpy(&nstep, s.nstep + t, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(&kdump, s.kdump + t, sizeof(int), cudaMemcpyDeviceToHost));
+    if (xyz) CUDA_OK(cudaMemcpy(xyz, s.xyz + t * nat * 3, nat * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (velo) CUDA_OK(cudaMemcpy(velo, s.velo + t * nat * 3, nat * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (grad) CUDA_OK(cudaMemcpy(grad, s.grad + t * nat * 3, nat * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (list) CUDA_OK(cudaMemcpy(list, s.list + t * nat, nat * sizeof(int), cudaMemcpyDeviceToHost));
+    // averages over the last kdump steps (reference src/md.f90:688-700)
+    if (achrg) {
+        CUDA_OK(cudaMemcpy(achrg, s.avchrg + t * nat, nat * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < nat; ++i) achrg[i] /= kdump;
+    }
+    if (axyz) {
+        CUDA_OK(cudaMemcpy(axyz, s.avxyz + t * nat * 3, nat * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < nat * 3; ++i) axyz[i] /= kdump;
+    }
+    if (res) {
+        double Tav, Epav, Ekav, aTlast;
+        CUDA_OK(cudaMemcpy(&res->mdok, s.mdok + t, sizeof(int), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&res->fragstate, s.fragstate + t, sizeof(int), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&res->nfrag, s.nfrag + t, sizeof(int), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&res->status, s.status + t, sizeof(int), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&res->scc_iter_total, s.scc_total + t, sizeof(int), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&Tav, s.Tav + t, sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&Epav, s.Epav + t, sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&Ekav, s.Ekav + t, sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&aTlast, s.aTlast + t, sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&res->dtime, s.dtime + t, sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&res->ttime, s.ttime + t, sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&res->Epot, s.epot + t, sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(&res->Ekin, s.ekin + t, sizeof(double), cudaMemcpyDeviceToHost));
+        res->nstep = nstep;
+        const int div = nstep > 0 ? nstep : 1;
+        res->Tav = Tav / div; res->Epav = Epav / div; res->Ekav = Ekav / div;
+        res->aTlast = aTlast / (kdump > 0 ? kdump : 1);
+    }
+    return 0;
+}
+
+extern "C" int qcxms_b200_ensemble_last_timing(qcxms_b200_ensemble_t *h, double *kernel_ms, int64_t *launches, int64_t *scc_iterations) {
+    if (!h) return fail(QCXMS_B200_ERR_ARG, "null handle");
+    if (kernel_ms) *kernel_ms = h->last_ms;
+    if (launches) *launches = h->launches;
+    if (scc_iterations) *scc_iterations = h->scc_iters;
+    return 0;
+}
+
+extern "C" int qcxms_b200_ensemble_histogram(qcxms_b200_ensemble_t *h, int nbins, double *bins_host, void **bins_device) {
+    if (!h || nbins < 1) return fail(QCXMS_B200_ERR_ARG, "bad argument");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    if (h->nbins != nbins) {
+        if (h->d_bins) cudaFree(h->d_bins);
+        CUDA_OK(cudaMalloc(&h->d_bins, nbins * sizeof(double)));
+        h->nbins = nbins;
+    }
+    CUDA_OK(cudaMemsetAsync(h->d_bins, 0, nbins * sizeof(double), h->stream));
+    k_histogram<<<(h->ntraj + 127) / 128, 128, 0, h->stream>>>(h->ctx.hm.dev, h->st, h->ntraj, nbins, h->d_bins);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (bins_host) CUDA_OK(cudaMemcpy(bins_host, h->d_bins, nbins * sizeof(double), cudaMemcpyDeviceToHost));
+    if (bins_device) *bins_device = h->d_bins;
+    return 0;
+}
+
+extern "C" const char *qcxms_b200_last_error(void) { return g_err.c_str(); }
+extern "C" const char *qcxms_b200_version(void) { return "qcxms_b200 0.1 (sm_100a)"; }

@@ -1,0 +1,679 @@
+// Device side of the GFN2-xTB energy/gradient evaluation: one CTA (QX_NT threads) per
+// trajectory, matrices of the SCC staged in shared memory, integrals in a per-CTA
+// global scratch slab that stays L2-resident.
+//
+// Replaces (for the batched ensemble) what the reference obtains from tblite through
+// get_xtb_egrad (reference src/tblite.f90:65-175; call protocol :111,:123,:133,:136):
+// zeroed wavefunction on every call, accuracy 1.0, Broyden-mixed SCC with Fermi smearing.
+// Every summation runs in a fixed order (no floating-point atomics) so that a trajectory
+// is bitwise reproducible from run to run.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "params/gfn2_params.h"
+#include "qx_model.h"
+
+namespace qx {
+
+#define QX_PI 3.14159265358979323846264338327950288
+#define QX_SQRT3 1.7320508075688772935
+
+struct SphTerm {
+    int n;
+    int ex[3][3];
+    double c[3];
+};
+// real solid harmonics, index l*l + (m+l), order m = -l..l (p: y,z,x)
+__constant__ SphTerm c_sph[9] = {
+    {1, {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, {1.0, 0, 0}},
+    {1, {{0, 1, 0}, {0, 0, 0}, {0, 0, 0}}, {1.0, 0, 0}},
+    {1, {{0, 0, 1}, {0, 0, 0}, {0, 0, 0}}, {1.0, 0, 0}},
+    {1, {{1, 0, 0}, {0, 0, 0}, {0, 0, 0}}, {1.0, 0, 0}},
+    {1, {{1, 1, 0}, {0, 0, 0}, {0, 0, 0}}, {QX_SQRT3, 0, 0}},
+    {1, {{0, 1, 1}, {0, 0, 0}, {0, 0, 0}}, {QX_SQRT3, 0, 0}},
+    {3, {{0, 0, 2}, {2, 0, 0}, {0, 2, 0}}, {1.0, -0.5, -0.5}},
+    {1, {{1, 0, 1}, {0, 0, 0}, {0, 0, 0}}, {QX_SQRT3, 0, 0}},
+    {2, {{2, 0, 0}, {0, 2, 0}, {0, 0, 0}}, {0.5 * QX_SQRT3, -0.5 * QX_SQRT3, 0}}};
+
+// quadrupole component index pairs, order xx,xy,yy,xz,yz,zz
+__constant__ int c_qa[6] = {0, 0, 1, 0, 1, 2};
+__constant__ int c_qb[6] = {0, 1, 1, 2, 2, 2};
+__constant__ double c_qscale[6] = {1.0, 2.0, 1.0, 2.0, 2.0, 1.0};
+
+struct Sm {
+    double *A, *C;
+    double *xyz, *cn, *cn4, *mrad, *dmr, *qat, *vat, *dpat, *vdp, *qpat, *vqp;
+    double *qsh, *vsh, *selfen, *vao, *emo, *focc, *gw, *gwd, *dEdcn, *dEdcn4, *grad, *red, *rot;
+    int *rotp;
+};
+
+__host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld) {
+    return 2 * (size_t)nao * ld + 3 * nat + 6 * nat /*cn cn4 mrad dmr qat vat*/ + 6 * nat /*dpat vdp*/ + 12 * nat /*qpat vqp*/
+           + 3 * nsh + 3 * nao + 14 * nat /*gw gwd*/ + 2 * nat + 3 * nat /*grad*/ + 64 + 2 * (nao / 2 + 2) + (nao / 2 + 2) /*rotp as ints*/;
+}
+
+__device__ inline void carve(const DevModel &m, double *base, Sm &s) {
+    int nat = m.nat, nsh = m.nsh, nao = m.nao;
+    double *p = base;
+    s.A = p; p += (size_t)nao * m.ld;
+    s.C = p; p += (size_t)nao * m.ld;
+    s.xyz = p; p += 3 * nat;
+    s.cn = p; p += nat; s.cn4 = p; p += nat; s.mrad = p; p += nat; s.dmr = p; p += nat;
+    s.qat = p; p += nat; s.vat = p; p += nat;
+    s.dpat = p; p += 3 * nat; s.vdp = p; p += 3 * nat;
+    s.qpat = p; p += 6 * nat; s.vqp = p; p += 6 * nat;
+    s.qsh = p; p += nsh; s.vsh = p; p += nsh; s.selfen = p; p += nsh;
+    s.vao = p; p += nao; s.emo = p; p += nao; s.focc = p; p += nao;
+    s.gw = p; p += 7 * nat; s.gwd = p; p += 7 * nat;
+    s.dEdcn = p; p += nat; s.dEdcn4 = p; p += nat;
+    s.grad = p; p += 3 * nat;
+    s.red = p; p += 64;
+    s.rot = p; p += 2 * (nao / 2 + 2);
+    s.rotp = (int *)p;
+}
+
+__device__ inline double block_sum(double v, double *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < QX_NT / 32; ++i) acc += red[i];
+    return acc;
+}
+
+__device__ inline double block_max(double v, double *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double acc = red[0];
+#pragma unroll
+    for (int i = 1; i < QX_NT / 32; ++i) acc = fmax(acc, red[i]);
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------
+// coordination numbers (GFN double-exponential; D4 erf with EN weighting) + pair derivative
+// tables dcnp[i*nat+j] = (1/r) d f(r_ij)/dr, so that d cn_i/d R_i = sum_j dcnp_ij (R_i - R_j).
+__device__ inline void phase_cn(const DevModel &m, Sm &s, double *dcnp, double *dcnp4) {
+    const int nat = m.nat;
+    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+        double cn = 0.0, cn4 = 0.0;
+        double xi = s.xyz[3 * i], yi = s.xyz[3 * i + 1], zi = s.xyz[3 * i + 2];
+        double rci = m.at_rcov[i], eni = m.at_en[i];
+        for (int j = 0; j < nat; ++j) {
+            double g = 0.0, g4 = 0.0;
+            if (j != i) {
+                double vx = xi - s.xyz[3 * j], vy = yi - s.xyz[3 * j + 1], vz = zi - s.xyz[3 * j + 2];
+                double r2 = vx * vx + vy * vy + vz * vz, r = sqrt(r2), rc = rci + m.at_rcov[j];
+                if (r2 <= 625.0) {
+                    double ea = exp(-10.0 * (rc / r - 1.0)), eb = exp(-20.0 * ((rc + 2.0) / r - 1.0));
+                    double fa = 1.0 / (1.0 + ea), fb = 1.0 / (1.0 + eb);
+                    double dfa = -10.0 * rc / r2 * ea * fa * fa, dfb = -20.0 * (rc + 2.0) / r2 * eb * fb * fb;
+                    cn += fa * fb;
+                    g = (dfa * fb + fa * dfb) / r;
+                }
+                if (r2 <= 900.0) {
+                    const double k4 = 4.10451, k5 = 19.08857, k6 = 2.0 * 11.28174 * 11.28174;
+                    double den = fabs(eni - m.at_en[j]) + k5;
+                    den = k4 * exp(-den * den / k6);
+                    double arg = 7.5 * (r / rc - 1.0);
+                    cn4 += den * 0.5 * erfc(arg);
+                    g4 = -den * 7.5 / rc * 0.56418958354775628695 * exp(-arg * arg) / r;
+                }
+            }
+            dcnp[i * nat + j] = g;
+            dcnp4[i * nat + j] = g4;
+        }
+        s.cn[i] = cn;
+        s.cn4[i] = cn4;
+    }
+    __syncthreads();
+}
+
+// classical repulsion: returns the CTA-wide energy; initialises s.grad
+__device__ inline double phase_repulsion(const DevModel &m, Sm &s) {
+    const int nat = m.nat;
+    double e = 0.0;
+    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+        double gx = 0, gy = 0, gz = 0;
+        for (int j = 0; j < nat; ++j) {
+            if (j == i) continue;
+            double vx = s.xyz[3 * i] - s.xyz[3 * j], vy = s.xyz[3 * i + 1] - s.xyz[3 * j + 1], vz = s.xyz[3 * i + 2] - s.xyz[3 * j + 2];
+            double r2 = vx * vx + vy * vy + vz * vz, r = sqrt(r2);
+            bool light = m.num[i] <= 2 && m.num[j] <= 2;
+            double kexp = light ? GFN2_REP_KEXP_LIGHT : GFN2_REP_KEXP;
+            double alpha = sqrt(m.at_repa[i] * m.at_repa[j]), zz = m.at_repz[i] * m.at_repz[j];
+            double rk = light ? r : r * sqrt(r);
+            double eij = zz * exp(-alpha * rk) / r;
+            e += 0.5 * eij;
+            double dedr = -(alpha * rk * kexp + 1.0) * eij / r2;
+            gx += dedr * vx; gy += dedr * vy; gz += dedr * vz;
+        }
+        s.grad[3 * i] = gx; s.grad[3 * i + 1] = gy; s.grad[3 * i + 2] = gz;
+        s.dEdcn[i] = 0.0;
+        s.dEdcn4[i] = 0.0;
+    }
+    return block_sum(e, s.red);
+}
+
+// ------------------------------------------------------------------------------------ D4
+__device__ inline double d4_zeta(double a, double c, double qref, double qmod) {
+    return qmod < 0.0 ? exp(a) : exp(a * (1.0 - exp(c * (1.0 - qref / qmod))));
+}
+__device__ inline double d4_dzeta(double a, double c, double qref, double qmod) {
+    return qmod < 0.0 ? 0.0 : -a * c * exp(c * (1.0 - qref / qmod)) * d4_zeta(a, c, qref, qmod) * qref / (qmod * qmod);
+}
+
+// Gaussian CN weights x charge scaling for atom i.  gw/gwdcn/gwdq point to 7-vectors (may be null).
+__device__ inline void d4_weights_atom(const DevModel &m, int i, double cn, double q, double *gw, double *gwdcn, double *gwdq) {
+    const int nref = m.at_nref[i];
+    const double *refcn = m.at_refcn + i * QX_MAXREF, *refq = m.at_refq + i * QX_MAXREF;
+    const int *ngw = m.at_ngw + i * QX_MAXREF;
+    const double zi = m.at_zeff[i], gi = m.at_gam[i] * GFN2_D4_GC;
+    double norm = 0.0, dnorm = 0.0, maxcn = -1.0;
+    for (int r = 0; r < nref; ++r) {
+        double dc = cn - refcn[r];
+        for (int g = 1; g <= ngw[r]; ++g) {
+            double wf = g * GFN2_D4_WF, w = exp(-wf * dc * dc);
+            norm += w;
+            dnorm += 2.0 * wf * (-dc) * w;
+        }
+        maxcn = fmax(maxcn, refcn[r]);
+    }
+    norm = 1.0 / norm;
+    for (int r = 0; r < nref; ++r) {
+        double dc = cn - refcn[r], expw = 0.0, expd = 0.0;
+        for (int g = 1; g <= ngw[r]; ++g) {
+            double wf = g * GFN2_D4_WF, w = exp(-wf * dc * dc);
+            expw += w;
+            expd += 2.0 * wf * (-dc) * w;
+        }
+        double gwk = expw * norm;
+        if (gwk != gwk || fabs(gwk) > 1e300) gwk = (maxcn == refcn[r]) ? 1.0 : 0.0;
+        double dgwk = norm * (expd - expw * dnorm * norm);
+        if (dgwk != dgwk || fabs(dgwk) > 1e300) dgwk = 0.0;
+        double zt = d4_zeta(GFN2_D4_GA, gi, refq[r] + zi, q + zi);
+        if (gw) gw[r] = gwk * zt;
+        if (gwdcn) gwdcn[r] = dgwk * zt;
+        if (gwdq) gwdq[r] = gwk * d4_dzeta(GFN2_D4_GA, gi, refq[r] + zi, q + zi);
+    }
+    for (int r = nref; r < QX_MAXREF; ++r) {
+        if (gw) gw[r] = 0.0;
+        if (gwdcn) gwdcn[r] = 0.0;
+        if (gwdq) gwdq[r] = 0.0;
+    }
+}
+
+__device__ inline double bj_r0(const DevModel &m, int i, int j) { return GFN2_D4_A1 * sqrt(3.0 * m.at_r4r2[i] * m.at_r4r2[j]) + GFN2_D4_A2; }
+
+// atomic C6(i,j) and d C6(i,j)/d cn_i from the weights currently in s.gw / gwdcn (global tmp)
+__device__ inline void d4_c6_tables(const DevModel &m, const double *gw, const double *gwdcn, double *c6, double *dc6) {
+    const int nat = m.nat;
+    for (int ij = threadIdx.x; ij < nat * nat; ij += QX_NT) {
+        int i = ij / nat, j = ij - i * nat;
+        const double *ref = m.c6ref + ((size_t)m.type[i] * m.ntype + m.type[j]) * QX_MAXREF * QX_MAXREF;
+        double v = 0.0, dv = 0.0;
+        int ni = m.at_nref[i], nj = m.at_nref[j];
+        for (int ri = 0; ri < ni; ++ri) {
+            double t = 0.0;
+            for (int rj = 0; rj < nj; ++rj) t += ref[ri * QX_MAXREF + rj] * gw[j * QX_MAXREF + rj];
+            v += gw[i * QX_MAXREF + ri] * t;
+            dv += gwdcn[i * QX_MAXREF + ri] * t;
+        }
+        c6[ij] = v;
+        dc6[ij] = dv;
+    }
+}
+
+// non-self-consistent part of D4: ATM with q = 0 weights; also fills edisp[i*nat+j] (two-body BJ kernel).
+// tmp: >= 14*nat + 5*nat*nat doubles of global scratch.
+__device__ inline double phase_d4_nonsc(const DevModel &m, Sm &s, double *edisp, double *c6, double *dc6, double *tmp) {
+    const int nat = m.nat;
+    double *gw0 = tmp, *gwdcn0 = tmp + 7 * nat, *part = tmp + 14 * nat;
+    for (int i = threadIdx.x; i < nat; i += QX_NT) d4_weights_atom(m, i, s.cn4[i], 0.0, gw0 + 7 * i, gwdcn0 + 7 * i, nullptr);
+    for (int ij = threadIdx.x; ij < nat * nat; ij += QX_NT) {
+        int i = ij / nat, j = ij - i * nat;
+        double e = 0.0;
+        if (i != j) {
+            double vx = s.xyz[3 * i] - s.xyz[3 * j], vy = s.xyz[3 * i + 1] - s.xyz[3 * j + 1], vz = s.xyz[3 * i + 2] - s.xyz[3 * j + 2];
+            double r2 = vx * vx + vy * vy + vz * vz;
+            if (r2 <= 3600.0) {
+                double r0 = bj_r0(m, i, j), rrij = 3.0 * m.at_r4r2[i] * m.at_r4r2[j];
+                double r02 = r0 * r0, r06 = r02 * r02 * r02, r6 = r2 * r2 * r2;
+                e = GFN2_D4_S6 / (r6 + r06) + GFN2_D4_S8 * rrij / (r6 * r2 + r06 * r02);
+            }
+        }
+        edisp[ij] = e;
+    }
+    __syncthreads();
+    d4_c6_tables(m, gw0, gwdcn0, c6, dc6);
+    __syncthreads();
+    // triples: task (i, j != i), inner k > j, k != i; force and dE/dcn on vertex i only
+    double e3 = 0.0;
+    const double alp = GFN2_D4_ALP;
+    for (int ij = threadIdx.x; ij < nat * nat; ij += QX_NT) {
+        int i = ij / nat, j = ij - i * nat;
+        double gx = 0, gy = 0, gz = 0, dcn = 0;
+        if (i != j) {
+            double vij[3] = {s.xyz[3 * j] - s.xyz[3 * i], s.xyz[3 * j + 1] - s.xyz[3 * i + 1], s.xyz[3 * j + 2] - s.xyz[3 * i + 2]};
+            double r2ij = vij[0] * vij[0] + vij[1] * vij[1] + vij[2] * vij[2];
+            if (r2ij <= 1600.0) {
+                double c6ij = c6[i * nat + j], r0ij = bj_r0(m, i, j);
+                for (int k = j + 1; k < nat; ++k) {
+                    if (k == i) continue;
+                    double vik[3] = {s.xyz[3 * k] - s.xyz[3 * i], s.xyz[3 * k + 1] - s.xyz[3 * i + 1], s.xyz[3 * k + 2] - s.xyz[3 * i + 2]};
+                    double r2ik = vik[0] * vik[0] + vik[1] * vik[1] + vik[2] * vik[2];
+                    double dx = vik[0] - vij[0], dy = vik[1] - vij[1], dz = vik[2] - vij[2];
+                    double r2jk = dx * dx + dy * dy + dz * dz;
+                    if (r2ik > 1600.0 || r2jk > 1600.0) continue;
+                    double c6ik = c6[i * nat + k], c6jk = c6[j * nat + k];
+                    double r0 = r0ij * bj_r0(m, i, k) * bj_r0(m, j, k);
+                    double c9 = -GFN2_D4_S9 * sqrt(fabs(c6ij * c6ik * c6jk));
+                    double r2 = r2ij * r2ik * r2jk, r1 = sqrt(r2), r3 = r2 * r1, r5 = r3 * r2;
+                    double rr0 = pow(r0 / r1, alp / 3.0);
+                    double fdmp = 1.0 / (1.0 + 6.0 * rr0);
+                    double ang = 0.375 * (r2ij + r2jk - r2ik) * (r2ij - r2jk + r2ik) * (-r2ij + r2jk + r2ik) / r5 + 1.0 / r3;
+                    double dE = ang * fdmp * c9;
+                    e3 -= dE / 3.0;
+                    double dfdmp = -2.0 * alp * rr0 * fdmp * fdmp;
+                    double dang_ij = -0.375 * (r2ij * r2ij * r2ij + r2ij * r2ij * (r2jk + r2ik) +
+                                               r2ij * (3.0 * r2jk * r2jk + 2.0 * r2jk * r2ik + 3.0 * r2ik * r2ik) -
+                                               5.0 * (r2jk - r2ik) * (r2jk - r2ik) * (r2jk + r2ik)) / r5;
+                    double dang_ik = -0.375 * (r2ik * r2ik * r2ik + r2ik * r2ik * (r2jk + r2ij) +
+                                               r2ik * (3.0 * r2jk * r2jk + 2.0 * r2jk * r2ij + 3.0 * r2ij * r2ij) -
+                                               5.0 * (r2jk - r2ij) * (r2jk - r2ij) * (r2jk + r2ij)) / r5;
+                    double gij = c9 * (-dang_ij * fdmp + ang * dfdmp) / r2ij;
+                    double gik = c9 * (-dang_ik * fdmp + ang * dfdmp) / r2ik;
+                    gx += -gij * vij[0] - gik * vik[0];
+                    gy += -gij * vij[1] - gik * vik[1];
+                    gz += -gij * vij[2] - gik * vik[2];
+                    dcn -= dE * 0.5 * (dc6[i * nat + j] / c6ij + dc6[i * nat + k] / c6ik);
+                }
+            }
+        }
+        part[4 * ij] = gx; part[4 * ij + 1] = gy; part[4 * ij + 2] = gz; part[4 * ij + 3] = dcn;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+        double gx = 0, gy = 0, gz = 0, dcn = 0;
+        for (int j = 0; j < nat; ++j) {
+            const double *p = part + 4 * (i * nat + j);
+            gx += p[0]; gy += p[1]; gz += p[2]; dcn += p[3];
+        }
+        s.grad[3 * i] += gx; s.grad[3 * i + 1] += gy; s.grad[3 * i + 2] += gz;
+        s.dEdcn4[i] += dcn;
+    }
+    return block_sum(e3, s.red);
+}
+
+// ------------------------------------------------------------------------------------ Coulomb set-up
+__device__ inline void phase_coulomb_setup(const DevModel &m, Sm &s, double *gamma) {
+    const int nat = m.nat, nsh = m.nsh;
+    for (int ab = threadIdx.x; ab < nsh * nsh; ab += QX_NT) {
+        int a = ab / nsh, b = ab - a * nsh, i = m.sh_at[a], j = m.sh_at[b];
+        double gam = 0.5 * (m.sh_hub[a] + m.sh_hub[b]);
+        if (i != j) {
+            double vx = s.xyz[3 * i] - s.xyz[3 * j], vy = s.xyz[3 * i + 1] - s.xyz[3 * j + 1], vz = s.xyz[3 * i + 2] - s.xyz[3 * j + 2];
+            gam = 1.0 / sqrt(vx * vx + vy * vy + vz * vz + 1.0 / (gam * gam));
+        }
+        gamma[ab] = gam;
+    }
+    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+        double arg = s.cn[i] - m.at_mpvcn[i] - GFN2_MP_SHIFT;
+        double t1 = exp(-GFN2_MP_KEXP * arg), t2 = (GFN2_MP_RMAX - m.at_mprad[i]) / (1.0 + t1);
+        s.mrad[i] = m.at_mprad[i] + t2;
+        s.dmr[i] = t2 * GFN2_MP_KEXP * t1 / (1.0 + t1);
+    }
+    for (int a = threadIdx.x; a < nsh; a += QX_NT) s.selfen[a] = m.sh_level[a] - m.sh_kcn[a] * s.cn[m.sh_at[a]];
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------ integrals
+// <a| O |b> with the multipole operator centred on atom(b); a on the bra atom J, b on the ket atom I,
+// vec = R_I - R_J.  out: S, D(3), Q(6, traceless).  If grad != nullptr additionally returns
+// grad[k] = d/dvec_k of  sum_c coef[c] * out_raw[c]  where out_raw are the raw (not traceless) moments
+// -- used by the gradient kernel with pre-contracted coefficients.
+__device__ inline void ao_pair_multipole(const DevModel &m, int sa, int ma, int sb, int mb, const double vec[3], double r2,
+                                         double out[10], const double *coef, double *grad) {
+    const int la = m.sh_l[sa], lb = m.sh_l[sb];
+    const SphTerm &ta = c_sph[la * la + ma], &tb = c_sph[lb * lb + mb];
+    for (int c = 0; c < 10; ++c) out[c] = 0.0;
+    if (grad) grad[0] = grad[1] = grad[2] = 0.0;
+    const int npa = m.sh_np[sa], npb = m.sh_np[sb];
+    const int amax = la + (grad ? 1 : 0), bmax = lb + 2;
+    for (int pa_ = 0; pa_ < npa; ++pa_) {
+        const double aj = m.sh_alpha[sa * QX_MAXPRIM + pa_], cj = m.sh_coef[sa * QX_MAXPRIM + pa_];
+        for (int pb_ = 0; pb_ < npb; ++pb_) {
+            const double ai = m.sh_alpha[sb * QX_MAXPRIM + pb_], ci = m.sh_coef[sb * QX_MAXPRIM + pb_];
+            const double gam = ai + aj, est = ai * aj * r2 / gam;
+            if (est > 25.0) continue;
+            const double pg = QX_PI / gam;
+            const double pre = exp(-est) * pg * sqrt(pg) * ci * cj;
+            const double oog = 0.5 / gam;
+            double t[3][4][5];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const double pa = ai / gam * vec[d], pb = -aj / gam * vec[d];
+                t[d][0][0] = 1.0;
+                for (int b = 0; b < bmax; ++b) t[d][0][b + 1] = pb * t[d][0][b] + (b > 0 ? b * oog * t[d][0][b - 1] : 0.0);
+                for (int a = 0; a < amax; ++a)
+                    for (int b = 0; b <= bmax; ++b)
+                        t[d][a + 1][b] = pa * t[d][a][b] + (a > 0 ? a * oog * t[d][a - 1][b] : 0.0) + (b > 0 ? b * oog * t[d][a][b - 1] : 0.0);
+            }
+            for (int ka = 0; ka < ta.n; ++ka) {
+                const int *ea = ta.ex[ka];
+                for (int kb = 0; kb < tb.n; ++kb) {
+                    const int *eb = tb.ex[kb];
+                    const double w = pre * ta.c[ka] * tb.c[kb];
+                    double f[3][3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int mm = 0; mm < 3; ++mm) f[d][mm] = t[d][ea[d]][eb[d] + mm];
+                    out[0] += w * f[0][0] * f[1][0] * f[2][0];
+                    out[1] += w * f[0][1] * f[1][0] * f[2][0];
+                    out[2] += w * f[0][0] * f[1][1] * f[2][0];
+                    out[3] += w * f[0][0] * f[1][0] * f[2][1];
+                    out[4] += w * f[0][2] * f[1][0] * f[2][0];
+                    out[5] += w * f[0][1] * f[1][1] * f[2][0];
+                    out[6] += w * f[0][0] * f[1][2] * f[2][0];
+                    out[7] += w * f[0][1] * f[1][0] * f[2][1];
+                    out[8] += w * f[0][0] * f[1][1] * f[2][1];
+                    out[9] += w * f[0][0] * f[1][0] * f[2][2];
+                    if (grad) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            double g[3][3];
+#pragma unroll
+                            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                                for (int mm = 0; mm < 3; ++mm) {
+                                    if (d == k) {
+                                        double up = t[d][ea[d] + 1][eb[d] + mm];
+                                        double dn = ea[d] > 0 ? t[d][ea[d] - 1][eb[d] + mm] : 0.0;
+                                        g[d][mm] = -(2.0 * aj * up - ea[d] * dn);
+                                    } else
+                                        g[d][mm] = f[d][mm];
+                                }
+                            double acc = coef[0] * g[0][0] * g[1][0] * g[2][0];
+                            acc += coef[1] * g[0][1] * g[1][0] * g[2][0];
+                            acc += coef[2] * g[0][0] * g[1][1] * g[2][0];
+                            acc += coef[3] * g[0][0] * g[1][0] * g[2][1];
+                            acc += coef[4] * g[0][2] * g[1][0] * g[2][0];
+                            acc += coef[5] * g[0][1] * g[1][1] * g[2][0];
+                            acc += coef[6] * g[0][0] * g[1][2] * g[2][0];
+                            acc += coef[7] * g[0][1] * g[1][0] * g[2][1];
+                            acc += coef[8] * g[0][0] * g[1][1] * g[2][1];
+                            acc += coef[9] * g[0][0] * g[1][0] * g[2][2];
+                            grad[k] += w * acc;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+__device__ inline void make_traceless(double q[6]) {
+    double tr = 0.5 * (q[0] + q[2] + q[5]);
+    for (int c = 0; c < 6; ++c) q[c] *= 1.5;
+    q[0] -= tr; q[2] -= tr; q[5] -= tr;
+}
+
+// r - R_J = (r - R_I) + vec : move raw moments from centre I to centre J
+__device__ inline void shift_raw(const double vec[3], const double in[10], double out[10]) {
+    out[0] = in[0];
+    for (int c = 0; c < 3; ++c) out[1 + c] = in[1 + c] + vec[c] * in[0];
+    for (int c = 0; c < 6; ++c) {
+        int a = c_qa[c], b = c_qb[c];
+        out[4 + c] = in[4 + c] + vec[a] * in[1 + b] + vec[b] * in[1 + a] + vec[a] * vec[b] * in[0];
+    }
+}
+
+__device__ inline double shpoly_pair(const DevModel &m, int sa, int sb, double rr) {
+    return (1.0 + m.sh_poly[sa] * rr) * (1.0 + m.sh_poly[sb] * rr);
+}
+
+// Fills the per-CTA slab: S, H0 (symmetric), Dt/Qt in "operator on the FIRST index" layout:
+//   Dt[c][b][a] = <a| (r - R_atom(b))_c |b>   (row b contiguous in a).
+__device__ inline void phase_integrals(const DevModel &m, Sm &s, double *S, double *H0, double *Dt, double *Qt) {
+    const int nao = m.nao;
+    const size_t n2 = (size_t)nao * nao;
+    for (int t = threadIdx.x; t < m.ntask_int; t += QX_NT) {
+        const int a = m.task_int[t].x, b = m.task_int[t].y;
+        const int sa = m.ao_sh[a], sb = m.ao_sh[b], ja = m.ao_at[a], ib = m.ao_at[b];
+        double vec[3] = {s.xyz[3 * ib] - s.xyz[3 * ja], s.xyz[3 * ib + 1] - s.xyz[3 * ja + 1], s.xyz[3 * ib + 2] - s.xyz[3 * ja + 2]};
+        double r2 = vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2];
+        double raw[10];
+        ao_pair_multipole(m, sa, m.ao_m[a], sb, m.ao_m[b], vec, r2, raw, nullptr, nullptr);
+        double hij = 0.5 * (s.selfen[sa] + s.selfen[sb]);
+        if (ja != ib) {
+            double rr = sqrt(sqrt(r2) / (m.at_rad[ja] + m.at_rad[ib]));
+            hij *= m.hscale[sa * m.nsh + sb] * shpoly_pair(m, sa, sb, rr);
+        }
+        double q[6];
+        for (int c = 0; c < 6; ++c) q[c] = raw[4 + c];
+        make_traceless(q);
+        size_t ba = (size_t)b * nao + a;
+        S[ba] = raw[0];
+        H0[ba] = raw[0] * hij;
+        for (int c = 0; c < 3; ++c) Dt[c * n2 + ba] = raw[1 + c];
+        for (int c = 0; c < 6; ++c) Qt[c * n2 + ba] = q[c];
+        if (ja != ib) {
+            double sh[10];
+            shift_raw(vec, raw, sh);
+            for (int c = 0; c < 6; ++c) q[c] = sh[4 + c];
+            make_traceless(q);
+            size_t ab = (size_t)a * nao + b;
+            S[ab] = raw[0];
+            H0[ab] = raw[0] * hij;
+            for (int c = 0; c < 3; ++c) Dt[c * n2 + ab] = sh[1 + c];
+            for (int c = 0; c < 6; ++c) Qt[c * n2 + ab] = q[c];
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------ dense kernels in shared memory
+// out(n x n, ldo) = X^T-or-X (n x n, ldx) * Y (n x n, ldy); 4x4 register tiles
+template <bool TRANS_X>
+__device__ inline void gemm_nn(int n, const double *X, int ldx, const double *Y, int ldy, double *out, int ldo) {
+    const int nt = (n + 3) / 4;
+    for (int tile = threadIdx.x; tile < nt * nt; tile += QX_NT) {
+        const int i0 = (tile / nt) * 4, j0 = (tile % nt) * 4;
+        double acc[4][4] = {{0}};
+        for (int k = 0; k < n; ++k) {
+            double x[4], y[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                int i = i0 + r;
+                x[r] = i < n ? (TRANS_X ? X[(size_t)k * ldx + i] : X[(size_t)i * ldx + k]) : 0.0;
+                int j = j0 + r;
+                y[r] = j < n ? Y[(size_t)k * ldy + j] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] += x[r] * y[c];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (i0 + r < n && j0 + c < n) out[(size_t)(i0 + r) * ldo + j0 + c] = acc[r][c];
+    }
+}
+
+// out = C diag(w) C^T (symmetric), C (n x n, ldc)
+__device__ inline void gemm_cwct(int n, const double *C, int ldc, const double *w, double *out, int ldo) {
+    const int nt = (n + 3) / 4;
+    for (int tile = threadIdx.x; tile < nt * nt; tile += QX_NT) {
+        const int i0 = (tile / nt) * 4, j0 = (tile % nt) * 4;
+        if (j0 > i0) continue;
+        double acc[4][4] = {{0}};
+        for (int k = 0; k < n; ++k) {
+            const double wk = w[k];
+            if (wk == 0.0) continue;
+            double x[4], y[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                x[r] = i0 + r < n ? C[(size_t)(i0 + r) * ldc + k] * wk : 0.0;
+                y[r] = j0 + r < n ? C[(size_t)(j0 + r) * ldc + k] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] += x[r] * y[c];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (i0 + r < n && j0 + c < n) {
+                    out[(size_t)(i0 + r) * ldo + j0 + c] = acc[r][c];
+                    out[(size_t)(j0 + c) * ldo + i0 + r] = acc[r][c];
+                }
+    }
+}
+
+// In-place Cholesky S = L L^T on the lower triangle of A (n x n, ld), then C = L^{-T} (upper triangular):
+// an S-orthonormal starting basis.  Returns false if S is not positive definite.
+__device__ inline bool cholesky_basis(int n, double *A, double *C, int ld, double *red) {
+    for (int j = 0; j < n; ++j) {
+        double d = A[(size_t)j * ld + j];
+        if (!(d > 0.0)) return false;  // uniform across the CTA (all threads read the same value)
+        d = sqrt(d);
+        __syncthreads();
+        for (int i = j + threadIdx.x; i < n; i += QX_NT) A[(size_t)i * ld + j] = (i == j) ? d : A[(size_t)i * ld + j] / d;
+        __syncthreads();
+        // trailing update of the lower triangle
+        const int rem = n - j - 1;
+        for (int t = threadIdx.x; t < rem * rem; t += QX_NT) {
+            int i = j + 1 + t / rem, k = j + 1 + t % rem;
+            if (k <= i) A[(size_t)i * ld + k] -= A[(size_t)i * ld + j] * A[(size_t)k * ld + j];
+        }
+        __syncthreads();
+    }
+    // X = L^{-1} column by column (thread per column), stored transposed: C[j][i] = X[i][j]  => C = L^{-T}
+    for (int j = threadIdx.x; j < n; j += QX_NT) {
+        for (int i = 0; i < j; ++i) C[(size_t)j * ld + i] = 0.0;  // strictly lower part of C
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += QX_NT) {
+        // solve L x = e_j ; x_i for i >= j ; write C[j][i] = x_i  (row j of C, upper part)
+        C[(size_t)j * ld + j] = 1.0 / A[(size_t)j * ld + j];
+        for (int i = j + 1; i < n; ++i) {
+            double v = 0.0;
+            for (int k = j; k < i; ++k) v -= A[(size_t)i * ld + k] * C[(size_t)j * ld + k];
+            C[(size_t)j * ld + i] = v / A[(size_t)i * ld + i];
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// Parallel-order two-sided Jacobi on the symmetric A (n x n, ld); rotations are accumulated into the
+// columns of C (so C_new = C_old * J).  On exit diag(A) = eigenvalues.  Returns number of sweeps.
+__device__ inline int jacobi_eig(int n, double *A, double *C, int ld, Sm &s) {
+    const int mm = (n + 1) & ~1;  // players (one dummy if n is odd)
+    const int npair = mm / 2;
+    int sweep = 0;
+    for (; sweep < 40; ++sweep) {
+        // convergence: off-diagonal Frobenius norm against the diagonal
+        double off = 0.0, dg = 0.0;
+        for (int t = threadIdx.x; t < n * n; t += QX_NT) {
+            int i = t / n, j = t - i * n;
+            double v = A[(size_t)i * ld + j];
+            if (i == j) dg += v * v; else off += v * v;
+        }
+        off = block_sum(off, s.red);
+        dg = block_sum(dg, s.red);
+        if (off <= 1e-26 * dg) break;
+        for (int round = 0; round < mm - 1; ++round) {
+            if (threadIdx.x < npair) {
+                int k = threadIdx.x, p, q;
+                if (k == 0) { p = mm - 1; q = round; }
+                else { p = (round + k) % (mm - 1); q = (round - k + mm - 1) % (mm - 1); }
+                if (p > q) { int tt = p; p = q; q = tt; }
+                double c = 1.0, sn = 0.0;
+                if (q < n) {
+                    double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
+                    if (fabs(apq) > 1e-30 * (fabs(app) + fabs(aqq)) && apq != 0.0) {
+                        double tau = (aqq - app) / (2.0 * apq);
+                        double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + tt * tt);
+                        sn = tt * c;
+                    }
+                } else { q = -1; }
+                s.rotp[2 * k] = p; s.rotp[2 * k + 1] = q;
+                s.rot[2 * k] = c; s.rot[2 * k + 1] = sn;
+            }
+            __syncthreads();
+            // rows: A <- J^T A
+            for (int t = threadIdx.x; t < npair * n; t += QX_NT) {
+                int k = t / n, j = t - k * n, p = s.rotp[2 * k], q = s.rotp[2 * k + 1];
+                if (q < 0) continue;
+                double c = s.rot[2 * k], sn = s.rot[2 * k + 1];
+                double x = A[(size_t)p * ld + j], y = A[(size_t)q * ld + j];
+                A[(size_t)p * ld + j] = c * x - sn * y;
+                A[(size_t)q * ld + j] = sn * x + c * y;
+            }
+            __syncthreads();
+            // columns: A <- A J ; C <- C J
+            for (int t = threadIdx.x; t < 2 * npair * n; t += QX_NT) {
+                int which = t / (npair * n), r = t - which * npair * n;
+                int k = r / n, i = r - k * n, p = s.rotp[2 * k], q = s.rotp[2 * k + 1];
+                if (q < 0) continue;
+                double c = s.rot[2 * k], sn = s.rot[2 * k + 1];
+                double *M = which ? C : A;
+                double x = M[(size_t)i * ld + p], y = M[(size_t)i * ld + q];
+                M[(size_t)i * ld + p] = c * x - sn * y;
+                M[(size_t)i * ld + q] = sn * x + c * y;
+            }
+            __syncthreads();
+        }
+    }
+    return sweep;
+}
+
+// ------------------------------------------------------------------------------------ Fermi smearing
+// One warp runs the reference Newton iteration (tblite get_fermi_filling: start at the HOMO/LUMO
+// midpoint, <= 200 cycles, threshold sqrt(eps)); lanes stride over the orbitals.  Returns the Fermi
+// level the occupations of the final cycle were evaluated with (the reference updates e_fermi once
+// more after filling).  e_lo / e_hi: the homo-th and (homo+1)-th smallest eigenvalue.
+__device__ inline double fermi_level_warp(int n, int homo, double kt, const double *emo, double e_lo, double e_hi) {
+    const double thr = 1.4901161193847656e-08;
+    const int lane = threadIdx.x & 31;
+    double ef = 0.5 * (e_lo + e_hi), ef_used = ef;
+    const double occt = homo;
+    for (int cyc = 0; cyc < 200; ++cyc) {
+        double total = 0.0, dtotal = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            double x = (emo[i] - ef) / kt;
+            if (x < 50.0) {
+                double ex = exp(x), den = 1.0 / (ex + 1.0);
+                total += den;
+                dtotal += ex * den * den / kt;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            total += __shfl_xor_sync(0xffffffffu, total, o);
+            dtotal += __shfl_xor_sync(0xffffffffu, dtotal, o);
+        }
+        ef_used = ef;
+        ef += (occt - total) / dtotal;
+        if (fabs(occt - total) <= thr) break;
+    }
+    return ef_used;
+}
+
+}  // namespace qx

@@ -1,0 +1,40 @@
+// Per-composition model tables of the GFN2-xTB ensemble kernels (host-built, device-resident).
+// One DevModel describes ONE molecule composition; every trajectory of an ensemble shares it.
+#pragma once
+#include <cstdint>
+
+#define QX_MAXPRIM 6
+#define QX_MAXREF 7
+#define QX_MAX_ITER 250   // tblite max_iter (SCC cycles and Broyden memory)
+#define QX_NT 256         // threads per CTA; one CTA == one trajectory
+
+struct DevModel {
+    int nat, nsh, nao, ntype, ld, ndim;  // ld: odd leading dimension of the shared-memory matrices
+    int ntask_int, ntask_grad;
+    double nel[2];                        // alpha / beta electron numbers
+    // per atom
+    const int *num, *type, *at_sh0, *at_nsh, *at_ao0, *at_nao;
+    const double *at_rcov, *at_rad, *at_repa, *at_repz, *at_en, *at_mprad, *at_mpvcn, *at_dk, *at_qk, *at_r4r2,
+        *at_zeff, *at_gam, *at_qcrad, *mass;
+    const int *at_nref;
+    const double *at_refcn, *at_refq;  // [nat][QX_MAXREF]
+    const int *at_ngw;                 // [nat][QX_MAXREF]
+    // per shell
+    const int *sh_at, *sh_l, *sh_ao0, *sh_np;
+    const double *sh_alpha, *sh_coef;  // [nsh][QX_MAXPRIM]
+    const double *sh_level, *sh_kcn, *sh_poly, *sh_refocc, *sh_hub, *sh_gam3;
+    const double *hscale;              // [nsh][nsh]
+    // per AO
+    const int *ao_at, *ao_sh, *ao_m;
+    // type-pair D4 reference C6 [ntype][ntype][QX_MAXREF][QX_MAXREF]
+    const double *c6ref;
+    // work lists: AO pairs (a on the bra atom, b on the ket atom; atom(a) <= atom(b))
+    const int2 *task_int;   // all pairs incl. on-site ordered pairs
+    // gradient reduction lists (CSR by atom over off-site tasks; sign +1 ket atom / -1 bra atom)
+    const int *gr_ptr, *gr_task;
+};
+
+// per-CTA scratch in global memory (stays L2 resident); offsets in doubles
+struct ScratchLayout {
+    size_t S, H0, Dt, Qt, T, P, W, gamma, dcnp, dcnp4, edisp, c6, dc6, taskout, br_df, br_u, br_a, br_vec, total;
+};

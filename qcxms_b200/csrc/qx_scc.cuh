@@ -1,0 +1,635 @@
+// SCC loop, Broyden mixer and analytic gradient of the GFN2-xTB ensemble kernel (one CTA per trajectory).
+// Iteration protocol = tblite xtb_singlepoint as driven by the reference (src/tblite.f90:133-136):
+// zero start, potential -> H1 -> eigenproblem -> Fermi filling per spin channel -> density ->
+// Mulliken charges / atomic dipoles / quadrupoles -> energy -> modified Broyden (damping 0.4, full
+// history); converged when |dE| < 1e-6 and rms(dq) < 2e-5 (accuracy = 1.0, src/tblite.f90:46).
+#pragma once
+#include "qx_device.cuh"
+
+namespace qx {
+
+struct EgradOut {
+    double energy;
+    double e_rep, e_atm, e_el, e_es, e_aes, e_d4, e_ts;
+    int niter, stat, sweeps;
+};
+
+// damped multipole interaction kernels for the pair (i, j); v = R_j - R_i
+__device__ inline void aes_pair(const Sm &s, int i, int j, double v[3], double &g3f3, double &g3f5, double &g5f5) {
+    v[0] = s.xyz[3 * j] - s.xyz[3 * i]; v[1] = s.xyz[3 * j + 1] - s.xyz[3 * i + 1]; v[2] = s.xyz[3 * j + 2] - s.xyz[3 * i + 2];
+    double r2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], g1 = rsqrt(r2);
+    g1 = g1 * (1.5 - 0.5 * r2 * g1 * g1);  // one Newton step on top of rsqrt (full double accuracy)
+    double g3 = g1 * g1 * g1, g5 = g3 * g1 * g1;
+    double rr = 0.5 * (s.mrad[i] + s.mrad[j]) * g1, rr3 = rr * rr * rr;
+    double f3 = 1.0 / (1.0 + 6.0 * rr3), f5 = 1.0 / (1.0 + 6.0 * rr3 * rr);
+    g3f3 = g3 * f3; g3f5 = g3 * f5; g5f5 = g5 * f5;
+}
+
+__device__ inline double quad_contract(const double *q, const double v[3]) {
+    return q[0] * v[0] * v[0] + 2.0 * q[1] * v[0] * v[1] + q[2] * v[1] * v[1] + 2.0 * q[3] * v[0] * v[2] + 2.0 * q[4] * v[1] * v[2] + q[5] * v[2] * v[2];
+}
+
+// sum_j edisp_ij sum_rj c6ref(i,ri;j,rj) gw(j,rj)   for task (i, ri)
+__device__ inline double d4_vvec(const DevModel &m, const Sm &s, const double *edisp, int i, int ri) {
+    const int nat = m.nat;
+    double acc = 0.0;
+    for (int j = 0; j < nat; ++j) {
+        const double e = edisp[i * nat + j];
+        if (e == 0.0) continue;
+        const double *ref = m.c6ref + (((size_t)m.type[i] * m.ntype + m.type[j]) * QX_MAXREF + ri) * QX_MAXREF;
+        double t = 0.0;
+        const int nj = m.at_nref[j];
+        for (int rj = 0; rj < nj; ++rj) t += ref[rj] * s.gw[j * QX_MAXREF + rj];
+        acc += e * t;
+    }
+    return -acc;
+}
+
+// potentials from the (input) populations in s.qsh/qat/dpat/qpat -> s.vsh, vat, vdp, vqp, vao
+__device__ inline void phase_potential(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double *t7) {
+    const int nat = m.nat, nsh = m.nsh, nao = m.nao;
+    for (int i = threadIdx.x; i < nat; i += QX_NT) d4_weights_atom(m, i, s.cn4[i], s.qat[i], s.gw + 7 * i, nullptr, s.gwd + 7 * i);
+    for (int a = threadIdx.x; a < nsh; a += QX_NT) {
+        double v = 0.0;
+        for (int b = 0; b < nsh; ++b) v += gamma[a * nsh + b] * s.qsh[b];
+        s.vsh[a] = v + s.qsh[a] * s.qsh[a] * m.sh_gam3[a];
+    }
+    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+        double vd[3] = {0, 0, 0}, vq[6] = {0, 0, 0, 0, 0, 0}, va = 0.0;
+        for (int j = 0; j < nat; ++j) {
+            if (j == i) continue;
+            double v[3], g3f3, g3f5, g5f5;
+            aes_pair(s, i, j, v, g3f3, g3f5, g5f5);
+            const double qj = s.qat[j];
+            const double *mj = s.dpat + 3 * j;
+            double mv = mj[0] * v[0] + mj[1] * v[1] + mj[2] * v[2];
+            for (int k = 0; k < 3; ++k) vd[k] += v[k] * g3f3 * qj + g3f5 * mj[k] - 3.0 * g5f5 * v[k] * mv;
+            double tq = g5f5 * qj;
+            vq[0] += tq * v[0] * v[0]; vq[1] += 2.0 * tq * v[0] * v[1]; vq[2] += tq * v[1] * v[1];
+            vq[3] += 2.0 * tq * v[0] * v[2]; vq[4] += 2.0 * tq * v[1] * v[2]; vq[5] += tq * v[2] * v[2];
+            va += -g3f3 * mv + g5f5 * quad_contract(s.qpat + 6 * j, v);
+        }
+        for (int k = 0; k < 3; ++k) s.vdp[3 * i + k] = vd[k] + 2.0 * m.at_dk[i] * s.dpat[3 * i + k];
+        for (int k = 0; k < 6; ++k) s.vqp[6 * i + k] = vq[k] + 2.0 * m.at_qk[i] * s.qpat[6 * i + k] * c_qscale[k];
+        s.vat[i] = va;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nat * QX_MAXREF; t += QX_NT) {
+        int i = t / QX_MAXREF, ri = t - i * QX_MAXREF;
+        t7[t] = ri < m.at_nref[i] ? d4_vvec(m, s, edisp, i, ri) * s.gwd[t] : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+        double v = 0.0;
+        for (int r = 0; r < QX_MAXREF; ++r) v += t7[i * QX_MAXREF + r];
+        s.vat[i] += v;
+    }
+    __syncthreads();
+    for (int mu = threadIdx.x; mu < nao; mu += QX_NT) s.vao[mu] = s.vsh[m.ao_sh[mu]] + s.vat[m.ao_at[mu]];
+    __syncthreads();
+}
+
+// energies of the charge-dependent terms at the (output) populations
+__device__ inline void phase_scc_energy(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double &e_es, double &e_aes, double &e_d4) {
+    const int nat = m.nat, nsh = m.nsh;
+    for (int i = threadIdx.x; i < nat; i += QX_NT) d4_weights_atom(m, i, s.cn4[i], s.qat[i], s.gw + 7 * i, nullptr, nullptr);
+    double es = 0.0, ea = 0.0, ed = 0.0;
+    for (int a = threadIdx.x; a < nsh; a += QX_NT) {
+        double v = 0.0;
+        for (int b = 0; b < nsh; ++b) v += gamma[a * nsh + b] * s.qsh[b];
+        es += 0.5 * v * s.qsh[a] + s.qsh[a] * s.qsh[a] * s.qsh[a] * m.sh_gam3[a] / 3.0;
+    }
+    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+        double vd[3] = {0, 0, 0}, vq = 0.0;
+        const double *mi = s.dpat + 3 * i;
+        for (int j = 0; j < nat; ++j) {
+            if (j == i) continue;
+            double v[3], g3f3, g3f5, g5f5;
+            aes_pair(s, i, j, v, g3f3, g3f5, g5f5);
+            const double qj = s.qat[j];
+            const double *mj = s.dpat + 3 * j;
+            double mv = mj[0] * v[0] + mj[1] * v[1] + mj[2] * v[2];
+            for (int k = 0; k < 3; ++k) vd[k] += v[k] * g3f3 * qj + 0.5 * (g3f5 * mj[k] - 3.0 * g5f5 * v[k] * mv);
+            vq += g5f5 * qj * quad_contract(s.qpat + 6 * i, v);
+        }
+        double e = mi[0] * vd[0] + mi[1] * vd[1] + mi[2] * vd[2] + vq;
+        e += m.at_dk[i] * (mi[0] * mi[0] + mi[1] * mi[1] + mi[2] * mi[2]);
+        for (int k = 0; k < 6; ++k) e += m.at_qk[i] * s.qpat[6 * i + k] * s.qpat[6 * i + k] * c_qscale[k];
+        ea += e;
+    }
+    __syncthreads();  // gw complete
+    for (int t = threadIdx.x; t < nat * QX_MAXREF; t += QX_NT) {
+        int i = t / QX_MAXREF, ri = t - i * QX_MAXREF;
+        if (ri < m.at_nref[i]) ed += 0.5 * d4_vvec(m, s, edisp, i, ri) * s.gw[t];
+    }
+    e_es = block_sum(es, s.red);
+    e_aes = block_sum(ea, s.red);
+    e_d4 = block_sum(ed, s.red);
+}
+
+// H1 = H0 - 1/2 S (v_a + v_b) - 1/2 (D.vdp + D^T.vdp) - 1/2 (Q.vqp + ...) into s.A (symmetric)
+__device__ inline void phase_build_h1(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt) {
+    const int nao = m.nao, ld = m.ld;
+    const size_t n2 = (size_t)nao * nao;
+    for (int t = threadIdx.x; t < nao * nao; t += QX_NT) {
+        int b = t / nao, a = t - b * nao, ib = m.ao_at[b];
+        double g = 0.5 * H0[t] - 0.5 * S[t] * s.vao[b];
+        const double *vd = s.vdp + 3 * ib, *vq = s.vqp + 6 * ib;
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc += Dt[c * n2 + t] * vd[c];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc += Qt[c * n2 + t] * vq[c];
+        s.A[(size_t)b * ld + a] = g - 0.5 * acc;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nao * nao; t += QX_NT) {
+        int b = t / nao, a = t - b * nao;
+        if (a > b) continue;
+        double v = s.A[(size_t)b * ld + a] + s.A[(size_t)a * ld + b];
+        if (a == b) v = 2.0 * s.A[(size_t)b * ld + b];
+        s.A[(size_t)b * ld + a] = v;
+        s.A[(size_t)a * ld + b] = v;
+    }
+    __syncthreads();
+}
+
+// Mulliken populations from P (in s.A, symmetric): qsh, qat, dpat, qpat and tr(P H0); pop: 11*nao doubles of scratch
+__device__ inline double phase_mulliken(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt, double *pop) {
+    const int nao = m.nao, ld = m.ld, nat = m.nat, nsh = m.nsh;
+    const size_t n2 = (size_t)nao * nao;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = warp; b < nao; b += QX_NT / 32) {
+        double acc[11];
+#pragma unroll
+        for (int c = 0; c < 11; ++c) acc[c] = 0.0;
+        for (int a = lane; a < nao; a += 32) {
+            const double p = s.A[(size_t)b * ld + a];
+            const size_t t = (size_t)b * nao + a;
+            acc[0] += p * S[t];
+            acc[10] += p * H0[t];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[1 + c] += p * Dt[c * n2 + t];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[4 + c] += p * Qt[c * n2 + t];
+        }
+#pragma unroll
+        for (int c = 0; c < 11; ++c) {
+            double v = acc[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) pop[b * 11 + c] = v;
+        }
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < nsh; a += QX_NT) {
+        double v = m.sh_refocc[a];
+        int l = m.sh_l[a], ao0 = m.sh_ao0[a];
+        for (int mu = ao0; mu < ao0 + 2 * l + 1; ++mu) v -= pop[mu * 11];
+        s.qsh[a] = v;
+    }
+    double eel = 0.0;
+    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+        double d[3] = {0, 0, 0}, q[6] = {0, 0, 0, 0, 0, 0};
+        for (int mu = m.at_ao0[i]; mu < m.at_ao0[i] + m.at_nao[i]; ++mu) {
+            for (int c = 0; c < 3; ++c) d[c] -= pop[mu * 11 + 1 + c];
+            for (int c = 0; c < 6; ++c) q[c] -= pop[mu * 11 + 4 + c];
+            eel += pop[mu * 11 + 10];
+        }
+        for (int c = 0; c < 3; ++c) s.dpat[3 * i + c] = d[c];
+        for (int c = 0; c < 6; ++c) s.qpat[6 * i + c] = q[c];
+    }
+    eel = block_sum(eel, s.red);
+    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+        double v = 0.0;
+        for (int a = m.at_sh0[i]; a < m.at_sh0[i] + m.at_nsh[i]; ++a) v += s.qsh[a];
+        s.qat[i] = v;
+    }
+    __syncthreads();
+    return eel;
+}
+
+// ------------------------------------------------------------------------------------ Broyden
+struct Broyden {
+    double *q_in, *qlast, *dq, *dqlast, *df, *u, *a, *omega, *beta, *cvec;
+    int iter;
+};
+
+__device__ inline double warp_dot(const double *x, const double *y, int n) {
+    double acc = 0.0;
+    for (int i = threadIdx.x & 31; i < n; i += 32) acc += x[i] * y[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+
+// dense solve with partial pivoting on (beta[nb x nb], c[nb]) in global scratch; CTA-cooperative
+__device__ inline bool block_solve(int nb, double *beta, double *c, double *red) {
+    __shared__ int s_piv;
+    for (int k = 0; k < nb; ++k) {
+        if (threadIdx.x == 0) {
+            int piv = k;
+            double best = fabs(beta[k * nb + k]);
+            for (int i = k + 1; i < nb; ++i)
+                if (fabs(beta[i * nb + k]) > best) { best = fabs(beta[i * nb + k]); piv = i; }
+            s_piv = best == 0.0 ? -1 : piv;
+        }
+        __syncthreads();
+        int piv = s_piv;
+        if (piv < 0) return false;
+        if (piv != k) {
+            for (int j = threadIdx.x; j <= nb; j += QX_NT) {
+                if (j < nb) { double t = beta[k * nb + j]; beta[k * nb + j] = beta[piv * nb + j]; beta[piv * nb + j] = t; }
+                else { double t = c[k]; c[k] = c[piv]; c[piv] = t; }
+            }
+        }
+        __syncthreads();
+        const int rem = nb - k - 1;
+        const double pivv = beta[k * nb + k];
+        // column k multipliers are needed by every element of the row: compute on the fly
+        for (int t = threadIdx.x; t < rem * (rem + 1); t += QX_NT) {
+            int i = k + 1 + t / (rem + 1), jj = t % (rem + 1);
+            double f = beta[i * nb + k] / pivv;
+            if (jj < rem) beta[i * nb + k + 1 + jj] -= f * beta[k * nb + k + 1 + jj];
+            else c[i] -= f * c[k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int i = nb - 1; i >= 0; --i) {
+            double v = c[i];
+            for (int j = i + 1; j < nb; ++j) v -= beta[i * nb + j] * c[j];
+            c[i] = v / beta[i * nb + i];
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// One mixer step: q_in <- next input.  dq = (output - input) of the cycle just finished must be set.
+__device__ inline bool broyden_next(Broyden &b, int n, double damp, double *red) {
+    const int mem = QX_MAX_ITER;
+    const double omega0 = 0.01, minw = 1.0, maxw = 100000.0, wfac = 0.01;
+    b.iter += 1;
+    const int iter = b.iter, itn = iter - 1;
+    if (iter == 1) {
+        for (int i = threadIdx.x; i < n; i += QX_NT) {
+            b.dqlast[i] = b.dq[i];
+            b.qlast[i] = b.q_in[i];
+            b.q_in[i] += damp * b.dq[i];
+        }
+        __syncthreads();
+        return true;
+    }
+    const int it1 = (itn - 1) % mem;
+    const int nb = itn < mem ? itn : mem;
+    double nrm = 0.0, inv = 0.0;
+    for (int i = threadIdx.x; i < n; i += QX_NT) {
+        double d = b.dq[i], v = d - b.dqlast[i];
+        nrm += d * d;
+        inv += v * v;
+    }
+    nrm = sqrt(block_sum(nrm, red));
+    inv = sqrt(block_sum(inv, red));
+    double om = nrm > wfac / maxw ? wfac / nrm : maxw;
+    if (om < minw) om = minw;
+    if (inv < 2.220446049250313e-16) inv = 2.220446049250313e-16;
+    inv = 1.0 / inv;
+    for (int i = threadIdx.x; i < n; i += QX_NT) b.df[(size_t)it1 * n + i] = inv * (b.dq[i] - b.dqlast[i]);
+    if (threadIdx.x == 0) b.omega[it1] = om;
+    __syncthreads();
+    const int j0 = itn - mem + 1 > 1 ? itn - mem + 1 : 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = j0 + warp; j <= itn; j += QX_NT / 32) {
+        int i = (j - 1) % mem;
+        double aij = warp_dot(b.df + (size_t)i * n, b.df + (size_t)it1 * n, n);
+        double ci = warp_dot(b.df + (size_t)i * n, b.dq, n);
+        if (lane == 0) {
+            b.a[i * mem + it1] = aij;
+            b.a[it1 * mem + i] = aij;
+            b.cvec[i] = b.omega[i] * ci;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nb * nb; t += QX_NT) {
+        int k = t / nb, i = t - k * nb;
+        double v = b.omega[k] * b.omega[i] * b.a[k * mem + i];
+        if (k == i) v += omega0 * omega0;
+        b.beta[k * nb + i] = v;
+    }
+    __syncthreads();
+    if (!block_solve(nb, b.beta, b.cvec, red)) return false;
+    for (int i = threadIdx.x; i < n; i += QX_NT) {
+        b.u[(size_t)it1 * n + i] = damp * b.df[(size_t)it1 * n + i] + inv * (b.q_in[i] - b.qlast[i]);
+        b.dqlast[i] = b.dq[i];
+        b.qlast[i] = b.q_in[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += QX_NT) {
+        double v = b.q_in[i] + damp * b.dq[i];
+        for (int j = j0; j <= itn; ++j) {
+            int h = (j - 1) % mem;
+            v -= b.omega[h] * b.cvec[h] * b.u[(size_t)h * n + i];
+        }
+        b.q_in[i] = v;
+    }
+    __syncthreads();
+    return true;
+}
+
+// ------------------------------------------------------------------------------------ gradient of the AO-pair terms
+// s.A = P, s.C = W (energy weighted density); potentials in s.vao/vdp/vqp from the last SCC cycle.
+__device__ inline void phase_gradient_pairs(const DevModel &m, Sm &s, const int2 *tasks, int ntask, double *taskout) {
+    const int ld = m.ld;
+    for (int t = threadIdx.x; t < ntask; t += QX_NT) {
+        const int a = tasks[t].x, b = tasks[t].y;
+        const int sa = m.ao_sh[a], sb = m.ao_sh[b], ja = m.ao_at[a], ib = m.ao_at[b];
+        double *o = taskout + 5 * (size_t)t;
+        if (ja == ib) { o[0] = o[1] = o[2] = o[3] = o[4] = 0.0; continue; }
+        double vec[3] = {s.xyz[3 * ib] - s.xyz[3 * ja], s.xyz[3 * ib + 1] - s.xyz[3 * ja + 1], s.xyz[3 * ib + 2] - s.xyz[3 * ja + 2]};
+        const double r2 = vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2];
+        const double pij = s.A[(size_t)a * ld + b], wij = s.C[(size_t)a * ld + b];
+        const double rr = sqrt(sqrt(r2) / (m.at_rad[ja] + m.at_rad[ib]));
+        const double pla = 1.0 + m.sh_poly[sa] * rr, plb = 1.0 + m.sh_poly[sb] * rr;
+        const double shp = pla * plb, dshp = (m.sh_poly[sa] * plb + m.sh_poly[sb] * pla) * rr * 0.5 / r2;
+        const double hs = m.hscale[sa * m.nsh + sb], hav = 0.5 * (s.selfen[sa] + s.selfen[sb]);
+        const double sval = 2.0 * pij * hav * hs * shp - 2.0 * wij - pij * (s.vao[a] + s.vao[b]);
+        const double *vdI = s.vdp + 3 * ib, *vdJ = s.vdp + 3 * ja, *vqI = s.vqp + 6 * ib, *vqJ = s.vqp + 6 * ja;
+        // weights of the raw second moments: 3/2 vq_c - 1/2 tr(vq) delta_c
+        double wI[6], wJ[6];
+        const double trI = 0.5 * (vqI[0] + vqI[2] + vqI[5]), trJ = 0.5 * (vqJ[0] + vqJ[2] + vqJ[5]);
+        for (int c = 0; c < 6; ++c) { wI[c] = 1.5 * vqI[c]; wJ[c] = 1.5 * vqJ[c]; }
+        wI[0] -= trI; wI[2] -= trI; wI[5] -= trI;
+        wJ[0] -= trJ; wJ[2] -= trJ; wJ[5] -= trJ;
+        double coef[10];
+        coef[0] = sval - pij * (vec[0] * vdJ[0] + vec[1] * vdJ[1] + vec[2] * vdJ[2]);
+        for (int k = 0; k < 3; ++k) coef[1 + k] = -pij * (vdI[k] + vdJ[k]);
+        for (int c = 0; c < 6; ++c) {
+            const int qa = c_qa[c], qb = c_qb[c];
+            coef[4 + c] = -pij * (wI[c] + wJ[c]);
+            coef[0] -= pij * wJ[c] * vec[qa] * vec[qb];
+            coef[1 + qb] -= pij * wJ[c] * vec[qa];
+            coef[1 + qa] -= pij * wJ[c] * vec[qb];
+        }
+        double raw[10], g[3];
+        ao_pair_multipole(m, sa, m.ao_m[a], sb, m.ao_m[b], vec, r2, raw, coef, g);
+        // explicit vec-dependence of the coefficients + distance dependence of H0
+        for (int k = 0; k < 3; ++k) g[k] += -pij * vdJ[k] * raw[0] + 2.0 * pij * hav * hs * dshp * vec[k] * raw[0];
+        for (int c = 0; c < 6; ++c) {
+            const int qa = c_qa[c], qb = c_qb[c];
+            g[qa] -= pij * wJ[c] * (raw[1 + qb] + vec[qb] * raw[0]);
+            g[qb] -= pij * wJ[c] * (raw[1 + qa] + vec[qa] * raw[0]);
+        }
+        const double tcn = pij * hs * shp * raw[0];
+        o[0] = g[0]; o[1] = g[1]; o[2] = g[2];
+        o[3] = -m.sh_kcn[sb] * tcn;  // d/d cn of the ket atom
+        o[4] = -m.sh_kcn[sa] * tcn;  // d/d cn of the bra atom
+    }
+    __syncthreads();
+}
+
+// Everything: s.xyz in, s.grad / s.qat out.  scratch: per-CTA global slab.
+__device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, const ScratchLayout &L, double kt, EgradOut &out) {
+    const int nat = m.nat, nsh = m.nsh, nao = m.nao, ld = m.ld, ndim = m.ndim;
+    double *S = scratch + L.S, *H0 = scratch + L.H0, *Dt = scratch + L.Dt, *Qt = scratch + L.Qt, *T = scratch + L.T;
+    double *gamma = scratch + L.gamma, *dcnp = scratch + L.dcnp, *dcnp4 = scratch + L.dcnp4, *edisp = scratch + L.edisp;
+    double *c6 = scratch + L.c6, *dc6 = scratch + L.dc6, *taskout = scratch + L.taskout;
+    double *t7 = T;                 // [7*nat] temp (T is free whenever t7 is used)
+    double *pop = T + 7 * nat;      // [11*nao]
+    Broyden br;
+    {
+        double *v = scratch + L.br_vec;
+        br.q_in = v; br.qlast = v + ndim; br.dq = v + 2 * ndim; br.dqlast = v + 3 * ndim;
+        br.omega = v + 4 * ndim; br.cvec = br.omega + QX_MAX_ITER;
+        br.df = scratch + L.br_df; br.u = scratch + L.br_u; br.a = scratch + L.br_a;
+        br.beta = br.a + (size_t)QX_MAX_ITER * QX_MAX_ITER;
+        br.iter = 0;
+    }
+    out.stat = 0; out.niter = 0; out.sweeps = 0;
+
+    phase_cn(m, s, dcnp, dcnp4);
+    out.e_rep = phase_repulsion(m, s);
+    out.e_atm = phase_d4_nonsc(m, s, edisp, c6, dc6, taskout);
+    phase_coulomb_setup(m, s, gamma);
+    phase_integrals(m, s, S, H0, Dt, Qt);
+
+    // S-orthonormal start basis: C = L^{-T}
+    for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.A[(size_t)(t / nao) * ld + t % nao] = S[t];
+    __syncthreads();
+    if (!cholesky_basis(nao, s.A, s.C, ld, s.red)) { out.stat = -2; out.energy = 0.0; return; }  // hard failure: S not positive definite
+
+    for (int i = threadIdx.x; i < nsh; i += QX_NT) s.qsh[i] = 0.0;
+    for (int i = threadIdx.x; i < nat; i += QX_NT) s.qat[i] = 0.0;
+    for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.dpat[i] = 0.0;
+    for (int i = threadIdx.x; i < 6 * nat; i += QX_NT) s.qpat[i] = 0.0;
+    __syncthreads();
+
+    double eelec = 0.0;
+    bool converged = false;
+    int iscf = 0;
+    while (!converged && iscf < QX_MAX_ITER) {
+        const double elast = eelec;
+        if (iscf > 0) {
+            if (!broyden_next(br, ndim, 0.4, s.red)) { out.stat = -2; break; }
+            for (int i = threadIdx.x; i < ndim; i += QX_NT) {
+                double v = br.q_in[i];
+                if (i < nsh) s.qsh[i] = v;
+                else if (i < nsh + 3 * nat) s.dpat[i - nsh] = v;
+                else s.qpat[i - nsh - 3 * nat] = v;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < nat; i += QX_NT) {
+                double v = 0.0;
+                for (int a = m.at_sh0[i]; a < m.at_sh0[i] + m.at_nsh[i]; ++a) v += s.qsh[a];
+                s.qat[i] = v;
+            }
+            __syncthreads();
+        }
+        iscf += 1;
+        phase_potential(m, s, gamma, edisp, t7);
+        for (int i = threadIdx.x; i < ndim; i += QX_NT)
+            br.q_in[i] = i < nsh ? s.qsh[i] : (i < nsh + 3 * nat ? s.dpat[i - nsh] : s.qpat[i - nsh - 3 * nat]);
+        phase_build_h1(m, s, S, H0, Dt, Qt);
+        // A' = C^T H1 C in the current S-orthonormal basis, then Jacobi (C <- C J)
+        gemm_nn<false>(nao, s.A, ld, s.C, ld, T, nao);
+        __syncthreads();
+        gemm_nn<true>(nao, s.C, ld, T, nao, s.A, ld);
+        __syncthreads();
+        out.sweeps += jacobi_eig(nao, s.A, s.C, ld, s);
+        for (int k = threadIdx.x; k < nao; k += QX_NT) s.emo[k] = s.A[(size_t)k * ld + k];
+        __syncthreads();
+        // order statistics needed for the Fermi-level start value
+        int homo[2];
+        for (int sp = 0; sp < 2; ++sp) {
+            double ne = m.nel[sp];
+            homo[sp] = (int)floor(ne) + (fmod(ne, 1.0) > 0.5 ? 1 : 0);
+        }
+        for (int k = threadIdx.x; k < nao; k += QX_NT) {
+            const double ek = s.emo[k];
+            int rank = 0;
+            for (int j = 0; j < nao; ++j) rank += (s.emo[j] < ek) || (s.emo[j] == ek && j < k);
+            for (int sp = 0; sp < 2; ++sp) {
+                int lo = (homo[sp] > 1 ? homo[sp] : 1) - 1, hi = (homo[sp] + 1 < nao ? homo[sp] + 1 : nao) - 1;
+                if (rank == lo) s.red[32 + 2 * sp] = ek;
+                if (rank == hi) s.red[33 + 2 * sp] = ek;
+            }
+        }
+        __syncthreads();
+        {
+            const int warp = threadIdx.x >> 5;
+            if (warp < 2) {
+                double ef = 0.0;
+                if (homo[warp] > 0) ef = fermi_level_warp(nao, homo[warp], kt, s.emo, s.red[32 + 2 * warp], s.red[33 + 2 * warp]);
+                if ((threadIdx.x & 31) == 0) s.red[40 + warp] = ef;
+            }
+        }
+        __syncthreads();
+        double ts = 0.0;
+        for (int k = threadIdx.x; k < nao; k += QX_NT) {
+            double f = 0.0;
+            for (int sp = 0; sp < 2; ++sp) {
+                if (homo[sp] <= 0) continue;
+                double x = (s.emo[k] - s.red[40 + sp]) / kt, occ = 0.0;
+                if (x < 50.0) occ = 1.0 / (exp(x) + 1.0);
+                f += occ;
+                if (occ > 1.4901161193847656e-08 && 1.0 - occ > 1.4901161193847656e-08) ts += (occ * log(occ) + (1.0 - occ) * log(1.0 - occ)) * kt;
+            }
+            s.focc[k] = f;
+        }
+        ts = block_sum(ts, s.red);
+        // density into A
+        gemm_cwct(nao, s.C, ld, s.focc, s.A, ld);
+        __syncthreads();
+        double eel = phase_mulliken(m, s, S, H0, Dt, Qt, pop);
+        double err = 0.0;
+        for (int i = threadIdx.x; i < ndim; i += QX_NT) {
+            double o = i < nsh ? s.qsh[i] : (i < nsh + 3 * nat ? s.dpat[i - nsh] : s.qpat[i - nsh - 3 * nat]);
+            double d = o - br.q_in[i];
+            br.dq[i] = d;
+            err += d * d;
+        }
+        err = sqrt(block_sum(err, s.red) / ndim);
+        double e_es, e_aes, e_d4;
+        phase_scc_energy(m, s, gamma, edisp, e_es, e_aes, e_d4);
+        eelec = ts + eel + e_es + e_aes + e_d4;
+        out.e_el = eel; out.e_es = e_es; out.e_aes = e_aes; out.e_d4 = e_d4; out.e_ts = ts;
+        converged = fabs(eelec - elast) < 1e-6 && err < 2e-5;
+    }
+    out.niter = iscf;
+    out.energy = out.e_rep + out.e_atm + eelec;
+    if (out.stat == -2) return;
+    // "SCF not converged": flagged, but energy and gradient of the last cycle are still handed back -- the
+    // reference's egrad overrides stat with checkqc (src/iniqm.f90:646-651)
+    if (!converged) out.stat = -1;
+
+    // ---------------- gradient ----------------
+    // W = C diag(f e) C^T -> global T -> shared C (A holds P)
+    for (int k = threadIdx.x; k < nao; k += QX_NT) s.focc[k] *= s.emo[k];
+    __syncthreads();
+    gemm_cwct(nao, s.C, ld, s.focc, T, nao);
+    __syncthreads();
+    for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.C[(size_t)(t / nao) * ld + t % nao] = T[t];
+    __syncthreads();
+    phase_gradient_pairs(m, s, m.task_int, m.ntask_int, taskout);
+    for (int t = threadIdx.x; t < 3 * nat; t += QX_NT) {
+        int k = t / 3, c = t - 3 * k;
+        double g = 0.0;
+        for (int e = m.gr_ptr[k]; e < m.gr_ptr[k + 1]; ++e) {
+            int code = m.gr_task[e];
+            int task = code >> 1;
+            g += (code & 1) ? -taskout[5 * (size_t)task + c] : taskout[5 * (size_t)task + c];
+        }
+        s.grad[t] += g;
+    }
+    for (int k = threadIdx.x; k < nat; k += QX_NT) {
+        double dcn = 0.0;
+        for (int e = m.gr_ptr[k]; e < m.gr_ptr[k + 1]; ++e) {
+            int code = m.gr_task[e];
+            dcn += taskout[5 * (size_t)(code >> 1) + ((code & 1) ? 4 : 3)];
+        }
+        for (int mu = m.at_ao0[k]; mu < m.at_ao0[k] + m.at_nao[k]; ++mu) dcn += -m.sh_kcn[m.ao_sh[mu]] * s.A[(size_t)mu * ld + mu];
+        s.dEdcn[k] += dcn;
+    }
+    __syncthreads();
+    // D4 two-body with the final charges
+    double *gwq = taskout, *gwdcnq = taskout + 7 * nat;
+    for (int i = threadIdx.x; i < nat; i += QX_NT) d4_weights_atom(m, i, s.cn4[i], s.qat[i], gwq + 7 * i, gwdcnq + 7 * i, nullptr);
+    __syncthreads();
+    d4_c6_tables(m, gwq, gwdcnq, c6, dc6);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+        double gx = 0, gy = 0, gz = 0, dcn = 0, dcn4 = 0;
+        const double *mi = s.dpat + 3 * i, *ti = s.qpat + 6 * i;
+        const double qi = s.qat[i];
+        for (int j = 0; j < nat; ++j) {
+            if (j == i) continue;
+            // --- dispersion
+            {
+                double vx = s.xyz[3 * i] - s.xyz[3 * j], vy = s.xyz[3 * i + 1] - s.xyz[3 * j + 1], vz = s.xyz[3 * i + 2] - s.xyz[3 * j + 2];
+                double r2 = vx * vx + vy * vy + vz * vz;
+                if (r2 <= 3600.0) {
+                    double r0 = bj_r0(m, i, j), rrij = 3.0 * m.at_r4r2[i] * m.at_r4r2[j];
+                    double r02 = r0 * r0, r06 = r02 * r02 * r02, r6 = r2 * r2 * r2;
+                    double t6 = 1.0 / (r6 + r06), t8 = 1.0 / (r6 * r2 + r06 * r02);
+                    double gdisp = GFN2_D4_S6 * (-6.0 * r2 * r2 * t6 * t6) + GFN2_D4_S8 * rrij * (-8.0 * r6 * t8 * t8);
+                    double f = -c6[i * nat + j] * gdisp;
+                    gx += f * vx; gy += f * vy; gz += f * vz;
+                    dcn4 -= dc6[i * nat + j] * edisp[i * nat + j];
+                }
+            }
+            // --- anisotropic electrostatics, v = R_j - R_i
+            {
+                double v[3] = {s.xyz[3 * j] - s.xyz[3 * i], s.xyz[3 * j + 1] - s.xyz[3 * i + 1], s.xyz[3 * j + 2] - s.xyz[3 * i + 2]};
+                double r2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], r = sqrt(r2), g1 = 1.0 / r, g3 = g1 * g1 * g1, g5 = g3 * g1 * g1;
+                double R0 = 0.5 * (s.mrad[i] + s.mrad[j]), rr = R0 * g1, rr3 = rr * rr * rr;
+                double x3 = 6.0 * rr3, x5 = 6.0 * rr3 * rr;
+                double f3 = 1.0 / (1.0 + x3), f5 = 1.0 / (1.0 + x5);
+                double df3dr = f3 * f3 * GFN2_MP_DMP3 * x3 * g1, df5dr = f5 * f5 * GFN2_MP_DMP5 * x5 * g1;
+                double df3dR0 = -f3 * f3 * GFN2_MP_DMP3 * x3 / R0, df5dR0 = -f5 * f5 * GFN2_MP_DMP5 * x5 / R0;
+                const double *mj = s.dpat + 3 * j, *tj = s.qpat + 6 * j;
+                const double qj = s.qat[j];
+                double miv = mi[0] * v[0] + mi[1] * v[1] + mi[2] * v[2], mjv = mj[0] * v[0] + mj[1] * v[1] + mj[2] * v[2];
+                double mimj = mi[0] * mj[0] + mi[1] * mj[1] + mi[2] * mj[2];
+                double tiv[3] = {ti[0] * v[0] + ti[1] * v[1] + ti[3] * v[2], ti[1] * v[0] + ti[2] * v[1] + ti[4] * v[2], ti[3] * v[0] + ti[4] * v[1] + ti[5] * v[2]};
+                double tjv[3] = {tj[0] * v[0] + tj[1] * v[1] + tj[3] * v[2], tj[1] * v[0] + tj[2] * v[1] + tj[4] * v[2], tj[3] * v[0] + tj[4] * v[1] + tj[5] * v[2]};
+                double tivv = tiv[0] * v[0] + tiv[1] * v[1] + tiv[2] * v[2], tjvv = tjv[0] * v[0] + tjv[1] * v[1] + tjv[2] * v[2];
+                double Aa = qj * miv - qi * mjv, Bb = qj * tivv + qi * tjvv, Dd = -3.0 * miv * mjv;
+                double dg3 = -3.0 * g3 * g1, dg5 = -5.0 * g5 * g1;
+                double radial = (dg3 * f3 + g3 * df3dr) * Aa + (dg5 * f5 + g5 * df5dr) * (Bb + Dd) + (dg3 * f5 + g3 * df5dr) * mimj;
+                double dER0 = g3 * df3dR0 * Aa + g5 * df5dR0 * (Bb + Dd) + g3 * df5dR0 * mimj;
+                double dv[3];
+                for (int k = 0; k < 3; ++k)
+                    dv[k] = radial * v[k] * g1 + g3 * f3 * (qj * mi[k] - qi * mj[k]) +
+                            g5 * f5 * (2.0 * qj * tiv[k] + 2.0 * qi * tjv[k] - 3.0 * (mi[k] * mjv + mj[k] * miv));
+                gx -= dv[0]; gy -= dv[1]; gz -= dv[2];
+                dcn += 0.5 * dER0 * s.dmr[i];
+            }
+        }
+        // --- isotropic second order
+        for (int a = m.at_sh0[i]; a < m.at_sh0[i] + m.at_nsh[i]; ++a)
+            for (int b = 0; b < nsh; ++b) {
+                int j = m.sh_at[b];
+                if (j == i) continue;
+                double g = gamma[a * nsh + b];
+                double f = -s.qsh[a] * s.qsh[b] * g * g * g;
+                gx += f * (s.xyz[3 * i] - s.xyz[3 * j]); gy += f * (s.xyz[3 * i + 1] - s.xyz[3 * j + 1]); gz += f * (s.xyz[3 * i + 2] - s.xyz[3 * j + 2]);
+            }
+        s.grad[3 * i] += gx; s.grad[3 * i + 1] += gy; s.grad[3 * i + 2] += gz;
+        s.dEdcn[i] += dcn;
+        s.dEdcn4[i] += dcn4;
+    }
+    __syncthreads();
+    // chain rule through both coordination numbers
+    for (int k = threadIdx.x; k < nat; k += QX_NT) {
+        double gx = 0, gy = 0, gz = 0;
+        for (int j = 0; j < nat; ++j) {
+            if (j == k) continue;
+            double f = (s.dEdcn[k] + s.dEdcn[j]) * dcnp[k * nat + j] + (s.dEdcn4[k] + s.dEdcn4[j]) * dcnp4[k * nat + j];
+            gx += f * (s.xyz[3 * k] - s.xyz[3 * j]); gy += f * (s.xyz[3 * k + 1] - s.xyz[3 * j + 1]); gz += f * (s.xyz[3 * k + 2] - s.xyz[3 * j + 2]);
+        }
+        s.grad[3 * k] += gx; s.grad[3 * k + 1] += gy; s.grad[3 * k + 2] += gz;
+    }
+    __syncthreads();
+}
+
+}  // namespace qx

@@ -1,0 +1,49 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances are the ones BASELINE.json's north_star states: energy 1e-8 Eh, gradient 1e-6 Eh/bohr,
+Mulliken charges 1e-6; fragment ids bit-exact.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+E_TOL, G_TOL, Q_TOL = 1e-8, 1e-6, 1e-6
+
+
+def _compare(qx, oracle, num, xyz, charge, mult, etemp):
+    q, e, g, stat = qx.get_xtb_egrad(num, xyz, charge, mult, qx.gfn2_xtb, etemp)
+    ref = oracle.egrad(num, xyz, charge=charge, multiplicity=mult, etemp=etemp, detail=True)
+    assert stat == ref["stat"] == 0
+    assert abs(e - ref["energy"]) < E_TOL, (e, ref["energy"])
+    assert np.abs(g - ref["gradient"]).max() < G_TOL
+    assert np.abs(q - ref["qat"]).max() < Q_TOL
+    return ref
+
+
+@pytest.mark.parametrize("name,charge,mult,etemp", [
+    ("chloroethanol", 0, 1, 300.0), ("chloroethanol", 1, 2, 5000.0), ("monoethanolamine", 1, 2, 5000.0),
+    ("thf_h", 1, 1, 5000.0), ("dichlorobenzamide_h", 1, 1, 5000.0), ("caffeine", 1, 2, 5000.0), ("caffeine", 0, 1, 300.0)])
+def test_egrad_matches_oracle(qx, oracle, name, charge, mult, etemp):
+    num, xyz, _ = qx.load_molecule(name)
+    _compare(qx, oracle, num, xyz, charge, mult, etemp)
+
+
+def test_egrad_batch_distorted_geometries(qx, oracle):
+    num, xyz, _ = qx.load_molecule("caffeine")
+    rng = np.random.default_rng(7)
+    geoms = xyz[None] + 0.08 * rng.standard_normal((12,) + xyz.shape)
+    out = qx.egrad_batch(num, geoms, 1, 2, qx.gfn2_xtb, 5000.0)
+    for k in range(len(geoms)):
+        ref = oracle.egrad(num, geoms[k], charge=1, multiplicity=2, etemp=5000.0, detail=True)
+        assert out["stat"][k] == 0
+        assert out["niter"][k] == ref["niter"]
+        assert abs(out["energy"][k] - ref["energy"]) < E_TOL
+        assert np.abs(out["gradient"][k] - ref["gradient"]).max() < G_TOL
+        assert np.abs(out["qat"][k] - ref["qat"]).max() < Q_TOL
+
+
+def test_unknown_method_sets_stat_5(qx):
+    num, xyz, _ = qx.load_molecule("chloroethanol")
+    _, _, _, stat = qx.get_xtb_egrad(num, xyz, 0, 1, 99, 300.0)
+    assert stat == 5
