@@ -1,3 +1,33 @@
+/* TEST INFRASTRUCTURE -- CPU restatement of the MD side of the QCxMS hot path (see xtb_oracle.h).
+ * These functions follow the in-tree Fortran line by line (citations at each definition). */
 #ifndef MD_ORACLE_H
 #define MD_ORACLE_H
+#include <stdint.h>
+
+#include "../include/qcxms_b200.h" /* config / result PODs of the boundary (types only) */
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+void md_oracle_leapfrog(int nat, const double *grad, const double *amass, double tstp, double *xyz, double *vel, double *ke);
+void md_oracle_ekinet(int nat, const double *velo, const double *mass, double *e_kin, double *temp);
+int md_oracle_impactscale(int nuc, double *velo, const double *mass, const double *velof, double eimp, double ff, double e0);
+void md_oracle_fragment_structure(int nat, const int32_t *oz, const double *xyz, double rcut, int at1, int at2, int32_t *frag);
+void md_oracle_fragmass(int nat, const int32_t *iat, const int32_t *list, const double *mass, const int32_t *imass, int32_t *nfrag,
+                        double *fragx /*[10] amu*/, int32_t *fragat /*[10][200]*/);
+void md_oracle_intenergy(int nuc, const int32_t *list, const double *mass, const double *velo, int nfrag, double *T, double *e_int);
+int md_oracle_checkqc(int nuc, double *e, const double *grad, const double *qat, int mchrg);
+double md_oracle_setetemp(int nfrag, double eimp, double ax, double ieetemp);
+int md_oracle_getspin(int nat, const int32_t *ic, int chrg);
+void md_oracle_center_of_mass(int nat, const double *mass, const double *xyz, double *cm);
+/* egrad, xtb2 branch (src/iniqm.f90:641-655): returns gradfail; E = 0 on failure */
+int md_oracle_egrad(int nuc, const double *xyz, const int32_t *iat, int mchrg, double etemp, int method_id, double *E, double *grad,
+                    double *qat, int *niter);
+/* md() for it > 0, EI (method 0), icoll = 0  (src/md.f90:34-708) */
+int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
+                 const double *velof, double eimp, double tadd, int max_steps, double *grad, int32_t *list, double *achrg, double *axyz,
+                 qcxms_b200_md_result_t *res);
+#ifdef __cplusplus
+}
+#endif
 #endif

@@ -101,3 +101,111 @@ def syev(a):
     w = np.zeros(n)
     st = lib().xtb_oracle_syev(n, _dp(a), _dp(w))
     return w, a, st
+
+
+# ------------------------------------------------------------------ MD side (md_oracle.c)
+class MdConfig(C.Structure):
+    _fields_ = [("method_id", C.c_int32), ("mchrg", C.c_int32), ("nfragexit", C.c_int32), ("exit_rules", C.c_int32),
+                ("nmax", C.c_int32), ("isec", C.c_int32), ("tstep", C.c_double), ("etemp_in", C.c_double),
+                ("ieetemp", C.c_double), ("ax", C.c_double)]
+
+
+class MdResult(C.Structure):
+    _fields_ = [("mdok", C.c_int32), ("fragstate", C.c_int32), ("nstep", C.c_int32), ("nfrag", C.c_int32),
+                ("status", C.c_int32), ("scc_iter_total", C.c_int32)] + \
+        [(k, C.c_double) for k in ("Tav", "Epav", "Ekav", "aTlast", "dtime", "ttime", "Epot", "Ekin")]
+
+
+def leapfrog(grad, mass, tstep, xyz, velo):
+    xyz = np.array(xyz, dtype=np.float64); velo = np.array(velo, dtype=np.float64)
+    grad = np.ascontiguousarray(grad, dtype=np.float64); mass = np.ascontiguousarray(mass, dtype=np.float64)
+    ke = C.c_double()
+    f = lib().md_oracle_leapfrog
+    f.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    f(len(mass), _dp(grad), _dp(mass), float(tstep), _dp(xyz), _dp(velo), C.byref(ke))
+    return xyz, velo, ke.value
+
+
+def ekinet(velo, mass):
+    velo = np.ascontiguousarray(velo, dtype=np.float64); mass = np.ascontiguousarray(mass, dtype=np.float64)
+    e, t = C.c_double(), C.c_double()
+    f = lib().md_oracle_ekinet
+    f.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    f(len(mass), _dp(velo), _dp(mass), C.byref(e), C.byref(t))
+    return e.value, t.value
+
+
+def impactscale(velo, mass, velof, eimp, ff, e0):
+    velo = np.array(velo, dtype=np.float64); mass = np.ascontiguousarray(mass, dtype=np.float64)
+    velof = np.ascontiguousarray(velof, dtype=np.float64)
+    f = lib().md_oracle_impactscale
+    f.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double]
+    err = f(len(mass), _dp(velo), _dp(mass), _dp(velof), float(eimp), float(ff), float(e0))
+    return velo, err
+
+
+def fragment_structure(oz, xyz, rcut=3.0, at1=1, at2=0):
+    oz = np.ascontiguousarray(oz, dtype=np.int32); xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    frag = np.zeros(len(oz), dtype=np.int32)
+    f = lib().md_oracle_fragment_structure
+    f.argtypes = [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    f(len(oz), _ip(oz), _dp(xyz), float(rcut), at1, at2, _ip(frag))
+    return frag
+
+
+def fragmass(iat, list_, mass, imass=None):
+    iat = np.ascontiguousarray(iat, dtype=np.int32); list_ = np.ascontiguousarray(list_, dtype=np.int32)
+    mass = np.ascontiguousarray(mass, dtype=np.float64)
+    nfrag = C.c_int32()
+    fragx = np.zeros(10); fragat = np.zeros((10, 200), dtype=np.int32)
+    f = lib().md_oracle_fragmass
+    f.argtypes = [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                  C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    im = None if imass is None else _ip(np.ascontiguousarray(imass, dtype=np.int32))
+    f(len(iat), _ip(iat), _ip(list_), _dp(mass), im, C.byref(nfrag), _dp(fragx), _ip(fragat))
+    return nfrag.value, fragx, fragat
+
+
+def checkqc(e, grad, qat, mchrg):
+    grad = np.ascontiguousarray(grad, dtype=np.float64); qat = np.ascontiguousarray(qat, dtype=np.float64)
+    ee = C.c_double(e)
+    f = lib().md_oracle_checkqc
+    f.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
+    ok = f(len(qat), C.byref(ee), _dp(grad), _dp(qat), int(mchrg))
+    return bool(ok), ee.value
+
+
+def setetemp(nfrag, eimp, ax=0.0, ieetemp=0.0):
+    f = lib().md_oracle_setetemp
+    f.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+    f.restype = C.c_double
+    return f(int(nfrag), float(eimp), float(ax), float(ieetemp))
+
+
+def getspin(ic, chrg):
+    ic = np.ascontiguousarray(ic, dtype=np.int32)
+    f = lib().md_oracle_getspin
+    f.argtypes = [C.c_int, C.POINTER(C.c_int32), C.c_int]
+    return f(len(ic), _ip(ic), int(chrg))
+
+
+def md(num, mass, xyz, velo, velof, eimp, tadd, mchrg=1, tstep_fs=0.5, nmax=10000, nfragexit=3, exit_rules=True, method=2,
+       etemp=-1.0, ieetemp=0.0, ax=0.0, isec=1, max_steps=0):
+    """md() of the reference for it > 0 (EI).  Returns dict with final xyz, velo, grad, list, achrg, axyz and result fields."""
+    num = np.ascontiguousarray(num, dtype=np.int32); nat = len(num)
+    mass = np.ascontiguousarray(mass, dtype=np.float64)
+    xyz = np.array(xyz, dtype=np.float64).reshape(nat, 3); velo = np.array(velo, dtype=np.float64).reshape(nat, 3)
+    velof = np.ascontiguousarray(velof, dtype=np.float64)
+    cfg = MdConfig(int(method), int(mchrg), int(nfragexit), int(bool(exit_rules)), int(nmax), int(isec),
+                   float(tstep_fs) * 41.3413733365614, float(etemp), float(ieetemp), float(ax))
+    grad = np.zeros((nat, 3)); lst = np.zeros(nat, dtype=np.int32); achrg = np.zeros(nat); axyz = np.zeros((nat, 3))
+    res = MdResult()
+    f = lib().md_oracle_md
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    f.argtypes = [C.POINTER(MdConfig), C.c_int, ip, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int, dp, ip, dp, dp, C.POINTER(MdResult)]
+    f(C.byref(cfg), nat, _ip(num), _dp(mass), _dp(xyz), _dp(velo), _dp(velof), float(eimp), float(tadd), int(max_steps),
+      _dp(grad), _ip(lst), _dp(achrg), _dp(axyz), C.byref(res))
+    out = dict(xyz=xyz, velo=velo, grad=grad, list=lst, achrg=achrg, axyz=axyz)
+    for k, _ in MdResult._fields_:
+        out[k] = getattr(res, k)
+    return out

@@ -29,7 +29,7 @@ static int fail(int code, const std::string &msg) {
     } while (0)
 
 // ------------------------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(QX_NT) k_egrad_batch(DevModel m, ScratchLayout L, double *scratch, const double *xyz, double kt, int nsys,
+__global__ void __launch_bounds__(QX_NT, 2) k_egrad_batch(DevModel m, ScratchLayout L, double *scratch, const double *xyz, double kt, int nsys,
                                                        int *queue, double *energy, double *grad, double *qat, int *stat, int *niter) {
     extern __shared__ double smem[];
     __shared__ int s_next;
@@ -82,7 +82,7 @@ __device__ inline double md_egrad(const DevModel &m, Sm &s, double *my, const Sc
 }
 
 // md(): everything before the loop (reference src/md.f90:155-283)
-__global__ void __launch_bounds__(QX_NT) k_md_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int *queue) {
+__global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int *queue) {
     extern __shared__ double smem[];
     __shared__ int s_next;
     Sm s;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(QX_NT) k_md_init(DevModel m, ScratchLayout L, 
 }
 
 // up to `chunk` MD steps (reference src/md.f90:285-682) for every running trajectory
-__global__ void __launch_bounds__(QX_NT) k_md_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int chunk,
+__global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int chunk,
                                                     int step_limit, int *queue, unsigned long long *steps_done) {
     extern __shared__ double smem[];
     __shared__ int s_next, s_flag;
@@ -144,11 +144,11 @@ __global__ void __launch_bounds__(QX_NT) k_md_chunk(DevModel m, ScratchLayout L,
         const double fadd = st.fadd[t], eimp = st.eimp[t], ekinstart = st.ekinstart[t];
         double epot = st.epot[t], ekin = st.ekin[t], etemp = st.etemp[t], Tav = st.Tav[t], Epav = st.Epav[t], Ekav = st.Ekav[t], Edum = st.Edum[t];
         double aTlast = st.aTlast[t], dtime = st.dtime[t], ttime = st.ttime[t];
-        const int max_steps = step_limit > 0 && step_limit < cfg.nmax ? step_limit : cfg.nmax;
         for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.xyz[i] = xyz[i];
         __syncthreads();
         int done = 0;
         for (int it = 0; it < chunk && status == TRJ_RUNNING; ++it) {
+            if (step_limit > 0 && nstep >= step_limit) break;  // pause here: the host asked for a bounded number of steps
             nstep += 1;
             const double T = ekin / (0.5 * 3 * nat * kB);
             Tav += T; Epav += epot; Ekav += ekin;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(QX_NT) k_md_chunk(DevModel m, ScratchLayout L,
                     if (morestep > 250) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
                 }
             }
-            if (nstep >= max_steps) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
+            if (nstep >= cfg.nmax) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -607,3 +607,22 @@ extern "C" int qcxms_b200_ensemble_histogram(qcxms_b200_ensemble_t *h, int nbins
 
 extern "C" const char *qcxms_b200_last_error(void) { return g_err.c_str(); }
 extern "C" const char *qcxms_b200_version(void) { return "qcxms_b200 0.1 (sm_100a)"; }
+
+// profiling builds only (-DQX_PROFILE_PHASES): read and reset the per-phase cycle counters; returns 0 counters otherwise
+extern "C" int qcxms_b200_debug_phase_cycles(double *out16) {
+#ifdef QX_PROFILE_PHASES
+    unsigned long long h[16], z[16] = {0};
+    CUDA_OK(cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof(h)));
+    CUDA_OK(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)));
+    for (int i = 0; i < 16; ++i) out16[i] = (double)h[i];
+    unsigned long long sh[64], sz[64] = {0};
+    CUDA_OK(cudaMemcpyFromSymbol(sh, g_sweep_hist, sizeof(sh)));
+    CUDA_OK(cudaMemcpyToSymbol(g_sweep_hist, sz, sizeof(sz)));
+    fprintf(stderr, "sweeps per SCC cycle:");
+    for (int i = 0; i < 32; ++i) if (sh[32 + i]) fprintf(stderr, " %d:%.2f", i + 1, (double)sh[i] / (double)sh[32 + i]);
+    fprintf(stderr, "\n");
+#else
+    for (int i = 0; i < 16; ++i) out16[i] = 0.0;
+#endif
+    return 0;
+}

@@ -483,21 +483,23 @@ __device__ inline void phase_integrals(const DevModel &m, Sm &s, double *S, doub
 }
 
 // ------------------------------------------------------------------------------------ dense kernels in shared memory
-// out(n x n, ldo) = X^T-or-X (n x n, ldx) * Y (n x n, ldy); 4x4 register tiles
-template <bool TRANS_X>
-__device__ inline void gemm_nn(int n, const double *X, int ldx, const double *Y, int ldy, double *out, int ldo) {
-    const int nt = (n + 3) / 4;
-    for (int tile = threadIdx.x; tile < nt * nt; tile += QX_NT) {
-        const int i0 = (tile / nt) * 4, j0 = (tile % nt) * 4;
+// Eigenvectors are kept TRANSPOSED: Ct[k][i] = C[i][k] (orbital k contiguous), so that the one-sided Jacobi
+// rotates contiguous rows and the density build streams rows.
+//
+// out = X * Y (TRANS_Y = false) or X * Y^T (TRANS_Y = true); all n x n; 4x4 register tiles
+template <bool TRANS_Y>
+__device__ inline void gemm_small(int n, const double *X, int ldx, const double *Y, int ldy, double *out, int ldo) {
+    const int nt = (n + 3) >> 2, ntile = nt * nt;
+    for (int tile = threadIdx.x; tile < ntile; tile += QX_NT) {
+        const int ti = tile / nt, i0 = ti << 2, j0 = (tile - ti * nt) << 2;
         double acc[4][4] = {{0}};
         for (int k = 0; k < n; ++k) {
             double x[4], y[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                int i = i0 + r;
-                x[r] = i < n ? (TRANS_X ? X[(size_t)k * ldx + i] : X[(size_t)i * ldx + k]) : 0.0;
-                int j = j0 + r;
-                y[r] = j < n ? Y[(size_t)k * ldy + j] : 0.0;
+                const int i = i0 + r, j = j0 + r;
+                x[r] = i < n ? X[(size_t)i * ldx + k] : 0.0;
+                y[r] = j < n ? (TRANS_Y ? Y[(size_t)j * ldy + k] : Y[(size_t)k * ldy + j]) : 0.0;
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r)
@@ -512,21 +514,22 @@ __device__ inline void gemm_nn(int n, const double *X, int ldx, const double *Y,
     }
 }
 
-// out = C diag(w) C^T (symmetric), C (n x n, ldc)
-__device__ inline void gemm_cwct(int n, const double *C, int ldc, const double *w, double *out, int ldo) {
-    const int nt = (n + 3) / 4;
-    for (int tile = threadIdx.x; tile < nt * nt; tile += QX_NT) {
-        const int i0 = (tile / nt) * 4, j0 = (tile % nt) * 4;
+// out = Ct^T diag(w) Ct = C diag(w) C^T (symmetric); Ct (n x n, ldc), orbitals along rows
+__device__ inline void gemm_ctwc(int n, const double *Ct, int ldc, const double *w, double *out, int ldo) {
+    const int nt = (n + 3) >> 2, ntile = nt * nt;
+    for (int tile = threadIdx.x; tile < ntile; tile += QX_NT) {
+        const int ti = tile / nt, i0 = ti << 2, j0 = (tile - ti * nt) << 2;
         if (j0 > i0) continue;
         double acc[4][4] = {{0}};
         for (int k = 0; k < n; ++k) {
             const double wk = w[k];
             if (wk == 0.0) continue;
+            const double *row = Ct + (size_t)k * ldc;
             double x[4], y[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                x[r] = i0 + r < n ? C[(size_t)(i0 + r) * ldc + k] * wk : 0.0;
-                y[r] = j0 + r < n ? C[(size_t)(j0 + r) * ldc + k] : 0.0;
+                x[r] = i0 + r < n ? row[i0 + r] * wk : 0.0;
+                y[r] = j0 + r < n ? row[j0 + r] : 0.0;
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r)
@@ -544,9 +547,9 @@ __device__ inline void gemm_cwct(int n, const double *C, int ldc, const double *
     }
 }
 
-// In-place Cholesky S = L L^T on the lower triangle of A (n x n, ld), then C = L^{-T} (upper triangular):
-// an S-orthonormal starting basis.  Returns false if S is not positive definite.
-__device__ inline bool cholesky_basis(int n, double *A, double *C, int ld, double *red) {
+// In-place Cholesky S = L L^T on the lower triangle of A (n x n, ld), then Ct = L^{-1} (lower triangular),
+// i.e. C = L^{-T}: an S-orthonormal starting basis.  Returns false if S is not positive definite.
+__device__ inline bool cholesky_basis(int n, double *A, double *Ct, int ld, double *red) {
     for (int j = 0; j < n; ++j) {
         double d = A[(size_t)j * ld + j];
         if (!(d > 0.0)) return false;  // uniform across the CTA (all threads read the same value)
@@ -554,93 +557,101 @@ __device__ inline bool cholesky_basis(int n, double *A, double *C, int ld, doubl
         __syncthreads();
         for (int i = j + threadIdx.x; i < n; i += QX_NT) A[(size_t)i * ld + j] = (i == j) ? d : A[(size_t)i * ld + j] / d;
         __syncthreads();
-        // trailing update of the lower triangle
-        const int rem = n - j - 1;
-        for (int t = threadIdx.x; t < rem * rem; t += QX_NT) {
-            int i = j + 1 + t / rem, k = j + 1 + t % rem;
-            if (k <= i) A[(size_t)i * ld + k] -= A[(size_t)i * ld + j] * A[(size_t)k * ld + j];
+        // trailing update of the lower triangle: one thread per row, columns j+1..i
+        for (int i = j + 1 + threadIdx.x; i < n; i += QX_NT) {
+            const double lij = A[(size_t)i * ld + j];
+            for (int k = j + 1; k <= i; ++k) A[(size_t)i * ld + k] -= lij * A[(size_t)k * ld + j];
         }
         __syncthreads();
     }
-    // X = L^{-1} column by column (thread per column), stored transposed: C[j][i] = X[i][j]  => C = L^{-T}
+    // X = L^{-1}, thread per column j (forward substitution); zero the strictly upper part
     for (int j = threadIdx.x; j < n; j += QX_NT) {
-        for (int i = 0; i < j; ++i) C[(size_t)j * ld + i] = 0.0;  // strictly lower part of C
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < n; j += QX_NT) {
-        // solve L x = e_j ; x_i for i >= j ; write C[j][i] = x_i  (row j of C, upper part)
-        C[(size_t)j * ld + j] = 1.0 / A[(size_t)j * ld + j];
+        for (int i = 0; i < j; ++i) Ct[(size_t)i * ld + j] = 0.0;
+        Ct[(size_t)j * ld + j] = 1.0 / A[(size_t)j * ld + j];
         for (int i = j + 1; i < n; ++i) {
             double v = 0.0;
-            for (int k = j; k < i; ++k) v -= A[(size_t)i * ld + k] * C[(size_t)j * ld + k];
-            C[(size_t)j * ld + i] = v / A[(size_t)i * ld + i];
+            for (int k = j; k < i; ++k) v -= A[(size_t)i * ld + k] * Ct[(size_t)k * ld + j];
+            Ct[(size_t)i * ld + j] = v / A[(size_t)i * ld + i];
         }
     }
     __syncthreads();
     return true;
 }
 
-// Parallel-order two-sided Jacobi on the symmetric A (n x n, ld); rotations are accumulated into the
-// columns of C (so C_new = C_old * J).  On exit diag(A) = eigenvalues.  Returns number of sweeps.
-__device__ inline int jacobi_eig(int n, double *A, double *C, int ld, Sm &s) {
-    const int mm = (n + 1) & ~1;  // players (one dummy if n is odd)
-    const int npair = mm / 2;
-    int sweep = 0;
-    for (; sweep < 40; ++sweep) {
-        // convergence: off-diagonal Frobenius norm against the diagonal
-        double off = 0.0, dg = 0.0;
-        for (int t = threadIdx.x; t < n * n; t += QX_NT) {
-            int i = t / n, j = t - i * n;
-            double v = A[(size_t)i * ld + j];
-            if (i == j) dg += v * v; else off += v * v;
-        }
-        off = block_sum(off, s.red);
-        dg = block_sum(dg, s.red);
-        if (off <= 1e-26 * dg) break;
-        for (int round = 0; round < mm - 1; ++round) {
-            if (threadIdx.x < npair) {
-                int k = threadIdx.x, p, q;
-                if (k == 0) { p = mm - 1; q = round; }
-                else { p = (round + k) % (mm - 1); q = (round - k + mm - 1) % (mm - 1); }
-                if (p > q) { int tt = p; p = q; q = tt; }
-                double c = 1.0, sn = 0.0;
-                if (q < n) {
-                    double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
-                    if (fabs(apq) > 1e-30 * (fabs(app) + fabs(aqq)) && apq != 0.0) {
-                        double tau = (aqq - app) / (2.0 * apq);
-                        double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = 1.0 / sqrt(1.0 + tt * tt);
-                        sn = tt * c;
-                    }
-                } else { q = -1; }
-                s.rotp[2 * k] = p; s.rotp[2 * k + 1] = q;
-                s.rot[2 * k] = c; s.rot[2 * k + 1] = sn;
-            }
-            __syncthreads();
-            // rows: A <- J^T A
-            for (int t = threadIdx.x; t < npair * n; t += QX_NT) {
-                int k = t / n, j = t - k * n, p = s.rotp[2 * k], q = s.rotp[2 * k + 1];
-                if (q < 0) continue;
-                double c = s.rot[2 * k], sn = s.rot[2 * k + 1];
-                double x = A[(size_t)p * ld + j], y = A[(size_t)q * ld + j];
-                A[(size_t)p * ld + j] = c * x - sn * y;
-                A[(size_t)q * ld + j] = sn * x + c * y;
-            }
-            __syncthreads();
-            // columns: A <- A J ; C <- C J
-            for (int t = threadIdx.x; t < 2 * npair * n; t += QX_NT) {
-                int which = t / (npair * n), r = t - which * npair * n;
-                int k = r / n, i = r - k * n, p = s.rotp[2 * k], q = s.rotp[2 * k + 1];
-                if (q < 0) continue;
-                double c = s.rot[2 * k], sn = s.rot[2 * k + 1];
-                double *M = which ? C : A;
-                double x = M[(size_t)i * ld + p], y = M[(size_t)i * ld + q];
-                M[(size_t)i * ld + p] = c * x - sn * y;
-                M[(size_t)i * ld + q] = sn * x + c * y;
-            }
-            __syncthreads();
-        }
+// One-sided (Hestenes) Jacobi with round-robin ordering.  G (n x n, ld) holds the symmetric matrix
+// A' + sigma*I (positive definite thanks to the Gershgorin shift applied here); its rows (= columns) are
+// orthogonalised by plane rotations that are applied to the rows of Ct as well (C <- C J).  A sub-warp
+// group of LP lanes owns one pair per round, so a round needs a single __syncthreads.  On exit
+// emo[k] = |g_k| - sigma.  Returns the number of sweeps.
+__device__ inline int jacobi_onesided(int n, double *G, double *Ct, int ld, double *emo, double *red) {
+    const int mm = (n + 1) & ~1, npair = mm >> 1;
+    int LP = 32;
+    while (LP > 4 && npair * LP > QX_NT) LP >>= 1;
+    const int nslot = QX_NT / LP, slot = threadIdx.x / LP, lsub = threadIdx.x & (LP - 1), lane = threadIdx.x & 31;
+    const unsigned gmask = LP == 32 ? 0xffffffffu : (((1u << LP) - 1u) << (lane & ~(LP - 1)));
+    // Gershgorin shift
+    double rowsum = 0.0;
+    for (int i = threadIdx.x; i < n; i += QX_NT) {
+        double v = 0.0;
+        for (int j = 0; j < n; ++j) v += fabs(G[(size_t)i * ld + j]);
+        rowsum = fmax(rowsum, v);
     }
+    const double sigma = 1.0625 * block_max(rowsum, red) + 0.5;
+    for (int i = threadIdx.x; i < n; i += QX_NT) G[(size_t)i * ld + i] += sigma;
+    __syncthreads();
+    int sweep = 0;
+    for (; sweep < 60; ++sweep) {
+        double smax = 0.0;
+        for (int round = 0; round < mm - 1; ++round) {
+            for (int k = slot; k < npair; k += nslot) {
+                int p, q;
+                if (k == 0) { p = mm - 1; q = round; }
+                else { p = round + k; if (p >= mm - 1) p -= mm - 1; q = round - k; if (q < 0) q += mm - 1; }
+                if (p > q) { int t = p; p = q; q = t; }
+                if (q >= n) continue;
+                double *gp = G + (size_t)p * ld, *gq = G + (size_t)q * ld;
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int i = lsub; i < n; i += LP) {
+                    const double x = gp[i], y = gq[i];
+                    al += x * x; be += y * y; ga += x * y;
+                }
+                for (int o = LP >> 1; o > 0; o >>= 1) {
+                    al += __shfl_xor_sync(gmask, al, o);
+                    be += __shfl_xor_sync(gmask, be, o);
+                    ga += __shfl_xor_sync(gmask, ga, o);
+                }
+                const double ratio = fabs(ga) * rsqrt(al * be);
+                smax = fmax(smax, ratio);
+                if (ratio > 1e-15) {
+                    const double zeta = (be - al) / (2.0 * ga);
+                    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = rsqrt(1.0 + t * t), sn = c * t;
+                    double *cp = Ct + (size_t)p * ld, *cq = Ct + (size_t)q * ld;
+                    for (int i = lsub; i < n; i += LP) {
+                        const double x = gp[i], y = gq[i];
+                        gp[i] = c * x - sn * y;
+                        gq[i] = sn * x + c * y;
+                        const double u = cp[i], v = cq[i];
+                        cp[i] = c * u - sn * v;
+                        cq[i] = sn * u + c * v;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        smax = block_max(smax, red);
+        if (smax < 1e-10) { ++sweep; break; }  // quadratic convergence: the rotations of this sweep already finished the job
+    }
+    // eigenvalues from the row norms
+    const int warp = threadIdx.x >> 5;
+    for (int k = warp; k < n; k += QX_NT / 32) {
+        double acc = 0.0;
+        for (int i = lane; i < n; i += 32) { const double x = G[(size_t)k * ld + i]; acc += x * x; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) emo[k] = sqrt(acc) - sigma;
+    }
+    __syncthreads();
     return sweep;
 }
 

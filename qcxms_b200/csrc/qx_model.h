@@ -6,7 +6,7 @@
 #define QX_MAXPRIM 6
 #define QX_MAXREF 7
 #define QX_MAX_ITER 250   // tblite max_iter (SCC cycles and Broyden memory)
-#define QX_NT 256         // threads per CTA; one CTA == one trajectory
+#define QX_NT 288         // threads per CTA; one CTA == one trajectory
 
 struct DevModel {
     int nat, nsh, nao, ntype, ld, ndim;  // ld: odd leading dimension of the shared-memory matrices

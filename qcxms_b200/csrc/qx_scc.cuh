@@ -8,6 +8,26 @@
 
 namespace qx {
 
+// optional per-phase cycle accounting (profiling builds only: -DQX_PROFILE_PHASES)
+#ifdef QX_PROFILE_PHASES
+__device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned long long g_sweep_hist[64];  // [iteration index (<32)] -> sweeps, [32+..] -> count
+#define QX_PH_BEGIN() long long ph_t0_ = clock64()
+#define QX_PH(idx)                                                                  \
+    do {                                                                            \
+        __syncthreads();                                                            \
+        if (threadIdx.x == 0) {                                                     \
+            long long ph_t1_ = clock64();                                           \
+            atomicAdd(&g_phase_cycles[idx], (unsigned long long)(ph_t1_ - ph_t0_)); \
+            ph_t0_ = ph_t1_;                                                        \
+        } else                                                                      \
+            ph_t0_ = 0;                                                             \
+    } while (0)
+#else
+#define QX_PH_BEGIN() do {} while (0)
+#define QX_PH(idx) do {} while (0)
+#endif
+
 struct EgradOut {
     double energy;
     double e_rep, e_atm, e_el, e_es, e_aes, e_d4, e_ts;
@@ -407,11 +427,15 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     }
     out.stat = 0; out.niter = 0; out.sweeps = 0;
 
+    QX_PH_BEGIN();
     phase_cn(m, s, dcnp, dcnp4);
     out.e_rep = phase_repulsion(m, s);
+    QX_PH(0);
     out.e_atm = phase_d4_nonsc(m, s, edisp, c6, dc6, taskout);
+    QX_PH(1);
     phase_coulomb_setup(m, s, gamma);
     phase_integrals(m, s, S, H0, Dt, Qt);
+    QX_PH(2);
 
     // S-orthonormal start basis: C = L^{-T}
     for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.A[(size_t)(t / nao) * ld + t % nao] = S[t];
@@ -423,6 +447,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.dpat[i] = 0.0;
     for (int i = threadIdx.x; i < 6 * nat; i += QX_NT) s.qpat[i] = 0.0;
     __syncthreads();
+    QX_PH(3);
 
     double eelec = 0.0;
     bool converged = false;
@@ -445,19 +470,28 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
             }
             __syncthreads();
         }
+        QX_PH(4);
         iscf += 1;
         phase_potential(m, s, gamma, edisp, t7);
         for (int i = threadIdx.x; i < ndim; i += QX_NT)
             br.q_in[i] = i < nsh ? s.qsh[i] : (i < nsh + 3 * nat ? s.dpat[i - nsh] : s.qpat[i - nsh - 3 * nat]);
+        QX_PH(5);
         phase_build_h1(m, s, S, H0, Dt, Qt);
-        // A' = C^T H1 C in the current S-orthonormal basis, then Jacobi (C <- C J)
-        gemm_nn<false>(nao, s.A, ld, s.C, ld, T, nao);
+        QX_PH(6);
+        // A' = C^T H1 C in the current S-orthonormal basis (s.C holds C transposed), then Jacobi (C <- C J)
+        gemm_small<false>(nao, s.C, ld, s.A, ld, T, nao);   // Tt = Ct H1
         __syncthreads();
-        gemm_nn<true>(nao, s.C, ld, T, nao, s.A, ld);
+        gemm_small<true>(nao, s.C, ld, T, nao, s.A, ld);    // A' = Ct Tt^T
         __syncthreads();
-        out.sweeps += jacobi_eig(nao, s.A, s.C, ld, s);
-        for (int k = threadIdx.x; k < nao; k += QX_NT) s.emo[k] = s.A[(size_t)k * ld + k];
-        __syncthreads();
+        QX_PH(7);
+        {
+            int sw_ = jacobi_onesided(nao, s.A, s.C, ld, s.emo, s.red);
+            out.sweeps += sw_;
+#ifdef QX_PROFILE_PHASES
+            if (threadIdx.x == 0 && iscf <= 32) { atomicAdd(&g_sweep_hist[iscf - 1], (unsigned long long)sw_); atomicAdd(&g_sweep_hist[32 + iscf - 1], 1ull); }
+#endif
+        }
+        QX_PH(8);
         // order statistics needed for the Fermi-level start value
         int homo[2];
         for (int sp = 0; sp < 2; ++sp) {
@@ -497,10 +531,13 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
             s.focc[k] = f;
         }
         ts = block_sum(ts, s.red);
+        QX_PH(9);
         // density into A
-        gemm_cwct(nao, s.C, ld, s.focc, s.A, ld);
+        gemm_ctwc(nao, s.C, ld, s.focc, s.A, ld);
         __syncthreads();
+        QX_PH(10);
         double eel = phase_mulliken(m, s, S, H0, Dt, Qt, pop);
+        QX_PH(11);
         double err = 0.0;
         for (int i = threadIdx.x; i < ndim; i += QX_NT) {
             double o = i < nsh ? s.qsh[i] : (i < nsh + 3 * nat ? s.dpat[i - nsh] : s.qpat[i - nsh - 3 * nat]);
@@ -512,6 +549,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         double e_es, e_aes, e_d4;
         phase_scc_energy(m, s, gamma, edisp, e_es, e_aes, e_d4);
         eelec = ts + eel + e_es + e_aes + e_d4;
+        QX_PH(12);
         out.e_el = eel; out.e_es = e_es; out.e_aes = e_aes; out.e_d4 = e_d4; out.e_ts = ts;
         converged = fabs(eelec - elast) < 1e-6 && err < 2e-5;
     }
@@ -526,11 +564,13 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     // W = C diag(f e) C^T -> global T -> shared C (A holds P)
     for (int k = threadIdx.x; k < nao; k += QX_NT) s.focc[k] *= s.emo[k];
     __syncthreads();
-    gemm_cwct(nao, s.C, ld, s.focc, T, nao);
+    gemm_ctwc(nao, s.C, ld, s.focc, T, nao);
     __syncthreads();
     for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.C[(size_t)(t / nao) * ld + t % nao] = T[t];
     __syncthreads();
+    QX_PH(13);
     phase_gradient_pairs(m, s, m.task_int, m.ntask_int, taskout);
+    QX_PH(14);
     for (int t = threadIdx.x; t < 3 * nat; t += QX_NT) {
         int k = t / 3, c = t - 3 * k;
         double g = 0.0;
@@ -630,6 +670,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         s.grad[3 * k] += gx; s.grad[3 * k + 1] += gy; s.grad[3 * k + 2] += gz;
     }
     __syncthreads();
+    QX_PH(15);
 }
 
 }  // namespace qx

@@ -1,0 +1,103 @@
+"""GPU parity of the MD side: fragment ids (bit-exact), the md() state machine over short horizons, exit rules."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fragment_structure_bit_exact_random(qx, oracle):
+    num, xyz, _ = qx.load_molecule("caffeine")
+    rng = np.random.default_rng(3)
+    # expand / distort so that many pairs straddle the 1.5 (Rad_i + Rad_j) threshold
+    geoms = np.array([xyz * s + 0.3 * rng.standard_normal(xyz.shape) for s in np.linspace(0.9, 2.2, 64)])
+    got = qx.fragment_structure(num, geoms, 3.0)
+    nmulti = 0
+    for k in range(len(geoms)):
+        ref = oracle.fragment_structure(num, geoms[k], 3.0)
+        assert np.array_equal(got[k], ref)
+        nmulti += ref.max() > 1
+    assert nmulti > 5   # the sweep really produced fragmented geometries
+
+
+def test_fragment_structure_threshold_edge(qx, oracle):
+    # two hydrogens exactly around r = 1.5 * (Rad_H + Rad_H): one ulp either side must agree with the oracle
+    rad = 0.32 / 0.52917726
+    r0 = 3.0 * 0.5 * (rad + rad)
+    num = np.array([1, 1], dtype=np.int32)
+    ds = [np.nextafter(r0, 0), r0, np.nextafter(r0, 10), r0 * (1 - 1e-15), r0 * (1 + 1e-15)]
+    geoms = np.array([[[0, 0, 0], [0, 0, d]] for d in ds], dtype=np.float64)
+    got = qx.fragment_structure(num, geoms, 3.0)
+    for k in range(len(ds)):
+        assert np.array_equal(got[k], oracle.fragment_structure(num, geoms[k], 3.0))
+    assert got[0].tolist() == [1, 1] and got[2].tolist() == [1, 2]
+
+
+def _ic(qx, name, ntraj, seed=0):
+    from qcxms_b200 import ensemble_setup as es
+    num, xyz, _ = qx.load_molecule(name)
+    return num, es.synthetic_initial_conditions(num, xyz, ntraj, first_id=seed)
+
+
+def test_md_short_run_matches_oracle(qx, oracle):
+    num, ic = _ic(qx, "chloroethanol", 6)
+    nsteps = 25
+    ens = qx.Ensemble(num, ic["mass"], 6, mchrg=1, nmax=nsteps, exit_rules=True)
+    ens.set_all(ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+    steps = ens.run_md()
+    assert steps == 6 * nsteps
+    for k in range(6):
+        got = ens.result(k)
+        ref = oracle.md(num, ic["mass"], ic["xyz"][k], ic["velo"][k], ic["velof"][k], ic["eimp"][k], ic["tadd"][k], mchrg=1, nmax=nsteps)
+        assert got["nstep"] == ref["nstep"] == nsteps and got["mdok"] == ref["mdok"] == 1 and got["fragstate"] == ref["fragstate"]
+        assert got["scc_iter_total"] == ref["scc_iter_total"]
+        assert np.array_equal(got["list"], ref["list"])
+        assert np.abs(got["xyz"] - ref["xyz"]).max() < 1e-7
+        assert np.abs(got["velo"] - ref["velo"]).max() < 1e-9
+        assert np.abs(got["grad"] - ref["grad"]).max() < 2e-6
+        assert abs(got["Epot"] - ref["Epot"]) < 1e-7 and abs(got["Ekin"] - ref["Ekin"]) < 1e-8
+        assert abs(got["Epav"] - ref["Epav"]) < 1e-7 and abs(got["Tav"] - ref["Tav"]) < 1e-3
+        assert np.abs(got["achrg"] - ref["achrg"]).max() < 1e-5 and np.abs(got["axyz"] - ref["axyz"]).max() < 1e-7
+    ens.close()
+
+
+def test_md_exit_on_fragmentation(qx, oracle):
+    # pull the chlorine far away: nfrag = 2 from the first step; with nfragexit = 1 md must exit at step 1 (fragstate 1)
+    num, ic = _ic(qx, "chloroethanol", 2)
+    for k in range(2):
+        ic["xyz"][k][2] += np.array([12.0, -8.0, -8.0])
+    ens = qx.Ensemble(num, ic["mass"], 2, mchrg=1, nmax=50, nfragexit=1, exit_rules=True)
+    ens.set_all(ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+    ens.run_md()
+    for k in range(2):
+        got = ens.result(k)
+        ref = oracle.md(num, ic["mass"], ic["xyz"][k], ic["velo"][k], ic["velof"][k], ic["eimp"][k], ic["tadd"][k], mchrg=1, nmax=50, nfragexit=1)
+        assert got["nstep"] == ref["nstep"] == 1 and got["nfrag"] == ref["nfrag"] == 2
+        assert got["fragstate"] == ref["fragstate"] == 1 and got["mdok"] == ref["mdok"] == 1
+        assert np.array_equal(got["list"], ref["list"])
+    ens.close()
+
+
+def test_md_continue_in_chunks_equals_one_run(qx):
+    num, ic = _ic(qx, "chloroethanol", 3, seed=11)
+    def run(split):
+        ens = qx.Ensemble(num, ic["mass"], 3, mchrg=1, nmax=10 ** 6, exit_rules=False)
+        ens.set_all(ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+        for n in split:
+            ens.run_md(max_steps=n)
+        out = [ens.result(k) for k in range(3)]
+        ens.close()
+        return out
+    a, b = run([12]), run([5, 7])
+    for x, y in zip(a, b):
+        assert x["nstep"] == y["nstep"] == 12
+        assert np.array_equal(x["xyz"], y["xyz"]) and np.array_equal(x["velo"], y["velo"])   # bitwise reproducible
+
+
+def test_histogram_counts_fragments(qx):
+    num, ic = _ic(qx, "chloroethanol", 4)
+    ens = qx.Ensemble(num, ic["mass"], 4, mchrg=1, nmax=3, exit_rules=True)
+    ens.set_all(ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+    ens.run_md()
+    bins, dev = ens.histogram(256)
+    assert dev is not None and bins.sum() == 4 and (bins[80] + bins[81]) == 4   # intact C2H5ClO (average masses: 80.5 amu)
+    ens.close()
