@@ -31,7 +31,7 @@ static int fail(int code, const std::string &msg) {
 // ------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(QX_NT, 2) k_egrad_batch(DevModel m, ScratchLayout L, double *scratch, const double *xyz, double kt, int nsys,
                                                        int *queue, double *energy, double *grad, double *qat, int *stat, int *niter) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     __shared__ int s_next;
     Sm s;
     carve(m, smem, s);
@@ -83,7 +83,7 @@ __device__ inline double md_egrad(const DevModel &m, Sm &s, double *my, const Sc
 
 // md(): everything before the loop (reference src/md.f90:155-283)
 __global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int *queue) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     __shared__ int s_next;
     Sm s;
     carve(m, smem, s);
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout 
 // up to `chunk` MD steps (reference src/md.f90:285-682) for every running trajectory
 __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int chunk,
                                                     int step_limit, int *queue, unsigned long long *steps_done) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     __shared__ int s_next, s_flag;
     Sm s;
     carve(m, smem, s);

@@ -44,13 +44,12 @@ __constant__ double c_qscale[6] = {1.0, 2.0, 1.0, 2.0, 2.0, 1.0};
 struct Sm {
     double *A, *C;
     double *xyz, *cn, *cn4, *mrad, *dmr, *qat, *vat, *dpat, *vdp, *qpat, *vqp;
-    double *qsh, *vsh, *selfen, *vao, *emo, *focc, *gw, *gwd, *dEdcn, *dEdcn4, *grad, *red, *rot;
-    int *rotp;
+    double *qsh, *vsh, *selfen, *vao, *emo, *focc, *gw, *gwd, *dEdcn, *dEdcn4, *grad, *red, *jw;
 };
 
 __host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld) {
     return 2 * (size_t)nao * ld + 3 * nat + 6 * nat /*cn cn4 mrad dmr qat vat*/ + 6 * nat /*dpat vdp*/ + 12 * nat /*qpat vqp*/
-           + 3 * nsh + 3 * nao + 14 * nat /*gw gwd*/ + 2 * nat + 3 * nat /*grad*/ + 64 + 2 * (nao / 2 + 2) + (nao / 2 + 2) /*rotp as ints*/;
+           + 3 * nsh + 3 * nao + 14 * nat /*gw gwd*/ + 2 * nat + 3 * nat /*grad*/ + 64 + 3 * nao + 8 /*jw*/;
 }
 
 __device__ inline void carve(const DevModel &m, double *base, Sm &s) {
@@ -69,8 +68,7 @@ __device__ inline void carve(const DevModel &m, double *base, Sm &s) {
     s.dEdcn = p; p += nat; s.dEdcn4 = p; p += nat;
     s.grad = p; p += 3 * nat;
     s.red = p; p += 64;
-    s.rot = p; p += 2 * (nao / 2 + 2);
-    s.rotp = (int *)p;
+    s.jw = p;
 }
 
 __device__ inline double block_sum(double v, double *red) {
@@ -102,7 +100,7 @@ __device__ inline double block_max(double v, double *red) {
 // ------------------------------------------------------------------------------------
 // coordination numbers (GFN double-exponential; D4 erf with EN weighting) + pair derivative
 // tables dcnp[i*nat+j] = (1/r) d f(r_ij)/dr, so that d cn_i/d R_i = sum_j dcnp_ij (R_i - R_j).
-__device__ inline void phase_cn(const DevModel &m, Sm &s, double *dcnp, double *dcnp4) {
+__device__ __noinline__ void phase_cn(const DevModel &m, Sm &s, double *dcnp, double *dcnp4) {
     const int nat = m.nat;
     for (int i = threadIdx.x; i < nat; i += QX_NT) {
         double cn = 0.0, cn4 = 0.0;
@@ -139,7 +137,7 @@ __device__ inline void phase_cn(const DevModel &m, Sm &s, double *dcnp, double *
 }
 
 // classical repulsion: returns the CTA-wide energy; initialises s.grad
-__device__ inline double phase_repulsion(const DevModel &m, Sm &s) {
+__device__ __noinline__ double phase_repulsion(const DevModel &m, Sm &s) {
     const int nat = m.nat;
     double e = 0.0;
     for (int i = threadIdx.x; i < nat; i += QX_NT) {
@@ -235,7 +233,7 @@ __device__ inline void d4_c6_tables(const DevModel &m, const double *gw, const d
 
 // non-self-consistent part of D4: ATM with q = 0 weights; also fills edisp[i*nat+j] (two-body BJ kernel).
 // tmp: >= 14*nat + 5*nat*nat doubles of global scratch.
-__device__ inline double phase_d4_nonsc(const DevModel &m, Sm &s, double *edisp, double *c6, double *dc6, double *tmp) {
+__device__ __noinline__ double phase_d4_nonsc(const DevModel &m, Sm &s, double *edisp, double *c6, double *dc6, double *tmp) {
     const int nat = m.nat;
     double *gw0 = tmp, *gwdcn0 = tmp + 7 * nat, *part = tmp + 14 * nat;
     for (int i = threadIdx.x; i < nat; i += QX_NT) d4_weights_atom(m, i, s.cn4[i], 0.0, gw0 + 7 * i, gwdcn0 + 7 * i, nullptr);
@@ -315,7 +313,7 @@ __device__ inline double phase_d4_nonsc(const DevModel &m, Sm &s, double *edisp,
 }
 
 // ------------------------------------------------------------------------------------ Coulomb set-up
-__device__ inline void phase_coulomb_setup(const DevModel &m, Sm &s, double *gamma) {
+__device__ __noinline__ void phase_coulomb_setup(const DevModel &m, Sm &s, double *gamma) {
     const int nat = m.nat, nsh = m.nsh;
     for (int ab = threadIdx.x; ab < nsh * nsh; ab += QX_NT) {
         int a = ab / nsh, b = ab - a * nsh, i = m.sh_at[a], j = m.sh_at[b];
@@ -444,7 +442,7 @@ __device__ inline double shpoly_pair(const DevModel &m, int sa, int sb, double r
 
 // Fills the per-CTA slab: S, H0 (symmetric), Dt/Qt in "operator on the FIRST index" layout:
 //   Dt[c][b][a] = <a| (r - R_atom(b))_c |b>   (row b contiguous in a).
-__device__ inline void phase_integrals(const DevModel &m, Sm &s, double *S, double *H0, double *Dt, double *Qt) {
+__device__ __noinline__ void phase_integrals(const DevModel &m, Sm &s, double *S, double *H0, double *Dt, double *Qt) {
     const int nao = m.nao;
     const size_t n2 = (size_t)nao * nao;
     for (int t = threadIdx.x; t < m.ntask_int; t += QX_NT) {
@@ -483,73 +481,59 @@ __device__ inline void phase_integrals(const DevModel &m, Sm &s, double *S, doub
 }
 
 // ------------------------------------------------------------------------------------ dense kernels in shared memory
-// Eigenvectors are kept TRANSPOSED: Ct[k][i] = C[i][k] (orbital k contiguous), so that the one-sided Jacobi
-// rotates contiguous rows and the density build streams rows.
+// Eigenvectors are kept TRANSPOSED: Ct[k][i] = C[i][k] (orbital k contiguous).  The leading dimension of the
+// shared-memory matrices is == 4 or 12 (mod 16): with it both the DMMA fragment loads (8 rows x 4 columns)
+// and the 128-bit row accesses of the Jacobi are free of bank conflicts.
 //
-// out = X * Y (TRANS_Y = false) or X * Y^T (TRANS_Y = true); all n x n; 4x4 register tiles
-template <bool TRANS_Y>
-__device__ inline void gemm_small(int n, const double *X, int ldx, const double *Y, int ldy, double *out, int ldo) {
-    const int nt = (n + 3) >> 2, ntile = nt * nt;
-    for (int tile = threadIdx.x; tile < ntile; tile += QX_NT) {
-        const int ti = tile / nt, i0 = ti << 2, j0 = (tile - ti * nt) << 2;
-        double acc[4][4] = {{0}};
-        for (int k = 0; k < n; ++k) {
-            double x[4], y[4];
+// FP64 tensor-core GEMM  out(i,j) = sum_k A(i,k) B(k,j),  all n x n, operands given as element accessors.
+// One warp owns a strip of 8 output rows and walks the column tiles, so the A fragment of a k-step is
+// reused for every tile of the strip (mma.sync.m8n8k4.f64 == DMMA.8x8x4 on sm_100a).
+template <int MAXT, class FA, class FB, class FS>
+__device__ __noinline__ void dmma_gemm(int n, FA loadA, FB loadB, FS store) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = QX_NT / 32;
+    const int nt = (n + 7) >> 3, g = lane >> 2, tg = lane & 3;
+    for (int ti = warp; ti < nt; ti += nwarp) {
+        const int row = ti * 8 + g;
+        double acc[MAXT][2];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int i = i0 + r, j = j0 + r;
-                x[r] = i < n ? X[(size_t)i * ldx + k] : 0.0;
-                y[r] = j < n ? (TRANS_Y ? Y[(size_t)j * ldy + k] : Y[(size_t)k * ldy + j]) : 0.0;
+        for (int t = 0; t < MAXT; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll 2
+        for (int k0 = 0; k0 < n; k0 += 4) {
+            const int k = k0 + tg;
+            const double a = (row < n && k < n) ? loadA(row, k) : 0.0;
+#pragma unroll
+            for (int t = 0; t < MAXT; ++t) {
+                if (t < nt) {
+                    const int col = t * 8 + g;
+                    const double b = (k < n && col < n) ? loadB(k, col) : 0.0;
+                    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(a), "d"(b));
+                }
             }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] += x[r] * y[c];
         }
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (i0 + r < n && j0 + c < n) out[(size_t)(i0 + r) * ldo + j0 + c] = acc[r][c];
+        for (int t = 0; t < MAXT; ++t) {
+            if (t < nt) {
+                const int col = t * 8 + 2 * tg;
+                if (row < n && col < n) store(row, col, acc[t][0]);
+                if (row < n && col + 1 < n) store(row, col + 1, acc[t][1]);
+            }
+        }
     }
 }
 
-// out = Ct^T diag(w) Ct = C diag(w) C^T (symmetric); Ct (n x n, ldc), orbitals along rows
-__device__ inline void gemm_ctwc(int n, const double *Ct, int ldc, const double *w, double *out, int ldo) {
-    const int nt = (n + 3) >> 2, ntile = nt * nt;
-    for (int tile = threadIdx.x; tile < ntile; tile += QX_NT) {
-        const int ti = tile / nt, i0 = ti << 2, j0 = (tile - ti * nt) << 2;
-        if (j0 > i0) continue;
-        double acc[4][4] = {{0}};
-        for (int k = 0; k < n; ++k) {
-            const double wk = w[k];
-            if (wk == 0.0) continue;
-            const double *row = Ct + (size_t)k * ldc;
-            double x[4], y[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                x[r] = i0 + r < n ? row[i0 + r] * wk : 0.0;
-                y[r] = j0 + r < n ? row[j0 + r] : 0.0;
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] += x[r] * y[c];
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (i0 + r < n && j0 + c < n) {
-                    out[(size_t)(i0 + r) * ldo + j0 + c] = acc[r][c];
-                    out[(size_t)(j0 + c) * ldo + i0 + r] = acc[r][c];
-                }
-    }
+// run-time dispatch on the number of column tiles (keeps the accumulators in registers)
+template <class FA, class FB, class FS>
+__device__ inline void gemm_tc(int n, FA loadA, FB loadB, FS store) {
+    const int nt = (n + 7) >> 3;
+    if (nt <= 4) dmma_gemm<4>(n, loadA, loadB, store);
+    else if (nt <= 9) dmma_gemm<9>(n, loadA, loadB, store);
+    else dmma_gemm<16>(n, loadA, loadB, store);
 }
 
 // In-place Cholesky S = L L^T on the lower triangle of A (n x n, ld), then Ct = L^{-1} (lower triangular),
 // i.e. C = L^{-T}: an S-orthonormal starting basis.  Returns false if S is not positive definite.
-__device__ inline bool cholesky_basis(int n, double *A, double *Ct, int ld, double *red) {
+__device__ __noinline__ bool cholesky_basis(int n, double *A, double *Ct, int ld, double *red) {
     for (int j = 0; j < n; ++j) {
         double d = A[(size_t)j * ld + j];
         if (!(d > 0.0)) return false;  // uniform across the CTA (all threads read the same value)
@@ -578,36 +562,159 @@ __device__ inline bool cholesky_basis(int n, double *A, double *Ct, int ld, doub
     return true;
 }
 
-// One-sided (Hestenes) Jacobi with round-robin ordering.  G (n x n, ld) holds the symmetric matrix
-// A' + sigma*I (positive definite thanks to the Gershgorin shift applied here); its rows (= columns) are
-// orthogonalised by plane rotations that are applied to the rows of Ct as well (C <- C J).  A sub-warp
-// group of LP lanes owns one pair per round, so a round needs a single __syncthreads.  On exit
-// emo[k] = |g_k| - sigma.  Returns the number of sweeps.
-__device__ inline int jacobi_onesided(int n, double *G, double *Ct, int ld, double *emo, double *red) {
+// plane-rotation parameters from the 2x2 Gram matrix (al, ga; ga, be): the angle is evaluated in single
+// precision (it only steers convergence), c is refined to double so that c^2 + s^2 = 1 to rounding.
+__device__ inline bool rotation_from_gram(double al, double be, double ga, float &ratio, double &c, double &sn) {
+    const float gaf = (float)ga;
+    ratio = fabsf(gaf) * rsqrtf((float)al * (float)be);
+    if (!(ratio > 1e-15f)) return false;
+    const float zeta = (float)(be - al) / (2.0f * gaf);
+    const float tf = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
+    const double t = (double)tf, w = 1.0 + t * t;
+    double c0 = (double)rsqrtf((float)w);
+    c0 = c0 * (1.5 - 0.5 * w * c0 * c0);
+    c = c0 * (1.5 - 0.5 * w * c0 * c0);
+    sn = c * t;
+    return true;
+}
+
+// pair (p, q) of the round-robin tournament with mm players (mm even), slot k of round `round`
+__device__ inline void tournament_pair(int mm, int round, int k, int &p, int &q) {
+    if (k == 0) { p = mm - 1; q = round; }
+    else { p = round + k; if (p >= mm - 1) p -= mm - 1; q = round - k; if (q < 0) q += mm - 1; }
+    if (p > q) { int t = p; p = q; q = t; }
+}
+
+// One-sided (Hestenes) Jacobi on the rows of G = A' + sigma I (symmetric positive definite thanks to the
+// Gershgorin shift): rows are rotated pairwise until mutually orthogonal.  At convergence row k equals
+// (lambda_k + sigma) j_k, i.e. the eigenvectors are the normalised rows and the eigenvalues their norms, so
+// no eigenvector matrix has to be dragged through the sweeps.
+// Eight lanes own one pair per round and move the two rows through registers with 128-bit accesses; one
+// __syncthreads per round.  Rotations are applied in the scaled ("fast Givens") form: row_k = d_k * stored_k,
+// so an element update is a single DFMA; squared norms are tracked incrementally (recomputed every sweep),
+// so only the cross product needs a reduction.  Control flow is warp-uniform (idle groups do dummy loads).
+// jw: 4*n doubles of shared scratch (norms, scales, inverse scales).
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int R>
+__device__ __noinline__ int jacobi_rows_lp8(int n, double *G, int ld, double *red, float tol, double *jw) {
+    const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
+    const int nslot = QX_NT / 8, slot = threadIdx.x >> 3, lsub = threadIdx.x & 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int npass = (npair + nslot - 1) / nslot;
+    double *nrm2 = jw, *dsc = jw + n, *dinv = jw + 2 * n;
+    for (int i = threadIdx.x; i < n; i += QX_NT) { dsc[i] = 1.0; dinv[i] = 1.0; }
+    __syncthreads();
+    const bool tail_ok = 2 * lsub + 16 * (R - 1) < n;
+    const int tail_off = tail_ok ? 2 * lsub + 16 * (R - 1) : 0;
+    int sweep = 0;
+    for (; sweep < 60; ++sweep) {
+        // fold the scales into the rows and refresh the norms
+        for (int k = warp; k < n; k += QX_NT / 32) {
+            const double d = dsc[k];
+            double acc = 0.0;
+            for (int i = lane; i < n; i += 32) { const double x = G[(size_t)k * ld + i] * d; G[(size_t)k * ld + i] = x; acc += x * x; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            __syncwarp();
+            if (lane == 0) { nrm2[k] = acc; dsc[k] = 1.0; dinv[k] = 1.0; }
+        }
+        __syncthreads();
+        float smax = 0.0f;
+        for (int round = 0; round < m1; ++round) {
+            for (int pass = 0; pass < npass; ++pass) {
+                const int k = slot + pass * nslot;
+                // round-robin tournament: slot 0 pairs the fixed player m1 with `round`, slot k pairs round+k with round-k (mod m1)
+                int p = round + k, q = round - k;
+                if (p >= m1) p -= m1;
+                if (q < 0) q += m1;
+                if (k == 0) p = m1;
+                const int lo = min(p, q), hi = max(p, q);
+                const bool valid = k < npair && hi < n;
+                p = valid ? lo : 0;
+                q = valid ? hi : 0;
+                double *gp = G + p * ld + 2 * lsub, *gq = G + q * ld + 2 * lsub;
+                // scales / norms are read before the reduction: the group leader rewrites them after it
+                const double dp = dsc[p], dq = dsc[q], ip = dinv[p], iq = dinv[q], al = nrm2[p], be = nrm2[q];
+                double2 x[R], y[R];
+#pragma unroll
+                for (int r = 0; r < R - 1; ++r) {   // chunks r < R-1 are in range for every lane (n > 16 (R-1))
+                    x[r] = *reinterpret_cast<const double2 *>(gp + 16 * r);
+                    y[r] = *reinterpret_cast<const double2 *>(gq + 16 * r);
+                }
+                x[R - 1] = *reinterpret_cast<const double2 *>(G + p * ld + tail_off);
+                y[R - 1] = *reinterpret_cast<const double2 *>(G + q * ld + tail_off);
+                if (!tail_ok) { x[R - 1] = make_double2(0.0, 0.0); y[R - 1] = make_double2(0.0, 0.0); }
+                double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
+                double gs = g0 + g1;
+                gs += __shfl_xor_sync(0xffffffffu, gs, 4);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 2);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 1);
+                const double ga = dp * dq * gs;
+                const float gaf = (float)ga;
+                const float ratio = valid ? fabsf(gaf) * rsqrt_approx((float)al * (float)be) : 0.0f;
+                smax = fmaxf(smax, ratio);
+                if (ratio > 1e-15f) {   // group-uniform; rotation angle in single precision, c refined to double
+                    const float zeta = (float)(be - al) * rcp_approx(2.0f * gaf);
+                    const float tf = copysignf(rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.0f))), zeta);
+                    const double t = (double)tf, w = fma(t, t, 1.0);
+                    const double t1 = t * dq * ip, t2 = t * dp * iq;
+#pragma unroll
+                    for (int r = 0; r < R - 1; ++r) {
+                        double2 u, v;
+                        u.x = fma(-t1, y[r].x, x[r].x); u.y = fma(-t1, y[r].y, x[r].y);
+                        v.x = fma(t2, x[r].x, y[r].x); v.y = fma(t2, x[r].y, y[r].y);
+                        *reinterpret_cast<double2 *>(gp + 16 * r) = u;
+                        *reinterpret_cast<double2 *>(gq + 16 * r) = v;
+                    }
+                    if (tail_ok) {
+                        double2 u, v;
+                        u.x = fma(-t1, y[R - 1].x, x[R - 1].x); u.y = fma(-t1, y[R - 1].y, x[R - 1].y);
+                        v.x = fma(t2, x[R - 1].x, y[R - 1].x); v.y = fma(t2, x[R - 1].y, y[R - 1].y);
+                        *reinterpret_cast<double2 *>(gp + 16 * (R - 1)) = u;
+                        *reinterpret_cast<double2 *>(gq + 16 * (R - 1)) = v;
+                    }
+                    if (lsub == 0) {
+                        double c = (double)rsqrt_approx((float)w);
+                        c = c * fma(-0.5 * w * c, c, 1.5);
+                        c = c * fma(-0.5 * w * c, c, 1.5);
+                        const double wc = w * c, tg = t * ga;
+                        dsc[p] = c * dp; dsc[q] = c * dq; dinv[p] = wc * ip; dinv[q] = wc * iq;
+                        nrm2[p] = al - tg; nrm2[q] = be + tg;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const float m = (float)block_max((double)smax, red);
+        if (m < tol) { ++sweep; break; }
+    }
+    // fold the remaining scales
+    for (int k = warp; k < n; k += QX_NT / 32) {
+        const double d = dsc[k];
+        for (int i = lane; i < n; i += 32) G[(size_t)k * ld + i] *= d;
+    }
+    __syncthreads();
+    return sweep;
+}
+
+// generic fallback (any n): LP lanes per pair, scalar accesses
+__device__ __noinline__ int jacobi_rows_generic(int n, double *G, int ld, double *red, float tol) {
     const int mm = (n + 1) & ~1, npair = mm >> 1;
     int LP = 32;
     while (LP > 4 && npair * LP > QX_NT) LP >>= 1;
     const int nslot = QX_NT / LP, slot = threadIdx.x / LP, lsub = threadIdx.x & (LP - 1), lane = threadIdx.x & 31;
     const unsigned gmask = LP == 32 ? 0xffffffffu : (((1u << LP) - 1u) << (lane & ~(LP - 1)));
-    // Gershgorin shift
-    double rowsum = 0.0;
-    for (int i = threadIdx.x; i < n; i += QX_NT) {
-        double v = 0.0;
-        for (int j = 0; j < n; ++j) v += fabs(G[(size_t)i * ld + j]);
-        rowsum = fmax(rowsum, v);
-    }
-    const double sigma = 1.0625 * block_max(rowsum, red) + 0.5;
-    for (int i = threadIdx.x; i < n; i += QX_NT) G[(size_t)i * ld + i] += sigma;
-    __syncthreads();
     int sweep = 0;
     for (; sweep < 60; ++sweep) {
-        double smax = 0.0;
+        float smax = 0.0f;
         for (int round = 0; round < mm - 1; ++round) {
             for (int k = slot; k < npair; k += nslot) {
                 int p, q;
-                if (k == 0) { p = mm - 1; q = round; }
-                else { p = round + k; if (p >= mm - 1) p -= mm - 1; q = round - k; if (q < 0) q += mm - 1; }
-                if (p > q) { int t = p; p = q; q = t; }
+                tournament_pair(mm, round, k, p, q);
                 if (q >= n) continue;
                 double *gp = G + (size_t)p * ld, *gq = G + (size_t)q * ld;
                 double al = 0.0, be = 0.0, ga = 0.0;
@@ -620,39 +727,67 @@ __device__ inline int jacobi_onesided(int n, double *G, double *Ct, int ld, doub
                     be += __shfl_xor_sync(gmask, be, o);
                     ga += __shfl_xor_sync(gmask, ga, o);
                 }
-                const double ratio = fabs(ga) * rsqrt(al * be);
-                smax = fmax(smax, ratio);
-                if (ratio > 1e-15) {
-                    const double zeta = (be - al) / (2.0 * ga);
-                    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = rsqrt(1.0 + t * t), sn = c * t;
-                    double *cp = Ct + (size_t)p * ld, *cq = Ct + (size_t)q * ld;
+                float ratio;
+                double c, sn;
+                if (rotation_from_gram(al, be, ga, ratio, c, sn)) {
                     for (int i = lsub; i < n; i += LP) {
                         const double x = gp[i], y = gq[i];
                         gp[i] = c * x - sn * y;
                         gq[i] = sn * x + c * y;
-                        const double u = cp[i], v = cq[i];
-                        cp[i] = c * u - sn * v;
-                        cq[i] = sn * u + c * v;
                     }
                 }
+                smax = fmaxf(smax, ratio);
             }
             __syncthreads();
         }
-        smax = block_max(smax, red);
-        if (smax < 1e-10) { ++sweep; break; }  // quadratic convergence: the rotations of this sweep already finished the job
+        const float m = (float)block_max((double)smax, red);
+        if (m < tol) { ++sweep; break; }
     }
-    // eigenvalues from the row norms
-    const int warp = threadIdx.x >> 5;
+    return sweep;
+}
+
+// Eigen-decomposition of the symmetric A' held in G (n x n, ld).  On exit: emo[k] = eigenvalue k and row k of G
+// is the corresponding unit eigenvector (so G holds J^T).  Returns the number of sweeps.
+__device__ __noinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *emo, double *red, double *jw) {
+    // Gershgorin shift: makes G positive definite, so that singular values == eigenvalues + sigma
+    double rowsum = 0.0;
+    for (int i = threadIdx.x; i < n; i += QX_NT) {
+        double v = 0.0;
+        for (int j = 0; j < n; ++j) v += fabs(G[(size_t)i * ld + j]);
+        rowsum = fmax(rowsum, v);
+    }
+    const double sigma = 1.0625 * block_max(rowsum, red) + 0.5;
+    for (int i = threadIdx.x; i < n; i += QX_NT) G[(size_t)i * ld + i] += sigma;
+    __syncthreads();
+    const float tol = 1e-7f;  // pre-rotation ratio of the last sweep; its rotations leave O(tol^2) couplings
+    const int npair = (n + 1) >> 1;
+    int sweeps;
+    if (npair * 8 <= QX_NT && (ld & 1) == 0 && n <= 128) {
+        switch ((n + 15) >> 4) {
+            case 1: sweeps = jacobi_rows_lp8<1>(n, G, ld, red, tol, jw); break;
+            case 2: sweeps = jacobi_rows_lp8<2>(n, G, ld, red, tol, jw); break;
+            case 3: sweeps = jacobi_rows_lp8<3>(n, G, ld, red, tol, jw); break;
+            case 4: sweeps = jacobi_rows_lp8<4>(n, G, ld, red, tol, jw); break;
+            case 5: sweeps = jacobi_rows_lp8<5>(n, G, ld, red, tol, jw); break;
+            case 6: sweeps = jacobi_rows_lp8<6>(n, G, ld, red, tol, jw); break;
+            case 7: sweeps = jacobi_rows_lp8<7>(n, G, ld, red, tol, jw); break;
+            default: sweeps = jacobi_rows_lp8<8>(n, G, ld, red, tol, jw); break;
+        }
+    } else
+        sweeps = jacobi_rows_generic(n, G, ld, red, tol);
+    // eigenvalues from the row norms; normalise the rows
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = warp; k < n; k += QX_NT / 32) {
         double acc = 0.0;
         for (int i = lane; i < n; i += 32) { const double x = G[(size_t)k * ld + i]; acc += x * x; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) emo[k] = sqrt(acc) - sigma;
+        const double nrm = sqrt(acc), inv = 1.0 / nrm;
+        for (int i = lane; i < n; i += 32) G[(size_t)k * ld + i] *= inv;
+        if (lane == 0) emo[k] = nrm - sigma;
     }
     __syncthreads();
-    return sweep;
+    return sweeps;
 }
 
 // ------------------------------------------------------------------------------------ Fermi smearing

@@ -112,7 +112,8 @@ inline std::string build_host_model(HostModel &h, int nat, const int32_t *num, c
         h.nao += nao_at;
     }
     h.ntype = (int)types.size();
-    h.ld = h.nao | 1;
+    h.ld = h.nao;  // == 4 or 12 (mod 16): conflict-free DMMA fragment loads and 128-bit row accesses
+    while (h.ld % 16 != 4 && h.ld % 16 != 12) h.ld += 1;
     h.ndim = h.nsh + 9 * nat;
     // occupation numbers (tblite get_occupation / get_alpha_beta_occupation; uhf = min(mult-1, 0), tblite.f90:111)
     double nocc = -(double)charge;

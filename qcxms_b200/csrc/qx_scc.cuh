@@ -66,7 +66,7 @@ __device__ inline double d4_vvec(const DevModel &m, const Sm &s, const double *e
 }
 
 // potentials from the (input) populations in s.qsh/qat/dpat/qpat -> s.vsh, vat, vdp, vqp, vao
-__device__ inline void phase_potential(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double *t7) {
+__device__ __noinline__ void phase_potential(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double *t7) {
     const int nat = m.nat, nsh = m.nsh, nao = m.nao;
     for (int i = threadIdx.x; i < nat; i += QX_NT) d4_weights_atom(m, i, s.cn4[i], s.qat[i], s.gw + 7 * i, nullptr, s.gwd + 7 * i);
     for (int a = threadIdx.x; a < nsh; a += QX_NT) {
@@ -110,7 +110,7 @@ __device__ inline void phase_potential(const DevModel &m, Sm &s, const double *g
 }
 
 // energies of the charge-dependent terms at the (output) populations
-__device__ inline void phase_scc_energy(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double &e_es, double &e_aes, double &e_d4) {
+__device__ __noinline__ void phase_scc_energy(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double &e_es, double &e_aes, double &e_d4) {
     const int nat = m.nat, nsh = m.nsh;
     for (int i = threadIdx.x; i < nat; i += QX_NT) d4_weights_atom(m, i, s.cn4[i], s.qat[i], s.gw + 7 * i, nullptr, nullptr);
     double es = 0.0, ea = 0.0, ed = 0.0;
@@ -148,7 +148,7 @@ __device__ inline void phase_scc_energy(const DevModel &m, Sm &s, const double *
 }
 
 // H1 = H0 - 1/2 S (v_a + v_b) - 1/2 (D.vdp + D^T.vdp) - 1/2 (Q.vqp + ...) into s.A (symmetric)
-__device__ inline void phase_build_h1(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt) {
+__device__ __noinline__ void phase_build_h1(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt) {
     const int nao = m.nao, ld = m.ld;
     const size_t n2 = (size_t)nao * nao;
     for (int t = threadIdx.x; t < nao * nao; t += QX_NT) {
@@ -175,7 +175,7 @@ __device__ inline void phase_build_h1(const DevModel &m, Sm &s, const double *S,
 }
 
 // Mulliken populations from P (in s.A, symmetric): qsh, qat, dpat, qpat and tr(P H0); pop: 11*nao doubles of scratch
-__device__ inline double phase_mulliken(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt, double *pop) {
+__device__ __noinline__ double phase_mulliken(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt, double *pop) {
     const int nao = m.nao, ld = m.ld, nat = m.nat, nsh = m.nsh;
     const size_t n2 = (size_t)nao * nao;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -244,7 +244,7 @@ __device__ inline double warp_dot(const double *x, const double *y, int n) {
 }
 
 // dense solve with partial pivoting on (beta[nb x nb], c[nb]) in global scratch; CTA-cooperative
-__device__ inline bool block_solve(int nb, double *beta, double *c, double *red) {
+__device__ __noinline__ bool block_solve(int nb, double *beta, double *c, double *red) {
     __shared__ int s_piv;
     for (int k = 0; k < nb; ++k) {
         if (threadIdx.x == 0) {
@@ -287,7 +287,7 @@ __device__ inline bool block_solve(int nb, double *beta, double *c, double *red)
 }
 
 // One mixer step: q_in <- next input.  dq = (output - input) of the cycle just finished must be set.
-__device__ inline bool broyden_next(Broyden &b, int n, double damp, double *red) {
+__device__ __noinline__ bool broyden_next(Broyden &b, int n, double damp, double *red) {
     const int mem = QX_MAX_ITER;
     const double omega0 = 0.01, minw = 1.0, maxw = 100000.0, wfac = 0.01;
     b.iter += 1;
@@ -359,7 +359,7 @@ __device__ inline bool broyden_next(Broyden &b, int n, double damp, double *red)
 
 // ------------------------------------------------------------------------------------ gradient of the AO-pair terms
 // s.A = P, s.C = W (energy weighted density); potentials in s.vao/vdp/vqp from the last SCC cycle.
-__device__ inline void phase_gradient_pairs(const DevModel &m, Sm &s, const int2 *tasks, int ntask, double *taskout) {
+__device__ __noinline__ void phase_gradient_pairs(const DevModel &m, Sm &s, const int2 *tasks, int ntask, double *taskout) {
     const int ld = m.ld;
     for (int t = threadIdx.x; t < ntask; t += QX_NT) {
         const int a = tasks[t].x, b = tasks[t].y;
@@ -437,7 +437,10 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     phase_integrals(m, s, S, H0, Dt, Qt);
     QX_PH(2);
 
-    // S-orthonormal start basis: C = L^{-T}
+    // S-orthonormal start basis: C = L^{-T}.  Padding columns of the shared matrices are zeroed once: the
+    // 128-bit row accesses of the Jacobi read (and rewrite) them.
+    for (int t = threadIdx.x; t < nao * ld; t += QX_NT) { s.A[t] = 0.0; s.C[t] = 0.0; }
+    __syncthreads();
     for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.A[(size_t)(t / nao) * ld + t % nao] = S[t];
     __syncthreads();
     if (!cholesky_basis(nao, s.A, s.C, ld, s.red)) { out.stat = -2; out.energy = 0.0; return; }  // hard failure: S not positive definite
@@ -479,17 +482,31 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         phase_build_h1(m, s, S, H0, Dt, Qt);
         QX_PH(6);
         // A' = C^T H1 C in the current S-orthonormal basis (s.C holds C transposed), then Jacobi (C <- C J)
-        gemm_small<false>(nao, s.C, ld, s.A, ld, T, nao);   // Tt = Ct H1
-        __syncthreads();
-        gemm_small<true>(nao, s.C, ld, T, nao, s.A, ld);    // A' = Ct Tt^T
-        __syncthreads();
+        {
+            const double *Ct = s.C, *Hm = s.A;
+            // Tt = Ct H1  (global scratch), then A' = Ct Tt^T back into shared memory
+            gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)i * ld + k]; }, [=](int k, int j) { return Hm[(size_t)k * ld + j]; },
+                    [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; });
+            __syncthreads();
+            double *Ap = s.A;
+            gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)i * ld + k]; }, [=](int k, int j) { return T[(size_t)j * nao + k]; },
+                    [=](int i, int j, double v) { Ap[(size_t)i * ld + j] = v; });
+            __syncthreads();
+        }
         QX_PH(7);
         {
-            int sw_ = jacobi_onesided(nao, s.A, s.C, ld, s.emo, s.red);
+            int sw_ = jacobi_eigh_rows(nao, s.A, ld, s.emo, s.red, s.jw);
             out.sweeps += sw_;
 #ifdef QX_PROFILE_PHASES
             if (threadIdx.x == 0 && iscf <= 32) { atomicAdd(&g_sweep_hist[iscf - 1], (unsigned long long)sw_); atomicAdd(&g_sweep_hist[32 + iscf - 1], 1ull); }
 #endif
+            // rows of A now hold J^T: Ct_new = J^T Ct_old
+            const double *Jt = s.A, *Ct = s.C;
+            gemm_tc(nao, [=](int i, int k) { return Jt[(size_t)i * ld + k]; }, [=](int k, int j) { return Ct[(size_t)k * ld + j]; },
+                    [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; });
+            __syncthreads();
+            for (int t = threadIdx.x; t < nao * nao; t += QX_NT) { int i = t / nao; s.C[(size_t)i * ld + (t - i * nao)] = T[t]; }
+            __syncthreads();
         }
         QX_PH(8);
         // order statistics needed for the Fermi-level start value
@@ -533,7 +550,12 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         ts = block_sum(ts, s.red);
         QX_PH(9);
         // density into A
-        gemm_ctwc(nao, s.C, ld, s.focc, s.A, ld);
+        {
+            const double *Ct = s.C, *f = s.focc;
+            double *Pm = s.A;
+            gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)k * ld + i] * f[k]; }, [=](int k, int j) { return Ct[(size_t)k * ld + j]; },
+                    [=](int i, int j, double v) { Pm[(size_t)i * ld + j] = v; });
+        }
         __syncthreads();
         QX_PH(10);
         double eel = phase_mulliken(m, s, S, H0, Dt, Qt, pop);
@@ -564,7 +586,11 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     // W = C diag(f e) C^T -> global T -> shared C (A holds P)
     for (int k = threadIdx.x; k < nao; k += QX_NT) s.focc[k] *= s.emo[k];
     __syncthreads();
-    gemm_ctwc(nao, s.C, ld, s.focc, T, nao);
+    {
+        const double *Ct = s.C, *f = s.focc;
+        gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)k * ld + i] * f[k]; }, [=](int k, int j) { return Ct[(size_t)k * ld + j]; },
+                [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; });
+    }
     __syncthreads();
     for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.C[(size_t)(t / nao) * ld + t % nao] = T[t];
     __syncthreads();
