@@ -1,0 +1,124 @@
+"""CPU tests of the oracle's GFN2-xTB energy/gradient restatement (no GPU needed).
+
+The reference has no tests or golden vectors for this path and tblite cannot be built
+offline, so the oracle is pinned by (i) self-consistency (finite differences, invariances), (ii) the
+reference's own shipped GFN2-optimised example geometries, at which a correct GFN2 gradient must (nearly)
+vanish, and (iii) regression fixtures under tests/golden/.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from qcxms_b200.api import load_molecule
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_syev_matches_lapack(oracle):
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 26, 66):
+        a = rng.standard_normal((n, n)); a = a + a.T
+        w, v, st = oracle.syev(a)
+        assert st == 0
+        assert np.abs(w - np.linalg.eigvalsh(a)).max() < 1e-12
+        assert np.abs(a @ v - v * w).max() < 1e-12 and np.abs(v.T @ v - np.eye(n)).max() < 1e-13
+
+
+def test_overlap_and_multipole_integrals(oracle):
+    num, xyz, _ = load_molecule("chloroethanol")     # has s, p and d shells (Cl)
+    r = oracle.egrad(num, xyz, charge=0, multiplicity=1, etemp=300.0, detail=True)
+    S, D, Q = r["overlap"], r["dipole"], r["quadrupole"]
+    assert np.abs(S - S.T).max() < 1e-15 and np.abs(np.diag(S) - 1).max() < 1e-7   # STO-nG shells are normalised
+    assert np.linalg.eigvalsh(S).min() > 0
+    # quadrupole integrals are traceless (components xx, xy, yy, xz, yz, zz)
+    assert np.abs(Q[0] + Q[2] + Q[5]).max() < 1e-12
+    # D[c][a][b] is centred on atom(b): moving the centre to atom(a) shifts it by (R_b - R_a) S
+    nsh, nao = oracle.dims(num)
+    ao_at = []
+    for i, z in enumerate(num):
+        ao_at += [i] * {1: 1, 6: 4, 8: 4, 17: 9}[int(z)]
+    ao_at = np.array(ao_at)
+    for c in range(3):
+        shift = (xyz[ao_at][None, :, c] - xyz[ao_at][:, None, c]) * S   # [a][b] -> (R_b - R_a)_c S_ab
+        assert np.abs(D[c].T - (D[c] + shift)).max() < 1e-12
+
+
+@pytest.mark.parametrize("name,charge,mult,etemp", [("chloroethanol", 1, 2, 5000.0), ("monoethanolamine", 0, 1, 300.0)])
+def test_gradient_matches_finite_differences(oracle, name, charge, mult, etemp):
+    num, xyz, _ = load_molecule(name)
+    rng = np.random.default_rng(5)
+    x = xyz + 0.08 * rng.standard_normal(xyz.shape)
+    oracle.set_accuracy(1e-4)   # separate SCC-threshold noise from genuine errors
+    try:
+        g = oracle.egrad(num, x, charge, mult, 2, etemp)["gradient"]
+        h, fd = 1e-4, np.zeros_like(x)
+        for i in range(len(num)):
+            for c in range(3):
+                xp, xm = x.copy(), x.copy()
+                xp[i, c] += h; xm[i, c] -= h
+                fd[i, c] = (oracle.egrad(num, xp, charge, mult, 2, etemp)["energy"] - oracle.egrad(num, xm, charge, mult, 2, etemp)["energy"]) / (2 * h)
+    finally:
+        oracle.set_accuracy(1.0)
+    assert np.abs(g - fd).max() < 2e-7
+    assert np.abs(g.sum(0)).max() < 1e-10          # no net force
+
+
+def test_invariances(oracle):
+    num, xyz, _ = load_molecule("thf_h")
+    oracle.set_accuracy(1e-3)     # below the default SCC threshold the comparison would only see convergence noise
+    try:
+        _check_invariances(oracle, num, xyz)
+    finally:
+        oracle.set_accuracy(1.0)
+
+
+def _check_invariances(oracle, num, xyz):
+    ref = oracle.egrad(num, xyz, 1, 1, 2, 5000.0)
+    assert abs(ref["qat"].sum() - 1.0) < 1e-7
+    # translation + rotation
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]]) @ np.array([[1, 0, 0], [0, np.cos(0.3), -np.sin(0.3)], [0, np.sin(0.3), np.cos(0.3)]])
+    r2 = oracle.egrad(num, xyz @ R.T + np.array([1.0, -2.0, 0.5]), 1, 1, 2, 5000.0)
+    assert abs(r2["energy"] - ref["energy"]) < 1e-9
+    assert np.abs(r2["gradient"] - ref["gradient"] @ R.T).max() < 1e-8 and np.abs(r2["qat"] - ref["qat"]).max() < 1e-8
+    # permutation of atoms
+    perm = np.random.default_rng(1).permutation(len(num))
+    r3 = oracle.egrad(num[perm], xyz[perm], 1, 1, 2, 5000.0)
+    assert abs(r3["energy"] - ref["energy"]) < 1e-9 and np.abs(r3["gradient"] - ref["gradient"][perm]).max() < 1e-8
+
+
+def test_gradient_vanishes_at_the_reference_example_minima(oracle):
+    """share/examples geometries of the reference were optimised with GFN2-xTB: a faithful GFN2 restatement
+    (method AND element parameters for H, C, N, O, Cl) must give a near-zero gradient there."""
+    for name, chg, bound in (("dichlorobenzamide_h", 1, 1e-4), ("chloroethanol", 0, 1e-3), ("monoethanolamine", 0, 1e-3)):
+        num, xyz, _ = load_molecule(name)
+        r = oracle.egrad(num, xyz, chg, 1, 2, 300.0)
+        assert r["stat"] == 0 and np.abs(r["gradient"]).max() < bound, (name, np.abs(r["gradient"]).max())
+
+
+def test_protocol_details(oracle):
+    num, xyz, _ = load_molecule("chloroethanol")
+    # unknown method id -> stat 5 (reference src/tblite.f90:114-120)
+    assert oracle.egrad(num, xyz, 0, 1, 99, 300.0)["stat"] == 5
+    # multiplicity is discarded by uhf = min(mult-1, 0) (reference src/tblite.f90:111)
+    a = oracle.egrad(num, xyz, 1, 2, 2, 5000.0); b = oracle.egrad(num, xyz, 1, 4, 2, 5000.0)
+    assert a["energy"] == b["energy"]
+    # electronic temperature enters through kt = etemp * ktoau: entropy term is negative and grows with T
+    lo = oracle.egrad(num, xyz, 1, 2, 2, 300.0, detail=True); hi = oracle.egrad(num, xyz, 1, 2, 2, 5000.0, detail=True)
+    assert hi["e_ts"] < lo["e_ts"] <= 0.0
+    assert 5 <= hi["niter"] <= 30 and hi["converged"] == 1
+
+
+def test_golden_fixtures(oracle):
+    gold = json.load(open(os.path.join(GOLD, "egrad_golden.json")))
+    for c in gold["cases"]:
+        num, xyz, _ = load_molecule(c["molecule"])
+        r = oracle.egrad(num, xyz, c["charge"], c["multiplicity"], 2, c["etemp"], detail=True)
+        assert r["niter"] == c["niter"]
+        assert abs(r["energy"] - c["energy"]) < 1e-10
+        assert np.abs(r["gradient"] - np.array(c["gradient"])).max() < 1e-9
+        assert np.abs(r["qat"] - np.array(c["qat"])).max() < 1e-9
+        for k, v in c["terms"].items():
+            assert abs(r[k] - v) < 1e-9
