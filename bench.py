@@ -42,7 +42,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -123,14 +123,14 @@ def main():
         if rank != 0:
             return
         from oracle import pyoracle  # noqa: F401
-        ntraj_s, per_step = cores, 1
+        ntraj_s, per_step = cores, 8
         for _ in range(max(args.warmup, 1)):
             cpu_md_sample(num, xyz0, min(ntraj_s, 4), 1, cores)
         t0 = time.perf_counter()
         done = 0
         for _ in range(args.steps):
             d, _dt = cpu_md_sample(num, xyz0, ntraj_s, per_step, cores)
-            done += d
+            done += d + ntraj_s          # md() starts with one egrad before its first step: same work as a step
         dt = time.perf_counter() - t0
         val = done / dt
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -235,7 +235,8 @@ def main():
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("k_md_chunk_dram_bytes_per_launch")
+            per_step = json.load(open(prof)).get("k_md_chunk_dram_bytes_per_traj_step")
+            traffic = per_step * (total_steps / world) / max(int(launches / world), 1) if per_step else None
         except Exception:
             traffic = None
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
