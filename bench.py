@@ -192,8 +192,8 @@ def main():
     value = total_steps / dev_s_max
 
     # mean SCC cycles per egrad over the timed steps (scc counter is cumulative over the trajectory's life)
-    res0 = [ens.result(k) for k in range(min(args.ntraj, 8))]
-    n_it = float(np.mean([r["scc_iter_total"] / (r["nstep"] + 1) for r in res0]))
+    res0 = ens.results()
+    n_it = float(np.mean(res0["scc_iter_total"] / (res0["nstep"] + 1.0)))
     hist_bins, hist_dev = ens.histogram(512)
     ens.close()
 
@@ -202,7 +202,7 @@ def main():
     t0 = time.perf_counter()
     e2 = new_ensemble()
     e2_steps = e2.run_md(max_steps=args.steps)
-    outs = [e2.result(k) for k in range(args.ntraj)]
+    outs = e2.results()
     bins, _ = e2.histogram(512)
     hb = torch.from_numpy(bins).to(dev)
     es.allreduce_histogram(hb)

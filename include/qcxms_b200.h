@@ -107,6 +107,10 @@ int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_steps, int64_t 
 int qcxms_b200_ensemble_get_result(qcxms_b200_ensemble_t *h, int itrj, double *xyz, double *velo, double *grad,
                                    int32_t *list, double *achrg, double *axyz, qcxms_b200_md_result_t *res);
 
+/* bulk variant of get_result: arrays carry a leading [ntraj] axis, res is an array of ntraj structs (any pointer may be NULL) */
+int qcxms_b200_ensemble_get_all(qcxms_b200_ensemble_t *h, double *xyz, double *velo, double *grad, int32_t *list,
+                                double *achrg, double *axyz, qcxms_b200_md_result_t *res);
+
 /* device time (ms, CUDA events on the launching stream) and kernel launch count of the last run_md */
 int qcxms_b200_ensemble_last_timing(qcxms_b200_ensemble_t *h, double *kernel_ms, int64_t *launches,
                                     int64_t *scc_iterations);

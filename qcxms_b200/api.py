@@ -40,7 +40,7 @@ class MdResult(C.Structure):
 
 EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_egrad_batch", "qcxms_b200_fragment_structure", "qcxms_b200_ensemble_create",
            "qcxms_b200_ensemble_destroy", "qcxms_b200_ensemble_set_trajectory", "qcxms_b200_ensemble_set_all",
-           "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_last_timing",
+           "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_get_all", "qcxms_b200_ensemble_last_timing",
            "qcxms_b200_ensemble_histogram", "qcxms_b200_last_error", "qcxms_b200_version"]
 
 
@@ -62,6 +62,7 @@ def lib():
         L.qcxms_b200_ensemble_set_all.argtypes = [C.c_void_p, dp, dp, dp, dp, dp]
         L.qcxms_b200_ensemble_run_md.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
         L.qcxms_b200_ensemble_get_result.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, ip, dp, dp, C.POINTER(MdResult)]
+        L.qcxms_b200_ensemble_get_all.argtypes = [C.c_void_p, dp, dp, dp, ip, dp, dp, C.POINTER(MdResult)]
         L.qcxms_b200_ensemble_last_timing.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.qcxms_b200_ensemble_histogram.argtypes = [C.c_void_p, C.c_int, dp, C.POINTER(C.c_void_p)]
         L.qcxms_b200_last_error.restype = C.c_char_p
@@ -174,6 +175,20 @@ class Ensemble:
                                                     _ip(out["list"]), _dp(out["achrg"]), _dp(out["axyz"]), C.byref(res)))
         for k, _ in MdResult._fields_:
             out[k] = getattr(res, k)
+        return out
+
+    def results(self):
+        """All trajectories at once: dict of arrays with a leading [ntraj] axis + one record array of md() outputs."""
+        nt, nat = self.ntraj, self.nat
+        out = dict(xyz=np.zeros((nt, nat, 3)), velo=np.zeros((nt, nat, 3)), grad=np.zeros((nt, nat, 3)), list=np.zeros((nt, nat), dtype=np.int32),
+                   achrg=np.zeros((nt, nat)), axyz=np.zeros((nt, nat, 3)))
+        res = (MdResult * nt)()
+        _check(lib().qcxms_b200_ensemble_get_all(self._h, _dp(out["xyz"]), _dp(out["velo"]), _dp(out["grad"]), _ip(out["list"]),
+                                                 _dp(out["achrg"]), _dp(out["axyz"]), res))
+        rec = np.frombuffer(res, dtype=np.dtype([(k, np.int32) for k, t in MdResult._fields_ if t is C.c_int32] +
+                                                [(k, np.float64) for k, t in MdResult._fields_ if t is C.c_double])).copy()
+        for k in rec.dtype.names:
+            out[k] = rec[k]
         return out
 
     def last_timing(self):

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(QX_NT) k_fragments(DevModel m, const double *x
 }
 
 // one egrad + sanity gate for trajectory t; returns Epot (0 on failure, like the reference's checkqc)
-__device__ inline double md_egrad(const DevModel &m, Sm &s, double *my, const ScratchLayout &L, const MdConfig &cfg, const MdState &st, int t, double etemp) {
+__device__ inline double md_egrad(const DevModel &m, Sm &s, double *my, const ScratchLayout &L, const MdConfig &cfg, double etemp,
+                                  double *grad_out, double *achrg_out, int *niter_out) {
     const int nat = m.nat;
     EgradOut o;
     egrad_cta(m, s, my, L, etemp * QC_KTOAU, o);
@@ -73,11 +74,11 @@ __device__ inline double md_egrad(const DevModel &m, Sm &s, double *my, const Sc
     if (threadIdx.x == 0) {
         bool ok = o.stat != -2 && md_checkqc(m, o.energy, s.grad, s.qat, cfg.mchrg);
         s.red[48] = ok ? o.energy : 0.0;
-        st.scc_total[t] += o.niter;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) st.grad[(size_t)t * 3 * nat + i] = s.grad[i];
-    for (int i = threadIdx.x; i < nat; i += QX_NT) st.achrg[(size_t)t * nat + i] = s.qat[i];
+    for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) grad_out[i] = s.grad[i];
+    for (int i = threadIdx.x; i < nat; i += QX_NT) achrg_out[i] = s.qat[i];
+    *niter_out = o.niter;
     return s.red[48];
 }
 
@@ -99,8 +100,10 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout 
         __syncthreads();
         const double eimp = st.eimp[t];
         const double etemp = cfg.etemp_in < 0.0 ? md_setetemp(cfg, 1, eimp) : cfg.etemp_in;
-        const double epot = md_egrad(m, s, my, L, cfg, st, t, etemp);
+        int nit = 0;
+        const double epot = md_egrad(m, s, my, L, cfg, etemp, st.grad + (size_t)t * 3 * nat, st.achrg + (size_t)t * nat, &nit);
         if (threadIdx.x == 0) {
+            st.scc_total[t] = nit;
             const double ekin = md_ekinet_seq(nat, st.velo + (size_t)t * 3 * nat, m.mass, 0.0, nullptr);
             const double tadd = st.tadd[t];
             st.ekin[t] = ekin; st.ekinstart[t] = ekin; st.epot[t] = epot; st.etemp[t] = etemp;
@@ -117,8 +120,11 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout 
 }
 
 // up to `chunk` MD steps (reference src/md.f90:285-682) for every running trajectory
+// Work items are (sub-chunk r, trajectory t), r-major, so that the last partial wave of CTAs costs a few steps and
+// not a whole chunk.  progress[t] counts the finished sub-chunks of trajectory t in this launch: item (r, t) waits
+// until (r-1, t) -- possibly still running on another resident CTA -- is done.
 __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int chunk,
-                                                    int step_limit, int *queue, unsigned long long *steps_done) {
+                                                    int nsub, int step_limit, int *queue, int *progress, unsigned long long *steps_done) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_next, s_flag;
     Sm s;
@@ -130,21 +136,37 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
         __syncthreads();
         if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
         __syncthreads();
-        const int t = s_next;
-        if (t >= ntraj) break;
-        if (st.status[t] != TRJ_RUNNING) continue;
-        double *xyz = st.xyz + (size_t)t * 3 * nat, *velo = st.velo + (size_t)t * 3 * nat, *grad = st.grad + (size_t)t * 3 * nat;
-        double *achrg = st.achrg + (size_t)t * nat, *avchrg = st.avchrg + (size_t)t * nat, *avxyz = st.avxyz + (size_t)t * 3 * nat;
+        const int item = s_next;
+        if (item >= ntraj * nsub) break;
+        const int sub = item / ntraj, t = item - sub * ntraj;
+        if (threadIdx.x == 0) {
+            while (atomicAdd(&progress[t], 0) < sub) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+        if (__ldcg(st.status + t) != TRJ_RUNNING) {
+            if (threadIdx.x == 0) { __threadfence(); atomicAdd(&progress[t], 1); }
+            continue;
+        }
+        // per-trajectory arrays live in shared memory for the duration of the work item (read with ld.cg: the previous
+        // sub-chunk of this trajectory may have run on another SM)
+        double *velo = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8) + 8, *grad = velo + 3 * nat, *avxyz = grad + 3 * nat, *achrg = avxyz + 3 * nat,
+               *avchrg = achrg + nat;
+        double *gxyz = st.xyz + (size_t)t * 3 * nat, *gvelo = st.velo + (size_t)t * 3 * nat, *ggrad = st.grad + (size_t)t * 3 * nat;
+        double *gachrg = st.achrg + (size_t)t * nat, *gavchrg = st.avchrg + (size_t)t * nat, *gavxyz = st.avxyz + (size_t)t * 3 * nat;
         const double *velof = st.velof + (size_t)t * nat;
         int *list = st.list + (size_t)t * nat;
+        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) { s.xyz[i] = __ldcg(gxyz + i); velo[i] = __ldcg(gvelo + i); grad[i] = __ldcg(ggrad + i); avxyz[i] = __ldcg(gavxyz + i); }
+        for (int i = threadIdx.x; i < nat; i += QX_NT) { achrg[i] = __ldcg(gachrg + i); avchrg[i] = __ldcg(gavchrg + i); }
+        int scc_add = 0;
         // scalar state, kept redundantly in every thread
-        int nstep = st.nstep[t], kdump = st.kdump[t], fconst = st.fconst[t], morestep = st.morestep[t], nfrag = st.nfrag[t];
+        int nstep = __ldcg(st.nstep + t), kdump = __ldcg(st.kdump + t), fconst = __ldcg(st.fconst + t), morestep = __ldcg(st.morestep + t), nfrag = __ldcg(st.nfrag + t);
         int fragstate = 0, mdok = 0, status = TRJ_RUNNING;
-        const int nadd = st.nadd[t];
-        const double fadd = st.fadd[t], eimp = st.eimp[t], ekinstart = st.ekinstart[t];
-        double epot = st.epot[t], ekin = st.ekin[t], etemp = st.etemp[t], Tav = st.Tav[t], Epav = st.Epav[t], Ekav = st.Ekav[t], Edum = st.Edum[t];
-        double aTlast = st.aTlast[t], dtime = st.dtime[t], ttime = st.ttime[t];
-        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.xyz[i] = xyz[i];
+        const int nadd = __ldcg(st.nadd + t);
+        const double fadd = __ldcg(st.fadd + t), eimp = __ldcg(st.eimp + t), ekinstart = __ldcg(st.ekinstart + t);
+        double epot = __ldcg(st.epot + t), ekin = __ldcg(st.ekin + t), etemp = __ldcg(st.etemp + t), Tav = __ldcg(st.Tav + t), Epav = __ldcg(st.Epav + t),
+               Ekav = __ldcg(st.Ekav + t), Edum = __ldcg(st.Edum + t);
+        double aTlast = __ldcg(st.aTlast + t), dtime = __ldcg(st.dtime + t), ttime = __ldcg(st.ttime + t);
         __syncthreads();
         int done = 0;
         for (int it = 0; it < chunk && status == TRJ_RUNNING; ++it) {
@@ -180,7 +202,6 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
                 const double x = __dadd_rn(s.xyz[i], __dmul_rn(cfg.tstep, vnew));
                 velo[i] = vnew;
                 s.xyz[i] = x;
-                xyz[i] = x;
                 s.vdp[i] = __dmul_rn(0.5, __dmul_rn(__dmul_rn(mass, vavg), vavg));
             }
             __syncthreads();
@@ -192,7 +213,11 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
             __syncthreads();
             ekin = s.red[49];
             ttime += cfg.tstep / fstoau;
-            epot = md_egrad(m, s, my, L, cfg, st, t, etemp);
+            {
+                int nit = 0;
+                epot = md_egrad(m, s, my, L, cfg, etemp, grad, achrg, &nit);
+                scc_add += nit;
+            }
             done += 1;
             kdump += 1;
             if (nfrag == 1) morestep = 0;
@@ -222,13 +247,18 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
             if (nstep >= cfg.nmax) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
         }
         __syncthreads();
+        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) { gxyz[i] = s.xyz[i]; gvelo[i] = velo[i]; ggrad[i] = grad[i]; gavxyz[i] = avxyz[i]; }
+        for (int i = threadIdx.x; i < nat; i += QX_NT) { gachrg[i] = achrg[i]; gavchrg[i] = avchrg[i]; }
         if (threadIdx.x == 0) {
+            st.scc_total[t] = __ldcg(st.scc_total + t) + scc_add;
             st.nstep[t] = nstep; st.kdump[t] = kdump; st.fconst[t] = fconst; st.morestep[t] = morestep; st.nfrag[t] = nfrag;
             st.epot[t] = epot; st.ekin[t] = ekin; st.etemp[t] = etemp; st.Tav[t] = Tav; st.Epav[t] = Epav; st.Ekav[t] = Ekav; st.Edum[t] = Edum;
             st.aTlast[t] = aTlast; st.dtime[t] = dtime; st.ttime[t] = ttime;
             if (status != TRJ_RUNNING) { st.status[t] = status; st.fragstate[t] = fragstate; st.mdok[t] = mdok; }
             atomicAdd(steps_done, (unsigned long long)done);
         }
+        __syncthreads();   // every thread's global writes of this sub-chunk are issued ...
+        if (threadIdx.x == 0) { __threadfence(); atomicAdd(&progress[t], 1); }   // ... and published before the hand-over
     }
 }
 
@@ -265,7 +295,7 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
     CUDA_OK(upload_model(c.hm));
     c.L = make_layout(c.hm);
     c.device = device;
-    c.smem = smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld) * sizeof(double) + 64;
+    c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     if (c.smem > (size_t)prop.sharedMemPerBlockOptin)
@@ -380,6 +410,7 @@ struct qcxms_b200_ensemble {
     int ntraj = 0;
     std::vector<void *> allocs;
     unsigned long long *d_steps = nullptr;
+    int *d_progress = nullptr;
     double *d_bins = nullptr;
     int nbins = 0;
     cudaStream_t stream = nullptr;
@@ -425,6 +456,7 @@ extern "C" int qcxms_b200_ensemble_create(const qcxms_b200_md_config_t *cfg, int
     EA(list, n1); EA(scc_total, nt);
 #undef EA
     if (e == cudaSuccess) e = ens_alloc(h, &h->d_steps, 1);
+    if (e == cudaSuccess) e = ens_alloc(h, &h->d_progress, nt);
     if (e == cudaSuccess) e = cudaStreamCreate(&h->stream);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
@@ -503,12 +535,16 @@ extern "C" int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_step
     }
     const int limit = max_steps > 0 ? base_step + max_steps : 0;
     const int total = max_steps > 0 ? max_steps : h->cfg.nmax;
-    const int chunk = 64;
+    const int chunk = 64, sub_steps = 8;
     std::vector<int> status(h->ntraj);
     for (int done = 0; done < total; done += chunk) {
         const int this_chunk = total - done < chunk ? total - done : chunk;
+        const int nsub = (this_chunk + sub_steps - 1) / sub_steps;
         CUDA_OK(cudaMemsetAsync(c.d_queue, 0, sizeof(int), h->stream));
-        k_md_chunk<<<grid, QX_NT, c.smem, h->stream>>>(c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, this_chunk, limit, c.d_queue, h->d_steps);
+        CUDA_OK(cudaMemsetAsync(h->d_progress, 0, h->ntraj * sizeof(int), h->stream));
+        // the last sub-chunk may be shorter: the kernel bounds every sub-chunk by the launch's step limit as well
+        k_md_chunk<<<grid, QX_NT, c.smem, h->stream>>>(c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, sub_steps, nsub,
+                                                       max_steps > 0 ? limit : 0, c.d_queue, h->d_progress, h->d_steps);
         CUDA_OK(cudaGetLastError());
         h->launches += 1;
         // poll for completion every few chunks (cheap: ntraj ints)
@@ -576,6 +612,64 @@ extern "C" int qcxms_b200_ensemble_get_result(qcxms_b200_ensemble_t *h, int itrj
         const int div = nstep > 0 ? nstep : 1;
         res->Tav = Tav / div; res->Epav = Epav / div; res->Ekav = Ekav / div;
         res->aTlast = aTlast / (kdump > 0 ? kdump : 1);
+    }
+    return 0;
+}
+
+extern "C" int qcxms_b200_ensemble_get_all(qcxms_b200_ensemble_t *h, double *xyz, double *velo, double *grad, int32_t *list, double *achrg, double *axyz,
+                                           qcxms_b200_md_result_t *res) {
+    if (!h) return fail(QCXMS_B200_ERR_ARG, "null handle");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    const size_t nat = h->ctx.hm.nat, nt = h->ntraj, n1 = nt * nat;
+    const MdState &s = h->st;
+    std::vector<int> nstep(nt), kdump(nt), iv(nt);
+    std::vector<double> dv(nt);
+    CUDA_OK(cudaMemcpy(nstep.data(), s.nstep, nt * sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(kdump.data(), s.kdump, nt * sizeof(int), cudaMemcpyDeviceToHost));
+    if (xyz) CUDA_OK(cudaMemcpy(xyz, s.xyz, n1 * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (velo) CUDA_OK(cudaMemcpy(velo, s.velo, n1 * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (grad) CUDA_OK(cudaMemcpy(grad, s.grad, n1 * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (list) CUDA_OK(cudaMemcpy(list, s.list, n1 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (achrg) {
+        CUDA_OK(cudaMemcpy(achrg, s.avchrg, n1 * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t t = 0; t < nt; ++t)
+            for (size_t i = 0; i < nat; ++i) achrg[t * nat + i] /= kdump[t];
+    }
+    if (axyz) {
+        CUDA_OK(cudaMemcpy(axyz, s.avxyz, n1 * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t t = 0; t < nt; ++t)
+            for (size_t i = 0; i < 3 * nat; ++i) axyz[t * 3 * nat + i] /= kdump[t];
+    }
+    if (res) {
+        auto geti = [&](const int *src, int32_t qcxms_b200_md_result_t::*f) -> cudaError_t {
+            cudaError_t e = cudaMemcpy(iv.data(), src, nt * sizeof(int), cudaMemcpyDeviceToHost);
+            for (size_t t = 0; t < nt; ++t) res[t].*f = iv[t];
+            return e;
+        };
+        auto getd = [&](const double *src, double qcxms_b200_md_result_t::*f) -> cudaError_t {
+            cudaError_t e = cudaMemcpy(dv.data(), src, nt * sizeof(double), cudaMemcpyDeviceToHost);
+            for (size_t t = 0; t < nt; ++t) res[t].*f = dv[t];
+            return e;
+        };
+        CUDA_OK(geti(s.mdok, &qcxms_b200_md_result_t::mdok));
+        CUDA_OK(geti(s.fragstate, &qcxms_b200_md_result_t::fragstate));
+        CUDA_OK(geti(s.nfrag, &qcxms_b200_md_result_t::nfrag));
+        CUDA_OK(geti(s.status, &qcxms_b200_md_result_t::status));
+        CUDA_OK(geti(s.scc_total, &qcxms_b200_md_result_t::scc_iter_total));
+        CUDA_OK(getd(s.Tav, &qcxms_b200_md_result_t::Tav));
+        CUDA_OK(getd(s.Epav, &qcxms_b200_md_result_t::Epav));
+        CUDA_OK(getd(s.Ekav, &qcxms_b200_md_result_t::Ekav));
+        CUDA_OK(getd(s.aTlast, &qcxms_b200_md_result_t::aTlast));
+        CUDA_OK(getd(s.dtime, &qcxms_b200_md_result_t::dtime));
+        CUDA_OK(getd(s.ttime, &qcxms_b200_md_result_t::ttime));
+        CUDA_OK(getd(s.epot, &qcxms_b200_md_result_t::Epot));
+        CUDA_OK(getd(s.ekin, &qcxms_b200_md_result_t::Ekin));
+        for (size_t t = 0; t < nt; ++t) {
+            const int div = nstep[t] > 0 ? nstep[t] : 1;
+            res[t].nstep = nstep[t];
+            res[t].Tav /= div; res[t].Epav /= div; res[t].Ekav /= div;
+            res[t].aTlast /= (kdump[t] > 0 ? kdump[t] : 1);
+        }
     }
     return 0;
 }

@@ -47,23 +47,23 @@ struct Sm {
     double *qsh, *vsh, *selfen, *vao, *emo, *focc, *gw, *gwd, *dEdcn, *dEdcn4, *grad, *red, *jw;
 };
 
-__host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld) {
-    return 2 * (size_t)nao * ld + 3 * nat + 6 * nat /*cn cn4 mrad dmr qat vat*/ + 6 * nat /*dpat vdp*/ + 12 * nat /*qpat vqp*/
-           + 3 * nsh + 3 * nao + 14 * nat /*gw gwd*/ + 2 * nat + 3 * nat /*grad*/ + 64 + 3 * nao + 8 /*jw*/;
+__host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld, int rows8) {
+    return 2 * (size_t)rows8 * ld + 3 * nat + 6 * nat /*cn cn4 mrad dmr qat vat*/ + 6 * nat /*dpat vdp*/ + 12 * nat /*qpat vqp*/
+           + 3 * nsh + 3 * nao + 8 + 14 * nat /*gw gwd*/ + 2 * nat + 3 * nat /*grad*/ + 64 + 3 * nao + 8 /*jw*/;
 }
 
 __device__ inline void carve(const DevModel &m, double *base, Sm &s) {
     int nat = m.nat, nsh = m.nsh, nao = m.nao;
     double *p = base;
-    s.A = p; p += (size_t)nao * m.ld;
-    s.C = p; p += (size_t)nao * m.ld;
+    s.A = p; p += (size_t)m.rows8 * m.ld;
+    s.C = p; p += (size_t)m.rows8 * m.ld;
     s.xyz = p; p += 3 * nat;
     s.cn = p; p += nat; s.cn4 = p; p += nat; s.mrad = p; p += nat; s.dmr = p; p += nat;
     s.qat = p; p += nat; s.vat = p; p += nat;
     s.dpat = p; p += 3 * nat; s.vdp = p; p += 3 * nat;
     s.qpat = p; p += 6 * nat; s.vqp = p; p += 6 * nat;
     s.qsh = p; p += nsh; s.vsh = p; p += nsh; s.selfen = p; p += nsh;
-    s.vao = p; p += nao; s.emo = p; p += nao; s.focc = p; p += nao;
+    s.vao = p; p += nao; s.emo = p; p += nao; s.focc = p; p += nao + 8;  // focc is read up to the padded dimension
     s.gw = p; p += 7 * nat; s.gwd = p; p += 7 * nat;
     s.dEdcn = p; p += nat; s.dEdcn4 = p; p += nat;
     s.grad = p; p += 3 * nat;
@@ -531,6 +531,126 @@ __device__ inline void gemm_tc(int n, FA loadA, FB loadB, FS store) {
     else dmma_gemm<16>(n, loadA, loadB, store);
 }
 
+// ---- guard-free strip GEMMs on zero-padded shared-memory matrices (rows and columns padded to 8*NT8, padding == 0).
+// One warp owns one strip of 8 output rows (requires NT8 <= number of warps) and keeps the whole strip of the result in
+// registers, so that results can replace an input in place after a single barrier and no global temporary is needed.
+#define QX_DMMA(acc, a, b) asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"((acc)[0]), "+d"((acc)[1]) : "d"(a), "d"(b))
+
+// Matrices have 8*NT8 rows (zero padded) and ld >= 4*ceil(n/4) columns (padding columns zero); column tiles that stick out
+// of ld are predicated (only the last one does).
+// A' = Ct * H * Ct^T  (H symmetric in `A`, result overwrites `A`); Ct in `Ct`.  The strip of T = Ct*H is parked in the
+// warp's own rows of `A` (after a barrier: everybody has finished reading H) and read back as the A operand of the second product.
+template <int NT8>
+__device__ __noinline__ void tc_transform(int n, const double *Ct, double *A, int ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
+    double acc[NT8][2];
+    bool okb[NT8], oks[NT8];
+#pragma unroll
+    for (int t = 0; t < NT8; ++t) { okb[t] = 8 * t + g < ld; oks[t] = 8 * t + 2 * tg + 1 < ld; acc[t][0] = acc[t][1] = 0.0; }
+    double *myrow = A + (warp * 8 + g) * ld;
+    if (warp < NT8) {
+        const double *arow = Ct + (warp * 8 + g) * ld + tg;   // A fragment: Ct[row][k0 + tg]
+        const double *bcol = A + tg * ld + g;                  // B fragment: H[k0 + tg][8 t + g]
+#pragma unroll 2
+        for (int k0 = 0; k0 < kmax; k0 += 4) {
+            const double a = arow[k0];
+#pragma unroll
+            for (int t = 0; t < NT8; ++t) { const double b = okb[t] ? bcol[k0 * ld + 8 * t] : 0.0; QX_DMMA(acc[t], a, b); }
+        }
+    }
+    __syncthreads();   // every warp has finished reading H
+    if (warp < NT8) {
+#pragma unroll
+        for (int t = 0; t < NT8; ++t) {
+            if (oks[t]) *reinterpret_cast<double2 *>(myrow + 8 * t + 2 * tg) = make_double2(acc[t][0], acc[t][1]);
+            acc[t][0] = acc[t][1] = 0.0;
+        }
+        __syncwarp();
+        // second product: A'[strip][col] = sum_k T[strip][k] Ct[col][k]
+        const double *bct = Ct + g * ld + tg;                  // B fragment: Ct[8 t + g][k0 + tg]
+#pragma unroll 2
+        for (int k0 = 0; k0 < kmax; k0 += 4) {
+            const double a = myrow[k0 + tg];
+#pragma unroll
+            for (int t = 0; t < NT8; ++t) { const double b = bct[8 * t * ld + k0]; QX_DMMA(acc[t], a, b); }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < NT8; ++t)
+            if (oks[t]) *reinterpret_cast<double2 *>(myrow + 8 * t + 2 * tg) = make_double2(acc[t][0], acc[t][1]);
+    }
+    __syncthreads();
+}
+
+// Ct <- X * Ct (in place), X in `X` (row-major; here the normalised rows of the Jacobi = J^T)
+template <int NT8>
+__device__ __noinline__ void tc_left_apply(int n, const double *X, double *Ct, int ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
+    double acc[NT8][2];
+    bool okb[NT8], oks[NT8];
+#pragma unroll
+    for (int t = 0; t < NT8; ++t) { okb[t] = 8 * t + g < ld; oks[t] = 8 * t + 2 * tg + 1 < ld; }
+    if (warp < NT8) {
+#pragma unroll
+        for (int t = 0; t < NT8; ++t) acc[t][0] = acc[t][1] = 0.0;
+        const double *arow = X + (warp * 8 + g) * ld + tg;
+        const double *bcol = Ct + tg * ld + g;
+#pragma unroll 2
+        for (int k0 = 0; k0 < kmax; k0 += 4) {
+            const double a = arow[k0];
+#pragma unroll
+            for (int t = 0; t < NT8; ++t) { const double b = okb[t] ? bcol[k0 * ld + 8 * t] : 0.0; QX_DMMA(acc[t], a, b); }
+        }
+    }
+    __syncthreads();
+    if (warp < NT8) {
+        double *orow = Ct + (warp * 8 + g) * ld + 2 * tg;
+#pragma unroll
+        for (int t = 0; t < NT8; ++t)
+            if (oks[t]) *reinterpret_cast<double2 *>(orow + 8 * t) = make_double2(acc[t][0], acc[t][1]);
+    }
+    __syncthreads();
+}
+
+// out = Ct^T diag(w) Ct = C diag(w) C^T.  out may alias Ct (result held in registers across a barrier).
+template <int NT8>
+__device__ __noinline__ void tc_density(int n, const double *Ct, const double *w, double *out, int ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
+    double acc[NT8][2];
+    bool okb[NT8], oks[NT8];
+#pragma unroll
+    for (int t = 0; t < NT8; ++t) { okb[t] = 8 * t + g < ld; oks[t] = 8 * t + 2 * tg + 1 < ld; }
+    if (warp < NT8) {
+#pragma unroll
+        for (int t = 0; t < NT8; ++t) acc[t][0] = acc[t][1] = 0.0;
+        const bool oka = warp * 8 + g < ld;
+        const double *acol = Ct + tg * ld + (oka ? warp * 8 + g : 0);   // A fragment: (Ct^T)[row][k] = Ct[k0 + tg][row]
+        const double *bcol = Ct + tg * ld + g;                          // B fragment: Ct[k0 + tg][8 t + g]
+#pragma unroll 2
+        for (int k0 = 0; k0 < kmax; k0 += 4) {
+            const double a = oka ? acol[k0 * ld] * w[k0 + tg] : 0.0;
+#pragma unroll
+            for (int t = 0; t < NT8; ++t) { const double b = okb[t] ? bcol[k0 * ld + 8 * t] : 0.0; QX_DMMA(acc[t], a, b); }
+        }
+    }
+    __syncthreads();
+    if (warp < NT8) {
+        double *orow = out + (warp * 8 + g) * ld + 2 * tg;
+#pragma unroll
+        for (int t = 0; t < NT8; ++t)
+            if (oks[t]) *reinterpret_cast<double2 *>(orow + 8 * t) = make_double2(acc[t][0], acc[t][1]);
+    }
+    __syncthreads();
+}
+
+// padded dimension used by the strip GEMMs for a basis of n functions (0: not supported by the in-register path)
+__host__ __device__ inline int tc_padded_dim(int n) {   // = 8 * NT8 of the instantiated strip kernels
+    if (n <= 32) return 32;
+    if (n <= 64) return 64;
+    if (n <= 72) return 72;
+    return 0;
+}
+
 // In-place Cholesky S = L L^T on the lower triangle of A (n x n, ld), then Ct = L^{-1} (lower triangular),
 // i.e. C = L^{-T}: an S-orthonormal starting basis.  Returns false if S is not positive definite.
 __device__ __noinline__ bool cholesky_basis(int n, double *A, double *Ct, int ld, double *red) {
@@ -701,6 +821,132 @@ __device__ __noinline__ int jacobi_rows_lp8(int n, double *G, int ld, double *re
     return sweep;
 }
 
+// ---- register-blocked variant: a group of 16 lanes owns a PAIR OF 2-ROW BLOCKS per round, keeps the four rows in
+// registers and performs the four cross rotations (two independent ones at a time) before writing back.  Compared
+// with one row pair per round this halves the shared-memory traffic per rotation and the number of barriers
+// (ceil(n/2)-1 rounds per sweep); the pairs inside a block are rotated once per sweep (in round 0).
+// two independent row pairs (x0,y0) and (x1,y1), straight-line and branch-free so that the two dependency chains overlap
+template <int R>
+__device__ __forceinline__ void jacobi_rot_2pairs16(double2 (&x0)[R], double2 (&y0)[R], double2 (&x1)[R], double2 (&y1)[R],
+                                                    double &dx0, double &dy0, double &ix0, double &iy0, double &nx0, double &ny0, bool v0,
+                                                    double &dx1, double &dy1, double &ix1, double &iy1, double &nx1, double &ny1, bool v1, float &smax) {
+    double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        a0 = fma(x0[r].x, y0[r].x, a0); b0 = fma(x0[r].y, y0[r].y, b0);
+        a1 = fma(x1[r].x, y1[r].x, a1); b1 = fma(x1[r].y, y1[r].y, b1);
+    }
+    double g0 = a0 + b0, g1 = a1 + b1;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        const double h0 = __shfl_xor_sync(0xffffffffu, g0, o), h1 = __shfl_xor_sync(0xffffffffu, g1, o);
+        g0 += h0; g1 += h1;
+    }
+    const double ga0 = dx0 * dy0 * g0, ga1 = dx1 * dy1 * g1;
+    const float gf0 = (float)ga0, gf1 = (float)ga1;
+    const float r0 = v0 ? fabsf(gf0) * rsqrt_approx((float)nx0 * (float)ny0) : 0.0f;
+    const float r1 = v1 ? fabsf(gf1) * rsqrt_approx((float)nx1 * (float)ny1) : 0.0f;
+    smax = fmaxf(smax, fmaxf(r0, r1));
+    const float z0 = (float)(ny0 - nx0) * rcp_approx(2.0f * gf0), z1 = (float)(ny1 - nx1) * rcp_approx(2.0f * gf1);
+    float tf0 = copysignf(rcp_approx(fabsf(z0) + sqrt_approx(fmaf(z0, z0, 1.0f))), z0);
+    float tf1 = copysignf(rcp_approx(fabsf(z1) + sqrt_approx(fmaf(z1, z1, 1.0f))), z1);
+    tf0 = r0 > 1e-15f ? tf0 : 0.0f;   // also removes the NaN of a 0/0 pair
+    tf1 = r1 > 1e-15f ? tf1 : 0.0f;
+    const double t0 = (double)tf0, t1 = (double)tf1, w0 = fma(t0, t0, 1.0), w1 = fma(t1, t1, 1.0);
+    const double p0 = t0 * dy0 * ix0, q0 = t0 * dx0 * iy0, p1 = t1 * dy1 * ix1, q1 = t1 * dx1 * iy1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double ux0 = fma(-p0, y0[r].x, x0[r].x), uy0 = fma(-p0, y0[r].y, x0[r].y);
+        const double ux1 = fma(-p1, y1[r].x, x1[r].x), uy1 = fma(-p1, y1[r].y, x1[r].y);
+        y0[r].x = fma(q0, x0[r].x, y0[r].x); y0[r].y = fma(q0, x0[r].y, y0[r].y);
+        y1[r].x = fma(q1, x1[r].x, y1[r].x); y1[r].y = fma(q1, x1[r].y, y1[r].y);
+        x0[r].x = ux0; x0[r].y = uy0; x1[r].x = ux1; x1[r].y = uy1;
+    }
+    double c0 = (double)rsqrt_approx((float)w0), c1 = (double)rsqrt_approx((float)w1);
+    c0 = c0 * fma(-0.5 * w0 * c0, c0, 1.5); c1 = c1 * fma(-0.5 * w1 * c1, c1, 1.5);
+    c0 = c0 * fma(-0.5 * w0 * c0, c0, 1.5); c1 = c1 * fma(-0.5 * w1 * c1, c1, 1.5);
+    const double wc0 = w0 * c0, wc1 = w1 * c1, tg0 = t0 * ga0, tg1 = t1 * ga1;
+    dx0 *= c0; dy0 *= c0; ix0 *= wc0; iy0 *= wc0; nx0 -= tg0; ny0 += tg0;
+    dx1 *= c1; dy1 *= c1; ix1 *= wc1; iy1 *= wc1; nx1 -= tg1; ny1 += tg1;
+}
+
+template <int R>
+__device__ __noinline__ int jacobi_rows_blk2(int n, double *G, int ld, double *red, float tol, double *jw) {
+    const int nb = (n + 1) >> 1, mb = (nb + 1) & ~1, nbp = mb >> 1, m1 = mb - 1;
+    const int nslot = QX_NT / 16, slot = threadIdx.x >> 4, l16 = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int npass = (nbp + nslot - 1) / nslot;
+    double *nrm2 = jw, *dsc = jw + n, *dinv = jw + 2 * n;
+    for (int i = threadIdx.x; i < n; i += QX_NT) { dsc[i] = 1.0; dinv[i] = 1.0; }
+    __syncthreads();
+    const bool tail_ok = 2 * l16 + 32 * (R - 1) < n;
+    const int tail_off = tail_ok ? 2 * l16 + 32 * (R - 1) : 0;
+    int sweep = 0;
+    for (; sweep < 60; ++sweep) {
+        for (int k = warp; k < n; k += QX_NT / 32) {
+            const double d = dsc[k];
+            double acc = 0.0;
+            for (int i = lane; i < n; i += 32) { const double x = G[(size_t)k * ld + i] * d; G[(size_t)k * ld + i] = x; acc += x * x; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            __syncwarp();
+            if (lane == 0) { nrm2[k] = acc; dsc[k] = 1.0; dinv[k] = 1.0; }
+        }
+        __syncthreads();
+        float smax = 0.0f;
+        for (int round = 0; round < m1; ++round) {
+            for (int pass = 0; pass < npass; ++pass) {
+                const int k = slot + pass * nslot;
+                int P = round + k, Q = round - k;
+                if (P >= m1) P -= m1;
+                if (Q < 0) Q += m1;
+                if (k == 0) P = m1;
+                const bool gvalid = k < nbp;
+                int row[4] = {2 * P, 2 * P + 1, 2 * Q, 2 * Q + 1};
+                bool rv[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) { rv[a] = gvalid && row[a] < n; if (!rv[a]) row[a] = 0; }
+                double2 x[4][R];
+                double d[4], di[4], nr[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const double *g = G + row[a] * ld;
+#pragma unroll
+                    for (int r = 0; r < R - 1; ++r) x[a][r] = *reinterpret_cast<const double2 *>(g + 2 * l16 + 32 * r);
+                    x[a][R - 1] = *reinterpret_cast<const double2 *>(g + tail_off);
+                    if (!tail_ok) x[a][R - 1] = make_double2(0.0, 0.0);
+                    d[a] = dsc[row[a]]; di[a] = dinv[row[a]]; nr[a] = nrm2[row[a]];
+                }
+                if (round == 0)   // pairs inside the two blocks, once per sweep
+                    jacobi_rot_2pairs16<R>(x[0], x[1], x[2], x[3], d[0], d[1], di[0], di[1], nr[0], nr[1], rv[0] && rv[1],
+                                           d[2], d[3], di[2], di[3], nr[2], nr[3], rv[2] && rv[3], smax);
+                jacobi_rot_2pairs16<R>(x[0], x[2], x[1], x[3], d[0], d[2], di[0], di[2], nr[0], nr[2], rv[0] && rv[2],
+                                       d[1], d[3], di[1], di[3], nr[1], nr[3], rv[1] && rv[3], smax);
+                jacobi_rot_2pairs16<R>(x[0], x[3], x[1], x[2], d[0], d[3], di[0], di[3], nr[0], nr[3], rv[0] && rv[3],
+                                       d[1], d[2], di[1], di[2], nr[1], nr[2], rv[1] && rv[2], smax);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    if (rv[a]) {
+                        double *g = G + row[a] * ld;
+#pragma unroll
+                        for (int r = 0; r < R - 1; ++r) *reinterpret_cast<double2 *>(g + 2 * l16 + 32 * r) = x[a][r];
+                        if (tail_ok) *reinterpret_cast<double2 *>(g + 2 * l16 + 32 * (R - 1)) = x[a][R - 1];
+                        if (l16 == 0) { dsc[row[a]] = d[a]; dinv[row[a]] = di[a]; nrm2[row[a]] = nr[a]; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const float m = (float)block_max((double)smax, red);
+        if (m < tol) { ++sweep; break; }
+    }
+    for (int k = warp; k < n; k += QX_NT / 32) {
+        const double d = dsc[k];
+        for (int i = lane; i < n; i += 32) G[(size_t)k * ld + i] *= d;
+    }
+    __syncthreads();
+    return sweep;
+}
+
 // generic fallback (any n): LP lanes per pair, scalar accesses
 __device__ __noinline__ int jacobi_rows_generic(int n, double *G, int ld, double *red, float tol) {
     const int mm = (n + 1) & ~1, npair = mm >> 1;
@@ -762,6 +1008,16 @@ __device__ __noinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *e
     const float tol = 1e-7f;  // pre-rotation ratio of the last sweep; its rotations leave O(tol^2) couplings
     const int npair = (n + 1) >> 1;
     int sweeps;
+#ifdef QX_JACOBI_BLOCK2   // measured slower on B200 (issue-bound: 16 lanes repeat the scalar chain), kept for experiments
+    if ((ld & 1) == 0 && n <= 128) {
+        switch ((n + 31) >> 5) {
+            case 1: sweeps = jacobi_rows_blk2<1>(n, G, ld, red, tol, jw); break;
+            case 2: sweeps = jacobi_rows_blk2<2>(n, G, ld, red, tol, jw); break;
+            case 3: sweeps = jacobi_rows_blk2<3>(n, G, ld, red, tol, jw); break;
+            default: sweeps = jacobi_rows_blk2<4>(n, G, ld, red, tol, jw); break;
+        }
+    } else
+#endif
     if (npair * 8 <= QX_NT && (ld & 1) == 0 && n <= 128) {
         switch ((n + 15) >> 4) {
             case 1: sweeps = jacobi_rows_lp8<1>(n, G, ld, red, tol, jw); break;

@@ -19,9 +19,10 @@
 #include "qx_model.h"
 
 namespace qx {
+__host__ __device__ inline int tc_padded_dim(int n);
 
 struct HostModel {
-    int nat = 0, nsh = 0, nao = 0, ntype = 0, ld = 0, ndim = 0, charge = 0;
+    int nat = 0, nsh = 0, nao = 0, ntype = 0, ld = 0, ndim = 0, charge = 0, rows8 = 0;
     double nel[2] = {0, 0};
     std::vector<int> num, type, at_sh0, at_nsh, at_ao0, at_nao, at_nref, at_ngw;
     std::vector<double> at_rcov, at_rad, at_repa, at_repz, at_en, at_mprad, at_mpvcn, at_dk, at_qk, at_r4r2, at_zeff, at_gam,
@@ -112,7 +113,10 @@ inline std::string build_host_model(HostModel &h, int nat, const int32_t *num, c
         h.nao += nao_at;
     }
     h.ntype = (int)types.size();
-    h.ld = h.nao;  // == 4 or 12 (mod 16): conflict-free DMMA fragment loads and 128-bit row accesses
+    // shared-memory matrices are zero padded to the strip-GEMM dimension; ld == 4 or 12 (mod 16) keeps DMMA fragment loads
+    // and 128-bit row accesses free of bank conflicts
+    h.rows8 = tc_padded_dim(h.nao) ? tc_padded_dim(h.nao) : h.nao;
+    h.ld = h.nao;
     while (h.ld % 16 != 4 && h.ld % 16 != 12) h.ld += 1;
     h.ndim = h.nsh + 9 * nat;
     // occupation numbers (tblite get_occupation / get_alpha_beta_occupation; uhf = min(mult-1, 0), tblite.f90:111)
@@ -236,7 +240,7 @@ inline cudaError_t upload_model(HostModel &h) {
     if (err != cudaSuccess) return err;
     char *base = (char *)h.d_blob;
     DevModel &d = h.dev;
-    d.nat = h.nat; d.nsh = h.nsh; d.nao = h.nao; d.ntype = h.ntype; d.ld = h.ld; d.ndim = h.ndim;
+    d.nat = h.nat; d.nsh = h.nsh; d.nao = h.nao; d.ntype = h.ntype; d.ld = h.ld; d.ndim = h.ndim; d.rows8 = h.rows8;
     d.ntask_int = (int)h.task_int.size(); d.ntask_grad = 0;
     d.nel[0] = h.nel[0]; d.nel[1] = h.nel[1];
 #define PTR(name, T) d.name = (const T *)(base + o_##name)

@@ -9,7 +9,8 @@
 #define QX_NT 288         // threads per CTA; one CTA == one trajectory
 
 struct DevModel {
-    int nat, nsh, nao, ntype, ld, ndim;  // ld: odd leading dimension of the shared-memory matrices
+    int nat, nsh, nao, ntype, ld, ndim;  // ld: leading dimension of the shared-memory matrices (== 4 or 12 mod 16)
+    int rows8;                            // rows of the shared-memory matrices (zero padded; multiple of 8 when the strip GEMMs apply)
     int ntask_int, ntask_grad;
     double nel[2];                        // alpha / beta electron numbers
     // per atom

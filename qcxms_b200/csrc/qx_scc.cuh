@@ -74,24 +74,34 @@ __device__ __noinline__ void phase_potential(const DevModel &m, Sm &s, const dou
         for (int b = 0; b < nsh; ++b) v += gamma[a * nsh + b] * s.qsh[b];
         s.vsh[a] = v + s.qsh[a] * s.qsh[a] * m.sh_gam3[a];
     }
-    for (int i = threadIdx.x; i < nat; i += QX_NT) {
-        double vd[3] = {0, 0, 0}, vq[6] = {0, 0, 0, 0, 0, 0}, va = 0.0;
-        for (int j = 0; j < nat; ++j) {
-            if (j == i) continue;
-            double v[3], g3f3, g3f5, g5f5;
-            aes_pair(s, i, j, v, g3f3, g3f5, g5f5);
-            const double qj = s.qat[j];
-            const double *mj = s.dpat + 3 * j;
-            double mv = mj[0] * v[0] + mj[1] * v[1] + mj[2] * v[2];
-            for (int k = 0; k < 3; ++k) vd[k] += v[k] * g3f3 * qj + g3f5 * mj[k] - 3.0 * g5f5 * v[k] * mv;
-            double tq = g5f5 * qj;
-            vq[0] += tq * v[0] * v[0]; vq[1] += 2.0 * tq * v[0] * v[1]; vq[2] += tq * v[1] * v[1];
-            vq[3] += 2.0 * tq * v[0] * v[2]; vq[4] += 2.0 * tq * v[1] * v[2]; vq[5] += tq * v[2] * v[2];
-            va += -g3f3 * mv + g5f5 * quad_contract(s.qpat + 6 * j, v);
+    {   // anisotropic electrostatics: one warp per atom i, lanes over the partner j, fixed-order butterfly reduction
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int i = warp; i < nat; i += QX_NT / 32) {
+            double acc[10];
+#pragma unroll
+            for (int c = 0; c < 10; ++c) acc[c] = 0.0;
+            for (int j = lane; j < nat; j += 32) {
+                if (j == i) continue;
+                double v[3], g3f3, g3f5, g5f5;
+                aes_pair(s, i, j, v, g3f3, g3f5, g5f5);
+                const double qj = s.qat[j];
+                const double *mj = s.dpat + 3 * j;
+                const double mv = mj[0] * v[0] + mj[1] * v[1] + mj[2] * v[2];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc[k] += v[k] * g3f3 * qj + g3f5 * mj[k] - 3.0 * g5f5 * v[k] * mv;
+                const double tq = g5f5 * qj;
+                acc[3] += tq * v[0] * v[0]; acc[4] += 2.0 * tq * v[0] * v[1]; acc[5] += tq * v[1] * v[1];
+                acc[6] += 2.0 * tq * v[0] * v[2]; acc[7] += 2.0 * tq * v[1] * v[2]; acc[8] += tq * v[2] * v[2];
+                acc[9] += -g3f3 * mv + g5f5 * quad_contract(s.qpat + 6 * j, v);
+            }
+#pragma unroll
+            for (int c = 0; c < 10; ++c)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+            if (lane < 3) s.vdp[3 * i + lane] = acc[lane] + 2.0 * m.at_dk[i] * s.dpat[3 * i + lane];
+            if (lane >= 3 && lane < 9) s.vqp[6 * i + lane - 3] = acc[lane] + 2.0 * m.at_qk[i] * s.qpat[6 * i + lane - 3] * c_qscale[lane - 3];
+            if (lane == 9) s.vat[i] = acc[9];
         }
-        for (int k = 0; k < 3; ++k) s.vdp[3 * i + k] = vd[k] + 2.0 * m.at_dk[i] * s.dpat[3 * i + k];
-        for (int k = 0; k < 6; ++k) s.vqp[6 * i + k] = vq[k] + 2.0 * m.at_qk[i] * s.qpat[6 * i + k] * c_qscale[k];
-        s.vat[i] = va;
     }
     __syncthreads();
     for (int t = threadIdx.x; t < nat * QX_MAXREF; t += QX_NT) {
@@ -119,23 +129,31 @@ __device__ __noinline__ void phase_scc_energy(const DevModel &m, Sm &s, const do
         for (int b = 0; b < nsh; ++b) v += gamma[a * nsh + b] * s.qsh[b];
         es += 0.5 * v * s.qsh[a] + s.qsh[a] * s.qsh[a] * s.qsh[a] * m.sh_gam3[a] / 3.0;
     }
-    for (int i = threadIdx.x; i < nat; i += QX_NT) {
-        double vd[3] = {0, 0, 0}, vq = 0.0;
-        const double *mi = s.dpat + 3 * i;
-        for (int j = 0; j < nat; ++j) {
-            if (j == i) continue;
-            double v[3], g3f3, g3f5, g5f5;
-            aes_pair(s, i, j, v, g3f3, g3f5, g5f5);
-            const double qj = s.qat[j];
-            const double *mj = s.dpat + 3 * j;
-            double mv = mj[0] * v[0] + mj[1] * v[1] + mj[2] * v[2];
-            for (int k = 0; k < 3; ++k) vd[k] += v[k] * g3f3 * qj + 0.5 * (g3f5 * mj[k] - 3.0 * g5f5 * v[k] * mv);
-            vq += g5f5 * qj * quad_contract(s.qpat + 6 * i, v);
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int i = warp; i < nat; i += QX_NT / 32) {
+            const double *mi = s.dpat + 3 * i;
+            double e = 0.0;
+            for (int j = lane; j < nat; j += 32) {
+                if (j == i) continue;
+                double v[3], g3f3, g3f5, g5f5;
+                aes_pair(s, i, j, v, g3f3, g3f5, g5f5);
+                const double qj = s.qat[j];
+                const double *mj = s.dpat + 3 * j;
+                const double mv = mj[0] * v[0] + mj[1] * v[1] + mj[2] * v[2];
+                double vd0 = v[0] * g3f3 * qj + 0.5 * (g3f5 * mj[0] - 3.0 * g5f5 * v[0] * mv);
+                double vd1 = v[1] * g3f3 * qj + 0.5 * (g3f5 * mj[1] - 3.0 * g5f5 * v[1] * mv);
+                double vd2 = v[2] * g3f3 * qj + 0.5 * (g3f5 * mj[2] - 3.0 * g5f5 * v[2] * mv);
+                e += mi[0] * vd0 + mi[1] * vd1 + mi[2] * vd2 + g5f5 * qj * quad_contract(s.qpat + 6 * i, v);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            if (lane == 0) {
+                e += m.at_dk[i] * (mi[0] * mi[0] + mi[1] * mi[1] + mi[2] * mi[2]);
+                for (int k = 0; k < 6; ++k) e += m.at_qk[i] * s.qpat[6 * i + k] * s.qpat[6 * i + k] * c_qscale[k];
+                ea += e;
+            }
         }
-        double e = mi[0] * vd[0] + mi[1] * vd[1] + mi[2] * vd[2] + vq;
-        e += m.at_dk[i] * (mi[0] * mi[0] + mi[1] * mi[1] + mi[2] * mi[2]);
-        for (int k = 0; k < 6; ++k) e += m.at_qk[i] * s.qpat[6 * i + k] * s.qpat[6 * i + k] * c_qscale[k];
-        ea += e;
     }
     __syncthreads();  // gw complete
     for (int t = threadIdx.x; t < nat * QX_MAXREF; t += QX_NT) {
@@ -439,7 +457,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
 
     // S-orthonormal start basis: C = L^{-T}.  Padding columns of the shared matrices are zeroed once: the
     // 128-bit row accesses of the Jacobi read (and rewrite) them.
-    for (int t = threadIdx.x; t < nao * ld; t += QX_NT) { s.A[t] = 0.0; s.C[t] = 0.0; }
+    for (int t = threadIdx.x; t < m.rows8 * ld; t += QX_NT) { s.A[t] = 0.0; s.C[t] = 0.0; }
     __syncthreads();
     for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.A[(size_t)(t / nao) * ld + t % nao] = S[t];
     __syncthreads();
@@ -482,7 +500,13 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         phase_build_h1(m, s, S, H0, Dt, Qt);
         QX_PH(6);
         // A' = C^T H1 C in the current S-orthonormal basis (s.C holds C transposed), then Jacobi (C <- C J)
-        {
+        const int npad = tc_padded_dim(nao);
+        const bool strip = npad != 0 && npad / 8 <= QX_NT / 32;
+        if (strip) {
+            if (npad == 32) tc_transform<4>(nao, s.C, s.A, ld);
+            else if (npad == 64) tc_transform<8>(nao, s.C, s.A, ld);
+            else tc_transform<9>(nao, s.C, s.A, ld);
+        } else {
             const double *Ct = s.C, *Hm = s.A;
             // Tt = Ct H1  (global scratch), then A' = Ct Tt^T back into shared memory
             gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)i * ld + k]; }, [=](int k, int j) { return Hm[(size_t)k * ld + j]; },
@@ -501,12 +525,18 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
             if (threadIdx.x == 0 && iscf <= 32) { atomicAdd(&g_sweep_hist[iscf - 1], (unsigned long long)sw_); atomicAdd(&g_sweep_hist[32 + iscf - 1], 1ull); }
 #endif
             // rows of A now hold J^T: Ct_new = J^T Ct_old
-            const double *Jt = s.A, *Ct = s.C;
-            gemm_tc(nao, [=](int i, int k) { return Jt[(size_t)i * ld + k]; }, [=](int k, int j) { return Ct[(size_t)k * ld + j]; },
-                    [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; });
-            __syncthreads();
-            for (int t = threadIdx.x; t < nao * nao; t += QX_NT) { int i = t / nao; s.C[(size_t)i * ld + (t - i * nao)] = T[t]; }
-            __syncthreads();
+            if (strip) {
+                if (npad == 32) tc_left_apply<4>(nao, s.A, s.C, ld);
+                else if (npad == 64) tc_left_apply<8>(nao, s.A, s.C, ld);
+                else tc_left_apply<9>(nao, s.A, s.C, ld);
+            } else {
+                const double *Jt = s.A, *Ct = s.C;
+                gemm_tc(nao, [=](int i, int k) { return Jt[(size_t)i * ld + k]; }, [=](int k, int j) { return Ct[(size_t)k * ld + j]; },
+                        [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; });
+                __syncthreads();
+                for (int t = threadIdx.x; t < nao * nao; t += QX_NT) { int i = t / nao; s.C[(size_t)i * ld + (t - i * nao)] = T[t]; }
+                __syncthreads();
+            }
         }
         QX_PH(8);
         // order statistics needed for the Fermi-level start value
@@ -550,13 +580,19 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         ts = block_sum(ts, s.red);
         QX_PH(9);
         // density into A
-        {
+        if (strip) {
+            for (int k = nao + threadIdx.x; k < nao + 8; k += QX_NT) s.focc[k] = 0.0;   // padding orbitals carry no weight
+            __syncthreads();
+            if (npad == 32) tc_density<4>(nao, s.C, s.focc, s.A, ld);
+            else if (npad == 64) tc_density<8>(nao, s.C, s.focc, s.A, ld);
+            else tc_density<9>(nao, s.C, s.focc, s.A, ld);
+        } else {
             const double *Ct = s.C, *f = s.focc;
             double *Pm = s.A;
             gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)k * ld + i] * f[k]; }, [=](int k, int j) { return Ct[(size_t)k * ld + j]; },
                     [=](int i, int j, double v) { Pm[(size_t)i * ld + j] = v; });
+            __syncthreads();
         }
-        __syncthreads();
         QX_PH(10);
         double eel = phase_mulliken(m, s, S, H0, Dt, Qt, pop);
         QX_PH(11);
@@ -587,13 +623,20 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     for (int k = threadIdx.x; k < nao; k += QX_NT) s.focc[k] *= s.emo[k];
     __syncthreads();
     {
-        const double *Ct = s.C, *f = s.focc;
-        gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)k * ld + i] * f[k]; }, [=](int k, int j) { return Ct[(size_t)k * ld + j]; },
-                [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; });
+        const int npad = tc_padded_dim(nao);
+        if (npad != 0 && npad / 8 <= QX_NT / 32) {   // W replaces C^T in place
+            if (npad == 32) tc_density<4>(nao, s.C, s.focc, s.C, ld);
+            else if (npad == 64) tc_density<8>(nao, s.C, s.focc, s.C, ld);
+            else tc_density<9>(nao, s.C, s.focc, s.C, ld);
+        } else {
+            const double *Ct = s.C, *f = s.focc;
+            gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)k * ld + i] * f[k]; }, [=](int k, int j) { return Ct[(size_t)k * ld + j]; },
+                    [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; });
+            __syncthreads();
+            for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.C[(size_t)(t / nao) * ld + t % nao] = T[t];
+            __syncthreads();
+        }
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.C[(size_t)(t / nao) * ld + t % nao] = T[t];
-    __syncthreads();
     QX_PH(13);
     phase_gradient_pairs(m, s, m.task_int, m.ntask_int, taskout);
     QX_PH(14);
@@ -623,11 +666,12 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     __syncthreads();
     d4_c6_tables(m, gwq, gwdcnq, c6, dc6);
     __syncthreads();
-    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+    for (int i = threadIdx.x >> 5; i < nat; i += QX_NT / 32) {   // one warp per atom, lanes over the partners
+        const int lane = threadIdx.x & 31;
         double gx = 0, gy = 0, gz = 0, dcn = 0, dcn4 = 0;
         const double *mi = s.dpat + 3 * i, *ti = s.qpat + 6 * i;
         const double qi = s.qat[i];
-        for (int j = 0; j < nat; ++j) {
+        for (int j = lane; j < nat; j += 32) {
             if (j == i) continue;
             // --- dispersion
             {
@@ -673,16 +717,23 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         }
         // --- isotropic second order
         for (int a = m.at_sh0[i]; a < m.at_sh0[i] + m.at_nsh[i]; ++a)
-            for (int b = 0; b < nsh; ++b) {
+            for (int b = lane; b < nsh; b += 32) {
                 int j = m.sh_at[b];
                 if (j == i) continue;
                 double g = gamma[a * nsh + b];
                 double f = -s.qsh[a] * s.qsh[b] * g * g * g;
                 gx += f * (s.xyz[3 * i] - s.xyz[3 * j]); gy += f * (s.xyz[3 * i + 1] - s.xyz[3 * j + 1]); gz += f * (s.xyz[3 * i + 2] - s.xyz[3 * j + 2]);
             }
-        s.grad[3 * i] += gx; s.grad[3 * i + 1] += gy; s.grad[3 * i + 2] += gz;
-        s.dEdcn[i] += dcn;
-        s.dEdcn4[i] += dcn4;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            gx += __shfl_xor_sync(0xffffffffu, gx, o); gy += __shfl_xor_sync(0xffffffffu, gy, o); gz += __shfl_xor_sync(0xffffffffu, gz, o);
+            dcn += __shfl_xor_sync(0xffffffffu, dcn, o); dcn4 += __shfl_xor_sync(0xffffffffu, dcn4, o);
+        }
+        if (lane == 0) {
+            s.grad[3 * i] += gx; s.grad[3 * i + 1] += gy; s.grad[3 * i + 2] += gz;
+            s.dEdcn[i] += dcn;
+            s.dEdcn4[i] += dcn4;
+        }
     }
     __syncthreads();
     // chain rule through both coordination numbers

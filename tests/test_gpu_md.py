@@ -101,3 +101,18 @@ def test_histogram_counts_fragments(qx):
     bins, dev = ens.histogram(256)
     assert dev is not None and bins.sum() == 4 and (bins[80] + bins[81]) == 4   # intact C2H5ClO (average masses: 80.5 amu)
     ens.close()
+
+
+def test_bulk_results_match_per_trajectory_results(qx):
+    num, ic = _ic(qx, "chloroethanol", 5, seed=3)
+    ens = qx.Ensemble(num, ic["mass"], 5, mchrg=1, nmax=9, exit_rules=True)
+    ens.set_all(ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+    ens.run_md()
+    allr = ens.results()
+    for k in range(5):
+        one = ens.result(k)
+        for key in ("xyz", "velo", "grad", "list", "achrg", "axyz"):
+            assert np.array_equal(allr[key][k], one[key])
+        for key in ("mdok", "fragstate", "nstep", "nfrag", "status", "scc_iter_total", "Tav", "Epav", "Ekav", "aTlast", "dtime", "ttime", "Epot", "Ekin"):
+            assert allr[key][k] == one[key]
+    ens.close()
