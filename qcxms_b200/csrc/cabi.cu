@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(QX_NT, 2) k_egrad_batch(DevModel m, ScratchLay
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_next;
     Sm s;
-    carve(m, smem, s);
     double *my = scratch + (size_t)blockIdx.x * L.total;
+    carve(m, smem, s, my + L.matA);
     const int nat = m.nat;
     for (;;) {
         __syncthreads();
@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout 
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_next;
     Sm s;
-    carve(m, smem, s);
     double *my = scratch + (size_t)blockIdx.x * L.total;
+    carve(m, smem, s, my + L.matA);
     const int nat = m.nat;
     for (;;) {
         __syncthreads();
@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_next, s_flag;
     Sm s;
-    carve(m, smem, s);
     double *my = scratch + (size_t)blockIdx.x * L.total;
+    carve(m, smem, s, my + L.matA);
     const int nat = m.nat;
     const double fstoau = QC_FSTOAU, kB = QC_KB;
     for (;;) {
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
         }
         // per-trajectory arrays live in shared memory for the duration of the work item (read with ld.cg: the previous
         // sub-chunk of this trajectory may have run on another SM)
-        double *velo = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8) + 8, *grad = velo + 3 * nat, *avxyz = grad + 3 * nat, *achrg = avxyz + 3 * nat,
+        double *velo = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global) + 8, *grad = velo + 3 * nat, *avxyz = grad + 3 * nat, *achrg = avxyz + 3 * nat,
                *avchrg = achrg + nat;
         double *gxyz = st.xyz + (size_t)t * 3 * nat, *gvelo = st.velo + (size_t)t * 3 * nat, *ggrad = st.grad + (size_t)t * 3 * nat;
         double *gachrg = st.achrg + (size_t)t * nat, *gavchrg = st.avchrg + (size_t)t * nat, *gavxyz = st.avxyz + (size_t)t * 3 * nat;
@@ -293,13 +293,18 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
     std::string why = build_host_model(c.hm, nat, num, mass, charge, multiplicity);
     if (!why.empty()) return fail(QCXMS_B200_ERR_UNSUPPORTED, why);
     CUDA_OK(upload_model(c.hm));
-    c.L = make_layout(c.hm);
     c.device = device;
-    c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    if (c.smem > (size_t)prop.sharedMemPerBlockOptin)
-        return fail(QCXMS_B200_ERR_UNSUPPORTED, "basis too large for the shared-memory SCC kernel (nao = " + std::to_string(c.hm.nao) + ")");
+    c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 0) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
+    if (c.smem > (size_t)prop.sharedMemPerBlockOptin) {
+        // large basis (nao >~ 110): keep the two SCC matrices in the per-CTA global slab -- functional, slower
+        c.hm.dev.mat_in_global = 1;
+        c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 1) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
+        if (c.smem > (size_t)prop.sharedMemPerBlockOptin)
+            return fail(QCXMS_B200_ERR_UNSUPPORTED, "system too large for the per-CTA working set (nat = " + std::to_string(c.hm.nat) + ")");
+    }
+    c.L = make_layout(c.hm);
     CUDA_OK(cudaFuncSetAttribute(k_egrad_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     CUDA_OK(cudaFuncSetAttribute(k_md_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     CUDA_OK(cudaFuncSetAttribute(k_md_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));

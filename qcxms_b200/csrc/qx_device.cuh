@@ -47,16 +47,20 @@ struct Sm {
     double *qsh, *vsh, *selfen, *vao, *emo, *focc, *gw, *gwd, *dEdcn, *dEdcn4, *grad, *red, *jw;
 };
 
-__host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld, int rows8) {
-    return 2 * (size_t)rows8 * ld + 3 * nat + 6 * nat /*cn cn4 mrad dmr qat vat*/ + 6 * nat /*dpat vdp*/ + 12 * nat /*qpat vqp*/
+__host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld, int rows8, int mat_in_global = 0) {
+    return (mat_in_global ? 0 : 2 * (size_t)rows8 * ld) + 3 * nat + 6 * nat /*cn cn4 mrad dmr qat vat*/ + 6 * nat /*dpat vdp*/ + 12 * nat /*qpat vqp*/
            + 3 * nsh + 3 * nao + 8 + 14 * nat /*gw gwd*/ + 2 * nat + 3 * nat /*grad*/ + 64 + 3 * nao + 8 /*jw*/;
 }
 
-__device__ inline void carve(const DevModel &m, double *base, Sm &s) {
+__device__ inline void carve(const DevModel &m, double *base, Sm &s, double *gmat = nullptr) {
     int nat = m.nat, nsh = m.nsh, nao = m.nao;
     double *p = base;
-    s.A = p; p += (size_t)m.rows8 * m.ld;
-    s.C = p; p += (size_t)m.rows8 * m.ld;
+    if (m.mat_in_global) {   // large basis: matrices in the CTA's global slab (functional fallback, not the fast path)
+        s.A = gmat; s.C = gmat + (size_t)m.rows8 * m.ld;
+    } else {
+        s.A = p; p += (size_t)m.rows8 * m.ld;
+        s.C = p; p += (size_t)m.rows8 * m.ld;
+    }
     s.xyz = p; p += 3 * nat;
     s.cn = p; p += nat; s.cn4 = p; p += nat; s.mrad = p; p += nat; s.dmr = p; p += nat;
     s.qat = p; p += nat; s.vat = p; p += nat;
@@ -494,29 +498,31 @@ __device__ __noinline__ void dmma_gemm(int n, FA loadA, FB loadB, FS store) {
     const int nt = (n + 7) >> 3, g = lane >> 2, tg = lane & 3;
     for (int ti = warp; ti < nt; ti += nwarp) {
         const int row = ti * 8 + g;
-        double acc[MAXT][2];
+        for (int tb = 0; tb < nt; tb += MAXT) {   // column tiles in groups of MAXT (accumulators stay in registers)
+            double acc[MAXT][2];
 #pragma unroll
-        for (int t = 0; t < MAXT; ++t) acc[t][0] = acc[t][1] = 0.0;
+            for (int t = 0; t < MAXT; ++t) acc[t][0] = acc[t][1] = 0.0;
 #pragma unroll 2
-        for (int k0 = 0; k0 < n; k0 += 4) {
-            const int k = k0 + tg;
-            const double a = (row < n && k < n) ? loadA(row, k) : 0.0;
+            for (int k0 = 0; k0 < n; k0 += 4) {
+                const int k = k0 + tg;
+                const double a = (row < n && k < n) ? loadA(row, k) : 0.0;
 #pragma unroll
-            for (int t = 0; t < MAXT; ++t) {
-                if (t < nt) {
-                    const int col = t * 8 + g;
-                    const double b = (k < n && col < n) ? loadB(k, col) : 0.0;
-                    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                 : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(a), "d"(b));
+                for (int t = 0; t < MAXT; ++t) {
+                    if (tb + t < nt) {
+                        const int col = (tb + t) * 8 + g;
+                        const double b = (k < n && col < n) ? loadB(k, col) : 0.0;
+                        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                            : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(a), "d"(b));
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int t = 0; t < MAXT; ++t) {
-            if (t < nt) {
-                const int col = t * 8 + 2 * tg;
-                if (row < n && col < n) store(row, col, acc[t][0]);
-                if (row < n && col + 1 < n) store(row, col + 1, acc[t][1]);
+            for (int t = 0; t < MAXT; ++t) {
+                if (tb + t < nt) {
+                    const int col = (tb + t) * 8 + 2 * tg;
+                    if (row < n && col < n) store(row, col, acc[t][0]);
+                    if (row < n && col + 1 < n) store(row, col + 1, acc[t][1]);
+                }
             }
         }
     }

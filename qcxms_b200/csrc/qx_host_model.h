@@ -240,7 +240,7 @@ inline cudaError_t upload_model(HostModel &h) {
     if (err != cudaSuccess) return err;
     char *base = (char *)h.d_blob;
     DevModel &d = h.dev;
-    d.nat = h.nat; d.nsh = h.nsh; d.nao = h.nao; d.ntype = h.ntype; d.ld = h.ld; d.ndim = h.ndim; d.rows8 = h.rows8;
+    d.nat = h.nat; d.nsh = h.nsh; d.nao = h.nao; d.ntype = h.ntype; d.ld = h.ld; d.ndim = h.ndim; d.rows8 = h.rows8; d.mat_in_global = 0;
     d.ntask_int = (int)h.task_int.size(); d.ntask_grad = 0;
     d.nel[0] = h.nel[0]; d.nel[1] = h.nel[1];
 #define PTR(name, T) d.name = (const T *)(base + o_##name)
@@ -262,6 +262,7 @@ inline ScratchLayout make_layout(const HostModel &h) {
     L.S = take(n2); L.H0 = take(n2); L.Dt = take(3 * n2); L.Qt = take(6 * n2);
     L.T = take(std::max(n2, (size_t)(7 * nat + 11 * h.nao)));
     L.P = take(0); L.W = take(0);
+    L.matA = take(h.dev.mat_in_global ? 2 * (size_t)h.rows8 * h.ld + 4 : 0); L.matC = L.matA;
     L.gamma = take((size_t)h.nsh * h.nsh);
     L.dcnp = take(nat * nat); L.dcnp4 = take(nat * nat); L.edisp = take(nat * nat); L.c6 = take(nat * nat); L.dc6 = take(nat * nat);
     L.taskout = take(std::max((size_t)5 * h.task_int.size(), 14 * nat + 4 * nat * nat) + nat * nat / 8 + 2 * nat + 16);

@@ -10,6 +10,7 @@
 
 struct DevModel {
     int nat, nsh, nao, ntype, ld, ndim;  // ld: leading dimension of the shared-memory matrices (== 4 or 12 mod 16)
+    int mat_in_global;                    // 1: the two SCC matrices do not fit shared memory and live in the per-CTA global slab
     int rows8;                            // rows of the shared-memory matrices (zero padded; multiple of 8 when the strip GEMMs apply)
     int ntask_int, ntask_grad;
     double nel[2];                        // alpha / beta electron numbers
@@ -37,5 +38,5 @@ struct DevModel {
 
 // per-CTA scratch in global memory (stays L2 resident); offsets in doubles
 struct ScratchLayout {
-    size_t S, H0, Dt, Qt, T, P, W, gamma, dcnp, dcnp4, edisp, c6, dc6, taskout, br_df, br_u, br_a, br_vec, total;
+    size_t S, H0, Dt, Qt, T, P, W, matA, matC, gamma, dcnp, dcnp4, edisp, c6, dc6, taskout, br_df, br_u, br_a, br_vec, total;
 };

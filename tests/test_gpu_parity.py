@@ -47,3 +47,11 @@ def test_unknown_method_sets_stat_5(qx):
     num, xyz, _ = qx.load_molecule("chloroethanol")
     _, _, _, stat = qx.get_xtb_egrad(num, xyz, 0, 1, 99, 300.0)
     assert stat == 5
+
+
+def test_large_basis_fallback_alkane_c32(qx, oracle):
+    """98 atoms / 194 AOs: the SCC matrices no longer fit shared memory (functional global-memory fallback path)."""
+    num, xyz, _ = qx.load_molecule("alkane_c32")
+    rng = np.random.default_rng(2)
+    x = xyz + 0.03 * rng.standard_normal(xyz.shape)
+    _compare(qx, oracle, num, x, 1, 2, 5000.0)

@@ -71,3 +71,30 @@ num = [SYM[l[0].lower()] for l in lines]
 xyz = (np.array([[float(v) for v in l[1:]] for l in lines]) * AATOAU)
 out["caffeine"] = dict(num=num, xyz=relax(num, xyz), charge=0, source="standard 3-D structure relaxed with oracle GFN2 (tools/make_molecules.py)")
 json.dump(out, open(os.path.join(os.path.dirname(__file__), "..", "qcxms_b200", "data", "molecules.json"), "w"), indent=1)
+
+
+def alkane(nc):
+    """all-trans n-alkane C_n H_{2n+2} in idealised geometry (bohr): the ~100-atom stand-in of BASELINE config 5."""
+    rcc, rch, th = 1.53 * AATOAU, 1.10 * AATOAU, np.deg2rad(111.6)
+    dx, dz = rcc * np.sin(th / 2), rcc * np.cos(th / 2)
+    num, xyz = [], []
+    cs = [np.array([i * dx, 0.0, (i % 2) * dz]) for i in range(nc)]
+    for i, c in enumerate(cs):
+        num.append(6); xyz.append(c)
+    hy, hz = rch * np.sin(np.deg2rad(109.5) / 2), rch * np.cos(np.deg2rad(109.5) / 2)
+    for i, c in enumerate(cs):
+        sgn = -1.0 if i % 2 == 0 else 1.0
+        for s in (-1.0, 1.0):
+            num.append(1); xyz.append(c + np.array([0.0, s * hy, sgn * hz]))
+    for end, c in ((-1.0, cs[0]), (1.0, cs[-1])):     # terminal hydrogens along the chain direction
+        sgn = 1.0 if (0 if end < 0 else nc - 1) % 2 == 0 else -1.0
+        num.append(1); xyz.append(c + rch * np.array([end * np.sin(th / 2), 0.0, sgn * np.cos(th / 2)]))
+    return num, np.array(xyz)
+
+
+if "--alkane-only" in sys.argv:
+    path = os.path.join(os.path.dirname(__file__), "..", "qcxms_b200", "data", "molecules.json")
+    out = json.load(open(path))
+num, xyz = alkane(32)
+out["alkane_c32"] = dict(num=num, xyz=xyz.tolist(), charge=0, source="idealised all-trans C32H66 (98 atoms, 194 AOs), tools/make_molecules.py")
+json.dump(out, open(os.path.join(os.path.dirname(__file__), "..", "qcxms_b200", "data", "molecules.json"), "w"), indent=1)
