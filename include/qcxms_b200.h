@@ -121,6 +121,40 @@ int qcxms_b200_ensemble_last_timing(qcxms_b200_ensemble_t *h, double *kernel_ms,
  * the caller can hand it to NCCL without a host round trip (may be NULL). */
 int qcxms_b200_ensemble_histogram(qcxms_b200_ensemble_t *h, int nbins, double *bins_host, void **bins_device);
 
+/* ---------------------------------------------------------------------------------------
+ * CID: one ion + collision-gas-atom collision MD per trajectory, replaces cid() (reference src/cid.f90:24-1111;
+ * euler_rotation / rotation_velo src/rotation.f90, eigvec3x3 src/diag3x3.f90, vary_energies src/boxmuller.f90:46-76).
+ * The reference draws 9 uniform random numbers per call with the Fortran intrinsic; here the caller passes them
+ * (rnd[0..2] = a,b,c of euler_rotation; rnd[3..4] = dum,dum2 of vary_energies; rnd[5..8] = f,g,lmin,lpos of the
+ * gas-atom placement), so any RNG can sit on the host side and runs are reproducible.
+ * Supported gases: mono-atomic He / Ne / Ar (gas_z 2, 10, 18); options ConstVelo / MinPot / vScale are off (defaults). */
+typedef struct {
+    int32_t method_id, mchrg;
+    int32_t gas_z;        /* reference gas%IndAtom */
+    int32_t eexact;       /* reference eExact */
+    int32_t manual_dist;  /* reference manual_dist (0: automatic) */
+    int32_t ntot;         /* maximum number of steps, reference ntot = 15000 */
+    double gas_mass;      /* reference gas%mIatom (electron masses) */
+    double tstep;         /* a.u. */
+    double etemp;         /* <= 0: 5000 K (src/cid.f90:293-295) */
+    double elab, ecom;    /* eV; ecom > 0 wins (src/cid.f90:349-353) */
+} qcxms_b200_cid_config_t;
+
+typedef struct {
+    int32_t stopcid, nstep, nfrag, collided, status, scc_iter_total;
+    double velo_cm;       /* out: last centre-of-mass speed of the ion, m/s (reference velo_cm) */
+    double aTlast, ttime, epot;
+    double direc[3];
+} qcxms_b200_cid_result_t;
+
+/* One collision (index icoll >= 1) for ntraj ions of nuc atoms.  In/out arrays carry a leading [ntraj] axis:
+ * xyz, velo [ntraj][nuc][3] (in: ion before the collision; out: after), rnd [ntraj][9], velo_cm [ntraj] (in for icoll > 1),
+ * direc [ntraj][3] (in for icoll > 1, out for icoll == 1), collided [ntraj] (the reference's SAVEd flag, in/out),
+ * grad [ntraj][nuc][3], achrg [ntraj][nuc], axyz [ntraj][nuc][3], list [ntraj][nuc], res [ntraj]. */
+int qcxms_b200_cid_batch(const qcxms_b200_cid_config_t *cfg, int ntraj, int nuc, const int32_t *num, const double *mass, int icoll,
+                         double *xyz, double *velo, const double *rnd, const double *velo_cm, double *direc, int32_t *collided,
+                         double *grad, double *achrg, double *axyz, int32_t *list, qcxms_b200_cid_result_t *res, int device);
+
 const char *qcxms_b200_last_error(void);
 const char *qcxms_b200_version(void);
 

@@ -285,3 +285,331 @@ int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat,
     free(avchrg); free(avxyz);
     return 0;
 }
+
+/* ======================================================================================== CID
+ * reference src/diag3x3.f90:85-260 (analytic eigen-decomposition of a symmetric 3x3 matrix; Fortran a(i,j) == a[i-1][j-1]) */
+static void eigval3x3(double a[3][3], double w[3]) {
+    const double twothirdpi = 8.0 * atan(1.0) / 3.0;
+    double r = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+    double q = (a[0][0] + a[1][1] + a[2][2]) / 3.0;
+    w[0] = a[0][0] - q; w[1] = a[1][1] - q; w[2] = a[2][2] - q;
+    double p = sqrt((w[0] * w[0] + w[1] * w[1] + w[2] * w[2] + 2 * r) / 6.0);
+    r = (w[0] * (w[1] * w[2] - a[1][2] * a[1][2]) - a[0][1] * (a[0][1] * w[2] - a[1][2] * a[0][2]) +
+         a[0][2] * (a[0][1] * a[1][2] - w[1] * a[0][2])) / (p * p * p) * 0.5;
+    if (r <= -1.0) r = 0.5 * twothirdpi;
+    else if (r >= 1.0) r = 0.0;
+    else r = acos(r) / 3.0;
+    w[2] = q + 2 * p * cos(r);
+    w[0] = q + 2 * p * cos(r + twothirdpi);
+    w[1] = 3 * q - w[0] - w[2];
+}
+
+void md_oracle_eigvec3x3(double a[3][3], double w[3], double q[3][3]) {
+    const double eps = 2.220446049250313e-16;
+    double norm, n1, n2, n3, precon;
+    int i;
+    w[0] = fmax(fabs(a[0][0]), fabs(a[0][1]));
+    w[1] = fmax(fabs(a[0][2]), fabs(a[1][1]));
+    w[2] = fmax(fabs(a[1][2]), fabs(a[2][2]));
+    precon = fmax(w[0], fmax(w[1], w[2]));
+    if (precon < eps) {
+        w[0] = w[1] = w[2] = 0.0;
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) q[r][c] = r == c;
+        return;
+    }
+    norm = 1.0 / precon;
+    a[0][0] *= norm; a[0][1] *= norm; a[1][1] *= norm; a[0][2] *= norm; a[1][2] *= norm; a[2][2] *= norm;
+    eigval3x3(a, w);
+    a[0][0] -= w[0]; a[1][1] -= w[0]; a[2][2] -= w[0];
+    q[0][0] = a[0][1] * a[1][2] - a[0][2] * a[1][1];
+    q[1][0] = a[0][2] * a[0][1] - a[0][0] * a[1][2];
+    q[2][0] = a[0][0] * a[1][1] - a[0][1] * a[0][1];
+    q[0][1] = a[0][1] * a[2][2] - a[0][2] * a[1][2];
+    q[1][1] = a[0][2] * a[0][2] - a[0][0] * a[2][2];
+    q[2][1] = a[0][0] * a[1][2] - a[0][1] * a[0][2];
+    q[0][2] = a[1][1] * a[2][2] - a[1][2] * a[1][2];
+    q[1][2] = a[1][2] * a[0][2] - a[0][1] * a[2][2];
+    q[2][2] = a[0][1] * a[1][2] - a[1][1] * a[0][2];
+    n1 = q[0][0] * q[0][0] + q[1][0] * q[1][0] + q[2][0] * q[2][0];
+    n2 = q[0][1] * q[0][1] + q[1][1] * q[1][1] + q[2][1] * q[2][1];
+    n3 = q[0][2] * q[0][2] + q[1][2] * q[1][2] + q[2][2] * q[2][2];
+    norm = n1; i = 1;
+    if (n2 > norm) { i = 2; norm = n1; }   /* sic: the reference keeps norm = n1 here */
+    if (n3 > norm) i = 3;
+    if (i == 1) { norm = sqrt(1.0 / n1); q[0][0] *= norm; q[1][0] *= norm; q[2][0] *= norm; }
+    else if (i == 2) { norm = sqrt(1.0 / n2); q[0][0] = q[0][1] * norm; q[1][0] = q[1][1] * norm; q[2][0] = q[2][1] * norm; }
+    else { norm = sqrt(1.0 / n3); q[0][0] = q[0][2] * norm; q[1][0] = q[1][2] * norm; q[2][0] = q[2][2] * norm; }
+    if (fabs(q[0][0]) > fabs(q[1][0])) {
+        norm = sqrt(1.0 / (q[0][0] * q[0][0] + q[2][0] * q[2][0]));
+        q[0][1] = -q[2][0] * norm; q[1][1] = 0.0; q[2][1] = +q[0][0] * norm;
+    } else {
+        norm = sqrt(1.0 / (q[1][0] * q[1][0] + q[2][0] * q[2][0]));
+        q[0][1] = 0.0; q[1][1] = +q[2][0] * norm; q[2][1] = -q[1][0] * norm;
+    }
+    q[0][2] = q[1][0] * q[2][1] - q[2][0] * q[1][1];
+    q[1][2] = q[2][0] * q[0][1] - q[0][0] * q[2][1];
+    q[2][2] = q[0][0] * q[1][1] - q[1][0] * q[0][1];
+    a[0][0] += w[0]; a[1][1] += w[0]; a[2][2] += w[0];
+    n1 = a[0][0] * q[0][1] + a[0][1] * q[1][1] + a[0][2] * q[2][1];
+    n2 = a[0][1] * q[0][1] + a[1][1] * q[1][1] + a[1][2] * q[2][1];
+    n3 = a[0][2] * q[0][1] + a[1][2] * q[1][1] + a[2][2] * q[2][1];
+    a[2][2] = a[0][2] * q[0][2] + a[1][2] * q[1][2] + a[2][2] * q[2][2];
+    a[0][2] = a[0][0] * q[0][2] + a[0][1] * q[1][2] + a[0][2] * q[2][2];
+    a[1][2] = a[0][1] * q[0][2] + a[1][1] * q[1][2] + a[1][2] * q[2][2];
+    n1 = q[0][1] * n1 + q[1][1] * n2 + q[2][1] * n3 - w[1];
+    n2 = q[0][1] * a[0][2] + q[1][1] * a[1][2] + q[2][1] * a[2][2];
+    n3 = q[0][2] * a[0][2] + q[1][2] * a[1][2] + q[2][2] * a[2][2] - w[1];
+    if (fabs(n1) >= fabs(n3)) {
+        norm = fmax(fabs(n1), fabs(n2));
+        if (norm > eps) {
+            if (fabs(n1) >= fabs(n2)) { n2 = n2 / n1; n1 = sqrt(1.0 / (1.0 + n2 * n2)); n2 = n2 * n1; }
+            else { n1 = n1 / n2; n2 = sqrt(1.0 / (1.0 + n1 * n1)); n1 = n1 * n2; }
+            q[0][1] = n2 * q[0][1] - n1 * q[0][2];
+            q[1][1] = n2 * q[1][1] - n1 * q[1][2];
+            q[2][1] = n2 * q[2][1] - n1 * q[2][2];
+        }
+    } else {
+        norm = fmax(fabs(n3), fabs(n2));
+        if (norm > eps) {
+            if (fabs(n3) >= fabs(n2)) { n2 = n2 / n3; n3 = sqrt(1.0 / (1.0 + n2 * n2)); n2 = n2 * n3; }
+            else { n3 = n3 / n2; n2 = sqrt(1.0 / (1.0 + n3 * n3)); n3 = n3 * n2; }
+            q[0][1] = n3 * q[0][1] - n2 * q[0][2];
+            q[1][1] = n3 * q[1][1] - n2 * q[1][2];
+            q[2][1] = n3 * q[2][1] - n2 * q[2][2];
+        }
+    }
+    q[0][2] = q[1][0] * q[2][1] - q[2][0] * q[1][1];
+    q[1][2] = q[2][0] * q[0][1] - q[0][0] * q[2][1];
+    q[2][2] = q[0][0] * q[1][1] - q[1][0] * q[0][1];
+    w[0] *= precon; w[1] *= precon; w[2] *= precon;
+}
+
+/* reference src/rotation.f90:11-88: R = R_alpha R_beta R_gamma applied to coordinates and velocities */
+void md_oracle_euler_rotation(int nuc, double *xyz, double *velo, double a, double b, double c) {
+    const double pi = 3.14159265358979323846264338327950288;
+    double al = a * 2 * pi, be = b * 2 * pi, ga = c * pi;
+    /* Fortran reshape fills column-major: rot(i,j) below is the mathematical element (row i, column j) */
+    double ra[3][3] = {{1, 0, 0}, {0, cos(al), -sin(al)}, {0, sin(al), cos(al)}};
+    double rb[3][3] = {{cos(be), 0, sin(be)}, {0, 1, 0}, {-sin(be), 0, cos(be)}};
+    double rg[3][3] = {{cos(ga), -sin(ga), 0}, {sin(ga), cos(ga), 0}, {0, 0, 1}};
+    double d[3][3], R[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { d[i][j] = 0; for (int k = 0; k < 3; ++k) d[i][j] += ra[i][k] * rb[k][j]; }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { R[i][j] = 0; for (int k = 0; k < 3; ++k) R[i][j] += d[i][k] * rg[k][j]; }
+    for (int i = 0; i < nuc; ++i) {
+        double r[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, v[3] = {velo[3 * i], velo[3 * i + 1], velo[3 * i + 2]};
+        for (int k = 0; k < 3; ++k) {
+            xyz[3 * i + k] = R[k][0] * r[0] + R[k][1] * r[1] + R[k][2] * r[2];
+            velo[3 * i + k] = R[k][0] * v[0] + R[k][1] * v[1] + R[k][2] * v[2];
+        }
+    }
+}
+
+/* reference src/rotation.f90:92-182 */
+void md_oracle_rotation_velo(const double *xyz, int nuc, const double *mass, const double *velo, double *velo_rot, double *e_rot) {
+    double mat[3][3] = {{0}}, ev[3], evec[3][3], w_new[3], om[3][3], Ekin, Tinit;
+    for (int i = 0; i < nuc; ++i) {
+        double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2], m = mass[i];
+        mat[0][0] += (y * y + z * z) * m; mat[1][0] += (-x * y) * m; mat[2][0] += (-x * z) * m;
+        mat[0][1] += (-y * x) * m; mat[1][1] += (x * x + z * z) * m; mat[2][1] += (-y * z) * m;
+        mat[0][2] += (-z * x) * m; mat[1][2] += (-z * y) * m; mat[2][2] += (x * x + y * y) * m;
+    }
+    md_oracle_eigvec3x3(mat, ev, evec);
+    md_oracle_ekinet(nuc, velo, mass, &Ekin, &Tinit);
+    for (int k = 0; k < 3; ++k) w_new[k] = sqrt((QC_KB * Tinit) / ev[k]);
+    for (int i = 0; i < 3; ++i) for (int r = 0; r < 3; ++r) om[r][i] = evec[r][i] * w_new[i];
+    for (int i = 0; i < nuc; ++i) {
+        double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2], vx = 0, vy = 0, vz = 0;
+        for (int j = 0; j < 3; ++j) {
+            vx = vx + (om[1][j] * z - om[2][j] * y);
+            vy = vy + (om[2][j] * x - om[0][j] * z);
+            vz = vz + (om[0][j] * y - om[1][j] * x);
+        }
+        velo_rot[3 * i] = vx; velo_rot[3 * i + 1] = vy; velo_rot[3 * i + 2] = vz;
+    }
+    double e = 0.0;
+    for (int k = 0; k < 3; ++k) e = e + (0.5 * ev[k] * (w_new[k] * w_new[k]));
+    if (e_rot) *e_rot = e;
+}
+
+/* reference src/boxmuller.f90:46-76 */
+double md_oracle_vary_energies(double e_in, double e_distr, double dum, double dum2) {
+    const double pi = 3.14159265358979323846264338327950288;
+    double sigma = e_in * e_distr;
+    double z0 = sqrt(-2.0 * log(dum)) * cos(2.0 * pi * dum2), z1 = sqrt(-2.0 * log(dum)) * sin(2.0 * pi * dum2);
+    return dum > 0.5 ? z0 * sigma + e_in : z1 * sigma + e_in;
+}
+
+/* number of atoms per fragment as avg_frag_struc counts them (reference src/analyse.f90:452-502) */
+static void natf_count(int nuc, const int32_t *list, int nfrag, int *natf) {
+    for (int i = 0; i < 10; ++i) natf[i] = 0;
+    for (int i = 0; i < nuc; ++i) if (list[i] >= 1 && list[i] <= nfrag && list[i] <= 10) natf[list[i] - 1] += 1;
+}
+
+/* reference src/cid.f90:24-1111 for mono-atomic gases, ConstVelo / MinPot / vScale off */
+int md_oracle_cid(const qcxms_b200_cid_config_t *cfg, int nuc, const int32_t *iat, const double *mass, int icoll, double *xyz,
+                  double *velo, const double *rnd, double velo_cm_in, double *direc, int32_t *collided_io, double *grad, double *achrg,
+                  double *axyz, int32_t *list, qcxms_b200_cid_result_t *res) {
+    const double time_step = cfg->tstep, autofs = 1.0 / QC_FSTOAU;
+    const int nuc0 = nuc + 1, dumpdist = 10, dumpavg = 50, cnt_steps = 50;
+    int ntot = cfg->ntot > 0 ? cfg->ntot : 15000;
+    double etemp = cfg->etemp <= 0 ? 5000.0 : cfg->etemp;
+    int add_steps = 0;
+    if (nuc > 10) add_steps = (nuc / 10) * 500;
+    if (nuc >= 40) add_steps = (nuc / 10) * 1000;
+    int collided = *collided_io, fragmented = 0, count_average = 0, check_fragmented = 1, cnt = 0, nfrag = 1, scc_total = 0, niter = 0;
+    double cm[3], old_cm[3];
+    memset(res, 0, sizeof *res);
+    double *xyz0 = calloc(3 * nuc0, sizeof(double)), *velo0 = calloc(3 * nuc0, sizeof(double)), *grad0 = calloc(3 * nuc0, sizeof(double));
+    double *mass0 = calloc(nuc0, sizeof(double)), *achrg0 = calloc(nuc0, sizeof(double)), *velo_rot = calloc(3 * nuc, sizeof(double));
+    double *avxyz = calloc(3 * nuc, sizeof(double)), *avxyz2 = calloc(3 * nuc, sizeof(double)), *store = calloc(3 * nuc, sizeof(double));
+    int32_t *iat0 = calloc(nuc0, sizeof(int32_t));
+    int natf[10], save_natf[10] = {0};
+
+    if (icoll == 1) {
+        md_oracle_center_of_mass(nuc, mass, xyz, cm);
+        for (int i = 0; i < nuc; ++i) for (int k = 0; k < 3; ++k) xyz[3 * i + k] -= cm[k];
+        md_oracle_euler_rotation(nuc, xyz, velo, rnd[0], rnd[1], rnd[2]);
+        md_oracle_rotation_velo(xyz, nuc, mass, velo, velo_rot, NULL);
+        for (int i = 0; i < 3 * nuc; ++i) velo[i] = velo[i] + velo_rot[i];
+    }
+    double summass = 0.0;
+    for (int i = 0; i < nuc; ++i) summass = summass + mass[i];
+    double beta = cfg->gas_mass / (cfg->gas_mass + summass), E_velo, fasti = 0.0;
+    if (icoll == 1) {
+        double Eimpact = cfg->ecom > 0.0 ? cfg->ecom / beta : cfg->elab;
+        if (!cfg->eexact) E_velo = md_oracle_vary_energies(Eimpact, 0.1, rnd[3], rnd[4]) * QC_EVTOAU;
+        else E_velo = Eimpact * QC_EVTOAU;
+    } else
+        E_velo = 0.5 * summass * ((velo_cm_in * QC_MSTOAU) * (velo_cm_in * QC_MSTOAU));
+    double Ekin, Tinit, T;
+    md_oracle_ekinet(nuc, velo, mass, &Ekin, &Tinit);
+    if (icoll == 1) fasti = sqrt(2 * E_velo / summass);
+    md_oracle_center_of_mass(nuc, mass, xyz, cm);
+    double f = rnd[5], g = rnd[6], lmin = rnd[7], lpos = rnd[8];
+    double lowestx = 1.7976931348623157e308, lowesty = lowestx, highestx = -lowestx, highesty = -lowestx;
+    for (int i = 0; i < nuc; ++i) {
+        double x = xyz[3 * i], y = xyz[3 * i + 1];
+        if (x < lowestx) lowestx = x;
+        if (x > highestx) highestx = x;
+        if (y < lowesty) lowesty = y;
+        if (y > highesty) highesty = y;
+    }
+    double diff1 = lmin < 0.5 ? lowesty * f : highesty * f;
+    double diff2 = lpos < 0.5 ? lowestx * g : highestx * g;
+    int step_dist = cfg->manual_dist == 0 ? (2 * nuc * 10 > 800 ? 800 : 2 * nuc * 10) : cfg->manual_dist;
+    double start_dist, xyzAr[3], scale_velo[3];
+    if (icoll == 1) {
+        start_dist = fasti * (2 * time_step);
+        start_dist = step_dist * start_dist * QC_AUTOAA;   /* Angstrom value added to bohr coordinates as is (sic) */
+        if (start_dist < 10.0) start_dist = 10.0;
+        double xs[3] = {cm[0], cm[1], cm[2] + start_dist};
+        for (int k = 0; k < 3; ++k) direc[k] = xs[k];
+        for (int k = 0; k < 3; ++k) direc[k] = direc[k] / sqrt(direc[0] * direc[0] + direc[1] * direc[1] + direc[2] * direc[2]);  /* sic: sequential */
+        xyzAr[0] = xs[0] + diff2 * 0.8; xyzAr[1] = xs[1] + diff1 * 0.8; xyzAr[2] = xs[2];
+        for (int k = 0; k < 3; ++k) scale_velo[k] = direc[k] * fasti;
+    } else {
+        start_dist = (velo_cm_in * QC_MSTOAU) * (2 * time_step);
+        start_dist = step_dist * start_dist * QC_AUTOAA;
+        if (start_dist < 17.0) start_dist = 17.0;
+        for (int i = 0; i < nuc; ++i) for (int k = 0; k < 3; ++k) xyz[3 * i + k] -= cm[k];
+        xyzAr[0] = cm[0] + direc[0] * start_dist + diff2 * 0.7;
+        xyzAr[1] = cm[1] + direc[1] * start_dist + diff1 * 0.7;
+        xyzAr[2] = cm[2] + direc[2] * start_dist;
+        scale_velo[0] = scale_velo[1] = scale_velo[2] = 0.0;
+    }
+    for (int k = 0; k < 3; ++k) old_cm[k] = cm[k];
+    md_oracle_center_of_mass(nuc, mass, xyz, cm);
+    for (int i = 0; i < nuc; ++i) {
+        for (int k = 0; k < 3; ++k) { velo0[3 * i + k] = velo[3 * i + k] + scale_velo[k]; xyz0[3 * i + k] = xyz[3 * i + k]; }
+        mass0[i] = mass[i]; iat0[i] = iat[i];
+    }
+    for (int k = 0; k < 3; ++k) { xyz0[3 * nuc + k] = xyzAr[k]; velo0[3 * nuc + k] = 0.0; }
+    mass0[nuc] = cfg->gas_mass; iat0[nuc] = cfg->gas_z;
+
+    /* iniqm (one single point whose result is only checked) + initial egrad */
+    double E;
+    int gradfail = md_oracle_egrad(nuc0, xyz0, iat0, cfg->mchrg, etemp, cfg->method_id, &E, grad0, achrg0, &niter);
+    scc_total += niter;
+    if (gradfail) { res->stopcid = 1; res->status = 2; goto done; }
+
+    {
+        int nstep = 0, m = 0, step_counter = 0, distance_dump = 0, xyzavg_dump = 0, total_steps = ntot;
+        double Tav = 0.0, new_velo = 0.0, new_dist, lowestCOM, ttime = 0.0, aTlast = 0.0, avgT = 0.0, ke;
+        md_oracle_center_of_mass(nuc, mass, xyz, cm);
+        {
+            double d0 = xyz0[3 * nuc] - cm[0], d1 = xyz0[3 * nuc + 1] - cm[1], d2 = xyz0[3 * nuc + 2] - cm[2];
+            new_dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        }
+        lowestCOM = new_dist;
+        for (;;) {
+            nstep = nstep + 1;
+            if (xyzavg_dump == dumpavg) { xyzavg_dump = 0; memset(avxyz, 0, 3 * nuc * sizeof(double)); }
+            ttime = ttime + time_step * autofs;
+            distance_dump += 1; xyzavg_dump += 1;
+            md_oracle_leapfrog(nuc0, grad0, mass0, time_step, xyz0, velo0, &ke);
+            gradfail = md_oracle_egrad(nuc0, xyz0, iat0, cfg->mchrg, etemp, cfg->method_id, &E, grad0, achrg0, &niter);
+            scc_total += niter;
+            if (gradfail) { res->stopcid = 1; break; }
+            md_oracle_center_of_mass(nuc, mass0, xyz0, cm);
+            double dcm[3] = {cm[0] - old_cm[0], cm[1] - old_cm[1], cm[2] - old_cm[2]};
+            double cm_out = sqrt(dcm[0] * dcm[0] + dcm[1] * dcm[1] + dcm[2] * dcm[2]);
+            for (int k = 0; k < 3; ++k) old_cm[k] = cm[k];
+            new_velo = nstep != 1 ? (cm_out / time_step) / QC_MSTOAU : 0.0;
+            md_oracle_ekinet(nuc, velo0, mass0, &Ekin, &T);
+            E_velo = 0.5 * summass * ((new_velo * QC_MSTOAU) * (new_velo * QC_MSTOAU));
+            double new_temp = (2 * (Ekin - E_velo)) / (3 * QC_KB * nuc);
+            if (nstep == 1) new_temp = Tinit;
+            Tav = Tav + new_temp; m = m + 1; avgT = Tav / m;
+            md_oracle_fragment_structure(nuc, iat0, xyz0, 3.0, 1, 0, list);
+            md_oracle_fragmass(nuc, iat0, list, mass0, NULL, &nfrag, NULL, NULL);
+            for (int i = 0; i < 3 * nuc; ++i) avxyz[i] += xyz0[i];
+            if (nfrag > check_fragmented) { count_average = 1; check_fragmented = nfrag; }
+            if (nfrag < check_fragmented && count_average) {
+                cnt = 0; memset(avxyz2, 0, 3 * nuc * sizeof(double)); memset(store, 0, 3 * nuc * sizeof(double));
+                count_average = 0; check_fragmented = 1;
+            }
+            if (count_average) {
+                cnt = cnt + 1;
+                for (int i = 0; i < 3 * nuc; ++i) { avxyz2[i] += xyz0[i]; store[i] = avxyz2[i] / cnt; }
+                natf_count(nuc, list, nfrag, natf);
+                for (int i = 0; i < nfrag && i < 10; ++i) {
+                    if (cnt == 1) save_natf[i] = natf[i];
+                    if (natf[i] != save_natf[i]) {
+                        cnt = 0; memset(store, 0, 3 * nuc * sizeof(double)); memset(avxyz2, 0, 3 * nuc * sizeof(double));
+                        break;
+                    }
+                }
+                if (cnt == cnt_steps) {
+                    for (int i = 0; i < 3 * nuc; ++i) store[i] = avxyz2[i] / cnt;
+                    memset(avxyz2, 0, 3 * nuc * sizeof(double)); cnt = 0; count_average = 0;
+                }
+            }
+            aTlast = avgT;
+            if (distance_dump == dumpdist) {
+                distance_dump = 0;
+                md_oracle_center_of_mass(nuc, mass0, xyz0, cm);
+                double d0 = xyz0[3 * nuc] - cm[0], d1 = xyz0[3 * nuc + 1] - cm[1], d2 = xyz0[3 * nuc + 2] - cm[2];
+                new_dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                if (new_dist < lowestCOM) lowestCOM = new_dist;
+                if (lowestCOM < new_dist) step_counter = step_counter + 1; else step_counter = 0;
+                if (step_counter == 5) {
+                    total_steps = nstep + (int)lround(800.0 * (2 * time_step * autofs));
+                    collided = 1; Tav = 0; m = 0;
+                }
+            }
+            if (nfrag > 1 && collided && !fragmented) { total_steps = nstep + add_steps; fragmented = 1; }
+            if (nstep >= total_steps) { res->stopcid = 0; break; }
+        }
+        for (int i = 0; i < 3 * nuc; ++i) { xyz[i] = xyz0[i]; velo[i] = velo0[i]; grad[i] = grad0[i]; }
+        for (int i = 0; i < nuc; ++i) achrg[i] = achrg0[i];
+        for (int i = 0; i < 3 * nuc; ++i) axyz[i] = check_fragmented > 1 ? store[i] : avxyz[i] / xyzavg_dump;
+        res->nstep = nstep; res->nfrag = nfrag; res->velo_cm = new_velo; res->aTlast = aTlast; res->ttime = ttime; res->epot = E;
+        res->status = 1;
+    }
+done:
+    res->collided = collided; res->scc_iter_total = scc_total;
+    for (int k = 0; k < 3; ++k) res->direc[k] = direc[k];
+    *collided_io = collided;
+    free(xyz0); free(velo0); free(grad0); free(mass0); free(achrg0); free(velo_rot); free(avxyz); free(avxyz2); free(store); free(iat0);
+    return 0;
+}

@@ -27,6 +27,15 @@ int md_oracle_egrad(int nuc, const double *xyz, const int32_t *iat, int mchrg, d
 int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
                  const double *velof, double eimp, double tadd, int max_steps, double *grad, int32_t *list, double *achrg, double *axyz,
                  qcxms_b200_md_result_t *res);
+/* cid() pieces (src/rotation.f90, src/diag3x3.f90, src/boxmuller.f90, src/cid.f90) */
+void md_oracle_eigvec3x3(double a[3][3], double w[3], double q[3][3]);
+void md_oracle_euler_rotation(int nuc, double *xyz, double *velo, double a, double b, double c);
+void md_oracle_rotation_velo(const double *xyz, int nuc, const double *mass, const double *velo, double *velo_rot, double *e_rot);
+double md_oracle_vary_energies(double e_in, double e_distr, double dum, double dum2);
+/* one collision for one ion; arrays as in qcxms_b200_cid_batch without the leading trajectory axis */
+int md_oracle_cid(const qcxms_b200_cid_config_t *cfg, int nuc, const int32_t *iat, const double *mass, int icoll, double *xyz,
+                  double *velo, const double *rnd, double velo_cm_in, double *direc, int32_t *collided, double *grad, double *achrg,
+                  double *axyz, int32_t *list, qcxms_b200_cid_result_t *res);
 #ifdef __cplusplus
 }
 #endif

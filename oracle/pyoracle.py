@@ -209,3 +209,64 @@ def md(num, mass, xyz, velo, velof, eimp, tadd, mchrg=1, tstep_fs=0.5, nmax=1000
     for k, _ in MdResult._fields_:
         out[k] = getattr(res, k)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ CID (md_oracle.c)
+def eigvec3x3(a):
+    a = np.array(a, dtype=np.float64).reshape(3, 3)
+    w, q = np.zeros(3), np.zeros((3, 3))
+    f = lib().md_oracle_eigvec3x3
+    f.argtypes = [C.POINTER(C.c_double)] * 3
+    f.restype = None
+    f(_dp(a), _dp(w), _dp(q))
+    return w, q
+
+
+def euler_rotation(xyz, velo, a, b, c):
+    xyz = np.array(xyz, dtype=np.float64); velo = np.array(velo, dtype=np.float64)
+    f = lib().md_oracle_euler_rotation
+    f.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double]
+    f.restype = None
+    f(len(xyz), _dp(xyz), _dp(velo), float(a), float(b), float(c))
+    return xyz, velo
+
+
+def rotation_velo(xyz, mass, velo):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64); velo = np.ascontiguousarray(velo, dtype=np.float64)
+    mass = np.ascontiguousarray(mass, dtype=np.float64)
+    out, e = np.zeros_like(xyz), C.c_double(0.0)
+    f = lib().md_oracle_rotation_velo
+    f.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    f.restype = None
+    f(_dp(xyz), len(xyz), _dp(mass), _dp(velo), _dp(out), C.byref(e))
+    return out, e.value
+
+
+def vary_energies(e_in, e_distr, dum, dum2):
+    f = lib().md_oracle_vary_energies
+    f.argtypes = [C.c_double] * 4
+    f.restype = C.c_double
+    return f(float(e_in), float(e_distr), float(dum), float(dum2))
+
+
+def cid(cfg, num, mass, icoll, xyz, velo, rnd, velo_cm=0.0, direc=None, collided=0):
+    """cid() of the reference for one ion (mono-atomic gas); cfg is a qcxms_b200 CidConfig (same C layout)."""
+    from qcxms_b200.api import CidResult
+    num = np.ascontiguousarray(num, dtype=np.int32); nuc = len(num)
+    mass = np.ascontiguousarray(mass, dtype=np.float64)
+    xyz = np.array(xyz, dtype=np.float64).reshape(nuc, 3); velo = np.array(velo, dtype=np.float64).reshape(nuc, 3)
+    rnd = np.ascontiguousarray(rnd, dtype=np.float64)
+    direc = np.zeros(3) if direc is None else np.array(direc, dtype=np.float64)
+    coll = C.c_int32(int(collided))
+    grad, achrg, axyz, lst = np.zeros((nuc, 3)), np.zeros(nuc), np.zeros((nuc, 3)), np.zeros(nuc, dtype=np.int32)
+    res = CidResult()
+    f = lib().md_oracle_cid
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    f.argtypes = [C.c_void_p, C.c_int, ip, dp, C.c_int, dp, dp, dp, C.c_double, dp, ip, dp, dp, dp, ip, C.c_void_p]
+    f(C.byref(cfg), nuc, _ip(num), _dp(mass), int(icoll), _dp(xyz), _dp(velo), _dp(rnd), float(velo_cm), _dp(direc), C.byref(coll),
+      _dp(grad), _dp(achrg), _dp(axyz), _ip(lst), C.byref(res))
+    out = dict(xyz=xyz, velo=velo, grad=grad, achrg=achrg, axyz=axyz, list=lst, direc=direc, collided=coll.value)
+    for k, t in CidResult._fields_:
+        if k != "direc":
+            out[k] = getattr(res, k)
+    return out

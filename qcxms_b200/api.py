@@ -38,7 +38,24 @@ class MdResult(C.Structure):
         [(k, C.c_double) for k in ("Tav", "Epav", "Ekav", "aTlast", "dtime", "ttime", "Epot", "Ekin")]
 
 
-EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_egrad_batch", "qcxms_b200_fragment_structure", "qcxms_b200_ensemble_create",
+class CidConfig(C.Structure):
+    """qcxms_b200_cid_config_t"""
+    _fields_ = [("method_id", C.c_int32), ("mchrg", C.c_int32), ("gas_z", C.c_int32), ("eexact", C.c_int32),
+                ("manual_dist", C.c_int32), ("ntot", C.c_int32), ("gas_mass", C.c_double), ("tstep", C.c_double),
+                ("etemp", C.c_double), ("elab", C.c_double), ("ecom", C.c_double)]
+
+
+class CidResult(C.Structure):
+    """qcxms_b200_cid_result_t"""
+    _fields_ = [("stopcid", C.c_int32), ("nstep", C.c_int32), ("nfrag", C.c_int32), ("collided", C.c_int32),
+                ("status", C.c_int32), ("scc_iter_total", C.c_int32), ("velo_cm", C.c_double), ("aTlast", C.c_double),
+                ("ttime", C.c_double), ("epot", C.c_double), ("direc", C.c_double * 3)]
+
+
+# collision gases of the reference (src/input.f90:512-558): Z, mass / amu, radius / bohr
+GASES = {"he": (2, 4.002, 2.64560263), "ne": (10, 20.18, 2.91016289), "ar": (18, 39.948, 3.55266638)}
+
+EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_cid_batch", "qcxms_b200_egrad_batch", "qcxms_b200_fragment_structure", "qcxms_b200_ensemble_create",
            "qcxms_b200_ensemble_destroy", "qcxms_b200_ensemble_set_trajectory", "qcxms_b200_ensemble_set_all",
            "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_get_all", "qcxms_b200_ensemble_last_timing",
            "qcxms_b200_ensemble_histogram", "qcxms_b200_last_error", "qcxms_b200_version"]
@@ -65,6 +82,8 @@ def lib():
         L.qcxms_b200_ensemble_get_all.argtypes = [C.c_void_p, dp, dp, dp, ip, dp, dp, C.POINTER(MdResult)]
         L.qcxms_b200_ensemble_last_timing.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.qcxms_b200_ensemble_histogram.argtypes = [C.c_void_p, C.c_int, dp, C.POINTER(C.c_void_p)]
+        L.qcxms_b200_cid_batch.argtypes = [C.POINTER(CidConfig), C.c_int, C.c_int, ip, dp, C.c_int, dp, dp, dp, dp, dp, ip, dp, dp, dp, ip,
+                                           C.POINTER(CidResult), C.c_int]
         L.qcxms_b200_last_error.restype = C.c_char_p
         L.qcxms_b200_version.restype = C.c_char_p
         _LIB = L
@@ -201,6 +220,39 @@ class Ensemble:
         dev = C.c_void_p()
         _check(lib().qcxms_b200_ensemble_histogram(self._h, int(nbins), _dp(bins), C.byref(dev)))
         return bins, dev.value
+
+
+def cid_config(mchrg=1, gas="ar", tstep_fs=0.5, elab=40.0, ecom=0.0, eexact=False, manual_dist=0, ntot=15000, etemp=0.0, method=gfn2_xtb):
+    z, m, _ = GASES[gas.lower()]
+    return CidConfig(int(method), int(mchrg), z, int(bool(eexact)), int(manual_dist), int(ntot), m * AMUTOAU, float(tstep_fs) * FSTOAU,
+                     float(etemp), float(elab), float(ecom))
+
+
+def cid(cfg, num, mass, icoll, xyz, velo, rnd, velo_cm=None, direc=None, collided=None, device=0):
+    """One collision of cid() (reference src/cid.f90:24-28) for a batch of ions xyz[ntraj, nuc, 3].
+    rnd[ntraj, 9] are the uniform random numbers the reference draws inside the call.  Returns a dict of arrays
+    (xyz, velo, grad, achrg, axyz, list, direc, collided) + the per-trajectory result fields."""
+    num = np.ascontiguousarray(num, dtype=np.int32)
+    nuc = len(num)
+    mass = np.ascontiguousarray(mass, dtype=np.float64)
+    xyz = np.array(xyz, dtype=np.float64).reshape(-1, nuc, 3)
+    nt = xyz.shape[0]
+    velo = np.array(velo, dtype=np.float64).reshape(nt, nuc, 3)
+    rnd = np.ascontiguousarray(rnd, dtype=np.float64).reshape(nt, 9)
+    vcm = None if velo_cm is None else np.ascontiguousarray(velo_cm, dtype=np.float64).reshape(nt)
+    direc = np.zeros((nt, 3)) if direc is None else np.array(direc, dtype=np.float64).reshape(nt, 3)
+    collided = np.zeros(nt, dtype=np.int32) if collided is None else np.array(collided, dtype=np.int32).reshape(nt)
+    grad, achrg, axyz = np.zeros((nt, nuc, 3)), np.zeros((nt, nuc)), np.zeros((nt, nuc, 3))
+    lst = np.zeros((nt, nuc), dtype=np.int32)
+    res = (CidResult * nt)()
+    _check(lib().qcxms_b200_cid_batch(C.byref(cfg), nt, nuc, _ip(num), _dp(mass), int(icoll), _dp(xyz), _dp(velo), _dp(rnd),
+                                      None if vcm is None else _dp(vcm), _dp(direc), _ip(collided), _dp(grad), _dp(achrg), _dp(axyz), _ip(lst),
+                                      res, int(device)))
+    out = dict(xyz=xyz, velo=velo, grad=grad, achrg=achrg, axyz=axyz, list=lst, direc=direc, collided=collided)
+    for k, t in CidResult._fields_:
+        if k != "direc":
+            out[k] = np.array([getattr(r, k) for r in res])
+    return out
 
 
 def load_molecule(name):

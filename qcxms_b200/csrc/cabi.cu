@@ -13,7 +13,7 @@
 
 #include "../../include/qcxms_b200.h"
 #include "qx_host_model.h"
-#include "qx_md.cuh"
+#include "qx_cid.cuh"
 
 using namespace qx;
 
@@ -259,6 +259,178 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
         }
         __syncthreads();   // every thread's global writes of this sub-chunk are issued ...
         if (threadIdx.x == 0) { __threadfence(); atomicAdd(&progress[t], 1); }   // ... and published before the hand-over
+    }
+}
+
+// ------------------------------------------------------------------------------------ CID (reference src/cid.f90)
+// set-up of one collision + the two single points before the loop (iniqm's is only checked, so one evaluation serves both)
+__global__ void __launch_bounds__(QX_NT, 2) k_cid_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, CidConfig cc, CidState st, int ntraj,
+                                                    int nuc, int icoll, int *queue) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_next;
+    Sm s;
+    double *my = scratch + (size_t)blockIdx.x * L.total;
+    carve(m, smem, s, my + L.matA);
+    const int nuc0 = m.nat;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
+        __syncthreads();
+        const int t = s_next;
+        if (t >= ntraj) break;
+        CidScalars *sc = st.sc + t;
+        double *xyz0 = st.xyz0 + (size_t)t * 3 * nuc0, *velo0 = st.velo0 + (size_t)t * 3 * nuc0;
+        if (threadIdx.x == 0) {
+            double tinit, summass, old_cm[3];
+            cid_setup_thread0(m, cc, nuc, icoll, st.xyz + (size_t)t * 3 * nuc, st.velo + (size_t)t * 3 * nuc, st.rnd + (size_t)t * 9,
+                              st.velo_cm_in ? st.velo_cm_in[t] : 0.0, st.direc + (size_t)t * 3, xyz0, velo0, old_cm, &tinit, &summass);
+            CidScalars z{};
+            z.total_steps = cc.ntot; z.check_fragmented = 1; z.nfrag = 1; z.collided = sc->collided;
+            z.Tinit = tinit; z.summass = summass;
+            for (int k = 0; k < 3; ++k) z.old_cm[k] = old_cm[k];
+            *sc = z;
+            __threadfence_block();
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * nuc0; i += QX_NT) s.xyz[i] = xyz0[i];
+        for (int i = threadIdx.x; i < 3 * nuc; i += QX_NT) { st.avxyz[(size_t)t * 3 * nuc + i] = 0.0; st.avxyz2[(size_t)t * 3 * nuc + i] = 0.0; st.store[(size_t)t * 3 * nuc + i] = 0.0; }
+        for (int i = threadIdx.x; i < nuc; i += QX_NT) st.list[(size_t)t * nuc + i] = 1;
+        __syncthreads();
+        int nit = 0;
+        const double epot = md_egrad(m, s, my, L, cfg, cc.etemp, st.grad0 + (size_t)t * 3 * nuc0, st.achrg0 + (size_t)t * nuc0, &nit);
+        if (threadIdx.x == 0) {
+            sc->scc_total = nit; sc->epot = epot;
+            if (epot == 0.0) { sc->stopcid = 1; sc->status = TRJ_FAILED; }
+            else {
+                sc->status = TRJ_RUNNING;
+                // distance gas atom -- centre of mass of the ion as it was handed in (reference src/cid.f90:733-737)
+                double cm[3];
+                cid_center_of_mass(nuc, m.mass, st.xyz + (size_t)t * 3 * nuc, cm);
+                const double d0 = xyz0[3 * nuc] - cm[0], d1 = xyz0[3 * nuc + 1] - cm[1], d2 = xyz0[3 * nuc + 2] - cm[2];
+                sc->lowestCOM = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            }
+        }
+    }
+}
+
+// up to `chunk` steps of the collision loop (reference src/cid.f90:739-1052) for every running trajectory
+__global__ void __launch_bounds__(QX_NT, 2) k_cid_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, CidConfig cc, CidState st, int ntraj,
+                                                     int nuc, int chunk, int *queue) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_next, s_ops, s_cnt, s_stop;
+    __shared__ CidScalars sc;
+    Sm s;
+    double *my = scratch + (size_t)blockIdx.x * L.total;
+    carve(m, smem, s, my + L.matA);
+    const int nuc0 = m.nat;
+    const double autofs = 1.0 / QC_FSTOAU;
+    int add_steps = 0;
+    if (nuc > 10) add_steps = (nuc / 10) * 500;
+    if (nuc >= 40) add_steps = (nuc / 10) * 1000;
+    enum { OP_RESET_AV = 1, OP_ZERO_BEFORE = 2, OP_ACCUM = 4, OP_ZERO_AFTER = 8, OP_FINAL = 16 };
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
+        __syncthreads();
+        const int t = s_next;
+        if (t >= ntraj) break;
+        if (st.sc[t].status != TRJ_RUNNING) continue;
+        double *velo0 = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global) + 8, *grad0 = velo0 + 3 * nuc0, *achrg0 = grad0 + 3 * nuc0;
+        double *gxyz0 = st.xyz0 + (size_t)t * 3 * nuc0, *gvelo0 = st.velo0 + (size_t)t * 3 * nuc0, *ggrad0 = st.grad0 + (size_t)t * 3 * nuc0,
+               *gachrg0 = st.achrg0 + (size_t)t * nuc0;
+        double *avxyz = st.avxyz + (size_t)t * 3 * nuc, *avxyz2 = st.avxyz2 + (size_t)t * 3 * nuc, *store = st.store + (size_t)t * 3 * nuc;
+        int *list = st.list + (size_t)t * nuc;
+        for (int i = threadIdx.x; i < 3 * nuc0; i += QX_NT) { s.xyz[i] = gxyz0[i]; velo0[i] = gvelo0[i]; grad0[i] = ggrad0[i]; }
+        for (int i = threadIdx.x; i < nuc0; i += QX_NT) achrg0[i] = gachrg0[i];
+        if (threadIdx.x == 0) { sc = st.sc[t]; s_stop = 0; }
+        __syncthreads();
+        for (int it = 0; it < chunk; ++it) {
+            if (threadIdx.x == 0) {
+                sc.nstep += 1;
+                s_ops = 0;
+                if (sc.xyzavg_dump == 50) { sc.xyzavg_dump = 0; s_ops |= OP_RESET_AV; }
+                sc.ttime = sc.ttime + cc.tstep * autofs;
+                sc.distance_dump += 1; sc.xyzavg_dump += 1;
+            }
+            __syncthreads();
+            if (s_ops & OP_RESET_AV) for (int i = threadIdx.x; i < 3 * nuc; i += QX_NT) avxyz[i] = 0.0;
+            for (int i = threadIdx.x; i < 3 * nuc0; i += QX_NT) {   // leapfrog on ion + gas atom
+                const double mass = m.mass[i / 3];
+                const double vnew = __dsub_rn(velo0[i], __ddiv_rn(__dmul_rn(cc.tstep, grad0[i]), mass));
+                velo0[i] = vnew;
+                s.xyz[i] = __dadd_rn(s.xyz[i], __dmul_rn(cc.tstep, vnew));
+            }
+            __syncthreads();
+            int nit = 0;
+            const double epot = md_egrad(m, s, my, L, cfg, cc.etemp, grad0, achrg0, &nit);
+            if (threadIdx.x == 0) { sc.scc_total += nit; sc.epot = epot; }
+            if (epot == 0.0) {
+                if (threadIdx.x == 0) { sc.stopcid = 1; sc.status = TRJ_FINISHED; }
+                break;
+            }
+            md_fragments(m, s.xyz, 3.0, (unsigned char *)(my + L.taskout), list, (int *)(my + L.taskout) + (nuc * nuc + 3) / 4 + 4, nuc);
+            if (threadIdx.x == 0) {
+                double cm[3], T;
+                cid_center_of_mass(nuc, m.mass, s.xyz, cm);
+                const double dc0 = cm[0] - sc.old_cm[0], dc1 = cm[1] - sc.old_cm[1], dc2 = cm[2] - sc.old_cm[2];
+                const double cm_out = sqrt(dc0 * dc0 + dc1 * dc1 + dc2 * dc2);
+                sc.old_cm[0] = cm[0]; sc.old_cm[1] = cm[1]; sc.old_cm[2] = cm[2];
+                sc.new_velo = sc.nstep != 1 ? (cm_out / cc.tstep) / QC_MSTOAU : 0.0;
+                const double Ekin = cid_ekinet(nuc, velo0, m.mass, &T);
+                const double E_velo = 0.5 * sc.summass * ((sc.new_velo * QC_MSTOAU) * (sc.new_velo * QC_MSTOAU));
+                double new_temp = (2 * (Ekin - E_velo)) / (3 * QC_KB * nuc);
+                if (sc.nstep == 1) new_temp = sc.Tinit;
+                sc.Tav = sc.Tav + new_temp; sc.m = sc.m + 1;
+                const double avgT = sc.Tav / sc.m;
+                const int nfrag = md_nfrag(m, list, nuc);
+                sc.nfrag = nfrag;
+                if (nfrag > sc.check_fragmented) { sc.count_average = 1; sc.check_fragmented = nfrag; }
+                if (nfrag < sc.check_fragmented && sc.count_average) { sc.cnt = 0; s_ops |= OP_ZERO_BEFORE; sc.count_average = 0; sc.check_fragmented = 1; }
+                if (sc.count_average) {
+                    sc.cnt += 1;
+                    s_ops |= OP_ACCUM;
+                    s_cnt = sc.cnt;
+                    int natf[10];
+                    for (int i = 0; i < 10; ++i) natf[i] = 0;
+                    for (int i = 0; i < nuc; ++i) if (list[i] >= 1 && list[i] <= nfrag && list[i] <= 10) natf[list[i] - 1] += 1;
+                    for (int i = 0; i < nfrag && i < 10; ++i) {
+                        if (sc.cnt == 1) sc.save_natf[i] = natf[i];
+                        if (natf[i] != sc.save_natf[i]) { sc.cnt = 0; s_ops |= OP_ZERO_AFTER; break; }
+                    }
+                    if (sc.cnt == 50) { s_ops |= OP_FINAL; sc.cnt = 0; sc.count_average = 0; }
+                }
+                sc.aTlast = avgT;
+                if (sc.distance_dump == 10) {
+                    sc.distance_dump = 0;
+                    const double d0 = s.xyz[3 * nuc] - cm[0], d1 = s.xyz[3 * nuc + 1] - cm[1], d2 = s.xyz[3 * nuc + 2] - cm[2];
+                    const double new_dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                    if (new_dist < sc.lowestCOM) sc.lowestCOM = new_dist;
+                    if (sc.lowestCOM < new_dist) sc.step_counter += 1; else sc.step_counter = 0;
+                    if (sc.step_counter == 5) {
+                        sc.total_steps = sc.nstep + (int)llround(800.0 * (2 * cc.tstep * autofs));
+                        sc.collided = 1; sc.Tav = 0; sc.m = 0;
+                    }
+                }
+                if (nfrag > 1 && sc.collided && !sc.fragmented) { sc.total_steps = sc.nstep + add_steps; sc.fragmented = 1; }
+                if (sc.nstep >= sc.total_steps) { sc.stopcid = 0; sc.status = TRJ_FINISHED; s_stop = 1; }
+            }
+            __syncthreads();
+            const int ops = s_ops, stop = s_stop;
+            const double cnt = (double)s_cnt;
+            for (int i = threadIdx.x; i < 3 * nuc; i += QX_NT) {
+                avxyz[i] += s.xyz[i];
+                if (ops & OP_ZERO_BEFORE) { avxyz2[i] = 0.0; store[i] = 0.0; }
+                if (ops & OP_ACCUM) { const double v = avxyz2[i] + s.xyz[i]; avxyz2[i] = v; store[i] = v / cnt; }
+                if (ops & OP_ZERO_AFTER) { avxyz2[i] = 0.0; store[i] = 0.0; }
+                if (ops & OP_FINAL) avxyz2[i] = 0.0;
+            }
+            __syncthreads();   // thread 0 rewrites the flags at the top of the next step
+            if (stop) break;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * nuc0; i += QX_NT) { gxyz0[i] = s.xyz[i]; gvelo0[i] = velo0[i]; ggrad0[i] = grad0[i]; }
+        for (int i = threadIdx.x; i < nuc0; i += QX_NT) gachrg0[i] = achrg0[i];
+        if (threadIdx.x == 0) st.sc[t] = sc;
     }
 }
 
@@ -701,6 +873,122 @@ extern "C" int qcxms_b200_ensemble_histogram(qcxms_b200_ensemble_t *h, int nbins
     CUDA_OK(cudaStreamSynchronize(h->stream));
     if (bins_host) CUDA_OK(cudaMemcpy(bins_host, h->d_bins, nbins * sizeof(double), cudaMemcpyDeviceToHost));
     if (bins_device) *bins_device = h->d_bins;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ CID host entry
+extern "C" int qcxms_b200_cid_batch(const qcxms_b200_cid_config_t *cfg, int ntraj, int nuc, const int32_t *num, const double *mass, int icoll,
+                                    double *xyz, double *velo, const double *rnd, const double *velo_cm, double *direc, int32_t *collided,
+                                    double *grad, double *achrg, double *axyz, int32_t *list, qcxms_b200_cid_result_t *res, int device) {
+    if (!cfg || ntraj < 1 || nuc < 1 || !num || !mass || !xyz || !velo || !rnd || !direc || !collided || !grad || !achrg || !axyz || !list || !res)
+        return fail(QCXMS_B200_ERR_ARG, "null or empty argument");
+    if (icoll < 1 || (icoll > 1 && !velo_cm)) return fail(QCXMS_B200_ERR_ARG, "icoll >= 1; later collisions need velo_cm");
+    if (cfg->method_id != QCXMS_B200_GFN2) return fail(QCXMS_B200_ERR_UNSUPPORTED, "only GFN2-xTB (method id 2) is implemented");
+    if (cfg->gas_z != 2 && cfg->gas_z != 10 && cfg->gas_z != 18) return fail(QCXMS_B200_ERR_UNSUPPORTED, "collision gas must be He, Ne or Ar");
+    const int nuc0 = nuc + 1;
+    std::vector<int32_t> num0(num, num + nuc);
+    std::vector<double> mass0(mass, mass + nuc);
+    num0.push_back(cfg->gas_z);
+    mass0.push_back(cfg->gas_mass);
+    int zsum = 0;
+    for (int v : num0) zsum += v;
+    const int j = zsum - std::abs(cfg->mchrg);
+    const int mult = j < 1 ? -1 : 1 + j % 2;
+    Context ctx;
+    int rc = context_init(ctx, nuc0, num0.data(), mass0.data(), cfg->mchrg, mult, device, ntraj);
+    if (rc) { context_free(ctx); return rc; }
+    CUDA_OK(cudaFuncSetAttribute(k_cid_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx.smem));
+    CUDA_OK(cudaFuncSetAttribute(k_cid_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx.smem));
+    MdConfig mc{};
+    mc.mchrg = cfg->mchrg; mc.tstep = cfg->tstep;
+    CidConfig cc{};
+    cc.mchrg = cfg->mchrg; cc.gas_z = cfg->gas_z; cc.eexact = cfg->eexact; cc.manual_dist = cfg->manual_dist;
+    cc.ntot = cfg->ntot > 0 ? cfg->ntot : 15000;
+    cc.gas_mass = cfg->gas_mass; cc.tstep = cfg->tstep; cc.etemp = cfg->etemp <= 0.0 ? 5000.0 : cfg->etemp; cc.elab = cfg->elab; cc.ecom = cfg->ecom;
+    const size_t n3 = (size_t)ntraj * nuc * 3, n30 = (size_t)ntraj * nuc0 * 3;
+    std::vector<void *> allocs;
+    auto dalloc = [&](size_t bytes) -> void * {
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, bytes);
+        allocs.push_back(p);
+        return p;
+    };
+    auto cleanup = [&]() { for (void *p : allocs) cudaFree(p); context_free(ctx); };
+    CidState st{};
+    double *d_rnd, *d_vcm = nullptr;
+    st.xyz = (double *)dalloc(n3 * 8); st.velo = (double *)dalloc(n3 * 8); st.direc = (double *)dalloc((size_t)ntraj * 3 * 8);
+    d_rnd = (double *)dalloc((size_t)ntraj * 9 * 8); d_vcm = (double *)dalloc((size_t)ntraj * 8);
+    st.xyz0 = (double *)dalloc(n30 * 8); st.velo0 = (double *)dalloc(n30 * 8); st.grad0 = (double *)dalloc(n30 * 8); st.achrg0 = (double *)dalloc((size_t)ntraj * nuc0 * 8);
+    st.avxyz = (double *)dalloc(n3 * 8); st.avxyz2 = (double *)dalloc(n3 * 8); st.store = (double *)dalloc(n3 * 8);
+    st.list = (int *)dalloc((size_t)ntraj * nuc * 4);
+    st.sc = (CidScalars *)dalloc((size_t)ntraj * sizeof(CidScalars));
+    if (!st.xyz || !st.velo || !st.direc || !d_rnd || !d_vcm || !st.xyz0 || !st.velo0 || !st.grad0 || !st.achrg0 || !st.avxyz || !st.avxyz2 || !st.store ||
+        !st.list || !st.sc) { cleanup(); return fail(QCXMS_B200_ERR_CUDA, "cid: device allocation failed"); }
+    st.rnd = d_rnd; st.velo_cm_in = d_vcm;
+    std::vector<CidScalars> hsc(ntraj);
+    for (int t = 0; t < ntraj; ++t) { hsc[t] = CidScalars{}; hsc[t].collided = collided[t] ? 1 : 0; }
+#define CID_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(QCXMS_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    CID_OK(cudaMemcpy(st.xyz, xyz, n3 * 8, cudaMemcpyHostToDevice));
+    CID_OK(cudaMemcpy(st.velo, velo, n3 * 8, cudaMemcpyHostToDevice));
+    CID_OK(cudaMemcpy(st.direc, direc, (size_t)ntraj * 3 * 8, cudaMemcpyHostToDevice));
+    CID_OK(cudaMemcpy(d_rnd, rnd, (size_t)ntraj * 9 * 8, cudaMemcpyHostToDevice));
+    if (velo_cm) CID_OK(cudaMemcpy(d_vcm, velo_cm, (size_t)ntraj * 8, cudaMemcpyHostToDevice));
+    CID_OK(cudaMemcpy(st.sc, hsc.data(), (size_t)ntraj * sizeof(CidScalars), cudaMemcpyHostToDevice));
+    const int grid = ctx.ncta < ntraj ? ctx.ncta : ntraj;
+    CID_OK(cudaMemset(ctx.d_queue, 0, sizeof(int)));
+    k_cid_init<<<grid, QX_NT, ctx.smem>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, mc, cc, st, ntraj, nuc, icoll, ctx.d_queue);
+    CID_OK(cudaGetLastError());
+    const int chunk = 32;
+    for (int done = 0; done < cc.ntot + chunk; done += chunk) {
+        CID_OK(cudaMemset(ctx.d_queue, 0, sizeof(int)));
+        k_cid_chunk<<<grid, QX_NT, ctx.smem>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, mc, cc, st, ntraj, nuc, chunk, ctx.d_queue);
+        CID_OK(cudaGetLastError());
+        if ((done / chunk) % 4 == 3 || done + chunk >= cc.ntot) {
+            CID_OK(cudaMemcpy(hsc.data(), st.sc, (size_t)ntraj * sizeof(CidScalars), cudaMemcpyDeviceToHost));
+            bool any = false;
+            for (const CidScalars &v : hsc) any = any || v.status == TRJ_RUNNING;
+            if (!any) break;
+        }
+    }
+    CID_OK(cudaMemcpy(hsc.data(), st.sc, (size_t)ntraj * sizeof(CidScalars), cudaMemcpyDeviceToHost));
+    // hand-back (reference src/cid.f90:1058-1105): the ion part of the collision system; set-up changes to xyz / velo stay
+    // visible even when the first single point failed, as in the reference
+    std::vector<double> hx(n30), hv(n30), hg(n30), hq((size_t)ntraj * nuc0), hav(n3), hst(n3);
+    CID_OK(cudaMemcpy(hx.data(), st.xyz0, n30 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cudaMemcpy(hv.data(), st.velo0, n30 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cudaMemcpy(hg.data(), st.grad0, n30 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cudaMemcpy(hq.data(), st.achrg0, (size_t)ntraj * nuc0 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cudaMemcpy(hav.data(), st.avxyz, n3 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cudaMemcpy(hst.data(), st.store, n3 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cudaMemcpy(list, st.list, (size_t)ntraj * nuc * 4, cudaMemcpyDeviceToHost));
+    CID_OK(cudaMemcpy(direc, st.direc, (size_t)ntraj * 3 * 8, cudaMemcpyDeviceToHost));
+    std::vector<double> sx(n3), sv(n3);
+    CID_OK(cudaMemcpy(sx.data(), st.xyz, n3 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cudaMemcpy(sv.data(), st.velo, n3 * 8, cudaMemcpyDeviceToHost));
+#undef CID_OK
+    for (int t = 0; t < ntraj; ++t) {
+        const CidScalars &c = hsc[t];
+        qcxms_b200_cid_result_t &r = res[t];
+        r = qcxms_b200_cid_result_t{};
+        r.collided = c.collided; r.scc_iter_total = c.scc_total; r.stopcid = c.stopcid;
+        for (int k = 0; k < 3; ++k) r.direc[k] = direc[3 * t + k];
+        collided[t] = c.collided;
+        const size_t o = (size_t)t * nuc * 3, o0 = (size_t)t * nuc0 * 3;
+        if (c.status == TRJ_FAILED) {   // first single point failed: nothing but the set-up happened
+            r.status = 2;
+            for (int i = 0; i < 3 * nuc; ++i) { xyz[o + i] = sx[o + i]; velo[o + i] = sv[o + i]; }
+            continue;
+        }
+        for (int i = 0; i < 3 * nuc; ++i) {
+            xyz[o + i] = hx[o0 + i]; velo[o + i] = hv[o0 + i]; grad[o + i] = hg[o0 + i];
+            axyz[o + i] = c.check_fragmented > 1 ? hst[o + i] : hav[o + i] / c.xyzavg_dump;
+        }
+        for (int i = 0; i < nuc; ++i) achrg[(size_t)t * nuc + i] = hq[(size_t)t * nuc0 + i];
+        r.nstep = c.nstep; r.nfrag = c.nfrag; r.velo_cm = c.new_velo; r.aTlast = c.aTlast; r.ttime = c.ttime; r.epot = c.epot;
+        r.status = 1;
+    }
+    cleanup();
     return 0;
 }
 

@@ -39,8 +39,8 @@ __device__ inline double md_setetemp(const MdConfig &c, int nfrag, double eimp) 
 
 // fragment_structure(nat, oz, xyz, rcut, 1, 0, frag): thread 0 of the CTA propagates labels through the
 // connectivity computed by all threads.  conn: nat*nat bytes of scratch.
-__device__ inline void md_fragments(const DevModel &m, const double *xyz, double rcut, unsigned char *conn, int *frag, int *stack) {
-    const int nat = m.nat;
+__device__ inline void md_fragments(const DevModel &m, const double *xyz, double rcut, unsigned char *conn, int *frag, int *stack, int natoms = -1) {
+    const int nat = natoms > 0 ? natoms : m.nat;
     for (int t = threadIdx.x; t < nat * nat; t += QX_NT) {
         int i = t / nat, j = t - i * nat;
         unsigned char c = 0;
@@ -75,11 +75,12 @@ __device__ inline void md_fragments(const DevModel &m, const double *xyz, double
 }
 
 // number of fragments as fragmass counts them (at most 10 slots, mass > 0)
-__device__ inline int md_nfrag(const DevModel &m, const int *frag) {
+__device__ inline int md_nfrag(const DevModel &m, const int *frag, int natoms = -1) {
+    const int nat = natoms > 0 ? natoms : m.nat;
     int nf = 0;
     for (int f = 1; f <= 10; ++f) {
         double mass = 0.0;
-        for (int i = 0; i < m.nat; ++i)
+        for (int i = 0; i < nat; ++i)
             if (frag[i] == f) mass += m.mass[i];
         if (mass > 0.0) ++nf;
     }
