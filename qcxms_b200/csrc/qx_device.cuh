@@ -720,6 +720,13 @@ __device__ inline void tournament_pair(int mm, int round, int k, int &p, int &q)
 // so an element update is a single DFMA; squared norms are tracked incrementally (recomputed every sweep),
 // so only the cross product needs a reduction.  Control flow is warp-uniform (idle groups do dummy loads).
 // jw: 4*n doubles of shared scratch (norms, scales, inverse scales).
+// A sweep whose largest pre-rotation coupling |g_p.g_q| / (|g_p||g_q|) stays below QX_JACOBI_TOL is the last one: convergence
+// is quadratic, so what it leaves behind is O(tol^2).  Measured on 592 distorted caffeine cations against tol = 1e-7
+// (tools/phase_profile.py --dump): 3e-6 changes E by 2e-11 Eh, gradients by 2e-10, charges by 2e-10 and saves 8 % of the
+// sweeps; 3e-5 would save 15 % but moves charges by 4e-7 (too close to the 1e-6 parity gate).
+#ifndef QX_JACOBI_TOL
+#define QX_JACOBI_TOL 3e-6f
+#endif
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -827,127 +834,119 @@ __device__ __noinline__ int jacobi_rows_lp8(int n, double *G, int ld, double *re
     return sweep;
 }
 
-// ---- register-blocked variant: a group of 16 lanes owns a PAIR OF 2-ROW BLOCKS per round, keeps the four rows in
-// registers and performs the four cross rotations (two independent ones at a time) before writing back.  Compared
-// with one row pair per round this halves the shared-memory traffic per rotation and the number of barriers
-// (ceil(n/2)-1 rounds per sweep); the pairs inside a block are rotated once per sweep (in round 0).
-// two independent row pairs (x0,y0) and (x1,y1), straight-line and branch-free so that the two dependency chains overlap
+// ---- trimmed variant of the one-pair-per-round kernel (default).  The sub-partition pipes are what bounds the sweep
+// (tools/microbench/lat.cu: ~2.1 cycles per double-precision warp instruction, ~8.2 per F2F / MUFU; ncu: >45 % of the issued
+// instructions of jacobi_rows_lp8 are integer / control), so this version (1) walks the tournament incrementally
+// (p and q advance by one player per round), (2) decides convergence with a double-precision compare instead of a
+// single-precision ratio (flag + __syncthreads_or, no block-wide max), (3) gets the tangent from a two-MUFU chain
+// t = 2 ga / (d + sign(d) sqrt(d^2 + 4 ga^2)) and c from the single-precision t: 4 F2F + 3 MUFU per rotation instead of
+// 6 + 5, (4) is branch-free (t = 0 is an exact no-op), (5) keeps (scale, 1/scale) packed for 128-bit state accesses.
+// jw: nrm2[n] | dd[n] as double2 (scale, inverse scale), 16-byte aligned
 template <int R>
-__device__ __forceinline__ void jacobi_rot_2pairs16(double2 (&x0)[R], double2 (&y0)[R], double2 (&x1)[R], double2 (&y1)[R],
-                                                    double &dx0, double &dy0, double &ix0, double &iy0, double &nx0, double &ny0, bool v0,
-                                                    double &dx1, double &dy1, double &ix1, double &iy1, double &nx1, double &ny1, bool v1, float &smax) {
-    double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        a0 = fma(x0[r].x, y0[r].x, a0); b0 = fma(x0[r].y, y0[r].y, b0);
-        a1 = fma(x1[r].x, y1[r].x, a1); b1 = fma(x1[r].y, y1[r].y, b1);
-    }
-    double g0 = a0 + b0, g1 = a1 + b1;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        const double h0 = __shfl_xor_sync(0xffffffffu, g0, o), h1 = __shfl_xor_sync(0xffffffffu, g1, o);
-        g0 += h0; g1 += h1;
-    }
-    const double ga0 = dx0 * dy0 * g0, ga1 = dx1 * dy1 * g1;
-    const float gf0 = (float)ga0, gf1 = (float)ga1;
-    const float r0 = v0 ? fabsf(gf0) * rsqrt_approx((float)nx0 * (float)ny0) : 0.0f;
-    const float r1 = v1 ? fabsf(gf1) * rsqrt_approx((float)nx1 * (float)ny1) : 0.0f;
-    smax = fmaxf(smax, fmaxf(r0, r1));
-    const float z0 = (float)(ny0 - nx0) * rcp_approx(2.0f * gf0), z1 = (float)(ny1 - nx1) * rcp_approx(2.0f * gf1);
-    float tf0 = copysignf(rcp_approx(fabsf(z0) + sqrt_approx(fmaf(z0, z0, 1.0f))), z0);
-    float tf1 = copysignf(rcp_approx(fabsf(z1) + sqrt_approx(fmaf(z1, z1, 1.0f))), z1);
-    tf0 = r0 > 1e-15f ? tf0 : 0.0f;   // also removes the NaN of a 0/0 pair
-    tf1 = r1 > 1e-15f ? tf1 : 0.0f;
-    const double t0 = (double)tf0, t1 = (double)tf1, w0 = fma(t0, t0, 1.0), w1 = fma(t1, t1, 1.0);
-    const double p0 = t0 * dy0 * ix0, q0 = t0 * dx0 * iy0, p1 = t1 * dy1 * ix1, q1 = t1 * dx1 * iy1;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const double ux0 = fma(-p0, y0[r].x, x0[r].x), uy0 = fma(-p0, y0[r].y, x0[r].y);
-        const double ux1 = fma(-p1, y1[r].x, x1[r].x), uy1 = fma(-p1, y1[r].y, x1[r].y);
-        y0[r].x = fma(q0, x0[r].x, y0[r].x); y0[r].y = fma(q0, x0[r].y, y0[r].y);
-        y1[r].x = fma(q1, x1[r].x, y1[r].x); y1[r].y = fma(q1, x1[r].y, y1[r].y);
-        x0[r].x = ux0; x0[r].y = uy0; x1[r].x = ux1; x1[r].y = uy1;
-    }
-    double c0 = (double)rsqrt_approx((float)w0), c1 = (double)rsqrt_approx((float)w1);
-    c0 = c0 * fma(-0.5 * w0 * c0, c0, 1.5); c1 = c1 * fma(-0.5 * w1 * c1, c1, 1.5);
-    c0 = c0 * fma(-0.5 * w0 * c0, c0, 1.5); c1 = c1 * fma(-0.5 * w1 * c1, c1, 1.5);
-    const double wc0 = w0 * c0, wc1 = w1 * c1, tg0 = t0 * ga0, tg1 = t1 * ga1;
-    dx0 *= c0; dy0 *= c0; ix0 *= wc0; iy0 *= wc0; nx0 -= tg0; ny0 += tg0;
-    dx1 *= c1; dy1 *= c1; ix1 *= wc1; iy1 *= wc1; nx1 -= tg1; ny1 += tg1;
-}
-
-template <int R>
-__device__ __noinline__ int jacobi_rows_blk2(int n, double *G, int ld, double *red, float tol, double *jw) {
-    const int nb = (n + 1) >> 1, mb = (nb + 1) & ~1, nbp = mb >> 1, m1 = mb - 1;
-    const int nslot = QX_NT / 16, slot = threadIdx.x >> 4, l16 = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int npass = (nbp + nslot - 1) / nslot;
-    double *nrm2 = jw, *dsc = jw + n, *dinv = jw + 2 * n;
-    for (int i = threadIdx.x; i < n; i += QX_NT) { dsc[i] = 1.0; dinv[i] = 1.0; }
+__device__ __noinline__ int jacobi_rows_lp8t(int n, double *G, int ld, float tol, double *jw) {
+    const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
+    const int k = threadIdx.x >> 3, lsub = threadIdx.x & 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *nrm2 = jw;
+    double2 *dd = reinterpret_cast<double2 *>(jw + ((n + 1) & ~1));
+    for (int i = threadIdx.x; i < n; i += QX_NT) dd[i] = make_double2(1.0, 1.0);
     __syncthreads();
-    const bool tail_ok = 2 * l16 + 32 * (R - 1) < n;
-    const int tail_off = tail_ok ? 2 * l16 + 32 * (R - 1) : 0;
+    const bool tail_ok = 2 * lsub + 16 * (R - 1) < n;
+    const int tail_off = tail_ok ? 2 * lsub + 16 * (R - 1) : 0;
+    // the only invalid pair is the one with the dummy player m1 == n (n odd), always in slot 0
+    const bool valid = k < npair && !(k == 0 && (n & 1));
+    const bool wact = (warp << 2) < npair;   // warp-uniform
+    double *Gl = G + 2 * lsub, *Gt = G + tail_off;
+    const double tol2 = (double)tol * (double)tol;
     int sweep = 0;
     for (; sweep < 60; ++sweep) {
-        for (int k = warp; k < n; k += QX_NT / 32) {
-            const double d = dsc[k];
+        // fold the scales into the rows and refresh the norms
+        for (int r = warp; r < n; r += QX_NT / 32) {
+            const double d = dd[r].x;
             double acc = 0.0;
-            for (int i = lane; i < n; i += 32) { const double x = G[(size_t)k * ld + i] * d; G[(size_t)k * ld + i] = x; acc += x * x; }
+            for (int i = lane; i < n; i += 32) { const double x = G[(size_t)r * ld + i] * d; G[(size_t)r * ld + i] = x; acc = fma(x, x, acc); }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             __syncwarp();
-            if (lane == 0) { nrm2[k] = acc; dsc[k] = 1.0; dinv[k] = 1.0; }
+            if (lane == 0) { nrm2[r] = acc; dd[r] = make_double2(1.0, 1.0); }
         }
         __syncthreads();
-        float smax = 0.0f;
+        bool big = false;
+        // slot 0 pairs the fixed player m1 with `round`; slot k pairs (round + k) with (round - k) (mod m1)
+        int p = valid ? (k == 0 ? m1 : k) : 0, q = valid ? (k == 0 ? 0 : m1 - k) : 0;
         for (int round = 0; round < m1; ++round) {
-            for (int pass = 0; pass < npass; ++pass) {
-                const int k = slot + pass * nslot;
-                int P = round + k, Q = round - k;
-                if (P >= m1) P -= m1;
-                if (Q < 0) Q += m1;
-                if (k == 0) P = m1;
-                const bool gvalid = k < nbp;
-                int row[4] = {2 * P, 2 * P + 1, 2 * Q, 2 * Q + 1};
-                bool rv[4];
+            if (wact) {
+                double *gp = Gl + p * ld, *gq = Gl + q * ld, *tp = Gt + p * ld, *tq = Gt + q * ld;
+                const double2 sp = dd[p], sq = dd[q];
+                const double al = nrm2[p], be = nrm2[q];
+                double2 x[R], y[R];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) { rv[a] = gvalid && row[a] < n; if (!rv[a]) row[a] = 0; }
-                double2 x[4][R];
-                double d[4], di[4], nr[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const double *g = G + row[a] * ld;
-#pragma unroll
-                    for (int r = 0; r < R - 1; ++r) x[a][r] = *reinterpret_cast<const double2 *>(g + 2 * l16 + 32 * r);
-                    x[a][R - 1] = *reinterpret_cast<const double2 *>(g + tail_off);
-                    if (!tail_ok) x[a][R - 1] = make_double2(0.0, 0.0);
-                    d[a] = dsc[row[a]]; di[a] = dinv[row[a]]; nr[a] = nrm2[row[a]];
+                for (int r = 0; r < R - 1; ++r) {   // chunks r < R-1 are in range for every lane (n > 16 (R-1))
+                    x[r] = *reinterpret_cast<const double2 *>(gp + 16 * r);
+                    y[r] = *reinterpret_cast<const double2 *>(gq + 16 * r);
                 }
-                if (round == 0)   // pairs inside the two blocks, once per sweep
-                    jacobi_rot_2pairs16<R>(x[0], x[1], x[2], x[3], d[0], d[1], di[0], di[1], nr[0], nr[1], rv[0] && rv[1],
-                                           d[2], d[3], di[2], di[3], nr[2], nr[3], rv[2] && rv[3], smax);
-                jacobi_rot_2pairs16<R>(x[0], x[2], x[1], x[3], d[0], d[2], di[0], di[2], nr[0], nr[2], rv[0] && rv[2],
-                                       d[1], d[3], di[1], di[3], nr[1], nr[3], rv[1] && rv[3], smax);
-                jacobi_rot_2pairs16<R>(x[0], x[3], x[1], x[2], d[0], d[3], di[0], di[3], nr[0], nr[3], rv[0] && rv[3],
-                                       d[1], d[2], di[1], di[2], nr[1], nr[2], rv[1] && rv[2], smax);
+                x[R - 1] = *reinterpret_cast<const double2 *>(tp);
+                y[R - 1] = *reinterpret_cast<const double2 *>(tq);
+                if (!tail_ok) { x[R - 1] = make_double2(0.0, 0.0); y[R - 1] = make_double2(0.0, 0.0); }
+                double g0 = 0.0, g1 = 0.0;
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    if (rv[a]) {
-                        double *g = G + row[a] * ld;
+                for (int r = 0; r < R; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
+                double gs = g0 + g1;
+                gs += __shfl_xor_sync(0xffffffffu, gs, 4);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 2);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 1);
+                const double ga = (sp.x * sq.x) * gs, ga2 = ga * ga, nn = al * be;
+                big |= valid && ga2 > tol2 * nn;
+                const bool rot = valid && ga2 > 1e-30 * nn;
+                const float gf = (float)ga, df = (float)(be - al);
+                const float g2 = gf + gf;
+                const float hh = fmaf(df, df, g2 * g2);
+                const float den = fabsf(df) + hh * rsqrt_approx(hh);          // |d| + sqrt(d^2 + 4 ga^2)
+                float tf = g2 * rcp_approx(den);
+                tf = __int_as_float(__float_as_int(tf) ^ (__float_as_int(df) & 0x80000000));
+                tf = rot ? tf : 0.0f;    // also removes the NaN of a 0/0 pair; t == 0 leaves rows and scales untouched
+                const double t = (double)tf;
+                const double t1 = t * (sq.x * sp.y), t2 = t * (sp.x * sq.y);
 #pragma unroll
-                        for (int r = 0; r < R - 1; ++r) *reinterpret_cast<double2 *>(g + 2 * l16 + 32 * r) = x[a][r];
-                        if (tail_ok) *reinterpret_cast<double2 *>(g + 2 * l16 + 32 * (R - 1)) = x[a][R - 1];
-                        if (l16 == 0) { dsc[row[a]] = d[a]; dinv[row[a]] = di[a]; nrm2[row[a]] = nr[a]; }
+                for (int r = 0; r < R - 1; ++r) {
+                    double2 u, v;
+                    u.x = fma(-t1, y[r].x, x[r].x); u.y = fma(-t1, y[r].y, x[r].y);
+                    v.x = fma(t2, x[r].x, y[r].x); v.y = fma(t2, x[r].y, y[r].y);
+                    if (valid) {
+                        *reinterpret_cast<double2 *>(gp + 16 * r) = u;
+                        *reinterpret_cast<double2 *>(gq + 16 * r) = v;
                     }
                 }
+                if (tail_ok && valid) {
+                    double2 u, v;
+                    u.x = fma(-t1, y[R - 1].x, x[R - 1].x); u.y = fma(-t1, y[R - 1].y, x[R - 1].y);
+                    v.x = fma(t2, x[R - 1].x, y[R - 1].x); v.y = fma(t2, x[R - 1].y, y[R - 1].y);
+                    *reinterpret_cast<double2 *>(gp + 16 * (R - 1)) = u;
+                    *reinterpret_cast<double2 *>(gq + 16 * (R - 1)) = v;
+                }
+                {
+                    const double w = fma(t, t, 1.0);
+                    double c = (double)rsqrt_approx(fmaf(tf, tf, 1.0f));
+                    c = c * fma(-0.5 * w * c, c, 1.5);
+                    c = c * fma(-0.5 * w * c, c, 1.5);
+                    const double wc = w * c, tg = t * ga;
+                    if (lsub == 0 && valid) {
+                        dd[p] = make_double2(c * sp.x, wc * sp.y); dd[q] = make_double2(c * sq.x, wc * sq.y);
+                        nrm2[p] = al - tg; nrm2[q] = be + tg;
+                    }
+                }
+                // next round: both players of a slot move on by one (the fixed player stays)
+                if (k != 0) p = p + 1 == m1 ? 0 : p + 1;
+                q = q + 1 == m1 ? 0 : q + 1;
+                if (!valid) { p = 0; q = 0; }
             }
             __syncthreads();
         }
-        const float m = (float)block_max((double)smax, red);
-        if (m < tol) { ++sweep; break; }
+        if (!__syncthreads_or(big ? 1 : 0)) { ++sweep; break; }
     }
-    for (int k = warp; k < n; k += QX_NT / 32) {
-        const double d = dsc[k];
-        for (int i = lane; i < n; i += 32) G[(size_t)k * ld + i] *= d;
+    // fold the remaining scales
+    for (int r = warp; r < n; r += QX_NT / 32) {
+        const double d = dd[r].x;
+        for (int i = lane; i < n; i += 32) G[(size_t)r * ld + i] *= d;
     }
     __syncthreads();
     return sweep;
@@ -1014,13 +1013,18 @@ __device__ __noinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *e
     const float tol = 1e-7f;  // pre-rotation ratio of the last sweep; its rotations leave O(tol^2) couplings
     const int npair = (n + 1) >> 1;
     int sweeps;
-#ifdef QX_JACOBI_BLOCK2   // measured slower on B200 (issue-bound: 16 lanes repeat the scalar chain), kept for experiments
-    if ((ld & 1) == 0 && n <= 128) {
-        switch ((n + 31) >> 5) {
-            case 1: sweeps = jacobi_rows_blk2<1>(n, G, ld, red, tol, jw); break;
-            case 2: sweeps = jacobi_rows_blk2<2>(n, G, ld, red, tol, jw); break;
-            case 3: sweeps = jacobi_rows_blk2<3>(n, G, ld, red, tol, jw); break;
-            default: sweeps = jacobi_rows_blk2<4>(n, G, ld, red, tol, jw); break;
+#ifndef QX_JACOBI_LP8   // default: trimmed one-pair-per-round kernel
+    if (npair * 8 <= QX_NT && (ld & 1) == 0 && n <= 128) {
+        const float tolr = QX_JACOBI_TOL;
+        switch ((n + 15) >> 4) {
+            case 1: sweeps = jacobi_rows_lp8t<1>(n, G, ld, tolr, jw); break;
+            case 2: sweeps = jacobi_rows_lp8t<2>(n, G, ld, tolr, jw); break;
+            case 3: sweeps = jacobi_rows_lp8t<3>(n, G, ld, tolr, jw); break;
+            case 4: sweeps = jacobi_rows_lp8t<4>(n, G, ld, tolr, jw); break;
+            case 5: sweeps = jacobi_rows_lp8t<5>(n, G, ld, tolr, jw); break;
+            case 6: sweeps = jacobi_rows_lp8t<6>(n, G, ld, tolr, jw); break;
+            case 7: sweeps = jacobi_rows_lp8t<7>(n, G, ld, tolr, jw); break;
+            default: sweeps = jacobi_rows_lp8t<8>(n, G, ld, tolr, jw); break;
         }
     } else
 #endif

@@ -9,12 +9,20 @@ sys.path.insert(0, ROOT)
 so = os.path.join(ROOT, "qcxms_b200", "libqcxms_b200_prof.so")
 NAMES = ["cn+rep", "d4 nonsc/ATM", "coulomb+integrals", "cholesky basis", "broyden", "potential", "build H1", "transform C^T H C",
          "jacobi", "fermi", "density", "mulliken", "scc energy", "W matrix", "grad AO pairs", "grad rest"]
-def build():
+def build(out=so, extra=()):
     subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-DQX_PROFILE_PHASES",
-                           "-Xcompiler", "-fPIC", "-shared", "-o", so, os.path.join(ROOT, "qcxms_b200", "csrc", "cabi.cu")])
+                           *extra, "-Xcompiler", "-fPIC", "-shared", "-o", out, os.path.join(ROOT, "qcxms_b200", "csrc", "cabi.cu")])
 if __name__ == "__main__":
-    if "--build" in sys.argv:
-        build(); sys.exit(0)
+    # --so PATH: use (or with --build: write) another profiling library; -D... flags are passed to nvcc; --dump FILE: save results
+    args = [a for a in sys.argv[1:]]
+    dump = None
+    if "--so" in args:
+        so = args[args.index("--so") + 1]; del args[args.index("--so"):args.index("--so") + 2]
+    if "--dump" in args:
+        dump = args[args.index("--dump") + 1]; del args[args.index("--dump"):args.index("--dump") + 2]
+    if "--build" in args:
+        build(so, [a for a in args if a.startswith("-D")]); sys.exit(0)
+    sys.argv = [sys.argv[0]] + [a for a in args if not a.startswith("-")]
     import qcxms_b200.api as api
     api.LIB_PATH = so
     mol = sys.argv[1] if len(sys.argv) > 1 else "caffeine"
@@ -34,3 +42,5 @@ if __name__ == "__main__":
     print("%s: %d systems in %.3f s (%.1f egrad/s), mean SCC cycles %.2f" % (mol, nsys, dt, nsys / dt, out["niter"].mean()))
     for n, c in zip(NAMES, cyc):
         print("  %-20s %6.2f %%   %10.0f cycles/egrad" % (n, 100 * c / tot, c / nsys))
+    if dump:
+        np.savez(dump, energy=out["energy"], gradient=out["gradient"], qat=out["qat"], niter=out["niter"])
