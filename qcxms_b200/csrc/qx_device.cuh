@@ -41,10 +41,24 @@ __constant__ int c_qa[6] = {0, 0, 1, 0, 1, 2};
 __constant__ int c_qb[6] = {0, 1, 1, 2, 2, 2};
 __constant__ double c_qscale[6] = {1.0, 2.0, 1.0, 2.0, 2.0, 1.0};
 
+// A pointer that is KNOWN to point into shared memory.  The phase functions are __noinline__ and take the CTA's working set
+// through `Sm &`, so plain `double *` members reach them as generic pointers and every access becomes a generic LD/ST (ncu:
+// long-scoreboard stalls on what should be LDS).  Keeping the 32-bit shared-window offset instead lets the compiler emit
+// LDS/STS: cvta.shared->generic feeding a load is folded into ld.shared.
+struct SmPtr {
+    unsigned off;
+    __device__ __forceinline__ SmPtr &operator=(double *p) { off = (unsigned)__cvta_generic_to_shared(p); return *this; }
+    __device__ __forceinline__ double *ptr() const { return reinterpret_cast<double *>(__cvta_shared_to_generic(off)); }
+    __device__ __forceinline__ double &operator[](int i) const { return *reinterpret_cast<double *>(__cvta_shared_to_generic(off + 8u * (unsigned)i)); }
+    __device__ __forceinline__ double *operator+(int i) const { return reinterpret_cast<double *>(__cvta_shared_to_generic(off + 8u * (unsigned)i)); }
+    __device__ __forceinline__ operator double *() const { return ptr(); }
+};
+#define QX_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+
 struct Sm {
-    double *A, *C;
-    double *xyz, *cn, *cn4, *mrad, *dmr, *qat, *vat, *dpat, *vdp, *qpat, *vqp;
-    double *qsh, *vsh, *selfen, *vao, *emo, *focc, *gw, *gwd, *dEdcn, *dEdcn4, *grad, *red, *jw;
+    double *A, *C;   // shared memory, or the CTA's global slab when the basis is too large (DevModel::mat_in_global)
+    SmPtr xyz, cn, cn4, mrad, dmr, qat, vat, dpat, vdp, qpat, vqp;
+    SmPtr qsh, vsh, selfen, vao, emo, focc, gw, gwd, dEdcn, dEdcn4, grad, red, jw;
 };
 
 __host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld, int rows8, int mat_in_global = 0) {
@@ -548,6 +562,7 @@ __device__ inline void gemm_tc(int n, FA loadA, FB loadB, FS store) {
 // warp's own rows of `A` (after a barrier: everybody has finished reading H) and read back as the A operand of the second product.
 template <int NT8>
 __device__ __noinline__ void tc_transform(int n, const double *Ct, double *A, int ld) {
+    QX_ASSUME_SHARED(Ct); QX_ASSUME_SHARED(A);   // the strip kernels are only used when both matrices are in shared memory
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
     double acc[NT8][2];
     bool okb[NT8], oks[NT8];
@@ -591,6 +606,7 @@ __device__ __noinline__ void tc_transform(int n, const double *Ct, double *A, in
 // Ct <- X * Ct (in place), X in `X` (row-major; here the normalised rows of the Jacobi = J^T)
 template <int NT8>
 __device__ __noinline__ void tc_left_apply(int n, const double *X, double *Ct, int ld) {
+    QX_ASSUME_SHARED(X); QX_ASSUME_SHARED(Ct);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
     double acc[NT8][2];
     bool okb[NT8], oks[NT8];
@@ -621,6 +637,7 @@ __device__ __noinline__ void tc_left_apply(int n, const double *X, double *Ct, i
 // out = Ct^T diag(w) Ct = C diag(w) C^T.  out may alias Ct (result held in registers across a barrier).
 template <int NT8>
 __device__ __noinline__ void tc_density(int n, const double *Ct, const double *w, double *out, int ld) {
+    QX_ASSUME_SHARED(Ct); QX_ASSUME_SHARED(w); QX_ASSUME_SHARED(out);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
     double acc[NT8][2];
     bool okb[NT8], oks[NT8];
@@ -659,7 +676,10 @@ __host__ __device__ inline int tc_padded_dim(int n) {   // = 8 * NT8 of the inst
 
 // In-place Cholesky S = L L^T on the lower triangle of A (n x n, ld), then Ct = L^{-1} (lower triangular),
 // i.e. C = L^{-T}: an S-orthonormal starting basis.  Returns false if S is not positive definite.
+template <bool SH>
 __device__ __noinline__ bool cholesky_basis(int n, double *A, double *Ct, int ld, double *red) {
+    QX_ASSUME_SHARED(red);
+    if (SH) { QX_ASSUME_SHARED(A); QX_ASSUME_SHARED(Ct); }
     for (int j = 0; j < n; ++j) {
         double d = A[(size_t)j * ld + j];
         if (!(d > 0.0)) return false;  // uniform across the CTA (all threads read the same value)
@@ -733,6 +753,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.app
 
 template <int R>
 __device__ __noinline__ int jacobi_rows_lp8(int n, double *G, int ld, double *red, float tol, double *jw) {
+    QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(red); QX_ASSUME_SHARED(jw);   // n <= 72: matrices are in shared memory
     const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
     const int nslot = QX_NT / 8, slot = threadIdx.x >> 3, lsub = threadIdx.x & 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int npass = (npair + nslot - 1) / nslot;
@@ -844,6 +865,7 @@ __device__ __noinline__ int jacobi_rows_lp8(int n, double *G, int ld, double *re
 // jw: nrm2[n] | dd[n] as double2 (scale, inverse scale), 16-byte aligned
 template <int R>
 __device__ __noinline__ int jacobi_rows_lp8t(int n, double *G, int ld, float tol, double *jw) {
+    QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(jw);   // n <= 72: matrices are in shared memory
     const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
     const int k = threadIdx.x >> 3, lsub = threadIdx.x & 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *nrm2 = jw;
@@ -999,7 +1021,10 @@ __device__ __noinline__ int jacobi_rows_generic(int n, double *G, int ld, double
 
 // Eigen-decomposition of the symmetric A' held in G (n x n, ld).  On exit: emo[k] = eigenvalue k and row k of G
 // is the corresponding unit eigenvector (so G holds J^T).  Returns the number of sweeps.
+template <bool SH>
 __device__ __noinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *emo, double *red, double *jw) {
+    QX_ASSUME_SHARED(emo); QX_ASSUME_SHARED(red); QX_ASSUME_SHARED(jw);
+    if (SH) QX_ASSUME_SHARED(G);
     // Gershgorin shift: makes G positive definite, so that singular values == eigenvalues + sigma
     double rowsum = 0.0;
     for (int i = threadIdx.x; i < n; i += QX_NT) {

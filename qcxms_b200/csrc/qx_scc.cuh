@@ -166,8 +166,11 @@ __device__ __noinline__ void phase_scc_energy(const DevModel &m, Sm &s, const do
 }
 
 // H1 = H0 - 1/2 S (v_a + v_b) - 1/2 (D.vdp + D^T.vdp) - 1/2 (Q.vqp + ...) into s.A (symmetric)
+template <bool SH>
 __device__ __noinline__ void phase_build_h1(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt) {
     const int nao = m.nao, ld = m.ld;
+    double *const A = s.A;
+    if (SH) QX_ASSUME_SHARED(A);
     const size_t n2 = (size_t)nao * nao;
     for (int t = threadIdx.x; t < nao * nao; t += QX_NT) {
         int b = t / nao, a = t - b * nao, ib = m.ao_at[b];
@@ -178,23 +181,26 @@ __device__ __noinline__ void phase_build_h1(const DevModel &m, Sm &s, const doub
         for (int c = 0; c < 3; ++c) acc += Dt[c * n2 + t] * vd[c];
 #pragma unroll
         for (int c = 0; c < 6; ++c) acc += Qt[c * n2 + t] * vq[c];
-        s.A[(size_t)b * ld + a] = g - 0.5 * acc;
+        A[(size_t)b * ld + a] = g - 0.5 * acc;
     }
     __syncthreads();
     for (int t = threadIdx.x; t < nao * nao; t += QX_NT) {
         int b = t / nao, a = t - b * nao;
         if (a > b) continue;
-        double v = s.A[(size_t)b * ld + a] + s.A[(size_t)a * ld + b];
-        if (a == b) v = 2.0 * s.A[(size_t)b * ld + b];
-        s.A[(size_t)b * ld + a] = v;
-        s.A[(size_t)a * ld + b] = v;
+        double v = A[(size_t)b * ld + a] + A[(size_t)a * ld + b];
+        if (a == b) v = 2.0 * A[(size_t)b * ld + b];
+        A[(size_t)b * ld + a] = v;
+        A[(size_t)a * ld + b] = v;
     }
     __syncthreads();
 }
 
 // Mulliken populations from P (in s.A, symmetric): qsh, qat, dpat, qpat and tr(P H0); pop: 11*nao doubles of scratch
+template <bool SH>
 __device__ __noinline__ double phase_mulliken(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt, double *pop) {
     const int nao = m.nao, ld = m.ld, nat = m.nat, nsh = m.nsh;
+    const double *const A = s.A;
+    if (SH) QX_ASSUME_SHARED(A);
     const size_t n2 = (size_t)nao * nao;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int b = warp; b < nao; b += QX_NT / 32) {
@@ -202,7 +208,7 @@ __device__ __noinline__ double phase_mulliken(const DevModel &m, Sm &s, const do
 #pragma unroll
         for (int c = 0; c < 11; ++c) acc[c] = 0.0;
         for (int a = lane; a < nao; a += 32) {
-            const double p = s.A[(size_t)b * ld + a];
+            const double p = A[(size_t)b * ld + a];
             const size_t t = (size_t)b * nao + a;
             acc[0] += p * S[t];
             acc[10] += p * H0[t];
@@ -263,6 +269,7 @@ __device__ inline double warp_dot(const double *x, const double *y, int n) {
 
 // dense solve with partial pivoting on (beta[nb x nb], c[nb]) in global scratch; CTA-cooperative
 __device__ __noinline__ bool block_solve(int nb, double *beta, double *c, double *red) {
+    QX_ASSUME_SHARED(red);
     __shared__ int s_piv;
     for (int k = 0; k < nb; ++k) {
         if (threadIdx.x == 0) {
@@ -306,6 +313,7 @@ __device__ __noinline__ bool block_solve(int nb, double *beta, double *c, double
 
 // One mixer step: q_in <- next input.  dq = (output - input) of the cycle just finished must be set.
 __device__ __noinline__ bool broyden_next(Broyden &b, int n, double damp, double *red) {
+    QX_ASSUME_SHARED(red);
     const int mem = QX_MAX_ITER;
     const double omega0 = 0.01, minw = 1.0, maxw = 100000.0, wfac = 0.01;
     b.iter += 1;
@@ -377,8 +385,11 @@ __device__ __noinline__ bool broyden_next(Broyden &b, int n, double damp, double
 
 // ------------------------------------------------------------------------------------ gradient of the AO-pair terms
 // s.A = P, s.C = W (energy weighted density); potentials in s.vao/vdp/vqp from the last SCC cycle.
+template <bool SH>
 __device__ __noinline__ void phase_gradient_pairs(const DevModel &m, Sm &s, const int2 *tasks, int ntask, double *taskout) {
     const int ld = m.ld;
+    const double *const A = s.A, *const Cw = s.C;
+    if (SH) { QX_ASSUME_SHARED(A); QX_ASSUME_SHARED(Cw); }
     for (int t = threadIdx.x; t < ntask; t += QX_NT) {
         const int a = tasks[t].x, b = tasks[t].y;
         const int sa = m.ao_sh[a], sb = m.ao_sh[b], ja = m.ao_at[a], ib = m.ao_at[b];
@@ -386,7 +397,7 @@ __device__ __noinline__ void phase_gradient_pairs(const DevModel &m, Sm &s, cons
         if (ja == ib) { o[0] = o[1] = o[2] = o[3] = o[4] = 0.0; continue; }
         double vec[3] = {s.xyz[3 * ib] - s.xyz[3 * ja], s.xyz[3 * ib + 1] - s.xyz[3 * ja + 1], s.xyz[3 * ib + 2] - s.xyz[3 * ja + 2]};
         const double r2 = vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2];
-        const double pij = s.A[(size_t)a * ld + b], wij = s.C[(size_t)a * ld + b];
+        const double pij = A[(size_t)a * ld + b], wij = Cw[(size_t)a * ld + b];
         const double rr = sqrt(sqrt(r2) / (m.at_rad[ja] + m.at_rad[ib]));
         const double pla = 1.0 + m.sh_poly[sa] * rr, plb = 1.0 + m.sh_poly[sb] * rr;
         const double shp = pla * plb, dshp = (m.sh_poly[sa] * plb + m.sh_poly[sb] * pla) * rr * 0.5 / r2;
@@ -461,7 +472,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     __syncthreads();
     for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.A[(size_t)(t / nao) * ld + t % nao] = S[t];
     __syncthreads();
-    if (!cholesky_basis(nao, s.A, s.C, ld, s.red)) { out.stat = -2; out.energy = 0.0; return; }  // hard failure: S not positive definite
+    if (!(m.mat_in_global ? cholesky_basis<false>(nao, s.A, s.C, ld, s.red) : cholesky_basis<true>(nao, s.A, s.C, ld, s.red))) { out.stat = -2; out.energy = 0.0; return; }  // hard failure: S not positive definite
 
     for (int i = threadIdx.x; i < nsh; i += QX_NT) s.qsh[i] = 0.0;
     for (int i = threadIdx.x; i < nat; i += QX_NT) s.qat[i] = 0.0;
@@ -497,7 +508,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         for (int i = threadIdx.x; i < ndim; i += QX_NT)
             br.q_in[i] = i < nsh ? s.qsh[i] : (i < nsh + 3 * nat ? s.dpat[i - nsh] : s.qpat[i - nsh - 3 * nat]);
         QX_PH(5);
-        phase_build_h1(m, s, S, H0, Dt, Qt);
+        if (m.mat_in_global) phase_build_h1<false>(m, s, S, H0, Dt, Qt); else phase_build_h1<true>(m, s, S, H0, Dt, Qt);
         QX_PH(6);
         // A' = C^T H1 C in the current S-orthonormal basis (s.C holds C transposed), then Jacobi (C <- C J)
         const int npad = tc_padded_dim(nao);
@@ -519,7 +530,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         }
         QX_PH(7);
         {
-            int sw_ = jacobi_eigh_rows(nao, s.A, ld, s.emo, s.red, s.jw);
+            int sw_ = m.mat_in_global ? jacobi_eigh_rows<false>(nao, s.A, ld, s.emo, s.red, s.jw) : jacobi_eigh_rows<true>(nao, s.A, ld, s.emo, s.red, s.jw);
             out.sweeps += sw_;
 #ifdef QX_PROFILE_PHASES
             if (threadIdx.x == 0 && iscf <= 32) { atomicAdd(&g_sweep_hist[iscf - 1], (unsigned long long)sw_); atomicAdd(&g_sweep_hist[32 + iscf - 1], 1ull); }
@@ -594,7 +605,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
             __syncthreads();
         }
         QX_PH(10);
-        double eel = phase_mulliken(m, s, S, H0, Dt, Qt, pop);
+        double eel = m.mat_in_global ? phase_mulliken<false>(m, s, S, H0, Dt, Qt, pop) : phase_mulliken<true>(m, s, S, H0, Dt, Qt, pop);
         QX_PH(11);
         double err = 0.0;
         for (int i = threadIdx.x; i < ndim; i += QX_NT) {
@@ -638,7 +649,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         }
     }
     QX_PH(13);
-    phase_gradient_pairs(m, s, m.task_int, m.ntask_int, taskout);
+    if (m.mat_in_global) phase_gradient_pairs<false>(m, s, m.task_int, m.ntask_int, taskout); else phase_gradient_pairs<true>(m, s, m.task_int, m.ntask_int, taskout);
     QX_PH(14);
     for (int t = threadIdx.x; t < 3 * nat; t += QX_NT) {
         int k = t / 3, c = t - 3 * k;

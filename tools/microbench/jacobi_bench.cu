@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(QX_NT, 2) kj(int n, int ld, const double* A, d
         for (int t = threadIdx.x; t < n * n; t += QX_NT) G[(t / n) * ld + t % n] = A[(size_t)blockIdx.x % 4 * n * n + t];
         __syncthreads();
         long long t0 = clock64();
-        sweeps += qx::jacobi_eigh_rows(n, G, ld, emo, red, jw);
+        sweeps += qx::jacobi_eigh_rows<true>(n, G, ld, emo, red, jw);
         total += clock64() - t0;
     }
     if (threadIdx.x == 0) { cyc[blockIdx.x] = total; out[blockIdx.x] = sweeps; }
