@@ -228,6 +228,61 @@ __device__ inline void d4_weights_atom(const DevModel &m, int i, double cn, doub
     }
 }
 
+// ---- 8-lane groups: the O(nat), O(nsh) and O(nat^2) pieces of the SCC cycle have far fewer independent items than the CTA has
+// threads, so an item (atom / shell) is shared by a group of 8 lanes and reduced with three shuffle stages; trip counts are
+// the same for every lane of a warp (inactive groups work on a clamped index and do not store).
+__device__ __forceinline__ double oct_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// d4_weights_atom with the reference systems of atom i spread over the 8 lanes of a group (QX_MAXREF = 7 <= 8)
+__device__ __forceinline__ void d4_weights_oct(const DevModel &m, int i, bool active, double cn, double q, double *gw, double *gwdcn, double *gwdq) {
+    const int r = threadIdx.x & 7;
+    const bool on = r < m.at_nref[i];
+    const int ir = i * QX_MAXREF + (on ? r : 0);
+    const double refcn = m.at_refcn[ir], refq = m.at_refq[ir];
+    const int ngw = on ? m.at_ngw[ir] : 0;
+    const double zi = m.at_zeff[i], gi = m.at_gam[i] * GFN2_D4_GC;
+    const double dc = cn - refcn;
+    double expw = 0.0, expd = 0.0;
+    for (int g = 1; g <= ngw; ++g) {
+        const double wf = g * GFN2_D4_WF, w = exp(-wf * dc * dc);
+        expw += w;
+        expd += 2.0 * wf * (-dc) * w;
+    }
+    double norm = oct_sum(expw);
+    const double dnorm = oct_sum(expd);
+    double maxcn = on ? refcn : -1.0;
+    maxcn = fmax(maxcn, __shfl_xor_sync(0xffffffffu, maxcn, 4));
+    maxcn = fmax(maxcn, __shfl_xor_sync(0xffffffffu, maxcn, 2));
+    maxcn = fmax(maxcn, __shfl_xor_sync(0xffffffffu, maxcn, 1));
+    norm = 1.0 / norm;
+    double gwk = expw * norm;
+    if (gwk != gwk || fabs(gwk) > 1e300) gwk = (maxcn == refcn) ? 1.0 : 0.0;
+    double dgwk = norm * (expd - expw * dnorm * norm);
+    if (dgwk != dgwk || fabs(dgwk) > 1e300) dgwk = 0.0;
+    if (active && r < QX_MAXREF) {
+        const double zt = on ? d4_zeta(GFN2_D4_GA, gi, refq + zi, q + zi) : 0.0;
+        if (gw) gw[r] = on ? gwk * zt : 0.0;
+        if (gwdcn) gwdcn[r] = on ? dgwk * zt : 0.0;
+        if (gwdq) gwdq[r] = on ? gwk * d4_dzeta(GFN2_D4_GA, gi, refq + zi, q + zi) : 0.0;
+    }
+}
+
+// weights of every atom at the charges currently in s.qat (use_q) or at q = 0
+__device__ __forceinline__ void d4_weights_all(const DevModel &m, Sm &s, bool use_q, double *gw, double *gwdcn, double *gwdq) {
+    const int nat = m.nat, oct = threadIdx.x >> 3;
+    for (int base = 0; base < nat; base += QX_NT / 8) {
+        if (base + ((threadIdx.x >> 5) << 2) >= nat) continue;   // warp-uniform: none of this warp's four groups has an atom
+        const bool active = base + oct < nat;
+        const int i = active ? base + oct : 0;
+        d4_weights_oct(m, i, active, s.cn4[i], use_q ? s.qat[i] : 0.0, gw ? gw + 7 * i : nullptr, gwdcn ? gwdcn + 7 * i : nullptr, gwdq ? gwdq + 7 * i : nullptr);
+    }
+}
+
 __device__ inline double bj_r0(const DevModel &m, int i, int j) { return GFN2_D4_A1 * sqrt(3.0 * m.at_r4r2[i] * m.at_r4r2[j]) + GFN2_D4_A2; }
 
 // atomic C6(i,j) and d C6(i,j)/d cn_i from the weights currently in s.gw / gwdcn (global tmp)
@@ -254,7 +309,7 @@ __device__ inline void d4_c6_tables(const DevModel &m, const double *gw, const d
 __device__ __noinline__ double phase_d4_nonsc(const DevModel &m, Sm &s, double *edisp, double *c6, double *dc6, double *tmp) {
     const int nat = m.nat;
     double *gw0 = tmp, *gwdcn0 = tmp + 7 * nat, *part = tmp + 14 * nat;
-    for (int i = threadIdx.x; i < nat; i += QX_NT) d4_weights_atom(m, i, s.cn4[i], 0.0, gw0 + 7 * i, gwdcn0 + 7 * i, nullptr);
+    d4_weights_all(m, s, false, gw0, gwdcn0, nullptr);
     for (int ij = threadIdx.x; ij < nat * nat; ij += QX_NT) {
         int i = ij / nat, j = ij - i * nat;
         double e = 0.0;

@@ -65,42 +65,58 @@ __device__ inline double d4_vvec(const DevModel &m, const Sm &s, const double *e
     return -acc;
 }
 
+// v_a = sum_b gamma_ab q_b for shell a (group-wide result)
+__device__ __forceinline__ double gamma_row_oct(const Sm &s, const double *gamma, int nsh, int a) {
+    double v = 0.0;
+    for (int b = threadIdx.x & 7; b < nsh; b += 8) v += gamma[a * nsh + b] * s.qsh[b];
+    return oct_sum(v);
+}
+
 // potentials from the (input) populations in s.qsh/qat/dpat/qpat -> s.vsh, vat, vdp, vqp, vao
 __device__ __noinline__ void phase_potential(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double *t7) {
     const int nat = m.nat, nsh = m.nsh, nao = m.nao;
-    for (int i = threadIdx.x; i < nat; i += QX_NT) d4_weights_atom(m, i, s.cn4[i], s.qat[i], s.gw + 7 * i, nullptr, s.gwd + 7 * i);
-    for (int a = threadIdx.x; a < nsh; a += QX_NT) {
-        double v = 0.0;
-        for (int b = 0; b < nsh; ++b) v += gamma[a * nsh + b] * s.qsh[b];
-        s.vsh[a] = v + s.qsh[a] * s.qsh[a] * m.sh_gam3[a];
+    const int oct = threadIdx.x >> 3, l8 = threadIdx.x & 7, wbase = (threadIdx.x >> 5) << 2;
+    d4_weights_all(m, s, true, s.gw, nullptr, s.gwd);
+    for (int base = 0; base < nsh; base += QX_NT / 8) {
+        if (base + wbase >= nsh) continue;
+        const bool active = base + oct < nsh;
+        const int a = active ? base + oct : 0;
+        const double v = gamma_row_oct(s, gamma, nsh, a);
+        if (active && l8 == 0) s.vsh[a] = v + s.qsh[a] * s.qsh[a] * m.sh_gam3[a];
     }
-    {   // anisotropic electrostatics: one warp per atom i, lanes over the partner j, fixed-order butterfly reduction
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int i = warp; i < nat; i += QX_NT / 32) {
-            double acc[10];
+    // anisotropic electrostatics: one group per atom i, lanes over the partners j
+    for (int base = 0; base < nat; base += QX_NT / 8) {
+        if (base + wbase >= nat) continue;
+        const bool active = base + oct < nat;
+        const int i = active ? base + oct : 0;
+        double acc[10];
 #pragma unroll
-            for (int c = 0; c < 10; ++c) acc[c] = 0.0;
-            for (int j = lane; j < nat; j += 32) {
-                if (j == i) continue;
-                double v[3], g3f3, g3f5, g5f5;
-                aes_pair(s, i, j, v, g3f3, g3f5, g5f5);
-                const double qj = s.qat[j];
-                const double *mj = s.dpat + 3 * j;
-                const double mv = mj[0] * v[0] + mj[1] * v[1] + mj[2] * v[2];
+        for (int c = 0; c < 10; ++c) acc[c] = 0.0;
+        for (int j = l8; j < nat; j += 8) {
+            if (j == i) continue;
+            double v[3], g3f3, g3f5, g5f5;
+            aes_pair(s, i, j, v, g3f3, g3f5, g5f5);
+            const double qj = s.qat[j];
+            const double *mj = s.dpat + 3 * j;
+            const double mv = mj[0] * v[0] + mj[1] * v[1] + mj[2] * v[2];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) acc[k] += v[k] * g3f3 * qj + g3f5 * mj[k] - 3.0 * g5f5 * v[k] * mv;
-                const double tq = g5f5 * qj;
-                acc[3] += tq * v[0] * v[0]; acc[4] += 2.0 * tq * v[0] * v[1]; acc[5] += tq * v[1] * v[1];
-                acc[6] += 2.0 * tq * v[0] * v[2]; acc[7] += 2.0 * tq * v[1] * v[2]; acc[8] += tq * v[2] * v[2];
-                acc[9] += -g3f3 * mv + g5f5 * quad_contract(s.qpat + 6 * j, v);
+            for (int k = 0; k < 3; ++k) acc[k] += v[k] * g3f3 * qj + g3f5 * mj[k] - 3.0 * g5f5 * v[k] * mv;
+            const double tq = g5f5 * qj;
+            acc[3] += tq * v[0] * v[0]; acc[4] += 2.0 * tq * v[0] * v[1]; acc[5] += tq * v[1] * v[1];
+            acc[6] += 2.0 * tq * v[0] * v[2]; acc[7] += 2.0 * tq * v[1] * v[2]; acc[8] += tq * v[2] * v[2];
+            acc[9] += -g3f3 * mv + g5f5 * quad_contract(s.qpat + 6 * j, v);
+        }
+#pragma unroll
+        for (int c = 0; c < 10; ++c) acc[c] = oct_sum(acc[c]);
+        if (active) {
+#pragma unroll
+            for (int c = 0; c < 10; ++c) {
+                if (l8 == (c & 7)) {
+                    if (c < 3) s.vdp[3 * i + c] = acc[c] + 2.0 * m.at_dk[i] * s.dpat[3 * i + c];
+                    else if (c < 9) s.vqp[6 * i + c - 3] = acc[c] + 2.0 * m.at_qk[i] * s.qpat[6 * i + c - 3] * c_qscale[c - 3];
+                    else s.vat[i] = acc[9];
+                }
             }
-#pragma unroll
-            for (int c = 0; c < 10; ++c)
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-            if (lane < 3) s.vdp[3 * i + lane] = acc[lane] + 2.0 * m.at_dk[i] * s.dpat[3 * i + lane];
-            if (lane >= 3 && lane < 9) s.vqp[6 * i + lane - 3] = acc[lane] + 2.0 * m.at_qk[i] * s.qpat[6 * i + lane - 3] * c_qscale[lane - 3];
-            if (lane == 9) s.vat[i] = acc[9];
         }
     }
     __syncthreads();
@@ -122,37 +138,39 @@ __device__ __noinline__ void phase_potential(const DevModel &m, Sm &s, const dou
 // energies of the charge-dependent terms at the (output) populations
 __device__ __noinline__ void phase_scc_energy(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double &e_es, double &e_aes, double &e_d4) {
     const int nat = m.nat, nsh = m.nsh;
-    for (int i = threadIdx.x; i < nat; i += QX_NT) d4_weights_atom(m, i, s.cn4[i], s.qat[i], s.gw + 7 * i, nullptr, nullptr);
+    const int oct = threadIdx.x >> 3, l8 = threadIdx.x & 7, wbase = (threadIdx.x >> 5) << 2;
+    d4_weights_all(m, s, true, s.gw, nullptr, nullptr);
     double es = 0.0, ea = 0.0, ed = 0.0;
-    for (int a = threadIdx.x; a < nsh; a += QX_NT) {
-        double v = 0.0;
-        for (int b = 0; b < nsh; ++b) v += gamma[a * nsh + b] * s.qsh[b];
-        es += 0.5 * v * s.qsh[a] + s.qsh[a] * s.qsh[a] * s.qsh[a] * m.sh_gam3[a] / 3.0;
+    for (int base = 0; base < nsh; base += QX_NT / 8) {
+        if (base + wbase >= nsh) continue;
+        const bool active = base + oct < nsh;
+        const int a = active ? base + oct : 0;
+        const double v = gamma_row_oct(s, gamma, nsh, a);
+        if (active && l8 == 0) es += 0.5 * v * s.qsh[a] + s.qsh[a] * s.qsh[a] * s.qsh[a] * m.sh_gam3[a] / 3.0;
     }
-    {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int i = warp; i < nat; i += QX_NT / 32) {
-            const double *mi = s.dpat + 3 * i;
-            double e = 0.0;
-            for (int j = lane; j < nat; j += 32) {
-                if (j == i) continue;
-                double v[3], g3f3, g3f5, g5f5;
-                aes_pair(s, i, j, v, g3f3, g3f5, g5f5);
-                const double qj = s.qat[j];
-                const double *mj = s.dpat + 3 * j;
-                const double mv = mj[0] * v[0] + mj[1] * v[1] + mj[2] * v[2];
-                double vd0 = v[0] * g3f3 * qj + 0.5 * (g3f5 * mj[0] - 3.0 * g5f5 * v[0] * mv);
-                double vd1 = v[1] * g3f3 * qj + 0.5 * (g3f5 * mj[1] - 3.0 * g5f5 * v[1] * mv);
-                double vd2 = v[2] * g3f3 * qj + 0.5 * (g3f5 * mj[2] - 3.0 * g5f5 * v[2] * mv);
-                e += mi[0] * vd0 + mi[1] * vd1 + mi[2] * vd2 + g5f5 * qj * quad_contract(s.qpat + 6 * i, v);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-            if (lane == 0) {
-                e += m.at_dk[i] * (mi[0] * mi[0] + mi[1] * mi[1] + mi[2] * mi[2]);
-                for (int k = 0; k < 6; ++k) e += m.at_qk[i] * s.qpat[6 * i + k] * s.qpat[6 * i + k] * c_qscale[k];
-                ea += e;
-            }
+    for (int base = 0; base < nat; base += QX_NT / 8) {
+        if (base + wbase >= nat) continue;
+        const bool active = base + oct < nat;
+        const int i = active ? base + oct : 0;
+        const double *mi = s.dpat + 3 * i;
+        double e = 0.0;
+        for (int j = l8; j < nat; j += 8) {
+            if (j == i) continue;
+            double v[3], g3f3, g3f5, g5f5;
+            aes_pair(s, i, j, v, g3f3, g3f5, g5f5);
+            const double qj = s.qat[j];
+            const double *mj = s.dpat + 3 * j;
+            const double mv = mj[0] * v[0] + mj[1] * v[1] + mj[2] * v[2];
+            double vd0 = v[0] * g3f3 * qj + 0.5 * (g3f5 * mj[0] - 3.0 * g5f5 * v[0] * mv);
+            double vd1 = v[1] * g3f3 * qj + 0.5 * (g3f5 * mj[1] - 3.0 * g5f5 * v[1] * mv);
+            double vd2 = v[2] * g3f3 * qj + 0.5 * (g3f5 * mj[2] - 3.0 * g5f5 * v[2] * mv);
+            e += mi[0] * vd0 + mi[1] * vd1 + mi[2] * vd2 + g5f5 * qj * quad_contract(s.qpat + 6 * i, v);
+        }
+        e = oct_sum(e);
+        if (active && l8 == 0) {
+            e += m.at_dk[i] * (mi[0] * mi[0] + mi[1] * mi[1] + mi[2] * mi[2]);
+            for (int k = 0; k < 6; ++k) e += m.at_qk[i] * s.qpat[6 * i + k] * s.qpat[6 * i + k] * c_qscale[k];
+            ea += e;
         }
     }
     __syncthreads();  // gw complete
@@ -166,22 +184,48 @@ __device__ __noinline__ void phase_scc_energy(const DevModel &m, Sm &s, const do
 }
 
 // H1 = H0 - 1/2 S (v_a + v_b) - 1/2 (D.vdp + D^T.vdp) - 1/2 (Q.vqp + ...) into s.A (symmetric)
+// The integral slab (S, H0, 3 dipole, 6 quadrupole matrices: 11 nao^2 doubles) lives in the CTA's global scratch and is
+// streamed from L2 twice per SCC cycle (here and in phase_mulliken).  Both phases are latency-bound, so what matters is the
+// number of bytes in flight per round trip: 128-bit loads, all 11 matrices of an element pair issued back to back.
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+
 template <bool SH>
 __device__ __noinline__ void phase_build_h1(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt) {
     const int nao = m.nao, ld = m.ld;
     double *const A = s.A;
     if (SH) QX_ASSUME_SHARED(A);
     const size_t n2 = (size_t)nao * nao;
-    for (int t = threadIdx.x; t < nao * nao; t += QX_NT) {
-        int b = t / nao, a = t - b * nao, ib = m.ao_at[b];
-        double g = 0.5 * H0[t] - 0.5 * S[t] * s.vao[b];
-        const double *vd = s.vdp + 3 * ib, *vq = s.vqp + 6 * ib;
-        double acc = 0.0;
+    if ((nao & 1) == 0) {   // element pairs (t, t+1) of one row
+        for (int u = threadIdx.x; u < nao * nao / 2; u += QX_NT) {
+            const int t = 2 * u, b = t / nao, a = t - b * nao, ib = m.ao_at[b];
+            const double2 h0 = ld2(H0 + t), sv = ld2(S + t);
+            double2 d[3], q[6];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) acc += Dt[c * n2 + t] * vd[c];
+            for (int c = 0; c < 3; ++c) d[c] = ld2(Dt + c * n2 + t);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) acc += Qt[c * n2 + t] * vq[c];
-        A[(size_t)b * ld + a] = g - 0.5 * acc;
+            for (int c = 0; c < 6; ++c) q[c] = ld2(Qt + c * n2 + t);
+            const double vb = s.vao[b];
+            const double *vd = s.vdp + 3 * ib, *vq = s.vqp + 6 * ib;
+            double ax = 0.0, ay = 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { ax += d[c].x * vd[c]; ay += d[c].y * vd[c]; }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { ax += q[c].x * vq[c]; ay += q[c].y * vq[c]; }
+            *reinterpret_cast<double2 *>(A + (size_t)b * ld + a) =
+                make_double2(0.5 * h0.x - 0.5 * sv.x * vb - 0.5 * ax, 0.5 * h0.y - 0.5 * sv.y * vb - 0.5 * ay);
+        }
+    } else {
+        for (int t = threadIdx.x; t < nao * nao; t += QX_NT) {
+            int b = t / nao, a = t - b * nao, ib = m.ao_at[b];
+            double g = 0.5 * H0[t] - 0.5 * S[t] * s.vao[b];
+            const double *vd = s.vdp + 3 * ib, *vq = s.vqp + 6 * ib;
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc += Dt[c * n2 + t] * vd[c];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc += Qt[c * n2 + t] * vq[c];
+            A[(size_t)b * ld + a] = g - 0.5 * acc;
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < nao * nao; t += QX_NT) {
@@ -203,19 +247,47 @@ __device__ __noinline__ double phase_mulliken(const DevModel &m, Sm &s, const do
     if (SH) QX_ASSUME_SHARED(A);
     const size_t n2 = (size_t)nao * nao;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // One warp per row b.  Even nao: lanes take element pairs; the pairs beyond the last full group of 32 are either one
+    // more (partly idle) pass or -- when there are only a few of them, e.g. 1 of 33 for caffeine -- left to a second loop
+    // over (row, matrix) items, so that a nearly empty pass does not cost a full memory round trip per row.
+    const int npr = (nao & 1) ? 0 : nao >> 1, nfull = npr >> 5, rem = npr - (nfull << 5);
+    const bool tail_items = rem > 0 && rem < 8 && nfull > 0;
+    const int npass = (nao & 1) ? 0 : nfull + ((rem > 0 && !tail_items) ? 1 : 0);
     for (int b = warp; b < nao; b += QX_NT / 32) {
         double acc[11];
 #pragma unroll
         for (int c = 0; c < 11; ++c) acc[c] = 0.0;
-        for (int a = lane; a < nao; a += 32) {
-            const double p = A[(size_t)b * ld + a];
-            const size_t t = (size_t)b * nao + a;
-            acc[0] += p * S[t];
-            acc[10] += p * H0[t];
+        const size_t t0 = (size_t)b * nao;
+        for (int j = 0; j < npass; ++j) {
+            const int ap = lane + 32 * j;
+            if (ap < npr) {
+                const size_t t = t0 + 2 * ap;
+                const double2 sv = ld2(S + t), h0 = ld2(H0 + t);
+                double2 d[3], q[6];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) acc[1 + c] += p * Dt[c * n2 + t];
+                for (int c = 0; c < 3; ++c) d[c] = ld2(Dt + c * n2 + t);
 #pragma unroll
-            for (int c = 0; c < 6; ++c) acc[4 + c] += p * Qt[c * n2 + t];
+                for (int c = 0; c < 6; ++c) q[c] = ld2(Qt + c * n2 + t);
+                const double2 p = *reinterpret_cast<const double2 *>(A + (size_t)b * ld + 2 * ap);
+                acc[0] += p.x * sv.x + p.y * sv.y;
+                acc[10] += p.x * h0.x + p.y * h0.y;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[1 + c] += p.x * d[c].x + p.y * d[c].y;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) acc[4 + c] += p.x * q[c].x + p.y * q[c].y;
+            }
+        }
+        if (nao & 1) {
+            for (int a = lane; a < nao; a += 32) {
+                const double p = A[(size_t)b * ld + a];
+                const size_t t = t0 + a;
+                acc[0] += p * S[t];
+                acc[10] += p * H0[t];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[1 + c] += p * Dt[c * n2 + t];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) acc[4 + c] += p * Qt[c * n2 + t];
+            }
         }
 #pragma unroll
         for (int c = 0; c < 11; ++c) {
@@ -226,6 +298,20 @@ __device__ __noinline__ double phase_mulliken(const DevModel &m, Sm &s, const do
         }
     }
     __syncthreads();
+    if (tail_items) {
+        for (int it = threadIdx.x; it < nao * 11; it += QX_NT) {
+            const int b = it / 11, c = it - 11 * b;
+            const double *M = c == 0 ? S : (c == 10 ? H0 : (c < 4 ? Dt + (c - 1) * n2 : Qt + (c - 4) * n2));
+            double v = 0.0;
+            for (int ap = nfull << 5; ap < npr; ++ap) {
+                const double2 x = ld2(M + (size_t)b * nao + 2 * ap);
+                const double2 p = *reinterpret_cast<const double2 *>(A + (size_t)b * ld + 2 * ap);
+                v += p.x * x.x + p.y * x.y;
+            }
+            pop[it] += v;
+        }
+        __syncthreads();
+    }
     for (int a = threadIdx.x; a < nsh; a += QX_NT) {
         double v = m.sh_refocc[a];
         int l = m.sh_l[a], ao0 = m.sh_ao0[a];
@@ -673,7 +759,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     __syncthreads();
     // D4 two-body with the final charges
     double *gwq = taskout, *gwdcnq = taskout + 7 * nat;
-    for (int i = threadIdx.x; i < nat; i += QX_NT) d4_weights_atom(m, i, s.cn4[i], s.qat[i], gwq + 7 * i, gwdcnq + 7 * i, nullptr);
+    d4_weights_all(m, s, true, gwq, gwdcnq, nullptr);
     __syncthreads();
     d4_c6_tables(m, gwq, gwdcnq, c6, dc6);
     __syncthreads();
