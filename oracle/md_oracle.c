@@ -3,6 +3,7 @@
 #include "md_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -612,4 +613,44 @@ done:
     *collided_io = collided;
     free(xyz0); free(velo0); free(grad0); free(mass0); free(achrg0); free(velo_rot); free(avxyz); free(avxyz2); free(store); free(iat0);
     return 0;
+}
+
+/* ======================================================================================== fragment records
+ * reference src/utility.f90:469-498 (units 2: eV) */
+void md_oracle_boltz(int nfrag, double temp, const double *ip, double *pop) {
+    double f = temp * QC_KB * QC_AUTOEV, esum = 0;
+    for (int i = 0; i < nfrag; ++i) esum = esum + exp(-ip[i] / f);
+    for (int i = 0; i < nfrag; ++i) pop[i] = exp(-ip[i] / f) / esum;
+}
+
+/* One record in the format '(F10.7,i3,2i5,2i2,2x,i3,2x,20(i4,i3))' (reference src/write_fragments.f90:402-441).
+ * icoll < 0: EI item list (charge, mchrg, itrj, isec, j, l, pairs) -- one integer fewer than the descriptors expect. */
+static int put_int(char *p, int v, int w) {
+    char t[32];
+    int n = snprintf(t, sizeof t, "%d", v);
+    if (n > w) { memset(p, '*', w); return w; }
+    memset(p, ' ', w - n); memcpy(p + w - n, t, n);
+    return w;
+}
+int md_oracle_res_line(char *buf, double charge, int mchrg, int itrj, int icoll, int isec, int j, int ntypes, const int32_t *types,
+                       const int32_t *counts) {
+    int items[64], n = 0;
+    items[n++] = mchrg; items[n++] = itrj;
+    if (icoll >= 0) items[n++] = icoll;
+    items[n++] = isec; items[n++] = j; items[n++] = ntypes;
+    for (int m = 0; m < ntypes && n + 2 <= 64; ++m) { items[n++] = types[m]; items[n++] = counts[m]; }
+    /* widths of the integer edit descriptors; negative = nX */
+    int desc[8 + 40] = {3, 5, 5, 2, 2, -2, 3, -2};
+    for (int k = 0; k < 20; ++k) { desc[8 + 2 * k] = 4; desc[9 + 2 * k] = 3; }
+    char *p = buf;
+    p += snprintf(p, 16, "%10.7f", charge);
+    if (p - buf > 10) { memset(buf, '*', 10); p = buf + 10; }
+    int it = 0, pad = 0;
+    for (int d = 0; d < 48 && it < n; ++d) {
+        if (desc[d] < 0) { pad += -desc[d]; continue; }
+        memset(p, ' ', pad); p += pad; pad = 0;
+        p += put_int(p, items[it++], desc[d]);
+    }
+    *p = 0;
+    return (int)(p - buf);
 }

@@ -36,6 +36,10 @@ double md_oracle_vary_energies(double e_in, double e_distr, double dum, double d
 int md_oracle_cid(const qcxms_b200_cid_config_t *cfg, int nuc, const int32_t *iat, const double *mass, int icoll, double *xyz,
                   double *velo, const double *rnd, double velo_cm_in, double *direc, int32_t *collided, double *grad, double *achrg,
                   double *axyz, int32_t *list, qcxms_b200_cid_result_t *res);
+/* fragment records (src/utility.f90:469-498, src/write_fragments.f90:402-441) */
+void md_oracle_boltz(int nfrag, double temp, const double *ip, double *pop);
+int md_oracle_res_line(char *buf, double charge, int mchrg, int itrj, int icoll, int isec, int j, int ntypes, const int32_t *types,
+                       const int32_t *counts);
 #ifdef __cplusplus
 }
 #endif

@@ -270,3 +270,33 @@ def cid(cfg, num, mass, icoll, xyz, velo, rnd, velo_cm=0.0, direc=None, collided
         if k != "direc":
             out[k] = getattr(res, k)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ fragment records
+def boltz(temp, ip):
+    ip = np.ascontiguousarray(ip, dtype=np.float64)
+    pop = np.zeros_like(ip)
+    f = lib().md_oracle_boltz
+    f.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    f.restype = None
+    f(len(ip), float(temp), _dp(ip), _dp(pop))
+    return pop
+
+
+def res_line(charge, mchrg, itrj, isec, ifrag, pairs, icoll=None):
+    types = np.array([p[0] for p in pairs], dtype=np.int32); counts = np.array([p[1] for p in pairs], dtype=np.int32)
+    buf = C.create_string_buffer(256)
+    f = lib().md_oracle_res_line
+    f.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    f(buf, float(charge), int(mchrg), int(itrj), -1 if icoll is None else int(icoll), int(isec), int(ifrag), len(pairs), _ip(types), _ip(counts))
+    return buf.value.decode()
+
+
+def energies(jobs, etemp):
+    """energy provider for qcxms_b200.fragments (CPU oracle instead of the CUDA batch entry point)"""
+    from qcxms_b200.fragments import getspin
+    es, st = [], []
+    for num, xyz, chrg in jobs:
+        r = egrad(num, xyz, charge=chrg, multiplicity=getspin(num, chrg), etemp=etemp)
+        es.append(r["energy"]); st.append(r["stat"])
+    return es, st

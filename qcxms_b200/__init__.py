@@ -7,5 +7,7 @@ There is no CPU fallback: importing the API without the built CUDA library raise
 from .api import (CidConfig, CidResult, Ensemble, MdConfig, MdResult, cid, cid_config, egrad_batch, fragment_structure, get_xtb_egrad, gfn1_xtb, gfn2_xtb,
                   ipea1_xtb, lib, load_molecule, version)
 
-__all__ = ["CidConfig", "CidResult", "cid", "cid_config", "Ensemble", "MdConfig", "MdResult", "egrad_batch", "fragment_structure", "get_xtb_egrad", "gfn1_xtb",
+from . import fragments  # noqa: E402,F401
+
+__all__ = ["fragments", "CidConfig", "CidResult", "cid", "cid_config", "Ensemble", "MdConfig", "MdResult", "egrad_batch", "fragment_structure", "get_xtb_egrad", "gfn1_xtb",
            "gfn2_xtb", "ipea1_xtb", "lib", "load_molecule", "version"]

@@ -1,0 +1,53 @@
+"""GPU parity of the post-md() fragment bookkeeping: IPs through the batched CUDA single points vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from qcxms_b200 import ensemble_setup as es
+from qcxms_b200 import fragments as fr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fragment_ips_and_records_match_oracle(qx, oracle):
+    num, xyz, _ = qx.load_molecule("chloroethanol")
+    mass = es.masses_au(num)
+    x = xyz.copy(); x[2] += np.array([9.0, -6.0, -6.0])            # C-Cl cleavage
+    lst = qx.fragment_structure(num, x[None], 3.0)[0]
+    qat = np.full(len(num), 1.0 / len(num))
+    got = fr.manage_fragments(num, mass, x, lst, qat, aTlast=3000.0, itrj=3, isec=1)
+    ref = fr.manage_fragments(num, mass, x, lst, qat, aTlast=3000.0, itrj=3, isec=1, energies=oracle.energies)
+    assert got["nfrag"] == ref["nfrag"] == 2 and got["tcont"] == ref["tcont"] and got["mchrg"] == ref["mchrg"]
+    assert np.abs(got["fragip"] - ref["fragip"]).max() < 1e-6      # eV (1e-8 Eh energies)
+    assert np.abs(got["fragchrg3"] - ref["fragchrg3"]).max() < 1e-6
+    assert got["lines"] == ref["lines"] and got["asave"] == ref["asave"]
+
+
+def test_h_loss_uses_eself_for_the_bare_proton(qx, oracle):
+    # pull a hydrogen off: the H fragment has no electrons as a cation -> eself, IP = E(H+) - E(H)
+    num, xyz, _ = qx.load_molecule("chloroethanol")
+    mass = es.masses_au(num)
+    x = xyz.copy(); x[8] += np.array([7.0, 7.0, 7.0])
+    lst = qx.fragment_structure(num, x[None], 3.0)[0]
+    assert lst.max() == 2 and (lst == 2).sum() == 1 and num[lst == 2][0] == 1
+    got = fr.analyse(num, x, lst, 2)
+    ref = fr.analyse(num, x, lst, 2, energies=oracle.energies)
+    assert got["ipok"] and ref["ipok"]
+    assert np.abs(got["fragip"] - ref["fragip"]).max() < 1e-6
+    assert abs(got["e_ion"][1] - fr.eself([1], [1.0])) < 1e-15
+
+
+def test_ensemble_to_spectrum(qx):
+    """md() ensemble -> manage_fragments per trajectory -> records -> charge-weighted stick spectrum."""
+    num, xyz, _ = qx.load_molecule("chloroethanol")
+    ic = es.synthetic_initial_conditions(num, xyz, 4, first_id=7)
+    ens = qx.Ensemble(num, ic["mass"], 4, mchrg=1, nmax=12, exit_rules=True)
+    ens.set_all(ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+    ens.run_md()
+    res = ens.results()
+    ens.close()
+    lines = []
+    for k in range(4):
+        out = fr.manage_fragments(num, ic["mass"], res["axyz"][k], res["list"][k], res["achrg"][k], aTlast=float(res["aTlast"][k]), itrj=k + 1, isec=1)
+        lines += out["lines"] + ([out["asave"]] if out["asave"] else [])
+    bins = fr.spectrum_from_records(lines, 256)
+    assert abs(bins.sum() - 4.0) < 1e-9 and bins[80] == 4.0      # nothing fragments in 12 steps: M+ at m/z 80 (35Cl)
