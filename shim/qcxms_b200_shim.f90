@@ -34,6 +34,16 @@ module qcxms_tblite
       real(c_double) :: Tav, Epav, Ekav, aTlast, dtime, ttime, Epot, Ekin
    end type md_result
 
+   ! qcxms_b200_cid_config_t / qcxms_b200_cid_result_t (include/qcxms_b200.h)
+   type, bind(c) :: cid_config
+      integer(c_int32_t) :: method_id, mchrg, gas_z, eexact, manual_dist, ntot
+      real(c_double) :: gas_mass, tstep, etemp, elab, ecom
+   end type cid_config
+   type, bind(c) :: cid_result
+      integer(c_int32_t) :: stopcid, nstep, nfrag, collided, status, scc_iter_total
+      real(c_double) :: velo_cm, aTlast, ttime, epot, direc(3)
+   end type cid_result
+
    interface
       integer(c_int) function qcxms_b200_egrad(nat, num, xyz, charge, multiplicity, method_id, etemp, &
             & qat, energy, gradient, stat) bind(c, name="qcxms_b200_egrad")
@@ -86,6 +96,21 @@ module qcxms_tblite
          integer(c_int32_t), intent(out) :: list(*)
          type(md_result), intent(out) :: res
       end function ensemble_get_result
+      ! one collision of cid() for a batch of ions (reference src/cid.f90:24-28); rnd(9,ntraj): the uniform random
+      ! numbers the reference draws inside the call (euler_rotation a,b,c; vary_energies dum,dum2; placement f,g,lmin,lpos)
+      integer(c_int) function cid_batch(cfg, ntraj, nuc, num, mass, icoll, xyz, velo, rnd, velo_cm, direc, collided, &
+            & grad, achrg, axyz, list, res, device) bind(c, name="qcxms_b200_cid_batch")
+         import :: c_int, c_int32_t, c_double, cid_config, cid_result
+         type(cid_config), intent(in) :: cfg
+         integer(c_int), value :: ntraj, nuc, icoll, device
+         integer(c_int32_t), intent(in) :: num(*)
+         real(c_double), intent(in) :: mass(*), rnd(9, *), velo_cm(*)
+         real(c_double), intent(inout) :: xyz(3, nuc, *), velo(3, nuc, *), direc(3, *)
+         integer(c_int32_t), intent(inout) :: collided(*)
+         real(c_double), intent(out) :: grad(3, nuc, *), achrg(nuc, *), axyz(3, nuc, *)
+         integer(c_int32_t), intent(out) :: list(nuc, *)
+         type(cid_result), intent(out) :: res(*)
+      end function cid_batch
    end interface
 
 contains
