@@ -116,3 +116,37 @@ def test_bulk_results_match_per_trajectory_results(qx):
         for key in ("mdok", "fragstate", "nstep", "nfrag", "status", "scc_iter_total", "Tav", "Epav", "Ekav", "aTlast", "dtime", "ttime", "Epot", "Ekin"):
             assert allr[key][k] == one[key]
     ens.close()
+
+
+def test_ensemble_spectrum_cosine_similarity_vs_oracle(qx, oracle):
+    """Whole-ensemble check (north star: spectra agree within a stated cosine similarity, trajectories diverge chaotically):
+    64 strongly heated 2-chloroethanol cations, md() with the EI exit rules on the GPU and in the CPU oracle from identical
+    initial conditions; fragment-mass histograms (nominal amu bins, one count per fragment as k_histogram does) must have
+    cosine similarity >= 0.95 and most trajectories must end in the identical fragment assignment."""
+    from qcxms_b200 import ensemble_setup as es
+    num, xyz, _ = qx.load_molecule("chloroethanol")
+    nt = 64
+    ic = es.synthetic_initial_conditions(num, xyz, nt, first_id=500, ieeatm=2.0, tadd_fs=40.0)
+    ens = qx.Ensemble(num, ic["mass"], nt, mchrg=1, nmax=400, nfragexit=2, exit_rules=True)
+    ens.set_all(ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+    ens.run_md()
+    got = ens.results()
+    bins_gpu, _ = ens.histogram(128)
+    ens.close()
+    amu = ic["mass"] / qx.api.AMUTOAU
+    bins_ref = np.zeros(128)
+    same_list = same_nstep = 0
+    for k in range(nt):
+        ref = oracle.md(num, ic["mass"], ic["xyz"][k], ic["velo"][k], ic["velof"][k], ic["eimp"][k], ic["tadd"][k], mchrg=1, nmax=400, nfragexit=2)
+        if ref["status"] == 1 and ref["mdok"]:
+            for f in range(1, 11):
+                m = amu[ref["list"] == f].sum()
+                if m > 0:
+                    bins_ref[int(np.rint(m))] += 1
+        same_list += int(np.array_equal(ref["list"], got["list"][k]))
+        same_nstep += int(ref["nstep"] == got["nstep"][k])
+    assert bins_ref.sum() > nt            # the ensemble really fragments
+    cos = es.cosine_similarity(bins_gpu, bins_ref)
+    print("spectrum cosine similarity %.4f; identical fragment lists %d/%d, identical step counts %d/%d" % (cos, same_list, nt, same_nstep, nt))
+    assert cos >= 0.95
+    assert same_list >= int(0.8 * nt)
