@@ -493,6 +493,104 @@ __device__ inline void ao_pair_multipole(const DevModel &m, int sa, int ma, int 
     }
 }
 
+// ---- s / p specialisation of ao_pair_multipole.  The generic routine above indexes its Obara-Saika table with run-time
+// exponents, which forces the table into local memory (ncu: the recursion lines are the hottest of the integral and gradient
+// phases, all long-scoreboard stalls).  For s and p functions an AO is a single Cartesian monomial (p_m along axis (m+1) mod 3),
+// so with the angular momenta as template parameters every table index is a compile-time constant and the only run-time
+// choice -- "is this the axis of the p function?" -- is a register select.  Work lists are sorted by (la, lb), so the dispatch
+// is warp-uniform except at class boundaries.  Same arithmetic as the generic routine.
+template <int LA, int LB, bool GRAD>
+__device__ __forceinline__ void ao_pair_multipole_sp(const DevModel &m, int sa, int ka, int sb, int kb, const double vec[3], double r2,
+                                                     double out[10], const double *coef, double *grad) {
+    constexpr int AMAX = LA + (GRAD ? 1 : 0), BMAX = LB + 2;
+#pragma unroll
+    for (int c = 0; c < 10; ++c) out[c] = 0.0;
+    if (GRAD) grad[0] = grad[1] = grad[2] = 0.0;
+    const int npa = m.sh_np[sa], npb = m.sh_np[sb];
+    for (int pa_ = 0; pa_ < npa; ++pa_) {
+        const double aj = m.sh_alpha[sa * QX_MAXPRIM + pa_], cj = m.sh_coef[sa * QX_MAXPRIM + pa_];
+        for (int pb_ = 0; pb_ < npb; ++pb_) {
+            const double ai = m.sh_alpha[sb * QX_MAXPRIM + pb_], ci = m.sh_coef[sb * QX_MAXPRIM + pb_];
+            const double gam = ai + aj, est = ai * aj * r2 / gam;
+            if (est > 25.0) continue;
+            const double pg = QX_PI / gam;
+            const double w = exp(-est) * pg * sqrt(pg) * ci * cj;
+            const double oog = 0.5 / gam;
+            double f[3][3], g[3][3];   // f: plain 1-D factors for mm = 0..2; g: the same with the bra function differentiated
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const double pa = ai / gam * vec[d], pb = -aj / gam * vec[d];
+                double t[AMAX + 1][BMAX + 1];
+                t[0][0] = 1.0;
+#pragma unroll
+                for (int b = 0; b < BMAX; ++b) t[0][b + 1] = pb * t[0][b] + (b > 0 ? b * oog * t[0][b - 1] : 0.0);
+#pragma unroll
+                for (int a = 0; a < AMAX; ++a)
+#pragma unroll
+                    for (int b = 0; b <= BMAX; ++b)
+                        t[a + 1][b] = pa * t[a][b] + (a > 0 ? a * oog * t[a - 1][b] : 0.0) + (b > 0 ? b * oog * t[a][b - 1] : 0.0);
+                const bool ia = LA == 1 && d == ka, ib = LB == 1 && d == kb;   // exponent 1 along this axis?
+#pragma unroll
+                for (int mm = 0; mm < 3; ++mm) {
+                    // ket exponent (ib ? 1 : 0) + mm, bra exponent (ia ? 1 : 0)
+                    const double r0 = LB == 1 ? (ib ? t[0][1 + mm] : t[0][mm]) : t[0][mm];
+                    double r1 = 0.0, r2_ = 0.0;
+                    if (AMAX >= 1) r1 = LB == 1 ? (ib ? t[AMAX >= 1 ? 1 : 0][1 + mm] : t[AMAX >= 1 ? 1 : 0][mm]) : t[AMAX >= 1 ? 1 : 0][mm];
+                    if (AMAX >= 2) r2_ = LB == 1 ? (ib ? t[AMAX >= 2 ? 2 : 0][1 + mm] : t[AMAX >= 2 ? 2 : 0][mm]) : t[AMAX >= 2 ? 2 : 0][mm];
+                    f[d][mm] = LA == 1 ? (ia ? r1 : r0) : r0;
+                    if (GRAD) {
+                        const double up = LA == 1 ? (ia ? r2_ : r1) : r1;
+                        const double dn = LA == 1 ? (ia ? r0 : 0.0) : 0.0;     // e * t[e-1]: e = 1 only along the p axis
+                        g[d][mm] = -(2.0 * aj * up - dn);
+                    }
+                }
+            }
+            out[0] += w * f[0][0] * f[1][0] * f[2][0];
+            out[1] += w * f[0][1] * f[1][0] * f[2][0];
+            out[2] += w * f[0][0] * f[1][1] * f[2][0];
+            out[3] += w * f[0][0] * f[1][0] * f[2][1];
+            out[4] += w * f[0][2] * f[1][0] * f[2][0];
+            out[5] += w * f[0][1] * f[1][1] * f[2][0];
+            out[6] += w * f[0][0] * f[1][2] * f[2][0];
+            out[7] += w * f[0][1] * f[1][0] * f[2][1];
+            out[8] += w * f[0][0] * f[1][1] * f[2][1];
+            out[9] += w * f[0][0] * f[1][0] * f[2][2];
+            if (GRAD) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double *x = k == 0 ? g[0] : f[0], *y = k == 1 ? g[1] : f[1], *z = k == 2 ? g[2] : f[2];
+                    double acc = coef[0] * x[0] * y[0] * z[0];
+                    acc += coef[1] * x[1] * y[0] * z[0];
+                    acc += coef[2] * x[0] * y[1] * z[0];
+                    acc += coef[3] * x[0] * y[0] * z[1];
+                    acc += coef[4] * x[2] * y[0] * z[0];
+                    acc += coef[5] * x[1] * y[1] * z[0];
+                    acc += coef[6] * x[0] * y[2] * z[0];
+                    acc += coef[7] * x[1] * y[0] * z[1];
+                    acc += coef[8] * x[0] * y[1] * z[1];
+                    acc += coef[9] * x[0] * y[0] * z[2];
+                    grad[k] += w * acc;
+                }
+            }
+        }
+    }
+}
+
+// dispatch: s / p pairs through the specialisation, anything with a d function through the generic routine
+template <bool GRAD>
+__device__ __forceinline__ void ao_pair_dispatch(const DevModel &m, int sa, int ma, int sb, int mb, const double vec[3], double r2,
+                                                 double out[10], const double *coef, double *grad) {
+    const int la = m.sh_l[sa], lb = m.sh_l[sb];
+    if (la <= 1 && lb <= 1) {
+        const int ka = ma == 2 ? 0 : ma + 1, kb = mb == 2 ? 0 : mb + 1;   // p_m lies along axis (m + 1) mod 3 (order y, z, x)
+        if (la == 0 && lb == 0) ao_pair_multipole_sp<0, 0, GRAD>(m, sa, ka, sb, kb, vec, r2, out, coef, grad);
+        else if (la == 0) ao_pair_multipole_sp<0, 1, GRAD>(m, sa, ka, sb, kb, vec, r2, out, coef, grad);
+        else if (lb == 0) ao_pair_multipole_sp<1, 0, GRAD>(m, sa, ka, sb, kb, vec, r2, out, coef, grad);
+        else ao_pair_multipole_sp<1, 1, GRAD>(m, sa, ka, sb, kb, vec, r2, out, coef, grad);
+    } else
+        ao_pair_multipole(m, sa, ma, sb, mb, vec, r2, out, GRAD ? coef : nullptr, GRAD ? grad : nullptr);
+}
+
 __device__ inline void make_traceless(double q[6]) {
     double tr = 0.5 * (q[0] + q[2] + q[5]);
     for (int c = 0; c < 6; ++c) q[c] *= 1.5;
@@ -524,7 +622,7 @@ __device__ __noinline__ void phase_integrals(const DevModel &m, Sm &s, double *S
         double vec[3] = {s.xyz[3 * ib] - s.xyz[3 * ja], s.xyz[3 * ib + 1] - s.xyz[3 * ja + 1], s.xyz[3 * ib + 2] - s.xyz[3 * ja + 2]};
         double r2 = vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2];
         double raw[10];
-        ao_pair_multipole(m, sa, m.ao_m[a], sb, m.ao_m[b], vec, r2, raw, nullptr, nullptr);
+        ao_pair_dispatch<false>(m, sa, m.ao_m[a], sb, m.ao_m[b], vec, r2, raw, nullptr, nullptr);
         double hij = 0.5 * (s.selfen[sa] + s.selfen[sb]);
         if (ja != ib) {
             double rr = sqrt(sqrt(r2) / (m.at_rad[ja] + m.at_rad[ib]));

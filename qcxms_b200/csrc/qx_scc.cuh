@@ -507,7 +507,7 @@ __device__ __noinline__ void phase_gradient_pairs(const DevModel &m, Sm &s, cons
             coef[1 + qa] -= pij * wJ[c] * vec[qb];
         }
         double raw[10], g[3];
-        ao_pair_multipole(m, sa, m.ao_m[a], sb, m.ao_m[b], vec, r2, raw, coef, g);
+        ao_pair_dispatch<true>(m, sa, m.ao_m[a], sb, m.ao_m[b], vec, r2, raw, coef, g);
         // explicit vec-dependence of the coefficients + distance dependence of H0
         for (int k = 0; k < 3; ++k) g[k] += -pij * vdJ[k] * raw[0] + 2.0 * pij * hav * hs * dshp * vec[k] * raw[0];
         for (int c = 0; c < 6; ++c) {
