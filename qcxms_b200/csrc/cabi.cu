@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
         }
         // per-trajectory arrays live in shared memory for the duration of the work item (read with ld.cg: the previous
         // sub-chunk of this trajectory may have run on another SM)
-        double *velo = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global) + 8, *grad = velo + 3 * nat, *avxyz = grad + 3 * nat, *achrg = avxyz + 3 * nat,
+        double *velo = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global, m.ntype) + 8, *grad = velo + 3 * nat, *avxyz = grad + 3 * nat, *achrg = avxyz + 3 * nat,
                *avchrg = achrg + nat;
         double *gxyz = st.xyz + (size_t)t * 3 * nat, *gvelo = st.velo + (size_t)t * 3 * nat, *ggrad = st.grad + (size_t)t * 3 * nat;
         double *gachrg = st.achrg + (size_t)t * nat, *gavchrg = st.avchrg + (size_t)t * nat, *gavxyz = st.avxyz + (size_t)t * 3 * nat;
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(QX_NT, 2) k_cid_chunk(DevModel m, ScratchLayou
         const int t = s_next;
         if (t >= ntraj) break;
         if (st.sc[t].status != TRJ_RUNNING) continue;
-        double *velo0 = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global) + 8, *grad0 = velo0 + 3 * nuc0, *achrg0 = grad0 + 3 * nuc0;
+        double *velo0 = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global, m.ntype) + 8, *grad0 = velo0 + 3 * nuc0, *achrg0 = grad0 + 3 * nuc0;
         double *gxyz0 = st.xyz0 + (size_t)t * 3 * nuc0, *gvelo0 = st.velo0 + (size_t)t * 3 * nuc0, *ggrad0 = st.grad0 + (size_t)t * 3 * nuc0,
                *gachrg0 = st.achrg0 + (size_t)t * nuc0;
         double *avxyz = st.avxyz + (size_t)t * 3 * nuc, *avxyz2 = st.avxyz2 + (size_t)t * 3 * nuc, *store = st.store + (size_t)t * 3 * nuc;
@@ -468,11 +468,11 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
     c.device = device;
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 0) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
+    c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 0, c.hm.ntype) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
     if (c.smem > (size_t)prop.sharedMemPerBlockOptin) {
         // large basis (nao >~ 110): keep the two SCC matrices in the per-CTA global slab -- functional, slower
         c.hm.dev.mat_in_global = 1;
-        c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 1) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
+        c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 1, c.hm.ntype) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
         if (c.smem > (size_t)prop.sharedMemPerBlockOptin)
             return fail(QCXMS_B200_ERR_UNSUPPORTED, "system too large for the per-CTA working set (nat = " + std::to_string(c.hm.nat) + ")");
     }

@@ -55,15 +55,18 @@ struct SmPtr {
 };
 #define QX_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 
+#define QX_BSOL_N 13                              // largest Broyden system solved in shared memory
+#define QX_BSOL (QX_BSOL_N * (QX_BSOL_N + 1) + 2)
+
 struct Sm {
     double *A, *C;   // shared memory, or the CTA's global slab when the basis is too large (DevModel::mat_in_global)
     SmPtr xyz, cn, cn4, mrad, dmr, qat, vat, dpat, vdp, qpat, vqp;
-    SmPtr qsh, vsh, selfen, vao, emo, focc, gw, gwd, dEdcn, dEdcn4, grad, red, jw;
+    SmPtr qsh, vsh, selfen, vao, emo, focc, gw, gwd, dEdcn, dEdcn4, grad, red, jw, bsol, pop, d4u;
 };
 
-__host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld, int rows8, int mat_in_global = 0) {
+__host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld, int rows8, int mat_in_global, int ntype) {
     return (mat_in_global ? 0 : 2 * (size_t)rows8 * ld) + 3 * nat + 6 * nat /*cn cn4 mrad dmr qat vat*/ + 6 * nat /*dpat vdp*/ + 12 * nat /*qpat vqp*/
-           + 3 * nsh + 3 * nao + 8 + 14 * nat /*gw gwd*/ + 2 * nat + 3 * nat /*grad*/ + 64 + 3 * nao + 8 /*jw*/;
+           + 3 * nsh + 3 * nao + 8 + 14 * nat /*gw gwd*/ + 2 * nat + 3 * nat /*grad*/ + 64 + 3 * nao + 8 /*jw*/ + QX_BSOL /*Broyden solve*/ + 11 * nao + (nao & 1) /*pop*/ + 7 * nat * ntype /*d4u*/;
 }
 
 __device__ inline void carve(const DevModel &m, double *base, Sm &s, double *gmat = nullptr) {
@@ -86,7 +89,10 @@ __device__ inline void carve(const DevModel &m, double *base, Sm &s, double *gma
     s.dEdcn = p; p += nat; s.dEdcn4 = p; p += nat;
     s.grad = p; p += 3 * nat;
     s.red = p; p += 64;
-    s.jw = p;
+    s.jw = p; p += 3 * nao + 8;
+    s.bsol = p; p += QX_BSOL;
+    s.pop = p; p += 11 * nao + (nao & 1);
+    s.d4u = p;
 }
 
 __device__ inline double block_sum(double v, double *red) {

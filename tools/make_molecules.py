@@ -95,6 +95,9 @@ def alkane(nc):
 if "--alkane-only" in sys.argv:
     path = os.path.join(os.path.dirname(__file__), "..", "qcxms_b200", "data", "molecules.json")
     out = json.load(open(path))
+for _nc in (14, 17):      # medium bases between the strip-GEMM limit (72 AOs) and the shared-memory limit (~110)
+    num, xyz = alkane(_nc)
+    out["alkane_c%d" % _nc] = dict(num=num, xyz=xyz.tolist(), charge=0, source="idealised all-trans C%dH%d (%d atoms, %d AOs), tools/make_molecules.py" % (_nc, 2 * _nc + 2, 3 * _nc + 2, 6 * _nc + 2))
 num, xyz = alkane(32)
 out["alkane_c32"] = dict(num=num, xyz=xyz.tolist(), charge=0, source="idealised all-trans C32H66 (98 atoms, 194 AOs), tools/make_molecules.py")
 json.dump(out, open(os.path.join(os.path.dirname(__file__), "..", "qcxms_b200", "data", "molecules.json"), "w"), indent=1)
