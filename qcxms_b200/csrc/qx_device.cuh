@@ -1133,6 +1133,143 @@ __device__ __noinline__ int jacobi_rows_lp8t(int n, double *G, int ld, float tol
     return sweep;
 }
 
+#ifndef QX_JACOBI_NOKEEP   // default; -DQX_JACOBI_NOKEEP selects jacobi_rows_lp8t
+// predicated 128-bit shared-memory load into an existing value
+__device__ __forceinline__ void lds_v2_if(bool p, double2 &v, const double *ptr) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(ptr);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.shared.v2.f64 {%0, %1}, [%2];\n\t}" : "+d"(v.x), "+d"(v.y) : "r"(a), "r"((int)p));
+}
+// ---- "kept row" variant of the trimmed kernel (default).  Group g plays slot k = (g - round) mod K, whose "plus" player (round + k)
+// is the plus player of slot k - 1 in the next round, so the plus row stays in registers; only the "minus" rows (and both
+// rows of slot 0, which wraps to slot K - 1) travel through shared memory: half the row traffic of jacobi_rows_lp8t, whose
+// shared-memory pipe is 76 % busy at two CTAs per SM (ncu).  Same arithmetic in the same order: results are bitwise those of
+// jacobi_rows_lp8t.  Register budget is the constraint (96 per thread): the slot bookkeeping is re-derived from k every round,
+// the scale state of the kept row goes through shared memory like the other one's, and the kept row is (re)loaded with
+// predicated loads -- a branch around plain assignments made the compiler keep the loop-carried array in local memory
+// (65 M local loads per 1184 solves, 45 % slower than lp8t instead of 17 % faster).
+template <int R>
+__device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, float tol, double *jw) {
+    QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(jw);
+    const int mm = (n + 1) & ~1, K = mm >> 1, m1 = mm - 1;
+    const int grp = threadIdx.x >> 3, lsub = threadIdx.x & 7;
+    double *nrm2 = jw;
+    double2 *dd = reinterpret_cast<double2 *>(jw + ((n + 1) & ~1));
+    for (int i = threadIdx.x; i < n; i += QX_NT) dd[i] = make_double2(1.0, 1.0);
+    __syncthreads();
+    const bool tail_ok = 2 * lsub + 16 * (R - 1) < n;
+    const bool gact = grp < K, wact = ((threadIdx.x >> 5) << 2) < K;   // wact is warp-uniform
+    int sweep = 0;
+    for (; sweep < 60; ++sweep) {
+        {   // fold the scales into the rows and refresh the norms
+            const int lane = threadIdx.x & 31;
+            for (int r = threadIdx.x >> 5; r < n; r += QX_NT / 32) {
+                const double d = dd[r].x;
+                double acc = 0.0;
+                for (int i = lane; i < n; i += 32) { const double x = G[(size_t)r * ld + i] * d; G[(size_t)r * ld + i] = x; acc = fma(x, x, acc); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                __syncwarp();
+                if (lane == 0) { nrm2[r] = acc; dd[r] = make_double2(1.0, 1.0); }
+            }
+        }
+        __syncthreads();
+        bool big = false;
+        double2 x[R], y[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = make_double2(0.0, 0.0);   // lanes beyond the row end keep zeros in the tail chunk
+        int k = grp;                                     // slot of this group in the current round: (grp - round) mod K
+        for (int round = 0; round < m1; ++round) {
+            if (wact) {
+                // rows of slot k: kept row ra = round + k (slot 0: round), other row rb = round - k (slot 0: the fixed player m1)
+                int ra = round + k, rb = round - k;
+                if (ra >= m1) ra -= m1;
+                if (rb < 0) rb += m1;
+                if (k == 0) rb = m1;
+                const bool va = gact && ra < n, vb = gact && rb < n;
+                if (!va) ra = 0;
+                if (!vb) rb = 0;
+                double *gp = G + ra * ld + 2 * lsub, *gq = G + rb * ld + 2 * lsub;
+                {   // first round / freshly wrapped group: the kept row is new as well.  Predicated loads (not a branch around plain
+                    // assignments): with a conditionally assigned loop-carried array the compiler keeps x[] in local memory.
+                    const bool fresh = round == 0 || k == K - 1;
+#pragma unroll
+                    for (int r = 0; r < R - 1; ++r) lds_v2_if(fresh, x[r], gp + 16 * r);
+                    lds_v2_if(fresh && tail_ok, x[R - 1], gp + 16 * (R - 1));
+                }
+#pragma unroll
+                for (int r = 0; r < R - 1; ++r) y[r] = *reinterpret_cast<const double2 *>(gq + 16 * r);
+                y[R - 1] = make_double2(0.0, 0.0);
+                if (tail_ok) y[R - 1] = *reinterpret_cast<const double2 *>(gq + 16 * (R - 1));
+                const double2 sx = dd[ra], sq = dd[rb];
+                const double al = nrm2[ra], be = nrm2[rb];
+                double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
+                double gs = g0 + g1;
+                gs += __shfl_xor_sync(0xffffffffu, gs, 4);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 2);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 1);
+                const double ga = (sx.x * sq.x) * gs, ga2 = ga * ga, nn = al * be;
+                const bool valid = va && vb;
+                big |= valid && ga2 > ((double)tol * (double)tol) * nn;
+                const bool rot = valid && ga2 > 1e-30 * nn;
+                const float gf = (float)ga, df = (float)(be - al);
+                const float g2 = gf + gf;
+                const float hh = fmaf(df, df, g2 * g2);
+                const float den = fabsf(df) + hh * rsqrt_approx(hh);
+                float tf = g2 * rcp_approx(den);
+                tf = __int_as_float(__float_as_int(tf) ^ (__float_as_int(df) & 0x80000000));
+                tf = rot ? tf : 0.0f;
+                const double t = (double)tf;
+                const double t1 = t * (sq.x * sx.y), t2 = t * (sx.x * sq.y);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const double ux = fma(-t1, y[r].x, x[r].x), uy = fma(-t1, y[r].y, x[r].y);
+                    y[r].x = fma(t2, x[r].x, y[r].x); y[r].y = fma(t2, x[r].y, y[r].y);
+                    x[r].x = ux; x[r].y = uy;
+                }
+                if (vb) {
+#pragma unroll
+                    for (int r = 0; r < R - 1; ++r) *reinterpret_cast<double2 *>(gq + 16 * r) = y[r];
+                    if (tail_ok) *reinterpret_cast<double2 *>(gq + 16 * (R - 1)) = y[R - 1];
+                }
+                if (va && (k == 0 || round == m1 - 1)) {   // slot 0 hands both rows on; everything goes back at the end of a sweep
+#pragma unroll
+                    for (int r = 0; r < R - 1; ++r) *reinterpret_cast<double2 *>(gp + 16 * r) = x[r];
+                    if (tail_ok) *reinterpret_cast<double2 *>(gp + 16 * (R - 1)) = x[R - 1];
+                }
+                {
+                    const double w = fma(t, t, 1.0);
+                    double c = (double)rsqrt_approx(fmaf(tf, tf, 1.0f));
+                    c = c * fma(-0.5 * w * c, c, 1.5);
+                    c = c * fma(-0.5 * w * c, c, 1.5);
+                    const double wc = w * c, tg = t * ga;
+                    if (lsub == 0 && valid) {
+                        dd[ra] = make_double2(c * sx.x, wc * sx.y); dd[rb] = make_double2(c * sq.x, wc * sq.y);
+                        nrm2[ra] = al - tg; nrm2[rb] = be + tg;
+                    }
+                }
+                k = k == 0 ? K - 1 : k - 1;
+            }
+            __syncthreads();
+        }
+        if (!__syncthreads_or(big ? 1 : 0)) { ++sweep; break; }
+    }
+    {   // fold the remaining scales
+        const int lane = threadIdx.x & 31;
+        for (int r = threadIdx.x >> 5; r < n; r += QX_NT / 32) {
+            const double d = dd[r].x;
+            for (int i = lane; i < n; i += 32) G[(size_t)r * ld + i] *= d;
+        }
+    }
+    __syncthreads();
+    return sweep;
+}
+#define QX_JROWS jacobi_rows_lp8r
+#else
+#define QX_JROWS jacobi_rows_lp8t
+#endif
+
 // generic fallback (any n): LP lanes per pair, scalar accesses
 __device__ __noinline__ int jacobi_rows_generic(int n, double *G, int ld, double *red, float tol) {
     const int mm = (n + 1) & ~1, npair = mm >> 1;
@@ -1178,13 +1315,14 @@ __device__ __noinline__ int jacobi_rows_generic(int n, double *G, int ld, double
     return sweep;
 }
 
-// Eigen-decomposition of the symmetric A' held in G (n x n, ld).  On exit: emo[k] = eigenvalue k and row k of G
-// is the corresponding unit eigenvector (so G holds J^T).  Returns the number of sweeps.
+// The eigen-solver is three calls made from the SAME level as the other phases (not one wrapper that calls the sweep kernel):
+// a __noinline__ callee only gets the registers its callers do not keep live across the call, and one more call level
+// in between was enough to make the register-hungry sweep kernels spill inside the round loop.
+// (1) Gershgorin shift: makes G positive definite, so that singular values == eigenvalues + sigma; sigma is parked in red[60]
 template <bool SH>
-__device__ __noinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *emo, double *red, double *jw) {
-    QX_ASSUME_SHARED(emo); QX_ASSUME_SHARED(red); QX_ASSUME_SHARED(jw);
+__device__ __noinline__ void jacobi_shift(int n, double *G, int ld, double *red) {
+    QX_ASSUME_SHARED(red);
     if (SH) QX_ASSUME_SHARED(G);
-    // Gershgorin shift: makes G positive definite, so that singular values == eigenvalues + sigma
     double rowsum = 0.0;
     for (int i = threadIdx.x; i < n; i += QX_NT) {
         double v = 0.0;
@@ -1194,21 +1332,27 @@ __device__ __noinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *e
     const double sigma = 1.0625 * block_max(rowsum, red) + 0.5;
     for (int i = threadIdx.x; i < n; i += QX_NT) G[(size_t)i * ld + i] += sigma;
     __syncthreads();
+    if (threadIdx.x == 0) red[60] = sigma;
+    __syncthreads();
+}
+
+// (2) the sweeps
+__device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *red, double *jw) {
     const float tol = 1e-7f;  // pre-rotation ratio of the last sweep; its rotations leave O(tol^2) couplings
     const int npair = (n + 1) >> 1;
     int sweeps;
-#ifndef QX_JACOBI_LP8   // default: trimmed one-pair-per-round kernel
+#ifndef QX_JACOBI_LP8   // default: trimmed one-pair-per-round kernel, kept-row variant
     if (npair * 8 <= QX_NT && (ld & 1) == 0 && n <= 128) {
         const float tolr = QX_JACOBI_TOL;
         switch ((n + 15) >> 4) {
-            case 1: sweeps = jacobi_rows_lp8t<1>(n, G, ld, tolr, jw); break;
-            case 2: sweeps = jacobi_rows_lp8t<2>(n, G, ld, tolr, jw); break;
-            case 3: sweeps = jacobi_rows_lp8t<3>(n, G, ld, tolr, jw); break;
-            case 4: sweeps = jacobi_rows_lp8t<4>(n, G, ld, tolr, jw); break;
-            case 5: sweeps = jacobi_rows_lp8t<5>(n, G, ld, tolr, jw); break;
-            case 6: sweeps = jacobi_rows_lp8t<6>(n, G, ld, tolr, jw); break;
-            case 7: sweeps = jacobi_rows_lp8t<7>(n, G, ld, tolr, jw); break;
-            default: sweeps = jacobi_rows_lp8t<8>(n, G, ld, tolr, jw); break;
+            case 1: sweeps = QX_JROWS<1>(n, G, ld, tolr, jw); break;
+            case 2: sweeps = QX_JROWS<2>(n, G, ld, tolr, jw); break;
+            case 3: sweeps = QX_JROWS<3>(n, G, ld, tolr, jw); break;
+            case 4: sweeps = QX_JROWS<4>(n, G, ld, tolr, jw); break;
+            case 5: sweeps = QX_JROWS<5>(n, G, ld, tolr, jw); break;
+            case 6: sweeps = QX_JROWS<6>(n, G, ld, tolr, jw); break;
+            case 7: sweeps = QX_JROWS<7>(n, G, ld, tolr, jw); break;
+            default: sweeps = QX_JROWS<8>(n, G, ld, tolr, jw); break;
         }
     } else
 #endif
@@ -1225,7 +1369,16 @@ __device__ __noinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *e
         }
     } else
         sweeps = jacobi_rows_generic(n, G, ld, red, tol);
-    // eigenvalues from the row norms; normalise the rows
+    return sweeps;
+}
+
+// (3) eigenvalues from the row norms; normalise the rows.  On exit emo[k] = eigenvalue k and row k of G is the corresponding
+// unit eigenvector (so G holds J^T).
+template <bool SH>
+__device__ __noinline__ void jacobi_finish(int n, double *G, int ld, double *emo, const double *red) {
+    QX_ASSUME_SHARED(emo); QX_ASSUME_SHARED(red);
+    if (SH) QX_ASSUME_SHARED(G);
+    const double sigma = red[60];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = warp; k < n; k += QX_NT / 32) {
         double acc = 0.0;
@@ -1237,6 +1390,14 @@ __device__ __noinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *e
         if (lane == 0) emo[k] = nrm - sigma;
     }
     __syncthreads();
+}
+
+// Eigen-decomposition of the symmetric A' held in G (n x n, ld).  Returns the number of sweeps.
+template <bool SH>
+__device__ __forceinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *emo, double *red, double *jw) {
+    jacobi_shift<SH>(n, G, ld, red);
+    const int sweeps = jacobi_sweeps(n, G, ld, red, jw);
+    jacobi_finish<SH>(n, G, ld, emo, red);
     return sweeps;
 }
 
