@@ -300,3 +300,9 @@ def energies(jobs, etemp):
         r = egrad(num, xyz, charge=chrg, multiplicity=getspin(num, chrg), etemp=etemp)
         es.append(r["energy"]); st.append(r["stat"])
     return es, st
+
+
+def md_batch(num, mass, xyz, velo, velof, eimp, tadd, mchrg, nmax, nfragexit, isec, tstep_fs, etemp):
+    """md back end for qcxms_b200.production.run_ei (CPU oracle instead of the CUDA ensemble)"""
+    return [md(num, mass, xyz[k], velo[k], velof[k], eimp[k], tadd[k], mchrg=mchrg, tstep_fs=tstep_fs, nmax=nmax, nfragexit=nfragexit,
+               exit_rules=True, etemp=etemp, isec=isec) for k in range(len(xyz))]

@@ -51,3 +51,23 @@ def test_ensemble_to_spectrum(qx):
         lines += out["lines"] + ([out["asave"]] if out["asave"] else [])
     bins = fr.spectrum_from_records(lines, 256)
     assert abs(bins.sum() - 4.0) < 1e-9 and bins[80] == 4.0      # nothing fragments in 12 steps: M+ at m/z 80 (35Cl)
+
+
+def test_ei_cascade_records_match_oracle(qx, oracle):
+    """The whole EI production loop of one trajectory directory (main.F90:2199-2370) for 8 trajectories: GPU ensembles +
+    batched fragment single points vs. the same driver on the CPU oracle.  Integer fields of the qcxms.res records must be
+    identical, statistical charges within 2e-6 (they are Boltzmann weights of IPs that agree to 1e-6 eV)."""
+    from qcxms_b200 import production as prod
+    num, xyz, _ = qx.load_molecule("chloroethanol")
+    ic = es.synthetic_initial_conditions(num, xyz, 8, first_id=900, ieeatm=2.5, tadd_fs=40.0)
+    args = (num, ic["mass"], ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+    got = prod.run_ei(*args, mchrg=1, nmax=240, maxsec=3, first_itrj=11)
+    ref = prod.run_ei(*args, mchrg=1, nmax=240, maxsec=3, first_itrj=11, md_batch=oracle.md_batch, energies=oracle.energies)
+    assert len(got["records"]) == len(ref["records"]) > 8
+    for a, b in zip(got["records"], ref["records"]):
+        assert a[10:] == b[10:], (a, b)
+        assert abs(float(a[:10]) - float(b[:10])) <= 2e-6
+    for ta, tb in zip(got["per_traj"], ref["per_traj"]):
+        assert [(g["isec"], g["nat"], g["nstep"], g["nfrag"], g["fragstate"]) for g in ta["generations"]] == \
+               [(g["isec"], g["nat"], g["nstep"], g["nfrag"], g["fragstate"]) for g in tb["generations"]]
+    assert any(len(t["generations"]) > 1 for t in got["per_traj"])
