@@ -910,110 +910,6 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 __device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-template <int R>
-__device__ __noinline__ int jacobi_rows_lp8(int n, double *G, int ld, double *red, float tol, double *jw) {
-    QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(red); QX_ASSUME_SHARED(jw);   // n <= 72: matrices are in shared memory
-    const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
-    const int nslot = QX_NT / 8, slot = threadIdx.x >> 3, lsub = threadIdx.x & 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int npass = (npair + nslot - 1) / nslot;
-    double *nrm2 = jw, *dsc = jw + n, *dinv = jw + 2 * n;
-    for (int i = threadIdx.x; i < n; i += QX_NT) { dsc[i] = 1.0; dinv[i] = 1.0; }
-    __syncthreads();
-    const bool tail_ok = 2 * lsub + 16 * (R - 1) < n;
-    const int tail_off = tail_ok ? 2 * lsub + 16 * (R - 1) : 0;
-    int sweep = 0;
-    for (; sweep < 60; ++sweep) {
-        // fold the scales into the rows and refresh the norms
-        for (int k = warp; k < n; k += QX_NT / 32) {
-            const double d = dsc[k];
-            double acc = 0.0;
-            for (int i = lane; i < n; i += 32) { const double x = G[(size_t)k * ld + i] * d; G[(size_t)k * ld + i] = x; acc += x * x; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            __syncwarp();
-            if (lane == 0) { nrm2[k] = acc; dsc[k] = 1.0; dinv[k] = 1.0; }
-        }
-        __syncthreads();
-        float smax = 0.0f;
-        for (int round = 0; round < m1; ++round) {
-            for (int pass = 0; pass < npass; ++pass) {
-                const int k = slot + pass * nslot;
-                // round-robin tournament: slot 0 pairs the fixed player m1 with `round`, slot k pairs round+k with round-k (mod m1)
-                int p = round + k, q = round - k;
-                if (p >= m1) p -= m1;
-                if (q < 0) q += m1;
-                if (k == 0) p = m1;
-                const int lo = min(p, q), hi = max(p, q);
-                const bool valid = k < npair && hi < n;
-                p = valid ? lo : 0;
-                q = valid ? hi : 0;
-                double *gp = G + p * ld + 2 * lsub, *gq = G + q * ld + 2 * lsub;
-                // scales / norms are read before the reduction: the group leader rewrites them after it
-                const double dp = dsc[p], dq = dsc[q], ip = dinv[p], iq = dinv[q], al = nrm2[p], be = nrm2[q];
-                double2 x[R], y[R];
-#pragma unroll
-                for (int r = 0; r < R - 1; ++r) {   // chunks r < R-1 are in range for every lane (n > 16 (R-1))
-                    x[r] = *reinterpret_cast<const double2 *>(gp + 16 * r);
-                    y[r] = *reinterpret_cast<const double2 *>(gq + 16 * r);
-                }
-                x[R - 1] = *reinterpret_cast<const double2 *>(G + p * ld + tail_off);
-                y[R - 1] = *reinterpret_cast<const double2 *>(G + q * ld + tail_off);
-                if (!tail_ok) { x[R - 1] = make_double2(0.0, 0.0); y[R - 1] = make_double2(0.0, 0.0); }
-                double g0 = 0.0, g1 = 0.0;
-#pragma unroll
-                for (int r = 0; r < R; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
-                double gs = g0 + g1;
-                gs += __shfl_xor_sync(0xffffffffu, gs, 4);
-                gs += __shfl_xor_sync(0xffffffffu, gs, 2);
-                gs += __shfl_xor_sync(0xffffffffu, gs, 1);
-                const double ga = dp * dq * gs;
-                const float gaf = (float)ga;
-                const float ratio = valid ? fabsf(gaf) * rsqrt_approx((float)al * (float)be) : 0.0f;
-                smax = fmaxf(smax, ratio);
-                if (ratio > 1e-15f) {   // group-uniform; rotation angle in single precision, c refined to double
-                    const float zeta = (float)(be - al) * rcp_approx(2.0f * gaf);
-                    const float tf = copysignf(rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.0f))), zeta);
-                    const double t = (double)tf, w = fma(t, t, 1.0);
-                    const double t1 = t * dq * ip, t2 = t * dp * iq;
-#pragma unroll
-                    for (int r = 0; r < R - 1; ++r) {
-                        double2 u, v;
-                        u.x = fma(-t1, y[r].x, x[r].x); u.y = fma(-t1, y[r].y, x[r].y);
-                        v.x = fma(t2, x[r].x, y[r].x); v.y = fma(t2, x[r].y, y[r].y);
-                        *reinterpret_cast<double2 *>(gp + 16 * r) = u;
-                        *reinterpret_cast<double2 *>(gq + 16 * r) = v;
-                    }
-                    if (tail_ok) {
-                        double2 u, v;
-                        u.x = fma(-t1, y[R - 1].x, x[R - 1].x); u.y = fma(-t1, y[R - 1].y, x[R - 1].y);
-                        v.x = fma(t2, x[R - 1].x, y[R - 1].x); v.y = fma(t2, x[R - 1].y, y[R - 1].y);
-                        *reinterpret_cast<double2 *>(gp + 16 * (R - 1)) = u;
-                        *reinterpret_cast<double2 *>(gq + 16 * (R - 1)) = v;
-                    }
-                    if (lsub == 0) {
-                        double c = (double)rsqrt_approx((float)w);
-                        c = c * fma(-0.5 * w * c, c, 1.5);
-                        c = c * fma(-0.5 * w * c, c, 1.5);
-                        const double wc = w * c, tg = t * ga;
-                        dsc[p] = c * dp; dsc[q] = c * dq; dinv[p] = wc * ip; dinv[q] = wc * iq;
-                        nrm2[p] = al - tg; nrm2[q] = be + tg;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        const float m = (float)block_max((double)smax, red);
-        if (m < tol) { ++sweep; break; }
-    }
-    // fold the remaining scales
-    for (int k = warp; k < n; k += QX_NT / 32) {
-        const double d = dsc[k];
-        for (int i = lane; i < n; i += 32) G[(size_t)k * ld + i] *= d;
-    }
-    __syncthreads();
-    return sweep;
-}
-
 // ---- trimmed variant of the one-pair-per-round kernel (default).  The sub-partition pipes are what bounds the sweep
 // (tools/microbench/lat.cu: ~2.1 cycles per double-precision warp instruction, ~8.2 per F2F / MUFU; ncu: >45 % of the issued
 // instructions of jacobi_rows_lp8 are integer / control), so this version (1) walks the tournament incrementally
@@ -1341,31 +1237,14 @@ __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *r
     const float tol = 1e-7f;  // pre-rotation ratio of the last sweep; its rotations leave O(tol^2) couplings
     const int npair = (n + 1) >> 1;
     int sweeps;
-#ifndef QX_JACOBI_LP8   // default: trimmed one-pair-per-round kernel, kept-row variant
-    if (npair * 8 <= QX_NT && (ld & 1) == 0 && n <= 128) {
+    if (npair * 8 <= QX_NT && (ld & 1) == 0 && n <= 80) {
         const float tolr = QX_JACOBI_TOL;
         switch ((n + 15) >> 4) {
             case 1: sweeps = QX_JROWS<1>(n, G, ld, tolr, jw); break;
             case 2: sweeps = QX_JROWS<2>(n, G, ld, tolr, jw); break;
             case 3: sweeps = QX_JROWS<3>(n, G, ld, tolr, jw); break;
             case 4: sweeps = QX_JROWS<4>(n, G, ld, tolr, jw); break;
-            case 5: sweeps = QX_JROWS<5>(n, G, ld, tolr, jw); break;
-            case 6: sweeps = QX_JROWS<6>(n, G, ld, tolr, jw); break;
-            case 7: sweeps = QX_JROWS<7>(n, G, ld, tolr, jw); break;
-            default: sweeps = QX_JROWS<8>(n, G, ld, tolr, jw); break;
-        }
-    } else
-#endif
-    if (npair * 8 <= QX_NT && (ld & 1) == 0 && n <= 128) {
-        switch ((n + 15) >> 4) {
-            case 1: sweeps = jacobi_rows_lp8<1>(n, G, ld, red, tol, jw); break;
-            case 2: sweeps = jacobi_rows_lp8<2>(n, G, ld, red, tol, jw); break;
-            case 3: sweeps = jacobi_rows_lp8<3>(n, G, ld, red, tol, jw); break;
-            case 4: sweeps = jacobi_rows_lp8<4>(n, G, ld, red, tol, jw); break;
-            case 5: sweeps = jacobi_rows_lp8<5>(n, G, ld, red, tol, jw); break;
-            case 6: sweeps = jacobi_rows_lp8<6>(n, G, ld, red, tol, jw); break;
-            case 7: sweeps = jacobi_rows_lp8<7>(n, G, ld, red, tol, jw); break;
-            default: sweeps = jacobi_rows_lp8<8>(n, G, ld, red, tol, jw); break;
+            default: sweeps = QX_JROWS<5>(n, G, ld, tolr, jw); break;   // 8 lanes per pair and QX_NT threads: n <= 72
         }
     } else
         sweeps = jacobi_rows_generic(n, G, ld, red, tol);
