@@ -1002,6 +1002,14 @@ extern "C" int qcxms_b200_debug_phase_cycles(double *out16) {
     CUDA_OK(cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof(h)));
     CUDA_OK(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)));
     for (int i = 0; i < 16; ++i) out16[i] = (double)h[i];
+    {
+        unsigned long long sub[16], sz[16] = {0};
+        CUDA_OK(cudaMemcpyFromSymbol(sub, g_sub_cycles, sizeof(sub)));
+        CUDA_OK(cudaMemcpyToSymbol(g_sub_cycles, sz, sizeof(sz)));
+        fprintf(stderr, "sub-phase cycles (thread 0):");
+        for (int i = 0; i < 16; ++i) if (sub[i]) fprintf(stderr, " %d:%.0f", i, (double)sub[i]);
+        fprintf(stderr, "\n");
+    }
     unsigned long long sh[64], sz[64] = {0};
     CUDA_OK(cudaMemcpyFromSymbol(sh, g_sweep_hist, sizeof(sh)));
     CUDA_OK(cudaMemcpyToSymbol(g_sweep_hist, sz, sizeof(sz)));

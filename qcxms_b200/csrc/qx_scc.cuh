@@ -11,6 +11,9 @@ namespace qx {
 // optional per-phase cycle accounting (profiling builds only: -DQX_PROFILE_PHASES)
 #ifdef QX_PROFILE_PHASES
 __device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned long long g_sub_cycles[16];   // finer marks inside a phase (thread 0's clock, no extra barrier)
+#define QX_SUB_BEGIN() long long sub_t0_ = clock64()
+#define QX_SUB(idx) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_sub_cycles[idx], (unsigned long long)(t_ - sub_t0_)); sub_t0_ = t_; } } while (0)
 __device__ unsigned long long g_sweep_hist[64];  // [iteration index (<32)] -> sweeps, [32+..] -> count
 #define QX_PH_BEGIN() long long ph_t0_ = clock64()
 #define QX_PH(idx)                                                                  \
@@ -26,6 +29,8 @@ __device__ unsigned long long g_sweep_hist[64];  // [iteration index (<32)] -> s
 #else
 #define QX_PH_BEGIN() do {} while (0)
 #define QX_PH(idx) do {} while (0)
+#define QX_SUB_BEGIN() do {} while (0)
+#define QX_SUB(idx) do {} while (0)
 #endif
 
 struct EgradOut {
@@ -197,7 +202,6 @@ __device__ __noinline__ void phase_scc_energy(const DevModel &m, Sm &s, const do
 // streamed from L2 twice per SCC cycle (here and in phase_mulliken).  Both phases are latency-bound, so what matters is the
 // number of bytes in flight per round trip: 128-bit loads, all 11 matrices of an element pair issued back to back.
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
-
 template <bool SH>
 __device__ __noinline__ void phase_build_h1(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt) {
     const int nao = m.nao, ld = m.ld;
@@ -263,6 +267,7 @@ __device__ __noinline__ double phase_mulliken(const DevModel &m, Sm &s, const do
     const int npr = (nao & 1) ? 0 : nao >> 1, nfull = npr >> 5, rem = npr - (nfull << 5);
     const bool tail_items = rem > 0 && rem < 8 && nfull > 0;
     const int npass = (nao & 1) ? 0 : nfull + ((rem > 0 && !tail_items) ? 1 : 0);
+    QX_SUB_BEGIN();
     for (int b = warp; b < nao; b += QX_NT / 32) {
         double acc[11];
 #pragma unroll
@@ -299,15 +304,50 @@ __device__ __noinline__ double phase_mulliken(const DevModel &m, Sm &s, const do
                 for (int c = 0; c < 6; ++c) acc[4 + c] += p * Qt[c * n2 + t];
             }
         }
+        // Transposed warp reduction of the 11 sums (padded to 16): every stage halves the number of values a lane carries
+        // -- the half it gives away goes to the partner lane -- so 8 + 4 + 2 + 1 + 1 = 16 double shuffles instead of 55
+        // (the shuffle unit is shared with the co-resident CTA's Jacobi and was the bottleneck of this loop).  Fixed order.
+        double a8[8], a4[4], a2[2];
+        {
+            const bool up = lane & 16;
 #pragma unroll
-        for (int c = 0; c < 11; ++c) {
-            double v = acc[c];
+            for (int i = 0; i < 8; ++i) {
+                const double lo = acc[i], hi = i + 8 < 11 ? acc[i + 8] : 0.0;
+                const double got = __shfl_xor_sync(0xffffffffu, up ? lo : hi, 16);
+                a8[i] = (up ? hi : lo) + got;
+            }
+        }
+        {
+            const bool up = lane & 8;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) pop[b * 11 + c] = v;
+            for (int i = 0; i < 4; ++i) {
+                const double got = __shfl_xor_sync(0xffffffffu, up ? a8[i] : a8[i + 4], 8);
+                a4[i] = (up ? a8[i + 4] : a8[i]) + got;
+            }
+        }
+        {
+            const bool up = lane & 4;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double got = __shfl_xor_sync(0xffffffffu, up ? a4[i] : a4[i + 2], 4);
+                a2[i] = (up ? a4[i + 2] : a4[i]) + got;
+            }
+        }
+        double v;
+        {
+            const bool up = lane & 2;
+            const double got = __shfl_xor_sync(0xffffffffu, up ? a2[0] : a2[1], 2);
+            v = (up ? a2[1] : a2[0]) + got;
+        }
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        {   // lane l now holds component 8 b4 + 4 b3 + 2 b2 + b1 (b_k: bit k of l), summed over the whole warp
+            const int c = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if ((lane & 1) == 0 && c < 11) pop[b * 11 + c] = v;
         }
     }
+    QX_SUB(0);
     __syncthreads();
+    QX_SUB(1);
     if (tail_items) {
         for (int it = threadIdx.x; it < nao * 11; it += QX_NT) {
             const int b = it / 11, c = it - 11 * b;
@@ -322,6 +362,7 @@ __device__ __noinline__ double phase_mulliken(const DevModel &m, Sm &s, const do
         }
         __syncthreads();
     }
+    QX_SUB(2);
     for (int a = threadIdx.x; a < nsh; a += QX_NT) {
         double v = m.sh_refocc[a];
         int l = m.sh_l[a], ao0 = m.sh_ao0[a];
@@ -346,6 +387,7 @@ __device__ __noinline__ double phase_mulliken(const DevModel &m, Sm &s, const do
         s.qat[i] = v;
     }
     __syncthreads();
+    QX_SUB(3);
     return eel;
 }
 
@@ -429,6 +471,7 @@ __device__ __noinline__ bool broyden_next(Broyden &b, int n, double damp, double
     const int nb = itn < mem ? itn : mem;
     const bool small = nb <= QX_BSOL_N;
     double *beta = small ? bsol : b.beta, *cvec = small ? bsol + QX_BSOL_N * QX_BSOL_N : b.cvec;
+    QX_SUB_BEGIN();
     double nrm = 0.0, inv = 0.0;
     for (int i = threadIdx.x; i < n; i += QX_NT) {
         double d = b.dq[i], v = d - b.dqlast[i];
@@ -444,6 +487,7 @@ __device__ __noinline__ bool broyden_next(Broyden &b, int n, double damp, double
     for (int i = threadIdx.x; i < n; i += QX_NT) b.df[(size_t)it1 * n + i] = inv * (b.dq[i] - b.dqlast[i]);
     if (threadIdx.x == 0) b.omega[it1] = om;
     __syncthreads();
+    QX_SUB(4);
     const int j0 = itn - mem + 1 > 1 ? itn - mem + 1 : 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int j = j0 + warp; j <= itn; j += QX_NT / 32) {
@@ -464,7 +508,9 @@ __device__ __noinline__ bool broyden_next(Broyden &b, int n, double damp, double
         beta[k * nb + i] = v;
     }
     __syncthreads();
+    QX_SUB(5);
     if (!block_solve(nb, beta, cvec, red)) return false;
+    QX_SUB(6);
     for (int i = threadIdx.x; i < n; i += QX_NT) {
         b.u[(size_t)it1 * n + i] = damp * b.df[(size_t)it1 * n + i] + inv * (b.q_in[i] - b.qlast[i]);
         b.dqlast[i] = b.dq[i];
@@ -480,6 +526,7 @@ __device__ __noinline__ bool broyden_next(Broyden &b, int n, double damp, double
         b.q_in[i] = v;
     }
     __syncthreads();
+    QX_SUB(7);
     return true;
 }
 
