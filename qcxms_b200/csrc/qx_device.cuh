@@ -1220,9 +1220,11 @@ __device__ __noinline__ void jacobi_shift(int n, double *G, int ld, double *red)
     QX_ASSUME_SHARED(red);
     if (SH) QX_ASSUME_SHARED(G);
     double rowsum = 0.0;
-    for (int i = threadIdx.x; i < n; i += QX_NT) {
+    for (int i = threadIdx.x >> 5; i < n; i += QX_NT / 32) {   // one warp per row
         double v = 0.0;
-        for (int j = 0; j < n; ++j) v += fabs(G[(size_t)i * ld + j]);
+        for (int j = threadIdx.x & 31; j < n; j += 32) v += fabs(G[(size_t)i * ld + j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         rowsum = fmax(rowsum, v);
     }
     const double sigma = 1.0625 * block_max(rowsum, red) + 0.5;

@@ -703,14 +703,19 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
             double ne = m.nel[sp];
             homo[sp] = (int)floor(ne) + (fmod(ne, 1.0) > 0.5 ? 1 : 0);
         }
-        for (int k = threadIdx.x; k < nao; k += QX_NT) {
-            const double ek = s.emo[k];
+        for (int base = 0; base < nao; base += QX_NT / 4) {   // four lanes per orbital share the rank count
+            const int k = base + (threadIdx.x >> 2), part = threadIdx.x & 3, kk = k < nao ? k : 0;
+            const double ek = s.emo[kk];
             int rank = 0;
-            for (int j = 0; j < nao; ++j) rank += (s.emo[j] < ek) || (s.emo[j] == ek && j < k);
-            for (int sp = 0; sp < 2; ++sp) {
-                int lo = (homo[sp] > 1 ? homo[sp] : 1) - 1, hi = (homo[sp] + 1 < nao ? homo[sp] + 1 : nao) - 1;
-                if (rank == lo) s.red[32 + 2 * sp] = ek;
-                if (rank == hi) s.red[33 + 2 * sp] = ek;
+            for (int j = part; j < nao; j += 4) rank += (s.emo[j] < ek) || (s.emo[j] == ek && j < kk);
+            rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+            rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+            if (k < nao && part == 0) {
+                for (int sp = 0; sp < 2; ++sp) {
+                    int lo = (homo[sp] > 1 ? homo[sp] : 1) - 1, hi = (homo[sp] + 1 < nao ? homo[sp] + 1 : nao) - 1;
+                    if (rank == lo) s.red[32 + 2 * sp] = ek;
+                    if (rank == hi) s.red[33 + 2 * sp] = ek;
+                }
             }
         }
         __syncthreads();
@@ -798,24 +803,27 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     QX_PH(13);
     if (m.mat_in_global) phase_gradient_pairs<false>(m, s, m.task_int, m.ntask_int, taskout); else phase_gradient_pairs<true>(m, s, m.task_int, m.ntask_int, taskout);
     QX_PH(14);
-    for (int t = threadIdx.x; t < 3 * nat; t += QX_NT) {
-        int k = t / 3, c = t - 3 * k;
+    // per-atom reduction of the task outputs: four lanes share one (atom, component) -- the lists have ~200 entries per atom
+    for (int base = 0; base < 4 * nat; base += QX_NT / 4) {
+        const int t = base + (threadIdx.x >> 2), part = threadIdx.x & 3;
+        const bool on = t < 4 * nat;
+        const int k = on ? t >> 2 : 0, c = t & 3;      // c = 0..2: gradient component, c = 3: d/d cn
         double g = 0.0;
-        for (int e = m.gr_ptr[k]; e < m.gr_ptr[k + 1]; ++e) {
-            int code = m.gr_task[e];
-            int task = code >> 1;
-            g += (code & 1) ? -taskout[5 * (size_t)task + c] : taskout[5 * (size_t)task + c];
+        for (int e = m.gr_ptr[k] + part; e < m.gr_ptr[k + 1]; e += 4) {
+            const int code = m.gr_task[e];
+            const size_t o = 5 * (size_t)(code >> 1);
+            if (c < 3) g += (code & 1) ? -taskout[o + c] : taskout[o + c];
+            else g += taskout[o + ((code & 1) ? 4 : 3)];
         }
-        s.grad[t] += g;
-    }
-    for (int k = threadIdx.x; k < nat; k += QX_NT) {
-        double dcn = 0.0;
-        for (int e = m.gr_ptr[k]; e < m.gr_ptr[k + 1]; ++e) {
-            int code = m.gr_task[e];
-            dcn += taskout[5 * (size_t)(code >> 1) + ((code & 1) ? 4 : 3)];
+        g += __shfl_xor_sync(0xffffffffu, g, 1);
+        g += __shfl_xor_sync(0xffffffffu, g, 2);
+        if (on && part == 0) {
+            if (c < 3) s.grad[3 * k + c] += g;
+            else {
+                for (int mu = m.at_ao0[k]; mu < m.at_ao0[k] + m.at_nao[k]; ++mu) g += -m.sh_kcn[m.ao_sh[mu]] * s.A[(size_t)mu * ld + mu];
+                s.dEdcn[k] += g;
+            }
         }
-        for (int mu = m.at_ao0[k]; mu < m.at_ao0[k] + m.at_nao[k]; ++mu) dcn += -m.sh_kcn[m.ao_sh[mu]] * s.A[(size_t)mu * ld + mu];
-        s.dEdcn[k] += dcn;
     }
     __syncthreads();
     // D4 two-body with the final charges
