@@ -127,7 +127,8 @@ int qcxms_b200_ensemble_histogram(qcxms_b200_ensemble_t *h, int nbins, double *b
  * The reference draws 9 uniform random numbers per call with the Fortran intrinsic; here the caller passes them
  * (rnd[0..2] = a,b,c of euler_rotation; rnd[3..4] = dum,dum2 of vary_energies; rnd[5..8] = f,g,lmin,lpos of the
  * gas-atom placement), so any RNG can sit on the host side and runs are reproducible.
- * Supported gases: mono-atomic He / Ne / Ar (gas_z 2, 10, 18); options ConstVelo / MinPot / vScale are off (defaults). */
+ * Supported gases: He / Ne / Ar (gas_z 2, 10, 18) and N2 (gas_z 7: two atoms of mass gas_mass each, the second one 1.09 A above
+ * the first, src/cid.f90:660-667); options ConstVelo / MinPot / vScale are off (defaults). */
 typedef struct {
     int32_t method_id, mchrg;
     int32_t gas_z;        /* reference gas%IndAtom */

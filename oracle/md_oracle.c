@@ -451,7 +451,9 @@ int md_oracle_cid(const qcxms_b200_cid_config_t *cfg, int nuc, const int32_t *ia
                   double *velo, const double *rnd, double velo_cm_in, double *direc, int32_t *collided_io, double *grad, double *achrg,
                   double *axyz, int32_t *list, qcxms_b200_cid_result_t *res) {
     const double time_step = cfg->tstep, autofs = 1.0 / QC_FSTOAU;
-    const int nuc0 = nuc + 1, dumpdist = 10, dumpavg = 50, cnt_steps = 50;
+    const int ngas = cfg->gas_z == 7 ? 2 : 1;   /* N2: two atoms (reference src/cid.f90:179-180, 660-667) */
+    const int nuc0 = nuc + ngas, dumpdist = 10, dumpavg = 50, cnt_steps = 50;
+    const int ig = nuc0 - 1;                    /* the atom distArCOM looks at (src/cid.f90:1124-1139) */
     int ntot = cfg->ntot > 0 ? cfg->ntot : 15000;
     double etemp = cfg->etemp <= 0 ? 5000.0 : cfg->etemp;
     int add_steps = 0;
@@ -524,8 +526,13 @@ int md_oracle_cid(const qcxms_b200_cid_config_t *cfg, int nuc, const int32_t *ia
         for (int k = 0; k < 3; ++k) { velo0[3 * i + k] = velo[3 * i + k] + scale_velo[k]; xyz0[3 * i + k] = xyz[3 * i + k]; }
         mass0[i] = mass[i]; iat0[i] = iat[i];
     }
-    for (int k = 0; k < 3; ++k) { xyz0[3 * nuc + k] = xyzAr[k]; velo0[3 * nuc + k] = 0.0; }
-    mass0[nuc] = cfg->gas_mass; iat0[nuc] = cfg->gas_z;
+    for (int k = 0; k < 3; ++k) { xyz0[3 * ig + k] = xyzAr[k]; velo0[3 * ig + k] = 0.0; }
+    mass0[ig] = cfg->gas_mass; iat0[ig] = cfg->gas_z;
+    if (ngas == 2) {
+        xyz0[3 * nuc] = xyzAr[0]; xyz0[3 * nuc + 1] = xyzAr[1]; xyz0[3 * nuc + 2] = xyzAr[2] + 1.09 * QC_AATOAU;
+        velo0[3 * nuc] = velo0[3 * nuc + 1] = velo0[3 * nuc + 2] = 0.0;
+        mass0[nuc] = cfg->gas_mass; iat0[nuc] = cfg->gas_z;
+    }
 
     /* iniqm (one single point whose result is only checked) + initial egrad */
     double E;
@@ -538,7 +545,7 @@ int md_oracle_cid(const qcxms_b200_cid_config_t *cfg, int nuc, const int32_t *ia
         double Tav = 0.0, new_velo = 0.0, new_dist, lowestCOM, ttime = 0.0, aTlast = 0.0, avgT = 0.0, ke;
         md_oracle_center_of_mass(nuc, mass, xyz, cm);
         {
-            double d0 = xyz0[3 * nuc] - cm[0], d1 = xyz0[3 * nuc + 1] - cm[1], d2 = xyz0[3 * nuc + 2] - cm[2];
+            double d0 = xyz0[3 * ig] - cm[0], d1 = xyz0[3 * ig + 1] - cm[1], d2 = xyz0[3 * ig + 2] - cm[2];
             new_dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
         }
         lowestCOM = new_dist;
@@ -589,7 +596,7 @@ int md_oracle_cid(const qcxms_b200_cid_config_t *cfg, int nuc, const int32_t *ia
             if (distance_dump == dumpdist) {
                 distance_dump = 0;
                 md_oracle_center_of_mass(nuc, mass0, xyz0, cm);
-                double d0 = xyz0[3 * nuc] - cm[0], d1 = xyz0[3 * nuc + 1] - cm[1], d2 = xyz0[3 * nuc + 2] - cm[2];
+                double d0 = xyz0[3 * ig] - cm[0], d1 = xyz0[3 * ig + 1] - cm[1], d2 = xyz0[3 * ig + 2] - cm[2];
                 new_dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
                 if (new_dist < lowestCOM) lowestCOM = new_dist;
                 if (lowestCOM < new_dist) step_counter = step_counter + 1; else step_counter = 0;

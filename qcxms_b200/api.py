@@ -53,7 +53,7 @@ class CidResult(C.Structure):
 
 
 # collision gases of the reference (src/input.f90:512-558): Z, mass / amu, radius / bohr
-GASES = {"he": (2, 4.002, 2.64560263), "ne": (10, 20.18, 2.91016289), "ar": (18, 39.948, 3.55266638)}
+GASES = {"he": (2, 4.002, 2.64560263), "ne": (10, 20.18, 2.91016289), "ar": (18, 39.948, 3.55266638), "n2": (7, 14.007, 3.64)}
 
 EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_cid_batch", "qcxms_b200_egrad_batch", "qcxms_b200_fragment_structure", "qcxms_b200_ensemble_create",
            "qcxms_b200_ensemble_destroy", "qcxms_b200_ensemble_set_trajectory", "qcxms_b200_ensemble_set_all",

@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(QX_NT, 2) k_cid_init(DevModel m, ScratchLayout
                 // distance gas atom -- centre of mass of the ion as it was handed in (reference src/cid.f90:733-737)
                 double cm[3];
                 cid_center_of_mass(nuc, m.mass, st.xyz + (size_t)t * 3 * nuc, cm);
-                const double d0 = xyz0[3 * nuc] - cm[0], d1 = xyz0[3 * nuc + 1] - cm[1], d2 = xyz0[3 * nuc + 2] - cm[2];
+                const int ig = nuc0 - 1;
+                const double d0 = xyz0[3 * ig] - cm[0], d1 = xyz0[3 * ig + 1] - cm[1], d2 = xyz0[3 * ig + 2] - cm[2];
                 sc->lowestCOM = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
             }
         }
@@ -402,7 +403,8 @@ __global__ void __launch_bounds__(QX_NT, 2) k_cid_chunk(DevModel m, ScratchLayou
                 sc.aTlast = avgT;
                 if (sc.distance_dump == 10) {
                     sc.distance_dump = 0;
-                    const double d0 = s.xyz[3 * nuc] - cm[0], d1 = s.xyz[3 * nuc + 1] - cm[1], d2 = s.xyz[3 * nuc + 2] - cm[2];
+                    const int ig = nuc0 - 1;
+                    const double d0 = s.xyz[3 * ig] - cm[0], d1 = s.xyz[3 * ig + 1] - cm[1], d2 = s.xyz[3 * ig + 2] - cm[2];
                     const double new_dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
                     if (new_dist < sc.lowestCOM) sc.lowestCOM = new_dist;
                     if (sc.lowestCOM < new_dist) sc.step_counter += 1; else sc.step_counter = 0;
@@ -884,12 +886,13 @@ extern "C" int qcxms_b200_cid_batch(const qcxms_b200_cid_config_t *cfg, int ntra
         return fail(QCXMS_B200_ERR_ARG, "null or empty argument");
     if (icoll < 1 || (icoll > 1 && !velo_cm)) return fail(QCXMS_B200_ERR_ARG, "icoll >= 1; later collisions need velo_cm");
     if (cfg->method_id != QCXMS_B200_GFN2) return fail(QCXMS_B200_ERR_UNSUPPORTED, "only GFN2-xTB (method id 2) is implemented");
-    if (cfg->gas_z != 2 && cfg->gas_z != 10 && cfg->gas_z != 18) return fail(QCXMS_B200_ERR_UNSUPPORTED, "collision gas must be He, Ne or Ar");
-    const int nuc0 = nuc + 1;
+    if (cfg->gas_z != 2 && cfg->gas_z != 10 && cfg->gas_z != 18 && cfg->gas_z != 7)
+        return fail(QCXMS_B200_ERR_UNSUPPORTED, "collision gas must be He, Ne, Ar or N2");
+    const int ngas = cfg->gas_z == 7 ? 2 : 1;   // N2: two atoms of mass gas_mass each (reference src/cid.f90:179-180)
+    const int nuc0 = nuc + ngas;
     std::vector<int32_t> num0(num, num + nuc);
     std::vector<double> mass0(mass, mass + nuc);
-    num0.push_back(cfg->gas_z);
-    mass0.push_back(cfg->gas_mass);
+    for (int g = 0; g < ngas; ++g) { num0.push_back(cfg->gas_z); mass0.push_back(cfg->gas_mass); }
     int zsum = 0;
     for (int v : num0) zsum += v;
     const int j = zsum - std::abs(cfg->mchrg);

@@ -21,7 +21,7 @@ struct CidScalars {
     double Tav, new_velo, lowestCOM, ttime, aTlast, old_cm[3], Tinit, summass, epot;
 };
 
-struct CidState {   // leading [ntraj] axis; nuc0 = nuc + 1 atoms for the ion + gas-atom arrays
+struct CidState {   // leading [ntraj] axis; nuc0 = nuc + 1 (N2: + 2) atoms for the ion + gas arrays
     double *xyz, *velo, *direc;                       // ion, in/out [ntraj][nuc][3]; direc [ntraj][3]
     const double *rnd, *velo_cm_in;                   // [ntraj][9], [ntraj]
     double *xyz0, *velo0, *grad0, *achrg0;            // [ntraj][nuc0][3] / [ntraj][nuc0]
@@ -144,7 +144,7 @@ __device__ inline double cid_ekinet(int n, const double *velo, const double *mas
     return e;
 }
 
-// Collision set-up (thread 0): rotates / places the ion, positions the gas atom, fills xyz0 / velo0 (nuc0 = nuc + 1 atoms).
+// Collision set-up (thread 0): rotates / places the ion, positions the gas atom, fills xyz0 / velo0 (nuc0 = m.nat = nuc + 1 atoms, nuc + 2 for N2).
 // xyz, velo: the ion (global, in/out); returns Tinit and summass through pointers.
 __device__ inline void cid_setup_thread0(const DevModel &m, const CidConfig &c, int nuc, int icoll, double *xyz, double *velo, const double *rnd,
                                          double velo_cm_in, double *direc, double *xyz0, double *velo0, double *old_cm, double *tinit_out,
@@ -245,7 +245,12 @@ __device__ inline void cid_setup_thread0(const DevModel &m, const CidConfig &c, 
     for (int k = 0; k < 3; ++k) old_cm[k] = cm[k];
     for (int i = 0; i < nuc; ++i)
         for (int k = 0; k < 3; ++k) { velo0[3 * i + k] = velo[3 * i + k] + scale_velo[k]; xyz0[3 * i + k] = xyz[3 * i + k]; }
-    for (int k = 0; k < 3; ++k) { xyz0[3 * nuc + k] = xyzAr[k]; velo0[3 * nuc + k] = 0.0; }
+    const int ig = m.nat - 1;   // last atom of the collision system: the gas atom distArCOM looks at; N2 puts its second atom before it
+    for (int k = 0; k < 3; ++k) { xyz0[3 * ig + k] = xyzAr[k]; velo0[3 * ig + k] = 0.0; }
+    if (m.nat - nuc == 2) {     // reference src/cid.f90:660-667
+        xyz0[3 * nuc] = xyzAr[0]; xyz0[3 * nuc + 1] = xyzAr[1]; xyz0[3 * nuc + 2] = xyzAr[2] + 1.09 * QC_AATOAU;
+        velo0[3 * nuc] = velo0[3 * nuc + 1] = velo0[3 * nuc + 2] = 0.0;
+    }
     *tinit_out = Tinit;
     *summass_out = summass;
 }

@@ -59,3 +59,18 @@ def test_cid_head_on_collision_is_detected(qx, oracle):
     # distance checks happen every 10 steps: allow one check of slack for SCC-threshold noise amplified by the impact
     assert got["collided"][0] == ref["collided"] and abs(got["nstep"][0] - ref["nstep"]) <= 10 and got["nfrag"][0] == ref["nfrag"]
     assert np.array_equal(got["list"][0], ref["list"])
+
+
+def test_cid_n2_collision_gas_matches_oracle(qx, oracle):
+    """N2 as collision gas: two nitrogen atoms (the second 1.09 A above the first), distance checks on the last one
+    (reference src/cid.f90:179-180, 660-667, 1124-1139)."""
+    num, xyz, _ = qx.load_molecule("chloroethanol")
+    nt = 3
+    ic = es.synthetic_initial_conditions(num, xyz, nt, first_id=60)
+    rng = np.random.default_rng(5)
+    rnd = rng.random((nt, 9))
+    cfg = qx.cid_config(mchrg=1, gas="n2", elab=40.0, ntot=15)
+    got = qx.cid(cfg, num, ic["mass"], 1, ic["xyz"], ic["velo"], rnd)
+    for k in range(nt):
+        _compare(got, oracle.cid(cfg, num, ic["mass"], 1, ic["xyz"][k], ic["velo"][k], rnd[k]), k)
+    assert np.all(got["nstep"] == 15) and np.all(got["status"] == 1)

@@ -87,3 +87,19 @@ def test_cid_later_collision_keeps_velocities(oracle):
     vcm1 = (mass[:, None] * out["velo"]).sum(0) / mass.sum()
     assert np.abs(vcm1 - vcm0).max() < 1e-6   # the gas atom 17 bohr away pulls a little
     assert np.array_equal(out["direc"], direc)
+
+
+def test_cid_n2_has_two_gas_atoms(oracle):
+    """N2 (gas_z 7) adds two atoms: one more than Ar in the single points (more SCC work is not observable, the step count
+    and a clean exit are), and the ion still leaves with the laboratory-frame speed."""
+    num, xyz, _ = load_molecule("chloroethanol")
+    mass = es.masses_au(num)
+    ic = es.synthetic_initial_conditions(num, xyz, 1, first_id=4)
+    rnd = np.array([0.21, 0.33, 0.72, 0.6, 0.3, 0.4, 0.35, 0.2, 0.7])
+    cfg = cid_config(mchrg=1, gas="n2", elab=30.0, ntot=5, eexact=True)
+    assert cfg.gas_z == 7 and abs(cfg.gas_mass - 14.007 * 1822.888486) / cfg.gas_mass < 1e-6
+    out = oracle.cid(cfg, num, mass, 1, ic["xyz"][0], ic["velo"][0], rnd)
+    assert out["status"] == 1 and out["nstep"] == 5 and out["nfrag"] == 1
+    v_expect = np.sqrt(2 * 30.0 / AUTOEV / mass.sum())
+    vcm = (mass[:, None] * out["velo"]).sum(0) / mass.sum()
+    assert abs(np.linalg.norm(vcm) - v_expect) / v_expect < 5e-2
