@@ -1166,6 +1166,109 @@ __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, float tol
 #define QX_JROWS jacobi_rows_lp8t
 #endif
 
+// ---- multi-pass variant for bases between the one-pass limit (72 AOs: 36 groups of 8 lanes) and the shared-memory limit
+// (~110 AOs, one CTA per SM): the ceil(n/2) pairs of a round are worked off in passes of QX_NT/8 groups.  Same rotation as
+// jacobi_rows_lp8t; no kept row (a group would have to keep one per pass).
+template <int R>
+__device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, float tol, double *jw) {
+    QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(jw);
+    const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
+    const int nslot = QX_NT / 8, slot = threadIdx.x >> 3, lsub = threadIdx.x & 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int npass = (npair + nslot - 1) / nslot;
+    double *nrm2 = jw;
+    double2 *dd = reinterpret_cast<double2 *>(jw + ((n + 1) & ~1));
+    for (int i = threadIdx.x; i < n; i += QX_NT) dd[i] = make_double2(1.0, 1.0);
+    __syncthreads();
+    const bool tail_ok = 2 * lsub + 16 * (R - 1) < n;
+    double *Gl = G + 2 * lsub;
+    const double tol2 = (double)tol * (double)tol;
+    int sweep = 0;
+    for (; sweep < 60; ++sweep) {
+        for (int r = warp; r < n; r += QX_NT / 32) {
+            const double d = dd[r].x;
+            double acc = 0.0;
+            for (int i = lane; i < n; i += 32) { const double x = G[(size_t)r * ld + i] * d; G[(size_t)r * ld + i] = x; acc = fma(x, x, acc); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            __syncwarp();
+            if (lane == 0) { nrm2[r] = acc; dd[r] = make_double2(1.0, 1.0); }
+        }
+        __syncthreads();
+        bool big = false;
+        for (int round = 0; round < m1; ++round) {
+            for (int pass = 0; pass < npass; ++pass) {
+                if ((warp << 2) + pass * nslot >= npair) continue;   // warp-uniform
+                const int k = slot + pass * nslot;
+                int p = round + k, q = round - k;
+                if (p >= m1) p -= m1;
+                if (q < 0) q += m1;
+                if (k == 0) p = m1;
+                const bool valid = k < npair && p < n && q < n;
+                if (!valid) { p = 0; q = 0; }
+                double *gp = Gl + p * ld, *gq = Gl + q * ld;
+                const double2 sp = dd[p], sq = dd[q];
+                const double al = nrm2[p], be = nrm2[q];
+                double2 x[R], y[R];
+#pragma unroll
+                for (int r = 0; r < R - 1; ++r) {
+                    x[r] = *reinterpret_cast<const double2 *>(gp + 16 * r);
+                    y[r] = *reinterpret_cast<const double2 *>(gq + 16 * r);
+                }
+                x[R - 1] = make_double2(0.0, 0.0); y[R - 1] = make_double2(0.0, 0.0);
+                if (tail_ok) { x[R - 1] = *reinterpret_cast<const double2 *>(gp + 16 * (R - 1)); y[R - 1] = *reinterpret_cast<const double2 *>(gq + 16 * (R - 1)); }
+                double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
+                double gs = g0 + g1;
+                gs += __shfl_xor_sync(0xffffffffu, gs, 4);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 2);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 1);
+                const double ga = (sp.x * sq.x) * gs, ga2 = ga * ga, nn = al * be;
+                big |= valid && ga2 > tol2 * nn;
+                const bool rot = valid && ga2 > 1e-30 * nn;
+                const float gf = (float)ga, df = (float)(be - al);
+                const float g2 = gf + gf;
+                const float hh = fmaf(df, df, g2 * g2);
+                const float den = fabsf(df) + hh * rsqrt_approx(hh);
+                float tf = g2 * rcp_approx(den);
+                tf = __int_as_float(__float_as_int(tf) ^ (__float_as_int(df) & 0x80000000));
+                tf = rot ? tf : 0.0f;
+                const double t = (double)tf;
+                const double t1 = t * (sq.x * sp.y), t2 = t * (sp.x * sq.y);
+                if (valid) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        double2 u, v;
+                        u.x = fma(-t1, y[r].x, x[r].x); u.y = fma(-t1, y[r].y, x[r].y);
+                        v.x = fma(t2, x[r].x, y[r].x); v.y = fma(t2, x[r].y, y[r].y);
+                        if (r < R - 1 || tail_ok) {
+                            *reinterpret_cast<double2 *>(gp + 16 * r) = u;
+                            *reinterpret_cast<double2 *>(gq + 16 * r) = v;
+                        }
+                    }
+                }
+                const double w = fma(t, t, 1.0);
+                double c = (double)rsqrt_approx(fmaf(tf, tf, 1.0f));
+                c = c * fma(-0.5 * w * c, c, 1.5);
+                c = c * fma(-0.5 * w * c, c, 1.5);
+                const double wc = w * c, tg = t * ga;
+                if (lsub == 0 && valid) {
+                    dd[p] = make_double2(c * sp.x, wc * sp.y); dd[q] = make_double2(c * sq.x, wc * sq.y);
+                    nrm2[p] = al - tg; nrm2[q] = be + tg;
+                }
+            }
+            __syncthreads();
+        }
+        if (!__syncthreads_or(big ? 1 : 0)) { ++sweep; break; }
+    }
+    for (int r = warp; r < n; r += QX_NT / 32) {
+        const double d = dd[r].x;
+        for (int i = lane; i < n; i += 32) G[(size_t)r * ld + i] *= d;
+    }
+    __syncthreads();
+    return sweep;
+}
+
 // generic fallback (any n): LP lanes per pair, scalar accesses
 __device__ __noinline__ int jacobi_rows_generic(int n, double *G, int ld, double *red, float tol) {
     const int mm = (n + 1) & ~1, npair = mm >> 1;
@@ -1235,6 +1338,7 @@ __device__ __noinline__ void jacobi_shift(int n, double *G, int ld, double *red)
 }
 
 // (2) the sweeps
+template <bool SH>
 __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *red, double *jw) {
     const float tol = 1e-7f;  // pre-rotation ratio of the last sweep; its rotations leave O(tol^2) couplings
     const int npair = (n + 1) >> 1;
@@ -1247,6 +1351,12 @@ __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *r
             case 3: sweeps = QX_JROWS<3>(n, G, ld, tolr, jw); break;
             case 4: sweeps = QX_JROWS<4>(n, G, ld, tolr, jw); break;
             default: sweeps = QX_JROWS<5>(n, G, ld, tolr, jw); break;   // 8 lanes per pair and QX_NT threads: n <= 72
+        }
+    } else if ((ld & 1) == 0 && n <= 112 && SH) {   // matrices in shared memory, more pairs than 8-lane groups: several passes per round
+        switch ((n + 15) >> 4) {   // R = ceil(n / 16): every chunk but the last is in range for all lanes
+            case 5: sweeps = jacobi_rows_lp8m<5>(n, G, ld, QX_JACOBI_TOL, jw); break;
+            case 6: sweeps = jacobi_rows_lp8m<6>(n, G, ld, QX_JACOBI_TOL, jw); break;
+            default: sweeps = jacobi_rows_lp8m<7>(n, G, ld, QX_JACOBI_TOL, jw); break;
         }
     } else
         sweeps = jacobi_rows_generic(n, G, ld, red, tol);
@@ -1277,7 +1387,7 @@ __device__ __noinline__ void jacobi_finish(int n, double *G, int ld, double *emo
 template <bool SH>
 __device__ __forceinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *emo, double *red, double *jw) {
     jacobi_shift<SH>(n, G, ld, red);
-    const int sweeps = jacobi_sweeps(n, G, ld, red, jw);
+    const int sweeps = jacobi_sweeps<SH>(n, G, ld, red, jw);
     jacobi_finish<SH>(n, G, ld, emo, red);
     return sweeps;
 }

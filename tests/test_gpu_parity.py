@@ -55,3 +55,13 @@ def test_large_basis_fallback_alkane_c32(qx, oracle):
     rng = np.random.default_rng(2)
     x = xyz + 0.03 * rng.standard_normal(xyz.shape)
     _compare(qx, oracle, num, x, 1, 2, 5000.0)
+
+
+@pytest.mark.parametrize("name", ["alkane_c14", "alkane_c17"])
+def test_medium_basis_multi_pass_jacobi(qx, oracle, name):
+    """Bases between the one-pass Jacobi limit (72 AOs) and the shared-memory limit (~110): matrices in shared memory,
+    generic DMMA GEMMs, multi-pass Jacobi (jacobi_rows_lp8m)."""
+    num, xyz, _ = qx.load_molecule(name)
+    rng = np.random.default_rng(2)
+    x = xyz + 0.03 * rng.standard_normal(xyz.shape)
+    _compare(qx, oracle, num, x, 1, 2, 5000.0)
