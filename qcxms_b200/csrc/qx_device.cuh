@@ -846,10 +846,10 @@ __device__ __noinline__ bool cholesky_basis(int n, double *A, double *Ct, int ld
         __syncthreads();
         for (int i = j + threadIdx.x; i < n; i += QX_NT) A[(size_t)i * ld + j] = (i == j) ? d : A[(size_t)i * ld + j] / d;
         __syncthreads();
-        // trailing update of the lower triangle: one thread per row, columns j+1..i
-        for (int i = j + 1 + threadIdx.x; i < n; i += QX_NT) {
+        // trailing update of the lower triangle: one warp per row, lanes over the columns j+1..i
+        for (int i = j + 1 + (threadIdx.x >> 5); i < n; i += QX_NT / 32) {
             const double lij = A[(size_t)i * ld + j];
-            for (int k = j + 1; k <= i; ++k) A[(size_t)i * ld + k] -= lij * A[(size_t)k * ld + j];
+            for (int k = j + 1 + (threadIdx.x & 31); k <= i; k += 32) A[(size_t)i * ld + k] -= lij * A[(size_t)k * ld + j];
         }
         __syncthreads();
     }
