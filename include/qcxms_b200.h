@@ -102,6 +102,12 @@ int qcxms_b200_ensemble_set_all(qcxms_b200_ensemble_t *h, const double *xyz, con
 /* md(): initial egrad + MD loop until every trajectory has exited (or max_steps more steps were
  * taken per trajectory when max_steps > 0).  Returns the number of trajectory-MD-steps executed
  * in *steps_done (may be NULL). */
+/* OPT-IN fast mode, NOT the reference protocol: start the SCC of every MD step from the converged shell charges /
+ * atomic dipoles / quadrupoles of the previous step of the same trajectory instead of from zero (the reference creates a zeroed
+ * wavefunction on every call, src/tblite.f90:133).  Fewer SCC cycles per step; energies move within the SCC thresholds
+ * (~1e-7 Eh), so trajectories are no longer step-for-step comparable with the reference.  Off by default; call before run_md. */
+int qcxms_b200_ensemble_set_warm_start(qcxms_b200_ensemble_t *h, int on);
+
 int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_steps, int64_t *steps_done);
 
 int qcxms_b200_ensemble_get_result(qcxms_b200_ensemble_t *h, int itrj, double *xyz, double *velo, double *grad,

@@ -57,7 +57,7 @@ GASES = {"he": (2, 4.002, 2.64560263), "ne": (10, 20.18, 2.91016289), "ar": (18,
 
 EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_cid_batch", "qcxms_b200_egrad_batch", "qcxms_b200_fragment_structure", "qcxms_b200_ensemble_create",
            "qcxms_b200_ensemble_destroy", "qcxms_b200_ensemble_set_trajectory", "qcxms_b200_ensemble_set_all",
-           "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_get_all", "qcxms_b200_ensemble_last_timing",
+           "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_set_warm_start", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_get_all", "qcxms_b200_ensemble_last_timing",
            "qcxms_b200_ensemble_histogram", "qcxms_b200_last_error", "qcxms_b200_version"]
 
 
@@ -78,6 +78,7 @@ def lib():
         L.qcxms_b200_ensemble_set_trajectory.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, C.c_double, C.c_double]
         L.qcxms_b200_ensemble_set_all.argtypes = [C.c_void_p, dp, dp, dp, dp, dp]
         L.qcxms_b200_ensemble_run_md.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        L.qcxms_b200_ensemble_set_warm_start.argtypes = [C.c_void_p, C.c_int]
         L.qcxms_b200_ensemble_get_result.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, ip, dp, dp, C.POINTER(MdResult)]
         L.qcxms_b200_ensemble_get_all.argtypes = [C.c_void_p, dp, dp, dp, ip, dp, dp, C.POINTER(MdResult)]
         L.qcxms_b200_ensemble_last_timing.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -178,6 +179,10 @@ class Ensemble:
         a = [np.ascontiguousarray(v, dtype=np.float64) for v in (xyz, velo, velof, eimp, tadd)]
         assert a[0].size == self.ntraj * self.nat * 3 and a[3].size == self.ntraj
         _check(lib().qcxms_b200_ensemble_set_all(self._h, *[_dp(v) for v in a]))
+
+    def set_warm_start(self, on=True):
+        """Opt-in fast mode (not the reference protocol): SCC of each step starts from the previous step's converged populations."""
+        _check(lib().qcxms_b200_ensemble_set_warm_start(self._h, int(bool(on))))
 
     def run_md(self, max_steps=0):
         """Runs md() for every trajectory; returns the number of trajectory-MD-steps executed."""

@@ -66,10 +66,10 @@ __global__ void __launch_bounds__(QX_NT) k_fragments(DevModel m, const double *x
 
 // one egrad + sanity gate for trajectory t; returns Epot (0 on failure, like the reference's checkqc)
 __device__ inline double md_egrad(const DevModel &m, Sm &s, double *my, const ScratchLayout &L, const MdConfig &cfg, double etemp,
-                                  double *grad_out, double *achrg_out, int *niter_out) {
+                                  double *grad_out, double *achrg_out, int *niter_out, double *qstart = nullptr) {
     const int nat = m.nat;
     EgradOut o;
-    egrad_cta(m, s, my, L, etemp * QC_KTOAU, o);
+    egrad_cta(m, s, my, L, etemp * QC_KTOAU, o, qstart);
     __syncthreads();
     if (threadIdx.x == 0) {
         bool ok = o.stat != -2 && md_checkqc(m, o.energy, s.grad, s.qat, cfg.mchrg);
@@ -101,7 +101,12 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout 
         const double eimp = st.eimp[t];
         const double etemp = cfg.etemp_in < 0.0 ? md_setetemp(cfg, 1, eimp) : cfg.etemp_in;
         int nit = 0;
-        const double epot = md_egrad(m, s, my, L, cfg, etemp, st.grad + (size_t)t * 3 * nat, st.achrg + (size_t)t * nat, &nit);
+        double *qw = st.qwarm ? st.qwarm + (size_t)t * (2 * m.ndim + 1) : nullptr;
+        if (qw) {   // the first single point of a trajectory has nothing to start from: zero populations == the reference's cold start
+            for (int i = threadIdx.x; i < 2 * m.ndim + 1; i += QX_NT) qw[i] = 0.0;
+            __syncthreads();
+        }
+        const double epot = md_egrad(m, s, my, L, cfg, etemp, st.grad + (size_t)t * 3 * nat, st.achrg + (size_t)t * nat, &nit, qw);
         if (threadIdx.x == 0) {
             st.scc_total[t] = nit;
             const double ekin = md_ekinet_seq(nat, st.velo + (size_t)t * 3 * nat, m.mass, 0.0, nullptr);
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
             ttime += cfg.tstep / fstoau;
             {
                 int nit = 0;
-                epot = md_egrad(m, s, my, L, cfg, etemp, grad, achrg, &nit);
+                epot = md_egrad(m, s, my, L, cfg, etemp, grad, achrg, &nit, st.qwarm ? st.qwarm + (size_t)t * (2 * m.ndim + 1) : nullptr);
                 scc_add += nit;
             }
             done += 1;
@@ -687,6 +692,18 @@ extern "C" int qcxms_b200_ensemble_set_all(qcxms_b200_ensemble_t *h, const doubl
     CUDA_OK(cudaMemcpyAsync(h->st.tadd, tadd, h->ntraj * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
     h->initialised = false;
+    return 0;
+}
+
+extern "C" int qcxms_b200_ensemble_set_warm_start(qcxms_b200_ensemble_t *h, int on) {
+    if (!h) return fail(QCXMS_B200_ERR_ARG, "null handle");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    if (on && !h->st.qwarm) {
+        cudaError_t e = ens_alloc(h, &h->st.qwarm, (size_t)h->ntraj * (2 * h->ctx.hm.ndim + 1));
+        if (e != cudaSuccess) return fail(QCXMS_B200_ERR_CUDA, std::string("warm-start buffer: ") + cudaGetErrorString(e));
+        h->initialised = false;   // the populations are seeded by the initial single point of md()
+    } else if (!on)
+        h->st.qwarm = nullptr;    // (buffer stays owned by the handle)
     return 0;
 }
 

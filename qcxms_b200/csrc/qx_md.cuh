@@ -27,6 +27,7 @@ struct MdState {
     double *avchrg, *avxyz;                           // running sums
     double *eimp, *tadd, *epot, *ekin, *ekinstart, *etemp, *Tav, *Epav, *Ekav, *Edum, *aTlast, *dtime, *ttime, *fadd;
     int *nstep, *kdump, *fconst, *morestep, *nfrag, *status, *fragstate, *mdok, *nadd, *list, *scc_total;
+    double *qwarm;    // [ntraj][2 ndim + 1] converged populations of the last two steps + count; null unless the opt-in warm start is on
 };
 
 enum { TRJ_RUNNING = 0, TRJ_FINISHED = 1, TRJ_FAILED = 2 };

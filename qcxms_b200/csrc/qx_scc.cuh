@@ -585,7 +585,10 @@ __device__ __noinline__ void phase_gradient_pairs(const DevModel &m, Sm &s, cons
 }
 
 // Everything: s.xyz in, s.grad / s.qat out.  scratch: per-CTA global slab.
-__device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, const ScratchLayout &L, double kt, EgradOut &out) {
+// qstart (may be null): OPT-IN warm start, not the reference protocol.  [2 ndim + 1]: converged populations (shell
+// charges, atomic dipoles, quadrupoles) of the last and the last-but-one call and the number of valid entries; the SCC starts
+// from their linear extrapolation instead of from zero, and the history is advanced when this call converges.
+__device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, const ScratchLayout &L, double kt, EgradOut &out, double *qstart = nullptr) {
     const int nat = m.nat, nsh = m.nsh, nao = m.nao, ld = m.ld, ndim = m.ndim;
     double *S = scratch + L.S, *H0 = scratch + L.H0, *Dt = scratch + L.Dt, *Qt = scratch + L.Qt, *T = scratch + L.T;
     double *gamma = scratch + L.gamma, *dcnp = scratch + L.dcnp, *dcnp4 = scratch + L.dcnp4, *edisp = scratch + L.edisp;
@@ -621,10 +624,27 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     __syncthreads();
     if (!(m.mat_in_global ? cholesky_basis<false>(nao, s.A, s.C, ld, s.red) : cholesky_basis<true>(nao, s.A, s.C, ld, s.red))) { out.stat = -2; out.energy = 0.0; return; }  // hard failure: S not positive definite
 
-    for (int i = threadIdx.x; i < nsh; i += QX_NT) s.qsh[i] = 0.0;
-    for (int i = threadIdx.x; i < nat; i += QX_NT) s.qat[i] = 0.0;
-    for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.dpat[i] = 0.0;
-    for (int i = threadIdx.x; i < 6 * nat; i += QX_NT) s.qpat[i] = 0.0;
+    if (qstart) {   // warm start (opt-in): linear extrapolation of the converged populations of the last two steps of this trajectory
+        const bool two = __ldcg(qstart + 2 * ndim) >= 2.0;
+        for (int i = threadIdx.x; i < ndim; i += QX_NT) {
+            const double q0 = __ldcg(qstart + i);
+            const double v = two ? 2.0 * q0 - __ldcg(qstart + ndim + i) : q0;
+            if (i < nsh) s.qsh[i] = v;
+            else if (i < nsh + 3 * nat) s.dpat[i - nsh] = v;
+            else s.qpat[i - nsh - 3 * nat] = v;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nat; i += QX_NT) {
+            double v = 0.0;
+            for (int a = m.at_sh0[i]; a < m.at_sh0[i] + m.at_nsh[i]; ++a) v += s.qsh[a];
+            s.qat[i] = v;
+        }
+    } else {        // reference protocol: zeroed wavefunction on every call (src/tblite.f90:133)
+        for (int i = threadIdx.x; i < nsh; i += QX_NT) s.qsh[i] = 0.0;
+        for (int i = threadIdx.x; i < nat; i += QX_NT) s.qat[i] = 0.0;
+        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.dpat[i] = 0.0;
+        for (int i = threadIdx.x; i < 6 * nat; i += QX_NT) s.qpat[i] = 0.0;
+    }
     __syncthreads();
     QX_PH(3);
 
@@ -777,6 +797,13 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     out.niter = iscf;
     out.energy = out.e_rep + out.e_atm + eelec;
     if (out.stat == -2) return;
+    if (qstart && converged) {   // hand the converged populations to the next step of this trajectory: [latest | previous | count]
+        for (int i = threadIdx.x; i < ndim; i += QX_NT) {
+            qstart[ndim + i] = __ldcg(qstart + i);
+            qstart[i] = i < nsh ? s.qsh[i] : (i < nsh + 3 * nat ? s.dpat[i - nsh] : s.qpat[i - nsh - 3 * nat]);
+        }
+        if (threadIdx.x == 0) qstart[2 * ndim] = fmin(__ldcg(qstart + 2 * ndim) + 1.0, 2.0);
+    }
     // "SCF not converged": flagged, but energy and gradient of the last cycle are still handed back -- the
     // reference's egrad overrides stat with checkqc (src/iniqm.f90:646-651)
     if (!converged) out.stat = -1;

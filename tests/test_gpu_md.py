@@ -150,3 +150,26 @@ def test_ensemble_spectrum_cosine_similarity_vs_oracle(qx, oracle):
     print("spectrum cosine similarity %.4f; identical fragment lists %d/%d, identical step counts %d/%d" % (cos, same_list, nt, same_nstep, nt))
     assert cos >= 0.95
     assert same_list >= int(0.8 * nt)
+
+
+def test_warm_start_mode_is_close_and_cheaper(qx):
+    """Opt-in warm start (not the reference protocol): the SCC of a step starts from the previous step's converged
+    populations.  Same trajectory within the SCC thresholds over a short horizon, markedly fewer SCC cycles."""
+    num, ic = _ic(qx, "caffeine", 4, seed=21)
+    def run(warm):
+        ens = qx.Ensemble(num, ic["mass"], 4, mchrg=1, nmax=30, exit_rules=False)
+        if warm:
+            ens.set_warm_start(True)
+        ens.set_all(ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+        ens.run_md()
+        out = ens.results()
+        ens.close()
+        return out
+    cold, warm = run(False), run(True)
+    assert np.all(cold["nstep"] == 30) and np.all(warm["nstep"] == 30) and np.all(warm["status"] == 1)
+    assert np.abs(warm["Epot"] - cold["Epot"]).max() < 2e-6                 # Eh: the SCC energy threshold is 1e-6
+    assert np.abs(warm["xyz"] - cold["xyz"]).max() < 1e-4                   # bohr after 30 steps: forces differ within the SCC thresholds
+    assert np.abs(warm["achrg"] - cold["achrg"]).max() < 1e-3
+    ratio = warm["scc_iter_total"].sum() / cold["scc_iter_total"].sum()
+    print("warm/cold SCC cycles: %.2f" % ratio)
+    assert ratio < 0.7
