@@ -108,6 +108,16 @@ int qcxms_b200_ensemble_set_all(qcxms_b200_ensemble_t *h, const double *xyz, con
  * (~1e-7 Eh), so trajectories are no longer step-for-step comparable with the reference.  Off by default; call before run_md. */
 int qcxms_b200_ensemble_set_warm_start(qcxms_b200_ensemble_t *h, int on);
 
+/* Switches the ensemble to the mean-free-path MD between two collisions of a CID run: md() as the reference runs it with the
+ * global method == 3 and icoll >= 1 (call site src/main.F90:1860-1866; branches src/md.f90:246-255, 325, 365, 438, 466-621, 672,
+ * 694-699): no IEE heating, kinetic energy / temperature without the motion of the centre of mass, fragment structures averaged
+ * over 50 steps after a fragmentation, end of the run moved to nstep + add_steps by every counted fragmentation.
+ * new_velo [ntraj]: the reference's in/out argument new_velo (velocity of the ion's centre of mass, m/s) as cid() returned it.
+ * Call after set_all / set_trajectory and before run_md. */
+int qcxms_b200_ensemble_set_mfp(qcxms_b200_ensemble_t *h, int icoll, const double *new_velo);
+/* new_velo [ntraj] after run_md (mean-free-path mode only) */
+int qcxms_b200_ensemble_get_new_velo(qcxms_b200_ensemble_t *h, double *new_velo);
+
 int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_steps, int64_t *steps_done);
 
 int qcxms_b200_ensemble_get_result(qcxms_b200_ensemble_t *h, int itrj, double *xyz, double *velo, double *grad,

@@ -204,11 +204,20 @@ int md_oracle_egrad(int nuc, const double *xyz, const int32_t *iat, int mchrg, d
     return !ok;
 }
 
-/* reference src/md.f90:34-708 restricted to it > 0, method 0 (EI), icoll = 0, No_eTemp = .false. */
-int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
-                 const double *velof, double eimp, double tadd, int step_limit, double *grad, int32_t *list, double *achrg, double *axyz,
-                 qcxms_b200_md_result_t *res) {
+static void natf_count(int nuc, const int32_t *list, int nfrag, int *natf);
+
+/* reference src/md.f90:34-708 restricted to it > 0, No_eTemp = .false., Temprun = .false., starting_md = .false.:
+ *   icoll == 0: EI (global method 0)
+ *   icoll >= 1: the mean-free-path MD between two collisions of a CID run (global method 3; called from src/main.F90:1860-1866):
+ *               no IEE heating (:438), kinetic energy and temperature without the motion of the centre of mass (:246-255, :466-493),
+ *               fragment-structure averaging over 50 steps after a fragmentation (:496-621) with max_steps = nstep + add_steps (:507),
+ *               tmax as the only regular exit (:672), error threshold 0.2 (:325), axyz from the averaged fragments (:694-699).
+ *               new_velo (m/s) is in/out (:252, :474). */
+static int md_core(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
+                   const double *velof, double eimp, double tadd, int icoll, double *new_velo_io, int step_limit, double *grad,
+                   int32_t *list, double *achrg, double *axyz, qcxms_b200_md_result_t *res) {
     const double tstep = cfg->tstep;
+    const int cid = icoll > 0;
     double Ekin, T, Epot, etemp;
     int mdok = 0, nfrag = 1, fragstate = 0, scc_total = 0, niter = 0;
     md_oracle_ekinet(nuc, velo, mass, &Ekin, &T);
@@ -220,12 +229,27 @@ int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat,
     memset(res, 0, sizeof *res);
     for (int i = 0; i < nuc; ++i) list[i] = 1;
     if (Epot == 0) { res->status = 2; return 0; }
-    const int more = 250, avdump = 50;
+    const int more = 250, avdump = 50, cnt_steps = 50;
     double Tav = 0, Epav = 0, Ekav = 0, Edum = 0, Eerror = 0, aTlast = 0, dtime = 0, ttime = 0, Eav;
     int nstep = 0, morestep = 0, fconst = 0, kdump = avdump;
     double *avchrg = calloc(nuc, sizeof(double)), *avxyz = calloc(3 * nuc, sizeof(double));
+    double *avxyz2 = calloc(3 * nuc, sizeof(double)), *store = calloc(3 * nuc, sizeof(double));
     int nadd = (int)((tadd + tstep) / tstep - 1);
     double fadd = tstep / (tadd + tstep);
+    /* md.f90:209-235, 246-255, 283 */
+    int check_fragmented = 1, cnt = 0, count_average = 0, add_steps = 0, natf[10], save_natf[10] = {0};
+    if (nuc > 10) add_steps = (nuc / 10) * 500;
+    if (nuc >= 40) add_steps = (nuc / 10) * 1000;
+    double old_cm[3], cm[3], summass = 0, new_velo = new_velo_io ? *new_velo_io : 0.0, new_temp = 0;
+    md_oracle_center_of_mass(nuc, mass, xyz, old_cm);
+    for (int i = 0; i < nuc; ++i) summass = summass + mass[i];
+    {
+        double E_kin = 0.5 * summass * ((new_velo * QC_MSTOAU) * (new_velo * QC_MSTOAU));
+        double E_kin_diff = Ekin - E_kin;
+        new_temp = (2 * E_kin_diff) / (3 * QC_KB * nuc);
+        if (cid) Ekin = E_kin_diff;
+    }
+    int max_steps = cfg->nmax;
     for (;;) {
         if (step_limit > 0 && nstep >= step_limit) break; /* bounded run requested by the caller (not in the reference) */
         nstep = nstep + 1;
@@ -234,7 +258,7 @@ int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat,
         if (nstep > nadd) { Edum = Edum + Epot + Ekin; Eav = Edum / (double)(float)(nstep - nadd); }
         else Eav = Epot + Ekin;
         Eerror = Eav - Epot - Ekin;
-        int err1 = Epot == 0, err2 = fabs(Eerror) > (double)0.1f;
+        int err1 = Epot == 0, err2 = fabs(Eerror) > (cid ? (double)0.2f : (double)0.1f);
         if (err1 || (err2 && cfg->exit_rules)) {
             mdok = ((nfrag > 1 && nfrag <= 4) || cfg->isec > 1);
             break;
@@ -247,7 +271,7 @@ int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat,
         }
         for (int i = 0; i < nuc; ++i) avchrg[i] += achrg[i];
         for (int i = 0; i < 3 * nuc; ++i) avxyz[i] += xyz[i];
-        aTlast = aTlast + T;
+        aTlast = aTlast + (cid ? new_temp : T);
         md_oracle_leapfrog(nuc, grad, mass, tstep, xyz, velo, &Ekin);
         ttime = ttime + tstep / QC_FSTOAU;
         md_oracle_egrad(nuc, xyz, iat, cfg->mchrg, etemp, cfg->method_id, &Epot, grad, achrg, &niter);
@@ -255,16 +279,52 @@ int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat,
         kdump = kdump + 1;
         if (nfrag == 1) morestep = 0;
         if (nfrag > 1 && dtime < 1e-6) dtime = ttime / 1000.;
-        if (nstep <= nadd && nfrag == 1) {
-            if (md_oracle_impactscale(nuc, velo, mass, velof, eimp, fadd * nstep, Ekinstart)) { res->status = 2; break; }
-        }
-        if (cfg->etemp_in < 0) {
-            double dum = eimp - eimp * (double)(float)nstep / (double)(float)nadd;
-            etemp = md_oracle_setetemp(nfrag, dum, cfg->ax, cfg->ieetemp);
+        if (!cid) {
+            if (nstep <= nadd && nfrag == 1) {
+                if (md_oracle_impactscale(nuc, velo, mass, velof, eimp, fadd * nstep, Ekinstart)) { res->status = 2; break; }
+            }
+            if (cfg->etemp_in < 0) {
+                double dum = eimp - eimp * (double)(float)nstep / (double)(float)nadd;
+                etemp = md_oracle_setetemp(nfrag, dum, cfg->ax, cfg->ieetemp);
+            }
         }
         md_oracle_fragment_structure(nuc, iat, xyz, 3.0, 1, 0, list);
         md_oracle_fragmass(nuc, iat, list, mass, NULL, &nfrag, NULL, NULL);
-        if (cfg->exit_rules) {
+        if (cid) {
+            if (nfrag > 6) break;
+            /* kinetic energy without the centre-of-mass motion, md.f90:466-493 */
+            md_oracle_center_of_mass(nuc, mass, xyz, cm);
+            double d0 = cm[0] - old_cm[0], d1 = cm[1] - old_cm[1], d2 = cm[2] - old_cm[2];
+            double cm_out = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            new_velo = (cm_out / tstep) / QC_MSTOAU;
+            for (int k = 0; k < 3; ++k) old_cm[k] = cm[k];
+            double E_kin = 0.5 * summass * ((new_velo * QC_MSTOAU) * (new_velo * QC_MSTOAU));
+            double E_kin_diff = Ekin - E_kin;
+            new_temp = (2.0 * E_kin_diff) / (3.0 * QC_KB * nuc);
+            Ekin = E_kin_diff;
+            /* averaged fragment structures, md.f90:496-621 */
+            if (nfrag > check_fragmented) { count_average = 1; check_fragmented = nfrag; max_steps = nstep + add_steps; }
+            if (nfrag < check_fragmented && count_average) {
+                cnt = 0; memset(avxyz2, 0, 3 * nuc * sizeof(double)); memset(store, 0, 3 * nuc * sizeof(double));
+                count_average = 0; check_fragmented = 1;
+            }
+            if (count_average) {
+                cnt = cnt + 1;
+                for (int i = 0; i < 3 * nuc; ++i) { avxyz2[i] += xyz[i]; store[i] = avxyz2[i] / cnt; }
+                natf_count(nuc, list, nfrag, natf);
+                for (int i = 0; i < nfrag && i < 10; ++i) {
+                    if (cnt == 1) save_natf[i] = natf[i];
+                    if (natf[i] != save_natf[i]) {
+                        cnt = 0; memset(store, 0, 3 * nuc * sizeof(double)); memset(avxyz2, 0, 3 * nuc * sizeof(double));
+                        break;
+                    }
+                }
+                if (cnt == cnt_steps) {
+                    for (int i = 0; i < 3 * nuc; ++i) store[i] = avxyz2[i] / cnt;
+                    memset(avxyz2, 0, 3 * nuc * sizeof(double)); cnt = 0; count_average = 0;
+                }
+            }
+        } else if (cfg->exit_rules) {
             if (nfrag > 6) break;
             if (nfrag > cfg->nfragexit) { fragstate = 1; mdok = 1; break; }
             if (nfrag >= 2) fconst = fconst + 1; else fconst = 0;
@@ -274,17 +334,31 @@ int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat,
                 if (morestep > more) { fragstate = 1; mdok = 1; break; }
             }
         }
-        if (nstep >= cfg->nmax) { fragstate = 1; mdok = 1; break; }
+        if (nstep >= max_steps) { fragstate = 1; mdok = 1; break; }
     }
     res->mdok = mdok; res->fragstate = fragstate; res->nstep = nstep; res->nfrag = nfrag;
     if (res->status == 0) res->status = 1;
     res->scc_iter_total = scc_total;
     res->Tav = Tav / nstep; res->Epav = Epav / nstep; res->Ekav = Ekav / nstep;
     for (int i = 0; i < nuc; ++i) achrg[i] = avchrg[i] / kdump;
-    for (int i = 0; i < 3 * nuc; ++i) axyz[i] = avxyz[i] / kdump;
+    for (int i = 0; i < 3 * nuc; ++i) axyz[i] = (cid && check_fragmented > 1) ? store[i] : avxyz[i] / kdump;
     res->aTlast = aTlast / kdump; res->dtime = dtime; res->ttime = ttime; res->Epot = Epot; res->Ekin = Ekin;
-    free(avchrg); free(avxyz);
+    if (new_velo_io) *new_velo_io = new_velo;
+    free(avchrg); free(avxyz); free(avxyz2); free(store);
     return 0;
+}
+
+int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
+                 const double *velof, double eimp, double tadd, int step_limit, double *grad, int32_t *list, double *achrg, double *axyz,
+                 qcxms_b200_md_result_t *res) {
+    return md_core(cfg, nuc, iat, mass, xyz, velo, velof, eimp, tadd, 0, NULL, step_limit, grad, list, achrg, axyz, res);
+}
+
+int md_oracle_md_mfp(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
+                     int icoll, double *new_velo, int step_limit, double *grad, int32_t *list, double *achrg, double *axyz,
+                     qcxms_b200_md_result_t *res) {
+    if (icoll < 1 || !new_velo) return 1;
+    return md_core(cfg, nuc, iat, mass, xyz, velo, NULL, 0.0, 0.0, icoll, new_velo, step_limit, grad, list, achrg, axyz, res);
 }
 
 /* ======================================================================================== CID

@@ -211,6 +211,28 @@ def md(num, mass, xyz, velo, velof, eimp, tadd, mchrg=1, tstep_fs=0.5, nmax=1000
     return out
 
 
+def md_mfp(num, mass, xyz, velo, icoll, new_velo, mchrg=1, tstep_fs=0.5, nmax=1000, method=2, etemp=-1.0, ieetemp=0.0, ax=0.0, isec=2,
+           max_steps=0, exit_rules=True):
+    """md() of the reference as the mean-free-path MD of a CID run (method 3, icoll >= 1).  Adds new_velo (m/s) to the result."""
+    num = np.ascontiguousarray(num, dtype=np.int32); nat = len(num)
+    mass = np.ascontiguousarray(mass, dtype=np.float64)
+    xyz = np.array(xyz, dtype=np.float64).reshape(nat, 3); velo = np.array(velo, dtype=np.float64).reshape(nat, 3)
+    cfg = MdConfig(int(method), int(mchrg), 3, int(bool(exit_rules)), int(nmax), int(isec),
+                   float(tstep_fs) * 41.3413733365614, float(etemp), float(ieetemp), float(ax))
+    grad = np.zeros((nat, 3)); lst = np.zeros(nat, dtype=np.int32); achrg = np.zeros(nat); axyz = np.zeros((nat, 3))
+    res = MdResult()
+    nv = C.c_double(float(new_velo))
+    f = lib().md_oracle_md_mfp
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    f.argtypes = [C.POINTER(MdConfig), C.c_int, ip, dp, dp, dp, C.c_int, C.POINTER(C.c_double), C.c_int, dp, ip, dp, dp, C.POINTER(MdResult)]
+    f(C.byref(cfg), nat, _ip(num), _dp(mass), _dp(xyz), _dp(velo), int(icoll), C.byref(nv), int(max_steps),
+      _dp(grad), _ip(lst), _dp(achrg), _dp(axyz), C.byref(res))
+    out = dict(xyz=xyz, velo=velo, grad=grad, list=lst, achrg=achrg, axyz=axyz, new_velo=nv.value)
+    for k, _ in MdResult._fields_:
+        out[k] = getattr(res, k)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ CID (md_oracle.c)
 def eigvec3x3(a):
     a = np.array(a, dtype=np.float64).reshape(3, 3)
@@ -306,3 +328,15 @@ def md_batch(num, mass, xyz, velo, velof, eimp, tadd, mchrg, nmax, nfragexit, is
     """md back end for qcxms_b200.production.run_ei (CPU oracle instead of the CUDA ensemble)"""
     return [md(num, mass, xyz[k], velo[k], velof[k], eimp[k], tadd[k], mchrg=mchrg, tstep_fs=tstep_fs, nmax=nmax, nfragexit=nfragexit,
                exit_rules=True, etemp=etemp, isec=isec) for k in range(len(xyz))]
+
+
+def cid_batch(cfg, num, mass, icoll, xyz, velo, rnd, velo_cm, direc, collided):
+    """cid back end for qcxms_b200.production.run_cid (CPU oracle instead of qcxms_b200_cid_batch)"""
+    return [cid(cfg, num, mass, icoll, xyz[k], velo[k], rnd[k], velo_cm=velo_cm[k], direc=direc[k], collided=collided[k])
+            for k in range(len(xyz))]
+
+
+def mfp_batch(num, mass, xyz, velo, new_velo, icoll, isec, mchrg, nmax, tstep_fs, etemp):
+    """mean-free-path md back end for qcxms_b200.production.run_cid (CPU oracle instead of the CUDA ensemble)"""
+    return [md_mfp(num, mass, xyz[k], velo[k], icoll, new_velo[k], mchrg=mchrg, tstep_fs=tstep_fs, nmax=nmax, etemp=etemp, isec=isec)
+            for k in range(len(xyz))]

@@ -57,7 +57,7 @@ GASES = {"he": (2, 4.002, 2.64560263), "ne": (10, 20.18, 2.91016289), "ar": (18,
 
 EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_cid_batch", "qcxms_b200_egrad_batch", "qcxms_b200_fragment_structure", "qcxms_b200_ensemble_create",
            "qcxms_b200_ensemble_destroy", "qcxms_b200_ensemble_set_trajectory", "qcxms_b200_ensemble_set_all",
-           "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_set_warm_start", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_get_all", "qcxms_b200_ensemble_last_timing",
+           "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_set_warm_start", "qcxms_b200_ensemble_set_mfp", "qcxms_b200_ensemble_get_new_velo", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_get_all", "qcxms_b200_ensemble_last_timing",
            "qcxms_b200_ensemble_histogram", "qcxms_b200_last_error", "qcxms_b200_version"]
 
 
@@ -79,6 +79,8 @@ def lib():
         L.qcxms_b200_ensemble_set_all.argtypes = [C.c_void_p, dp, dp, dp, dp, dp]
         L.qcxms_b200_ensemble_run_md.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
         L.qcxms_b200_ensemble_set_warm_start.argtypes = [C.c_void_p, C.c_int]
+        L.qcxms_b200_ensemble_set_mfp.argtypes = [C.c_void_p, C.c_int, dp]
+        L.qcxms_b200_ensemble_get_new_velo.argtypes = [C.c_void_p, dp]
         L.qcxms_b200_ensemble_get_result.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, ip, dp, dp, C.POINTER(MdResult)]
         L.qcxms_b200_ensemble_get_all.argtypes = [C.c_void_p, dp, dp, dp, ip, dp, dp, C.POINTER(MdResult)]
         L.qcxms_b200_ensemble_last_timing.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -183,6 +185,17 @@ class Ensemble:
     def set_warm_start(self, on=True):
         """Opt-in fast mode (not the reference protocol): SCC of each step starts from the previous step's converged populations."""
         _check(lib().qcxms_b200_ensemble_set_warm_start(self._h, int(bool(on))))
+
+    def set_mfp(self, icoll, new_velo):
+        """Mean-free-path MD of a CID run: md() with the reference's method == 3, icoll >= 1; new_velo [ntraj] in m/s as cid() returned it."""
+        nv = np.ascontiguousarray(new_velo, dtype=np.float64)
+        assert nv.size == self.ntraj
+        _check(lib().qcxms_b200_ensemble_set_mfp(self._h, int(icoll), _dp(nv)))
+
+    def new_velo(self):
+        nv = np.zeros(self.ntraj)
+        _check(lib().qcxms_b200_ensemble_get_new_velo(self._h, _dp(nv)))
+        return nv
 
     def run_md(self, max_steps=0):
         """Runs md() for every trajectory; returns the number of trajectory-MD-steps executed."""

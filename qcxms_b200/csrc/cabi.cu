@@ -82,6 +82,30 @@ __device__ inline double md_egrad(const DevModel &m, Sm &s, double *my, const Sc
     return s.red[48];
 }
 
+// steps added after a fragmentation in the mean-free-path MD (reference src/md.f90:233-235)
+__device__ inline int mfp_add_steps(int nuc) { return nuc >= 40 ? (nuc / 10) * 1000 : (nuc > 10 ? (nuc / 10) * 500 : 0); }
+
+// scalar state of the mean-free-path mode of md() (reference src/md.f90:91-116, 209-255), one per trajectory in MdState::mfp_d / mfp_i
+struct MfpScalars {
+    double old_cm[3], new_velo, new_temp, summass, ekin, pad;
+    int cnt, count_average, check_fragmented, max_steps, save_natf[10], ops, pad2;
+};
+static_assert(sizeof(MfpScalars) == 8 * sizeof(double) + 16 * sizeof(int), "MfpScalars layout");
+enum { MFP_ZERO_BEFORE = 1, MFP_ACCUM = 2, MFP_ZERO_AFTER = 4, MFP_FINAL = 8 };
+
+__device__ inline void mfp_load(const MdState &st, int t, MfpScalars &q) {
+    double *d = (double *)&q;
+    int *i = (int *)(d + 8);
+    for (int k = 0; k < 8; ++k) d[k] = __ldcg(st.mfp_d + (size_t)t * 8 + k);
+    for (int k = 0; k < 16; ++k) i[k] = __ldcg(st.mfp_i + (size_t)t * 16 + k);
+}
+__device__ inline void mfp_store(const MdState &st, int t, const MfpScalars &q) {
+    const double *d = (const double *)&q;
+    const int *i = (const int *)(d + 8);
+    for (int k = 0; k < 8; ++k) st.mfp_d[(size_t)t * 8 + k] = d[k];
+    for (int k = 0; k < 16; ++k) st.mfp_i[(size_t)t * 16 + k] = i[k];
+}
+
 // md(): everything before the loop (reference src/md.f90:155-283)
 __global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int *queue) {
     extern __shared__ __align__(16) double smem[];
@@ -112,6 +136,18 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout 
             const double ekin = md_ekinet_seq(nat, st.velo + (size_t)t * 3 * nat, m.mass, 0.0, nullptr);
             const double tadd = st.tadd[t];
             st.ekin[t] = ekin; st.ekinstart[t] = ekin; st.epot[t] = epot; st.etemp[t] = etemp;
+            if (cfg.icoll > 0) {   // mean-free-path mode: kinetic energy without the motion of the centre of mass (src/md.f90:246-255, 283)
+                MfpScalars q{};
+                q.new_velo = st.mfp_d[(size_t)t * 8 + 3];
+                cid_center_of_mass(nat, m.mass, st.xyz + (size_t)t * 3 * nat, q.old_cm);
+                for (int i = 0; i < nat; ++i) q.summass = q.summass + m.mass[i];
+                const double E_kin = 0.5 * q.summass * ((q.new_velo * QC_MSTOAU) * (q.new_velo * QC_MSTOAU));
+                const double E_kin_diff = ekin - E_kin;
+                q.new_temp = (2 * E_kin_diff) / (3 * QC_KB * nat);
+                st.ekin[t] = E_kin_diff;
+                q.check_fragmented = 1; q.max_steps = cfg.nmax;
+                mfp_store(st, t, q);
+            }
             st.Tav[t] = 0; st.Epav[t] = 0; st.Ekav[t] = 0; st.Edum[t] = 0; st.aTlast[t] = 0; st.dtime[t] = 0; st.ttime[t] = 0;
             st.nstep[t] = 0; st.kdump[t] = 50; st.fconst[t] = 0; st.morestep[t] = 0; st.nfrag[t] = 1;
             st.fragstate[t] = 0; st.mdok[t] = 0;
@@ -121,6 +157,8 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout 
         }
         for (int i = threadIdx.x; i < nat; i += QX_NT) { st.avchrg[(size_t)t * nat + i] = 0.0; st.list[(size_t)t * nat + i] = 1; }
         for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) st.avxyz[(size_t)t * 3 * nat + i] = 0.0;
+        if (cfg.icoll > 0)
+            for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) { st.avxyz2[(size_t)t * 3 * nat + i] = 0.0; st.store[(size_t)t * 3 * nat + i] = 0.0; }
     }
 }
 
@@ -128,10 +166,14 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout 
 // Work items are (sub-chunk r, trajectory t), r-major, so that the last partial wave of CTAs costs a few steps and
 // not a whole chunk.  progress[t] counts the finished sub-chunks of trajectory t in this launch: item (r, t) waits
 // until (r-1, t) -- possibly still running on another resident CTA -- is done.
+// MFP = true: the mean-free-path md() of a CID run (cfg.icoll >= 1; reference global method == 3): no IEE heating, kinetic energy
+// without the centre-of-mass motion, averaged fragment structures, tmax as the only regular exit (src/md.f90:246-255, 466-621, 672).
+template <bool MFP>
 __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int chunk,
                                                     int nsub, int step_limit, int *queue, int *progress, unsigned long long *steps_done) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_next, s_flag;
+    __shared__ MfpScalars s_q;
     Sm s;
     double *my = scratch + (size_t)blockIdx.x * L.total;
     carve(m, smem, s, my + L.matA);
@@ -172,6 +214,11 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
         double epot = __ldcg(st.epot + t), ekin = __ldcg(st.ekin + t), etemp = __ldcg(st.etemp + t), Tav = __ldcg(st.Tav + t), Epav = __ldcg(st.Epav + t),
                Ekav = __ldcg(st.Ekav + t), Edum = __ldcg(st.Edum + t);
         double aTlast = __ldcg(st.aTlast + t), dtime = __ldcg(st.dtime + t), ttime = __ldcg(st.ttime + t);
+        double *gavxyz2 = nullptr, *gstore = nullptr;
+        if (MFP) {
+            gavxyz2 = st.avxyz2 + (size_t)t * 3 * nat; gstore = st.store + (size_t)t * 3 * nat;
+            if (threadIdx.x == 0) mfp_load(st, t, s_q);
+        }
         __syncthreads();
         int done = 0;
         for (int it = 0; it < chunk && status == TRJ_RUNNING; ++it) {
@@ -183,7 +230,7 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
             if (nstep > nadd) { Edum += epot + ekin; Eav = Edum / (double)(float)(nstep - nadd); }
             else Eav = epot + ekin;
             const double Eerror = Eav - epot - ekin;
-            const bool err1 = epot == 0.0, err2 = fabs(Eerror) > (double)0.1f;
+            const bool err1 = epot == 0.0, err2 = fabs(Eerror) > (MFP ? (double)0.2f : (double)0.1f);
             if (err1 || (err2 && cfg.exit_rules)) {
                 mdok = ((nfrag > 1 && nfrag <= 4) || cfg.isec > 1) ? 1 : 0;
                 status = TRJ_FINISHED;
@@ -197,7 +244,7 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
             }
             for (int i = threadIdx.x; i < nat; i += QX_NT) avchrg[i] += achrg[i];
             for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) avxyz[i] += s.xyz[i];
-            aTlast += T;
+            aTlast += MFP ? s_q.new_temp : T;
             // leapfrog (reference md.f90:749-773); kinetic-energy terms summed in the reference order
             for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) {
                 const double mass = m.mass[i / 3];
@@ -227,18 +274,74 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
             kdump += 1;
             if (nfrag == 1) morestep = 0;
             if (nfrag > 1 && dtime < 1e-6) dtime = ttime / 1000.0;
-            // IEE heating while the ion is intact
-            if (nstep <= nadd && nfrag == 1) {
-                if (!md_impactscale(m, velo, velof, eimp, fadd * nstep, ekinstart, &s_flag)) { status = TRJ_FAILED; break; }
-            }
-            if (cfg.etemp_in < 0.0) {
-                const double dum = eimp - eimp * (double)(float)nstep / (double)(float)nadd;
-                etemp = md_setetemp(cfg, nfrag, dum);
+            if (!MFP) {
+                // IEE heating while the ion is intact
+                if (nstep <= nadd && nfrag == 1) {
+                    if (!md_impactscale(m, velo, velof, eimp, fadd * nstep, ekinstart, &s_flag)) { status = TRJ_FAILED; break; }
+                }
+                if (cfg.etemp_in < 0.0) {
+                    const double dum = eimp - eimp * (double)(float)nstep / (double)(float)nadd;
+                    etemp = md_setetemp(cfg, nfrag, dum);
+                }
             }
             md_fragments(m, s.xyz, 3.0, (unsigned char *)(my + L.taskout), list, (int *)(my + L.taskout) + (nat * nat + 3) / 4 + 4);
             if (threadIdx.x == 0) s_flag = md_nfrag(m, list);
             __syncthreads();
             nfrag = s_flag;
+            if (MFP) {
+                if (nfrag > 6) { status = TRJ_FINISHED; break; }
+                if (threadIdx.x == 0) {
+                    MfpScalars &q = s_q;
+                    // kinetic energy without the centre-of-mass motion (src/md.f90:466-493)
+                    double cm[3];
+                    cid_center_of_mass(nat, m.mass, s.xyz, cm);
+                    const double d0 = cm[0] - q.old_cm[0], d1 = cm[1] - q.old_cm[1], d2 = cm[2] - q.old_cm[2];
+                    const double cm_out = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                    q.new_velo = (cm_out / cfg.tstep) / QC_MSTOAU;
+                    q.old_cm[0] = cm[0]; q.old_cm[1] = cm[1]; q.old_cm[2] = cm[2];
+                    const double E_kin = 0.5 * q.summass * ((q.new_velo * QC_MSTOAU) * (q.new_velo * QC_MSTOAU));
+                    const double E_kin_diff = ekin - E_kin;
+                    q.new_temp = (2.0 * E_kin_diff) / (3.0 * QC_KB * nat);
+                    q.ekin = E_kin_diff;
+                    // averaged fragment structures (src/md.f90:496-621)
+                    int ops = 0;
+                    if (nfrag > q.check_fragmented) { q.count_average = 1; q.check_fragmented = nfrag; q.max_steps = nstep + mfp_add_steps(nat); }
+                    if (nfrag < q.check_fragmented && q.count_average) { q.cnt = 0; ops |= MFP_ZERO_BEFORE; q.count_average = 0; q.check_fragmented = 1; }
+                    q.pad2 = 0;
+                    if (q.count_average) {
+                        q.cnt += 1;
+                        ops |= MFP_ACCUM;
+                        q.pad2 = q.cnt;   // divisor of this step's store_avxyz
+                        int natf[10];
+                        for (int i = 0; i < 10; ++i) natf[i] = 0;
+                        for (int i = 0; i < nat; ++i) if (list[i] >= 1 && list[i] <= nfrag && list[i] <= 10) natf[list[i] - 1] += 1;
+                        for (int i = 0; i < nfrag && i < 10; ++i) {
+                            if (q.cnt == 1) q.save_natf[i] = natf[i];
+                            if (natf[i] != q.save_natf[i]) { q.cnt = 0; ops |= MFP_ZERO_AFTER; break; }
+                        }
+                        if (q.cnt == 50) { ops |= MFP_FINAL; q.cnt = 0; q.count_average = 0; }
+                    }
+                    q.ops = ops;
+                }
+                __syncthreads();
+                ekin = s_q.ekin;
+                const int ops = s_q.ops;
+                if (ops) {
+                    const double cnt = (double)s_q.pad2;
+                    for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) {
+                        double a2 = __ldcg(gavxyz2 + i), sv = __ldcg(gstore + i);
+                        if (ops & MFP_ZERO_BEFORE) { a2 = 0.0; sv = 0.0; }
+                        if (ops & MFP_ACCUM) { a2 = a2 + s.xyz[i]; sv = a2 / cnt; }
+                        if (ops & MFP_ZERO_AFTER) { a2 = 0.0; sv = 0.0; }
+                        if (ops & MFP_FINAL) a2 = 0.0;
+                        gavxyz2[i] = a2; gstore[i] = sv;
+                    }
+                }
+                const int max_steps = s_q.max_steps;
+                __syncthreads();   // thread 0 rewrites s_q in the next step
+                if (nstep >= max_steps) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
+                continue;
+            }
             if (cfg.exit_rules) {
                 if (nfrag > 6) { status = TRJ_FINISHED; break; }
                 if (nfrag > cfg.nfragexit) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
@@ -260,6 +363,7 @@ __global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout
             st.epot[t] = epot; st.ekin[t] = ekin; st.etemp[t] = etemp; st.Tav[t] = Tav; st.Epav[t] = Epav; st.Ekav[t] = Ekav; st.Edum[t] = Edum;
             st.aTlast[t] = aTlast; st.dtime[t] = dtime; st.ttime[t] = ttime;
             if (status != TRJ_RUNNING) { st.status[t] = status; st.fragstate[t] = fragstate; st.mdok[t] = mdok; }
+            if (MFP) mfp_store(st, t, s_q);
             atomicAdd(steps_done, (unsigned long long)done);
         }
         __syncthreads();   // every thread's global writes of this sub-chunk are issued ...
@@ -486,9 +590,10 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
     c.L = make_layout(c.hm);
     CUDA_OK(cudaFuncSetAttribute(k_egrad_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     CUDA_OK(cudaFuncSetAttribute(k_md_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-    CUDA_OK(cudaFuncSetAttribute(k_md_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    CUDA_OK(cudaFuncSetAttribute(k_md_chunk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    CUDA_OK(cudaFuncSetAttribute(k_md_chunk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     int per_sm = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_chunk, QX_NT, c.smem));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_chunk<false>, QX_NT, c.smem));
     if (per_sm < 1) per_sm = 1;
     c.ncta = per_sm * prop.multiProcessorCount;
     if (nwork > 0 && c.ncta > nwork) c.ncta = nwork;
@@ -707,6 +812,50 @@ extern "C" int qcxms_b200_ensemble_set_warm_start(qcxms_b200_ensemble_t *h, int 
     return 0;
 }
 
+extern "C" int qcxms_b200_ensemble_set_mfp(qcxms_b200_ensemble_t *h, int icoll, const double *new_velo) {
+    if (!h || icoll < 1 || !new_velo) return fail(QCXMS_B200_ERR_ARG, "icoll >= 1 and new_velo [ntraj] required");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    const size_t nt = h->ntraj, n3 = nt * h->ctx.hm.nat * 3;
+    if (!h->st.mfp_d) {
+        cudaError_t e = ens_alloc(h, &h->st.mfp_d, nt * 8);
+        if (e == cudaSuccess) e = ens_alloc(h, &h->st.mfp_i, nt * 16);
+        if (e == cudaSuccess) e = ens_alloc(h, &h->st.avxyz2, n3);
+        if (e == cudaSuccess) e = ens_alloc(h, &h->st.store, n3);
+        if (e != cudaSuccess) return fail(QCXMS_B200_ERR_CUDA, std::string("mean-free-path buffers: ") + cudaGetErrorString(e));
+    }
+    std::vector<double> d(nt * 8, 0.0);
+    for (size_t t = 0; t < nt; ++t) d[t * 8 + 3] = new_velo[t];   // picked up by the initial single point of md()
+    CUDA_OK(cudaMemcpy(h->st.mfp_d, d.data(), d.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->cfg.icoll = icoll;
+    h->initialised = false;
+    return 0;
+}
+
+extern "C" int qcxms_b200_ensemble_get_new_velo(qcxms_b200_ensemble_t *h, double *new_velo) {
+    if (!h || !new_velo) return fail(QCXMS_B200_ERR_ARG, "null argument");
+    if (!h->st.mfp_d) return fail(QCXMS_B200_ERR_ARG, "ensemble is not in mean-free-path mode");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    std::vector<double> d((size_t)h->ntraj * 8);
+    CUDA_OK(cudaMemcpy(d.data(), h->st.mfp_d, d.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int t = 0; t < h->ntraj; ++t) new_velo[t] = d[(size_t)t * 8 + 3];
+    return 0;
+}
+
+// mean-free-path mode: axyz is the averaged fragment structure once a fragmentation was counted (reference src/md.f90:694-699)
+static cudaError_t mfp_fix_axyz(qcxms_b200_ensemble_t *h, size_t t0, size_t nt, double *axyz) {
+    if (h->cfg.icoll <= 0 || !axyz) return cudaSuccess;
+    const size_t n3 = (size_t)h->ctx.hm.nat * 3;
+    std::vector<int> mi(nt * 16);
+    std::vector<double> st(nt * n3);
+    cudaError_t e = cudaMemcpy(mi.data(), h->st.mfp_i + t0 * 16, mi.size() * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(st.data(), h->st.store + t0 * n3, st.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    for (size_t t = 0; t < nt; ++t)
+        if (mi[t * 16 + 2] > 1)
+            for (size_t i = 0; i < n3; ++i) axyz[t * n3 + i] = st[t * n3 + i];
+    return cudaSuccess;
+}
+
 extern "C" int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_steps, int64_t *steps_done) {
     if (!h) return fail(QCXMS_B200_ERR_ARG, "null handle");
     CUDA_OK(cudaSetDevice(h->ctx.device));
@@ -730,7 +879,9 @@ extern "C" int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_step
         for (int v : ns) base_step = v > base_step ? v : base_step;
     }
     const int limit = max_steps > 0 ? base_step + max_steps : 0;
-    const int total = max_steps > 0 ? max_steps : h->cfg.nmax;
+    // mean-free-path mode: every counted fragmentation moves the end to nstep + add_steps (src/md.f90:507); the loop ends when no
+    // trajectory is running any more, the bound is a safety net only
+    const int total = max_steps > 0 ? max_steps : (h->cfg.icoll > 0 ? h->cfg.nmax + 64 * (h->ctx.hm.nat / 10 + 1) * 1000 : h->cfg.nmax);
     const int chunk = 64, sub_steps = 8;
     std::vector<int> status(h->ntraj);
     for (int done = 0; done < total; done += chunk) {
@@ -739,8 +890,12 @@ extern "C" int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_step
         CUDA_OK(cudaMemsetAsync(c.d_queue, 0, sizeof(int), h->stream));
         CUDA_OK(cudaMemsetAsync(h->d_progress, 0, h->ntraj * sizeof(int), h->stream));
         // the last sub-chunk may be shorter: the kernel bounds every sub-chunk by the launch's step limit as well
-        k_md_chunk<<<grid, QX_NT, c.smem, h->stream>>>(c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, sub_steps, nsub,
-                                                       max_steps > 0 ? limit : 0, c.d_queue, h->d_progress, h->d_steps);
+        if (h->cfg.icoll > 0)
+            k_md_chunk<true><<<grid, QX_NT, c.smem, h->stream>>>(c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, sub_steps, nsub,
+                                                                 max_steps > 0 ? limit : 0, c.d_queue, h->d_progress, h->d_steps);
+        else
+            k_md_chunk<false><<<grid, QX_NT, c.smem, h->stream>>>(c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, sub_steps, nsub,
+                                                                  max_steps > 0 ? limit : 0, c.d_queue, h->d_progress, h->d_steps);
         CUDA_OK(cudaGetLastError());
         h->launches += 1;
         // poll for completion every few chunks (cheap: ntraj ints)
@@ -788,6 +943,7 @@ extern "C" int qcxms_b200_ensemble_get_result(qcxms_b200_ensemble_t *h, int itrj
     if (axyz) {
         CUDA_OK(cudaMemcpy(axyz, s.avxyz + t * nat * 3, nat * 3 * sizeof(double), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < nat * 3; ++i) axyz[i] /= kdump;
+        CUDA_OK(mfp_fix_axyz(h, t, 1, axyz));
     }
     if (res) {
         double Tav, Epav, Ekav, aTlast;
@@ -835,6 +991,7 @@ extern "C" int qcxms_b200_ensemble_get_all(qcxms_b200_ensemble_t *h, double *xyz
         CUDA_OK(cudaMemcpy(axyz, s.avxyz, n1 * 3 * sizeof(double), cudaMemcpyDeviceToHost));
         for (size_t t = 0; t < nt; ++t)
             for (size_t i = 0; i < 3 * nat; ++i) axyz[t * 3 * nat + i] /= kdump[t];
+        CUDA_OK(mfp_fix_axyz(h, 0, nt, axyz));
     }
     if (res) {
         auto geti = [&](const int *src, int32_t qcxms_b200_md_result_t::*f) -> cudaError_t {

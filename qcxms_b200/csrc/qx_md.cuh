@@ -19,6 +19,7 @@ namespace qx {
 struct MdConfig {
     int mchrg, nfragexit, exit_rules, nmax, isec;
     double tstep, etemp_in, ieetemp, ax;
+    int icoll;   // 0: EI md(); >= 1: mean-free-path md() of a CID run (reference global method == 3, src/main.F90:1860-1866)
 };
 
 // per-trajectory state, SoA over trajectories
@@ -27,6 +28,10 @@ struct MdState {
     double *avchrg, *avxyz;                           // running sums
     double *eimp, *tadd, *epot, *ekin, *ekinstart, *etemp, *Tav, *Epav, *Ekav, *Edum, *aTlast, *dtime, *ttime, *fadd;
     int *nstep, *kdump, *fconst, *morestep, *nfrag, *status, *fragstate, *mdok, *nadd, *list, *scc_total;
+    // mean-free-path mode only (null otherwise): [ntraj][8] old_cm(3), new_velo, new_temp; [ntraj][16] cnt, count_average,
+    // check_fragmented, max_steps, save_natf(10); [ntraj][3nat] avxyz2 and store_avxyz of src/md.f90:496-621
+    double *mfp_d, *avxyz2, *store;
+    int *mfp_i;
     double *qwarm;    // [ntraj][2 ndim + 1] converged populations of the last two steps + count; null unless the opt-in warm start is on
 };
 

@@ -26,6 +26,20 @@ GAM3 = [0.0, -0.02448, 0.178614, 0.194034, 0.154068, 0.173892, 0.167160, 0.15630
         0.189060, 0.146310, 0.136686, 0.123558, 0.122070, 0.119424, 0.115368]
 
 
+_RAD_AA = None
+
+
+def radii_bohr(num):
+    """Covalent radii Rad (reference src/covalent_radii.f90:89-115, bohr) from the same generated table the CUDA side compiles in."""
+    global _RAD_AA
+    if _RAD_AA is None:
+        import os, re
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "params", "elem_tables.h")) as f:
+            m = re.search(r"QCXMS_RAD_AA\[[^\]]*\]\s*=\s*\{([^}]*)\}", f.read())
+        _RAD_AA = np.array([float(v) for v in m.group(1).split(",")])
+    return _RAD_AA[np.asarray(num, dtype=np.int64)] * (1.0 / 0.52917726)
+
+
 def get_core_e(z):
     """reference src/iniqm.f90:17-41 (H..Ar)"""
     return 0 if z <= 2 else (2 if z <= 10 else 10)
@@ -239,6 +253,8 @@ def manage_fragments(num, mass, axyz, lst, qat, aTlast, itrj, isec, mchrg=1, chr
         rec = res_line(fragchrg3[j - 1], mchrg, itrj, isec, j, fragat_pairs(num, lst, j, imass), icoll=icoll)
         if tcont > 0 and tcont == j:
             asave = rec
+        elif tcont == 0 and icoll is not None:
+            asave = rec      # CID (method 3): held back as well, each fragment overwriting the last (src/write_fragments.f90:411-421)
         else:
             lines.append(rec)
     out.update(nfrag=nfrag, lines=lines, asave=asave, tcont=tcont, chrgcont=chrgcont, mchrg=mchrg, fragchrg3=fragchrg3,
