@@ -105,6 +105,8 @@ def main():
     ap.add_argument("--ntraj", type=int, default=1000, help="trajectories per GPU")
     ap.add_argument("--molecule", default="caffeine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--warm-start", action="store_true", help="opt-in fast mode, NOT the reference protocol (SURVEY 8f-4): SCC of a step "
+                    "starts from the previous step's converged populations; never the headline number")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -117,6 +119,10 @@ def main():
     config = {"workload": "%s cation GFN2-xTB EI, %d trajectories per GPU, tstep 0.5 fs, etemp 5000 K, cold-start SCC acc=1.0, exit rules off"
                           % (args.molecule, args.ntraj), "nat": nat, "ntraj_per_gpu": args.ntraj,
               "l2": "per-step working set (453 KB scratch x resident CTAs + state) is re-streamed every SCC cycle; inputs are not cached between steps"}
+
+    if args.warm_start:
+        config["workload"] = config["workload"].replace("cold-start SCC", "WARM-START SCC (opt-in, not the reference protocol)")
+        config["warm_start"] = True
 
     if args.impl == "reference":
         # The reference's own CPU implementation cannot be built here (no Fortran, tblite un-vendored): the oracle port is timed.
@@ -164,6 +170,8 @@ def main():
 
     def new_ensemble():
         e = qx.Ensemble(num, ic["mass"], args.ntraj, mchrg=1, tstep_fs=0.5, nmax=10 ** 6, exit_rules=False, device=local_rank)
+        if args.warm_start:
+            e.set_warm_start(True)
         e.set_all(*[pin[k].numpy() for k in ("xyz", "velo", "velof", "eimp", "tadd")])
         return e
 
