@@ -49,6 +49,18 @@ int qcxms_b200_egrad_batch(int nsys, int nat, const int32_t *num, const double *
                            int multiplicity, int method_id, double etemp_kelvin, double *qat, double *energy,
                            double *gradient, int32_t *stat, int32_t *niter);
 
+/* Number of basis functions of a composition (sizes the arrays of qcxms_b200_egrad_spec). */
+int qcxms_b200_basis_size(int nat, const int32_t *num, int method_id, int32_t *nao);
+
+/* get_xtb_egrad with spec_calc = .true. (reference src/tblite.f90:152-164): besides energy / gradient / charges it hands back
+ * what write_qmo (reference src/mo_energ.f90:7-80) puts into tmp.mspec and qcxms.Mspec.tbxtb for getspec (src/mo_spec.f90):
+ * nao, ihomo = max(HOMO of the alpha channel, 1) (1-based), orbital energies emo [nao] (Eh, ascending), occupations focc [nao],
+ * and qmo [nao][nat] = Mulliken population of every orbital on every atom, + 1e-10, normalised per orbital.  The file writing
+ * itself stays on the Fortran side (shim) so that the list-directed format is the compiler's own. */
+int qcxms_b200_egrad_spec(int nat, const int32_t *num, const double *xyz, int charge, int multiplicity, int method_id,
+                          double etemp_kelvin, double *qat, double *energy, double *gradient, int32_t *stat,
+                          int32_t *nao, int32_t *ihomo, double *emo, double *focc, double *qmo);
+
 /* ---------------------------------------------------------------------------------------
  * Small routines of the path exposed 1:1 for parity tests (device implementations).
  * fragment_structure(nat, oz, xyz, rcut, at1=1, at2=0, frag): reference src/fragments.f90:93-182

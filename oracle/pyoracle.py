@@ -25,7 +25,8 @@ class Detail(C.Structure):
     _fields_ = [("nsh", C.c_int), ("nao", C.c_int), ("niter", C.c_int), ("converged", C.c_int)] + \
         [(k, C.c_double) for k in ("e_rep", "e_disp_atm", "e_disp_sc", "e_el", "e_es2", "e_es3", "e_aes", "e_ts")] + \
         [(k, C.POINTER(C.c_double)) for k in ("cn", "cn_d4", "overlap", "h0", "dipole", "quadrupole", "emo", "focc",
-                                              "qsh", "dpat", "qpat", "e_iter")]
+                                              "qsh", "dpat", "qpat", "e_iter", "coeff")] + \
+        [("ao2at", C.POINTER(C.c_int32)), ("ihomo", C.c_int)]
 
 
 def lib():
@@ -75,19 +76,33 @@ def egrad(num, xyz, charge=0, multiplicity=1, method=2, etemp=300.0, detail=Fals
         bufs = dict(cn=np.zeros(nat), cn_d4=np.zeros(nat), overlap=np.zeros((nao, nao)), h0=np.zeros((nao, nao)),
                     dipole=np.zeros((3, nao, nao)), quadrupole=np.zeros((6, nao, nao)), emo=np.zeros(nao),
                     focc=np.zeros(nao), qsh=np.zeros(nsh), dpat=np.zeros((nat, 3)), qpat=np.zeros((nat, 6)),
-                    e_iter=np.zeros(250))
+                    e_iter=np.zeros(250), coeff=np.zeros((nao, nao)))
         for k, v in bufs.items():
             setattr(d, k, _dp(v))
+        ao2at = np.zeros(nao, dtype=np.int32)
+        d.ao2at = _ip(ao2at)
+        bufs["ao2at"] = ao2at
         st = lib().xtb_oracle_egrad(nat, _ip(num), _dp(xyz), charge, multiplicity, method, etemp, _dp(qat),
                                     C.byref(e), _dp(grad), C.byref(d))
         out.update(bufs)
         for k in ("nsh", "nao", "niter", "converged", "e_rep", "e_disp_atm", "e_disp_sc", "e_el", "e_es2", "e_es3",
-                  "e_aes", "e_ts"):
+                  "e_aes", "e_ts", "ihomo"):
             out[k] = getattr(d, k)
     else:
         st = lib().xtb_oracle_egrad(nat, _ip(num), _dp(xyz), charge, multiplicity, method, etemp, _dp(qat),
                                     C.byref(e), _dp(grad), None)
     out.update(energy=e.value, gradient=grad, qat=qat, stat=st)
+    return out
+
+
+def qmo(ao2at, coeff, overlap, nat):
+    """write_qmo of the reference without the files (src/mo_energ.f90:31-54): qmo[nao, nat], every orbital normalised over the atoms."""
+    nao = len(ao2at)
+    out = np.zeros((nao, nat))
+    f = lib().xtb_oracle_qmo
+    f.restype = None
+    f.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    f(int(nat), nao, _ip(np.ascontiguousarray(ao2at, dtype=np.int32)), _dp(np.ascontiguousarray(coeff)), _dp(np.ascontiguousarray(overlap)), _dp(out))
     return out
 
 

@@ -1470,6 +1470,13 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
         if (detail->qsh) memcpy(detail->qsh, qsh, nsh * sizeof(double));
         if (detail->dpat) memcpy(detail->dpat, dpat, 3 * nat * sizeof(double));
         if (detail->qpat) memcpy(detail->qpat, qpat, 6 * nat * sizeof(double));
+        if (detail->coeff) memcpy(detail->coeff, C, n2 * sizeof(double));
+        if (detail->ao2at) for (int a = 0; a < nao; ++a) detail->ao2at[a] = s.ao_at[a];
+        {
+            int homo = (int)floor(nel[0]);
+            if (fmod(nel[0], 1.0) > 0.5) homo += 1;
+            detail->ihomo = homo > 1 ? homo : 1;
+        }
     }
 
     free(s.at_sh0); free(s.at_nsh); free(s.sh_at); free(s.sh_l); free(s.sh_ao0); free(s.sh_np); free(s.ao_at); free(s.ao_sh);
@@ -1482,4 +1489,23 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
     free(H1); free(C); free(P); free(Linv); free(work); free(emo); free(focc); free(ftmp);
     free(mix.q_in); free(mix.qlast_in); free(mix.dq); free(mix.dqlast); free(mix.df); free(mix.u); free(mix.a); free(mix.omega);
     return stat;
+}
+
+/* reference src/mo_energ.f90:31-54 (write_qmo): qmo(n, ia) = sum_{j on ia} sum_k c(j,n) c(k,n) S(j,k) + 1e-10, then every orbital
+ * is normalised over the atoms */
+void xtb_oracle_qmo(int nat, int nao, const int32_t *ao2at, const double *coeff, const double *overlap, double *qmo) {
+    for (int ia = 0; ia < nat; ++ia)
+        for (int n = 0; n < nao; ++n) {
+            double qmo_sum = 0.0;
+            for (int j = 0; j < nao; ++j)
+                if (ao2at[j] == ia)
+                    for (int k = 0; k < nao; ++k) qmo_sum = qmo_sum + coeff[(size_t)j * nao + n] * coeff[(size_t)k * nao + n] * overlap[(size_t)j * nao + k];
+            qmo_sum = qmo_sum + 1.e-10;
+            qmo[(size_t)n * nat + ia] = qmo_sum;
+        }
+    for (int k = 0; k < nao; ++k) {
+        double summa = 0.0;
+        for (int j = 0; j < nat; ++j) summa = summa + qmo[(size_t)k * nat + j];
+        for (int j = 0; j < nat; ++j) qmo[(size_t)k * nat + j] = qmo[(size_t)k * nat + j] / summa;
+    }
 }

@@ -31,6 +31,9 @@ typedef struct {
     double *dpat;     /* [3*nat] atom-major */
     double *qpat;     /* [6*nat] atom-major */
     double *e_iter;   /* [250] electronic energy per SCC iteration */
+    double *coeff;    /* [nao*nao] eigenvectors, coeff[a*nao + k] = AO a of orbital k (orbitals in ascending energy) */
+    int32_t *ao2at;   /* [nao] atom (0-based) of every AO */
+    int ihomo;        /* max(homo of the alpha channel, 1), 1-based (reference src/tblite.f90:160) */
 } xtb_oracle_detail_t;
 
 /* Restates get_xtb_egrad (reference src/tblite.f90:65-175): cold-start SCC with
@@ -39,6 +42,10 @@ typedef struct {
 int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge, int multiplicity,
                      int method_id, double etemp, double *qat, double *energy, double *gradient,
                      xtb_oracle_detail_t *detail);
+
+/* write_qmo without the files (reference src/mo_energ.f90:31-54): Mulliken population of every orbital on every atom,
+ * + 1e-10, normalised per orbital.  coeff/overlap as in the detail struct; qmo [nao][nat]. */
+void xtb_oracle_qmo(int nat, int nao, const int32_t *ao2at, const double *coeff, const double *overlap, double *qmo);
 
 /* test hook: scale the SCC thresholds (reference value 1.0, src/tblite.f90:46) */
 void xtb_oracle_set_accuracy(double acc);

@@ -55,7 +55,7 @@ class CidResult(C.Structure):
 # collision gases of the reference (src/input.f90:512-558): Z, mass / amu, radius / bohr
 GASES = {"he": (2, 4.002, 2.64560263), "ne": (10, 20.18, 2.91016289), "ar": (18, 39.948, 3.55266638), "n2": (7, 14.007, 3.64)}
 
-EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_cid_batch", "qcxms_b200_egrad_batch", "qcxms_b200_fragment_structure", "qcxms_b200_ensemble_create",
+EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_egrad_spec", "qcxms_b200_basis_size", "qcxms_b200_cid_batch", "qcxms_b200_egrad_batch", "qcxms_b200_fragment_structure", "qcxms_b200_ensemble_create",
            "qcxms_b200_ensemble_destroy", "qcxms_b200_ensemble_set_trajectory", "qcxms_b200_ensemble_set_all",
            "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_set_warm_start", "qcxms_b200_ensemble_set_mfp", "qcxms_b200_ensemble_get_new_velo", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_get_all", "qcxms_b200_ensemble_last_timing",
            "qcxms_b200_ensemble_histogram", "qcxms_b200_last_error", "qcxms_b200_version"]
@@ -78,6 +78,9 @@ def lib():
         L.qcxms_b200_ensemble_set_trajectory.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, C.c_double, C.c_double]
         L.qcxms_b200_ensemble_set_all.argtypes = [C.c_void_p, dp, dp, dp, dp, dp]
         L.qcxms_b200_ensemble_run_md.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        L.qcxms_b200_basis_size.argtypes = [C.c_int, ip, C.c_int, C.POINTER(C.c_int32)]
+        L.qcxms_b200_egrad_spec.argtypes = [C.c_int, ip, dp, C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, dp, C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), dp, dp, dp]
         L.qcxms_b200_ensemble_set_warm_start.argtypes = [C.c_void_p, C.c_int]
         L.qcxms_b200_ensemble_set_mfp.argtypes = [C.c_void_p, C.c_int, dp]
         L.qcxms_b200_ensemble_get_new_velo.argtypes = [C.c_void_p, dp]
@@ -120,6 +123,39 @@ def get_xtb_egrad(num, xyz, charge, multiplicity, method, etemp):
     _check(lib().qcxms_b200_egrad(len(num), _ip(num), _dp(xyz), int(charge), int(multiplicity), int(method), float(etemp),
                                   _dp(qat), C.byref(e), _dp(grad), C.byref(stat)))
     return qat, e.value, grad, stat.value
+
+
+def get_xtb_egrad_spec(num, xyz, charge, multiplicity, method, etemp, write_files=None):
+    """get_xtb_egrad with spec_calc = .true. (reference src/tblite.f90:152-164): adds nao, ihomo, emo [nao] (Eh), focc [nao] and
+    qmo [nao, nat] (write_qmo, src/mo_energ.f90:31-54).  write_files: directory to put tmp.mspec and qcxms.Mspec.tbxtb into, with the
+    record structure of src/mo_energ.f90:56-74 (getspec reads them list-directed)."""
+    num = np.ascontiguousarray(num, dtype=np.int32)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    nat = len(num)
+    nao = C.c_int32(0)
+    _check(lib().qcxms_b200_basis_size(nat, _ip(num), int(method), C.byref(nao)))
+    n = nao.value
+    qat = np.zeros(nat); grad = np.zeros((nat, 3)); e = C.c_double(0.0); stat = C.c_int32(0)
+    emo, focc, qmo = np.zeros(n), np.zeros(n), np.zeros((n, nat))
+    ihomo = C.c_int32(0)
+    _check(lib().qcxms_b200_egrad_spec(nat, _ip(num), _dp(xyz), int(charge), int(multiplicity), int(method), float(etemp), _dp(qat),
+                                       C.byref(e), _dp(grad), C.byref(stat), C.byref(nao), C.byref(ihomo), _dp(emo), _dp(focc), _dp(qmo)))
+    out = dict(qat=qat, energy=e.value, gradient=grad, stat=stat.value, nao=n, ihomo=ihomo.value, emo=emo, focc=focc, qmo=qmo)
+    if write_files is not None and stat.value == 0:
+        with open(os.path.join(write_files, "qcxms.Mspec.tbxtb"), "w") as f:
+            f.write(" %11d %11d\n" % (n, ihomo.value))
+            for k in range(n):
+                f.write("\n%3d %10.3f\n" % (k + 1, emo[k] * AUTOEV))
+                f.write(" %6.2f\n" % focc[k])
+                for j0 in range(0, nat, 10):
+                    f.write("".join(" %6.2f" % (v * 100.0) for v in qmo[k, j0:j0 + 10]) + "\n")
+        with open(os.path.join(write_files, "tmp.mspec"), "w") as f:
+            f.write(" %11d %11d\n" % (n, ihomo.value))
+            for k in range(n):
+                f.write("  %.16E\n  %.16E\n" % (emo[k] * AUTOEV, focc[k]))
+                for j in range(nat):
+                    f.write("  %.16E\n" % qmo[k, j])
+    return out
 
 
 def egrad_batch(num, xyz, charge, multiplicity, method, etemp):

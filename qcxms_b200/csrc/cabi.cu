@@ -5,6 +5,7 @@
 // and the integral slab in its private, L2-resident global scratch.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -30,7 +31,7 @@ static int fail(int code, const std::string &msg) {
 
 // ------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(QX_NT, 2) k_egrad_batch(DevModel m, ScratchLayout L, double *scratch, const double *xyz, double kt, int nsys,
-                                                       int *queue, double *energy, double *grad, double *qat, int *stat, int *niter) {
+                                                       int *queue, double *energy, double *grad, double *qat, int *stat, int *niter, double *spec) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_next;
     Sm s;
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(QX_NT, 2) k_egrad_batch(DevModel m, ScratchLay
         for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.xyz[i] = xyz[(size_t)t * 3 * nat + i];
         __syncthreads();
         EgradOut o;
-        egrad_cta(m, s, my, L, kt, o);
+        egrad_cta(m, s, my, L, kt, o, nullptr, spec ? spec + (size_t)t * (2 * m.nao + m.nao * nat + 1) : nullptr);
         __syncthreads();
         for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) grad[(size_t)t * 3 * nat + i] = s.grad[i];
         for (int i = threadIdx.x; i < nat; i += QX_NT) qat[(size_t)t * nat + i] = s.qat[i];
@@ -609,8 +610,9 @@ static void context_free(Context &c) {
     c.d_scratch = nullptr; c.d_queue = nullptr; c.hm.d_blob = nullptr;
 }
 
-extern "C" int qcxms_b200_egrad_batch(int nsys, int nat, const int32_t *num, const double *xyz, int charge, int multiplicity, int method_id,
-                                      double etemp, double *qat, double *energy, double *gradient, int32_t *stat, int32_t *niter) {
+static int egrad_batch_impl(int nsys, int nat, const int32_t *num, const double *xyz, int charge, int multiplicity, int method_id,
+                            double etemp, double *qat, double *energy, double *gradient, int32_t *stat, int32_t *niter,
+                            std::vector<double> *spec, int *nao_out) {
     if (nsys < 1 || nat < 1 || !num || !xyz || !qat || !energy || !gradient || !stat) return fail(QCXMS_B200_ERR_ARG, "null or empty argument");
     if (method_id != QCXMS_B200_GFN2) {
         // reference: unknown method -> stat = 5, outputs untouched (src/tblite.f90:114-120).  GFN1/IPEA1 are not built yet.
@@ -644,9 +646,18 @@ extern "C" int qcxms_b200_egrad_batch(int nsys, int nat, const int32_t *num, con
     CUDA_OK(cudaMemcpy(d_xyz, xyz, n3 * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemset(ctx.d_queue, 0, sizeof(int)));
     int grid = ctx.ncta < nsys ? ctx.ncta : nsys;
-    k_egrad_batch<<<grid, QX_NT, ctx.smem>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, d_xyz, etemp * QC_KTOAU, nsys, ctx.d_queue, d_e, d_g, d_q, d_stat, d_nit);
+    double *d_spec = nullptr;
+    const size_t nspec = (size_t)nsys * (2 * ctx.hm.nao + (size_t)ctx.hm.nao * nat + 1);
+    if (spec) CUDA_OK(cudaMalloc(&d_spec, nspec * sizeof(double)));
+    if (nao_out) *nao_out = ctx.hm.nao;
+    k_egrad_batch<<<grid, QX_NT, ctx.smem>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, d_xyz, etemp * QC_KTOAU, nsys, ctx.d_queue, d_e, d_g, d_q, d_stat, d_nit, d_spec);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaDeviceSynchronize());
+    if (spec) {
+        spec->resize(nspec);
+        CUDA_OK(cudaMemcpy(spec->data(), d_spec, nspec * sizeof(double), cudaMemcpyDeviceToHost));
+        cudaFree(d_spec);
+    }
     CUDA_OK(cudaMemcpy(energy, d_e, nsys * sizeof(double), cudaMemcpyDeviceToHost));
     CUDA_OK(cudaMemcpy(gradient, d_g, n3 * sizeof(double), cudaMemcpyDeviceToHost));
     CUDA_OK(cudaMemcpy(qat, d_q, (size_t)nsys * nat * sizeof(double), cudaMemcpyDeviceToHost));
@@ -656,9 +667,54 @@ extern "C" int qcxms_b200_egrad_batch(int nsys, int nat, const int32_t *num, con
     return 0;
 }
 
+extern "C" int qcxms_b200_egrad_batch(int nsys, int nat, const int32_t *num, const double *xyz, int charge, int multiplicity, int method_id,
+                                      double etemp, double *qat, double *energy, double *gradient, int32_t *stat, int32_t *niter) {
+    return egrad_batch_impl(nsys, nat, num, xyz, charge, multiplicity, method_id, etemp, qat, energy, gradient, stat, niter, nullptr, nullptr);
+}
+
 extern "C" int qcxms_b200_egrad(int nat, const int32_t *num, const double *xyz, int charge, int multiplicity, int method_id, double etemp,
                                 double *qat, double *energy, double *gradient, int32_t *stat) {
     return qcxms_b200_egrad_batch(1, nat, num, xyz, charge, multiplicity, method_id, etemp, qat, energy, gradient, stat, nullptr);
+}
+
+extern "C" int qcxms_b200_basis_size(int nat, const int32_t *num, int method_id, int32_t *nao) {
+    if (nat < 1 || !num || !nao) return fail(QCXMS_B200_ERR_ARG, "null or empty argument");
+    if (method_id != QCXMS_B200_GFN2) return fail(QCXMS_B200_ERR_UNSUPPORTED, "only GFN2-xTB (method id 2) is implemented");
+    int n = 0;
+    for (int i = 0; i < nat; ++i) {
+        if (num[i] < 1 || num[i] > GFN2_MAXZ) return fail(QCXMS_B200_ERR_UNSUPPORTED, "GFN2-xTB parameters are available for H-Ar");
+        const gfn2_elem_t &e = GFN2_ELEM[num[i]];
+        for (int k = 0; k < e.nshell; ++k) n += 2 * e.ang[k] + 1;
+    }
+    *nao = n;
+    return 0;
+}
+
+// get_xtb_egrad with spec_calc = .true. (reference src/tblite.f90:152-164): the arrays write_qmo puts into tmp.mspec / qcxms.Mspec.tbxtb
+extern "C" int qcxms_b200_egrad_spec(int nat, const int32_t *num, const double *xyz, int charge, int multiplicity, int method_id, double etemp,
+                                     double *qat, double *energy, double *gradient, int32_t *stat, int32_t *nao_out, int32_t *ihomo,
+                                     double *emo, double *focc, double *qmo) {
+    if (!nao_out || !ihomo || !emo || !focc || !qmo) return fail(QCXMS_B200_ERR_ARG, "null spec output");
+    std::vector<double> spec;
+    int nao = 0;
+    int rc = egrad_batch_impl(1, nat, num, xyz, charge, multiplicity, method_id, etemp, qat, energy, gradient, stat, nullptr, &spec, &nao);
+    if (rc || *stat == QCXMS_B200_STAT_UNKNOWN_METHOD) return rc;
+    // orbitals in ascending energy like the reference's LAPACK solver (stable for degenerate levels)
+    std::vector<int> ord(nao);
+    for (int k = 0; k < nao; ++k) ord[k] = k;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return spec[a] < spec[b]; });
+    for (int k = 0; k < nao; ++k) {
+        const int o = ord[k];
+        emo[k] = spec[o];
+        focc[k] = spec[nao + o];
+        // src/mo_energ.f90:41-54: + 1e-10, then normalised over the atoms
+        double summa = 0.0;
+        for (int j = 0; j < nat; ++j) { qmo[(size_t)k * nat + j] = spec[2 * nao + (size_t)o * nat + j] + 1.e-10; summa = summa + qmo[(size_t)k * nat + j]; }
+        for (int j = 0; j < nat; ++j) qmo[(size_t)k * nat + j] = qmo[(size_t)k * nat + j] / summa;
+    }
+    *nao_out = nao;
+    *ihomo = (int)spec[2 * nao + (size_t)nao * nat];
+    return 0;
 }
 
 extern "C" int qcxms_b200_fragment_structure(int nsys, int nat, const int32_t *num, const double *xyz, double rcut, int32_t *frag) {

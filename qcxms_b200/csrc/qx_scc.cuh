@@ -588,7 +588,11 @@ __device__ __noinline__ void phase_gradient_pairs(const DevModel &m, Sm &s, cons
 // qstart (may be null): OPT-IN warm start, not the reference protocol.  [2 ndim + 1]: converged populations (shell
 // charges, atomic dipoles, quadrupoles) of the last and the last-but-one call and the number of valid entries; the SCC starts
 // from their linear extrapolation instead of from zero, and the history is advanced when this call converges.
-__device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, const ScratchLayout &L, double kt, EgradOut &out, double *qstart = nullptr) {
+// spec (may be null): the reference's spec_calc output (src/tblite.f90:152-164, src/mo_energ.f90:31-43) -- [nao] orbital energies,
+// [nao] occupations, [nao][nat] raw Mulliken population of every orbital on every atom (orbitals in solver order: the host sorts
+// and normalises), [1] HOMO index of the alpha channel.
+__device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, const ScratchLayout &L, double kt, EgradOut &out, double *qstart = nullptr,
+                                 double *spec = nullptr) {
     const int nat = m.nat, nsh = m.nsh, nao = m.nao, ld = m.ld, ndim = m.ndim;
     double *S = scratch + L.S, *H0 = scratch + L.H0, *Dt = scratch + L.Dt, *Qt = scratch + L.Qt, *T = scratch + L.T;
     double *gamma = scratch + L.gamma, *dcnp = scratch + L.dcnp, *dcnp4 = scratch + L.dcnp4, *edisp = scratch + L.edisp;
@@ -803,6 +807,26 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
             qstart[i] = i < nsh ? s.qsh[i] : (i < nsh + 3 * nat ? s.dpat[i - nsh] : s.qpat[i - nsh - 3 * nat]);
         }
         if (threadIdx.x == 0) qstart[2 * ndim] = fmin(__ldcg(qstart + 2 * ndim) + 1.0, 2.0);
+    }
+    if (spec) {
+        for (int k = threadIdx.x; k < nao; k += QX_NT) { spec[k] = s.emo[k]; spec[nao + k] = s.focc[k]; }
+        for (int t = threadIdx.x; t < nao * nat; t += QX_NT) {
+            const int k = t / nat, ia = t - k * nat;
+            const double *ck = s.C + (size_t)k * ld;      // row k of C^T = orbital k
+            double q = 0.0;
+            for (int j = 0; j < nao; ++j) {
+                if (m.ao_at[j] != ia) continue;
+                double sc = 0.0;
+                for (int l = 0; l < nao; ++l) sc += S[(size_t)j * nao + l] * ck[l];
+                q += ck[j] * sc;
+            }
+            spec[2 * nao + t] = q;
+        }
+        if (threadIdx.x == 0) {
+            const double ne = m.nel[0];
+            const int homo = (int)floor(ne) + (fmod(ne, 1.0) > 0.5 ? 1 : 0);
+            spec[2 * nao + nao * nat] = (double)(homo > 1 ? homo : 1);
+        }
     }
     // "SCF not converged": flagged, but energy and gradient of the last cycle are still handed back -- the
     // reference's egrad overrides stat with checkqc (src/iniqm.f90:646-651)

@@ -56,6 +56,24 @@ module qcxms_tblite
          integer(c_int32_t), intent(out) :: stat
       end function qcxms_b200_egrad
 
+      integer(c_int) function qcxms_b200_basis_size(nat, num, method_id, nao) bind(c, name="qcxms_b200_basis_size")
+         import :: c_int, c_int32_t
+         integer(c_int), value :: nat, method_id
+         integer(c_int32_t), intent(in) :: num(*)
+         integer(c_int32_t), intent(out) :: nao
+      end function qcxms_b200_basis_size
+
+      integer(c_int) function qcxms_b200_egrad_spec(nat, num, xyz, charge, multiplicity, method_id, etemp, qat, energy, gradient, &
+            & stat, nao, ihomo, emo, focc, qmo) bind(c, name="qcxms_b200_egrad_spec")
+         import :: c_int, c_int32_t, c_double
+         integer(c_int), value :: nat, charge, multiplicity, method_id
+         integer(c_int32_t), intent(in) :: num(*)
+         real(c_double), intent(in) :: xyz(3, *)
+         real(c_double), value :: etemp
+         real(c_double), intent(out) :: qat(*), energy, gradient(3, *), emo(*), focc(*), qmo(nat, *)
+         integer(c_int32_t), intent(out) :: stat, nao, ihomo
+      end function qcxms_b200_egrad_spec
+
       integer(c_int) function ensemble_create(cfg, ntraj, nat, num, mass, device, handle) &
             & bind(c, name="qcxms_b200_ensemble_create")
          import :: c_int, c_int32_t, c_double, c_ptr, md_config
@@ -131,9 +149,11 @@ subroutine get_xtb_egrad(num, xyz, charge, multiplicity, method, etemp, &
    integer, intent(out) :: stat
    logical :: spec_calc
 
-   integer(c_int32_t) :: cstat
+   integer(c_int32_t) :: cstat, cnao, cihomo
    integer(c_int) :: rc
-   integer :: unit
+   integer :: unit, nat, k, j, io_tmp, io_mspec
+   real(c_double), allocatable :: emo(:), focc(:), qmo(:, :)
+   real(wp), parameter :: autoev = 27.21138505_wp
 
    ! the reference redirects tblite's printout to output_file on every call (src/tblite.f90:108,173);
    ! keep the file so that downstream scripts find it, but write a one-line stub only
@@ -141,12 +161,47 @@ subroutine get_xtb_egrad(num, xyz, charge, multiplicity, method, etemp, &
    write(unit, '(a)') "[Info] qcxms_b200: GFN-xTB calculation on the GPU"
    close(unit)
 
-   rc = qcxms_b200_egrad(int(size(num), c_int), int(num, c_int32_t), xyz, int(charge, c_int), &
-      & int(multiplicity, c_int), int(method%id, c_int), real(etemp, c_double), qat, energy, gradient, cstat)
+   nat = size(num)
+   if (.not. spec_calc) then
+      rc = qcxms_b200_egrad(int(nat, c_int), int(num, c_int32_t), xyz, int(charge, c_int), &
+         & int(multiplicity, c_int), int(method%id, c_int), real(etemp, c_double), qat, energy, gradient, cstat)
+      stat = int(cstat)
+      if (rc /= 0) stat = -1   ! stat_fatal (src/tblite.f90:55)
+      return
+   end if
+
+   ! spec_calc: MO energies, occupations and atomic populations for getspec; the files are written with the statements of
+   ! write_qmo (reference src/mo_energ.f90:56-74) so that their layout is the compiler's own list-directed one
+   rc = qcxms_b200_basis_size(int(nat, c_int), int(num, c_int32_t), int(method%id, c_int), cnao)
+   if (rc /= 0) then
+      stat = -1
+      return
+   end if
+   allocate(emo(cnao), focc(cnao), qmo(nat, cnao))      ! C layout [nao][nat]
+   rc = qcxms_b200_egrad_spec(int(nat, c_int), int(num, c_int32_t), xyz, int(charge, c_int), int(multiplicity, c_int), &
+      & int(method%id, c_int), real(etemp, c_double), qat, energy, gradient, cstat, cnao, cihomo, emo, focc, qmo)
    stat = int(cstat)
-   if (rc /= 0) stat = -1   ! stat_fatal (src/tblite.f90:55)
-   ! spec_calc (MO dump for getspec, set-up mode only) is not on the production path: unsupported here
-   if (spec_calc .and. stat == 0) stat = -1
+   if (rc /= 0) stat = -1
+   if (stat /= 0) return
+   open(file='tmp.mspec', newunit=io_tmp, status='replace')
+   open(file='qcxms.Mspec.tbxtb', newunit=io_mspec, status='replace')
+   write(io_mspec,*) int(cnao), int(cihomo)
+   do k = 1, cnao
+      write (io_mspec, *)
+      write (io_mspec,'(1(i3 ,1x, f10.3))') k, emo(k)*autoev
+      write (io_mspec,'(1(1x, f6.2))')     focc(k)
+      write (io_mspec,'(10(1x, f6.2))')   (qmo(j,k)*100.0d0, j=1,nat)
+   enddo
+   write(io_tmp,*) int(cnao), int(cihomo)
+   do k = 1, cnao
+      write(io_tmp,*) emo(k)*autoev
+      write(io_tmp,*) focc(k)
+      do j = 1, nat
+         write (io_tmp, *) qmo(j,k)
+      end do
+   enddo
+   close(io_tmp)
+   close(io_mspec)
 end subroutine get_xtb_egrad
 
 end module qcxms_tblite

@@ -65,3 +65,32 @@ def test_medium_basis_multi_pass_jacobi(qx, oracle, name):
     rng = np.random.default_rng(2)
     x = xyz + 0.03 * rng.standard_normal(xyz.shape)
     _compare(qx, oracle, num, x, 1, 2, 5000.0)
+
+
+@pytest.mark.parametrize("name,charge,etemp", [("chloroethanol", 0, 300.0), ("chloroethanol", 1, 5000.0), ("thf_h", 1, 300.0)])
+def test_spec_calc_output_matches_oracle(qx, oracle, tmp_path, name, charge, etemp):
+    """get_xtb_egrad(..., spec_calc = .true.) (reference src/tblite.f90:152-164, write_qmo src/mo_energ.f90:7-80): orbital energies,
+    occupations, HOMO index and the normalised atomic populations of every orbital; energy / gradient / charges unchanged."""
+    from qcxms_b200.fragments import getspin
+    num, xyz, _ = qx.load_molecule(name)
+    mult = getspin(num, charge)
+    ref = oracle.egrad(num, xyz, charge=charge, multiplicity=mult, etemp=etemp, detail=True)
+    qref = oracle.qmo(ref["ao2at"], ref["coeff"], ref["overlap"], len(num))
+    got = qx.get_xtb_egrad_spec(num, xyz, charge, mult, qx.gfn2_xtb, etemp, write_files=str(tmp_path))
+    pq, pe, pg, pstat = qx.get_xtb_egrad(num, xyz, charge, mult, qx.gfn2_xtb, etemp)
+    plain = dict(qat=pq, energy=pe, gradient=pg)
+    assert got["stat"] == 0 and pstat == 0 and got["nao"] == ref["nao"] and got["ihomo"] == ref["ihomo"]
+    assert got["energy"] == plain["energy"] and np.array_equal(got["gradient"], plain["gradient"]) and np.array_equal(got["qat"], plain["qat"])
+    assert np.abs(got["emo"] - ref["emo"]).max() < 1e-6          # Eh; both stop at the SCC thresholds
+    assert np.abs(got["focc"] - ref["focc"]).max() < 1e-5
+    assert np.all(np.diff(got["emo"]) >= 0) and abs(got["focc"].sum() - ref["focc"].sum()) < 1e-9
+    assert np.abs(got["qmo"].sum(1) - 1.0).max() < 1e-12
+    gaps = np.diff(ref["emo"])
+    ok = np.concatenate(([True], gaps > 1e-3)) & np.concatenate((gaps > 1e-3, [True]))     # populations of degenerate levels are not unique
+    assert ok.sum() >= ref["nao"] - 4
+    assert np.abs(got["qmo"][ok] - qref[ok]).max() < 1e-4
+    # the two files getspec reads (src/mo_spec.f90): header and record count
+    tmp = (tmp_path / "tmp.mspec").read_text().split()
+    assert int(tmp[0]) == ref["nao"] and int(tmp[1]) == ref["ihomo"] and len(tmp) == 2 + ref["nao"] * (2 + len(num))
+    assert abs(float(tmp[2]) - got["emo"][0] * 27.21138505) < 1e-9
+    assert (tmp_path / "qcxms.Mspec.tbxtb").read_text().split()[0] == str(ref["nao"])

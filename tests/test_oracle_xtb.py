@@ -122,3 +122,17 @@ def test_golden_fixtures(oracle):
         assert np.abs(r["qat"] - np.array(c["qat"])).max() < 1e-9
         for k, v in c["terms"].items():
             assert abs(r[k] - v) < 1e-9
+
+
+def test_qmo_restatement_properties(oracle):
+    """write_qmo (reference src/mo_energ.f90:31-54): per-orbital atomic populations sum to one; weighted with the occupations they
+    give back the Mulliken atomic populations of the SCC (up to the 1e-10 offset of the reference)."""
+    from qcxms_b200.api import load_molecule
+    num, xyz, _ = load_molecule("chloroethanol")
+    r = oracle.egrad(num, xyz, charge=0, multiplicity=1, etemp=300.0, detail=True)
+    q = oracle.qmo(r["ao2at"], r["coeff"], r["overlap"], len(num))
+    assert q.shape == (r["nao"], len(num)) and np.abs(q.sum(1) - 1.0).max() < 1e-13
+    assert r["ihomo"] == 13 and np.all(np.diff(r["emo"]) >= 0)
+    pop = (r["focc"][:, None] * q).sum(0)                        # electrons per atom
+    zval = np.array([{1: 1, 6: 4, 8: 6, 17: 7}[int(z)] for z in num], dtype=float)
+    assert np.abs((zval - pop) - r["qat"]).max() < 1e-6
