@@ -587,6 +587,16 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 1, c.hm.ntype) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
         if (c.smem > (size_t)prop.sharedMemPerBlockOptin)
             return fail(QCXMS_B200_ERR_UNSUPPORTED, "system too large for the per-CTA working set (nat = " + std::to_string(c.hm.nat) + ")");
+        // the rest of the shared memory is the block buffer of the blocked Jacobi (2 * jblock rows of the SCC matrix)
+        const size_t row = (size_t)c.hm.ld * sizeof(double);
+        const size_t avail = (size_t)prop.sharedMemPerBlockOptin - c.smem - 16;
+        int jb = (int)(avail / (2 * row));
+        if (jb >= 8 && c.hm.nao <= 256) {
+            const int nb = (c.hm.nao + jb - 1) / jb;
+            jb = (c.hm.nao + nb - 1) / nb;          // balanced blocks
+            c.hm.dev.jblock = jb;
+            c.smem += 16 + 2 * (size_t)jb * row;
+        }
     }
     c.L = make_layout(c.hm);
     CUDA_OK(cudaFuncSetAttribute(k_egrad_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
@@ -596,6 +606,11 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
     int per_sm = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_chunk<false>, QX_NT, c.smem));
     if (per_sm < 1) per_sm = 1;
+    // global-slab mode: the Jacobi matrix of every resident CTA has to stay in L2 (two resident CTAs per SM thrashed it for C32H66:
+    // 608 instead of 778 single points/s and 0.45 GB of DRAM write-back per single point)
+    if (c.hm.dev.mat_in_global && per_sm > 1 &&
+        (size_t)per_sm * prop.multiProcessorCount * c.hm.rows8 * c.hm.ld * sizeof(double) > (size_t)prop.l2CacheSize / 2)
+        per_sm = 1;
     c.ncta = per_sm * prop.multiProcessorCount;
     if (nwork > 0 && c.ncta > nwork) c.ncta = nwork;
     CUDA_OK(cudaMalloc(&c.d_scratch, c.L.total * sizeof(double) * (size_t)c.ncta));

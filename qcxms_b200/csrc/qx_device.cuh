@@ -60,6 +60,7 @@ struct SmPtr {
 
 struct Sm {
     double *A, *C;   // shared memory, or the CTA's global slab when the basis is too large (DevModel::mat_in_global)
+    double *jblk;    // global-slab mode: shared-memory buffer of 2 * DevModel::jblock rows for the blocked Jacobi
     SmPtr xyz, cn, cn4, mrad, dmr, qat, vat, dpat, vdp, qpat, vqp;
     SmPtr qsh, vsh, selfen, vao, emo, focc, gw, gwd, dEdcn, dEdcn4, grad, red, jw, bsol, pop, d4u;
 };
@@ -93,6 +94,7 @@ __device__ inline void carve(const DevModel &m, double *base, Sm &s, double *gma
     s.bsol = p; p += QX_BSOL;
     s.pop = p; p += 11 * nao + (nao & 1);
     s.d4u = p;
+    s.jblk = base + ((smem_doubles(nat, nsh, nao, m.ld, m.rows8, m.mat_in_global, m.ntype) + 11 * (size_t)nat + 16 + 1) & ~(size_t)1);
 }
 
 __device__ inline double block_sum(double v, double *red) {
@@ -1269,6 +1271,247 @@ __device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, float tol
     return sweep;
 }
 
+// ---- large bases (matrices in the CTA's global slab, L2-resident): LP = 16 or 32 lanes per row pair, 128-bit coalesced row
+// accesses (a group reads 16 LP contiguous bytes per request), the rows of the group's next pair of the round prefetched into L1
+// while the current pair is rotated.  Same scaled rotation, norm tracking and stop rule as jacobi_rows_lp8m; n <= 2 LP R.
+// The sweep is bound by the latency of the dependent chain load -> dot -> shuffles -> rotation parameters -> store with only the
+// CTA's 9 warps to hide it: two pairs per warp (LP = 16) halve the number of passes of a round.
+template <int R, int LP>
+__device__ __noinline__ int jacobi_rows_glob(int n, double *G, int ld, float tol, double *jw) {
+    QX_ASSUME_SHARED(jw);
+    const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = QX_NT / 32;
+    const int nslot = QX_NT / LP, slot = threadIdx.x / LP, lsub = threadIdx.x & (LP - 1);
+    const int npass = (npair + nslot - 1) / nslot;
+    double *nrm2 = jw;
+    double2 *dd = reinterpret_cast<double2 *>(jw + ((n + 1) & ~1));
+    for (int i = threadIdx.x; i < n; i += QX_NT) dd[i] = make_double2(1.0, 1.0);
+    __syncthreads();
+    double *Gl = G + 2 * lsub;
+    const bool tail_ok = 2 * lsub + 2 * LP * (R - 1) < n, tail_odd = 2 * lsub + 2 * LP * (R - 1) + 1 == n;
+    const double tol2 = (double)tol * (double)tol;
+    int sweep = 0;
+    for (; sweep < 60; ++sweep) {
+        for (int r = warp; r < n; r += nwarp) {
+            const double d = dd[r].x;
+            double acc = 0.0;
+            for (int i = lane; i < n; i += 32) { const double x = G[(size_t)r * ld + i] * d; G[(size_t)r * ld + i] = x; acc = fma(x, x, acc); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            __syncwarp();
+            if (lane == 0) { nrm2[r] = acc; dd[r] = make_double2(1.0, 1.0); }
+        }
+        __syncthreads();
+        bool big = false;
+        for (int round = 0; round < m1; ++round) {
+            for (int pass = 0; pass < npass; ++pass) {
+                if ((warp * 32) / LP + pass * nslot >= npair) continue;   // warp-uniform: no group of this warp has a pair
+                const int k = slot + pass * nslot;
+                int p = round + k, q = round - k;
+                if (p >= m1) p -= m1;
+                if (q < 0) q += m1;
+                if (k == 0) p = m1;
+                const bool valid = k < npair && p < n && q < n;
+                if (!valid) { p = 0; q = 0; }
+                {   // rows of this group's next pair of the round -> L1
+                    const int k2 = k + nslot;
+                    int p2 = round + k2, q2 = round - k2;
+                    if (p2 >= m1) p2 -= m1;
+                    if (q2 < 0) q2 += m1;
+                    if (k2 < npair && p2 < n && q2 < n) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            if (2 * lsub + 2 * LP * r < n) {
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(Gl + (size_t)p2 * ld + 2 * LP * r));
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(Gl + (size_t)q2 * ld + 2 * LP * r));
+                            }
+                    }
+                }
+                double *gp = Gl + (size_t)p * ld, *gq = Gl + (size_t)q * ld;
+                const double2 sp = dd[p], sq = dd[q];
+                const double al = nrm2[p], be = nrm2[q];
+                double2 x[R], y[R];
+                // every chunk but the last is in range for all lanes (2 LP (R - 1) < n for the R the dispatcher picks)
+#pragma unroll
+                for (int r = 0; r < R - 1; ++r) {
+                    x[r] = *reinterpret_cast<const double2 *>(gp + 2 * LP * r);
+                    y[r] = *reinterpret_cast<const double2 *>(gq + 2 * LP * r);
+                }
+                x[R - 1] = make_double2(0.0, 0.0); y[R - 1] = make_double2(0.0, 0.0);
+                if (tail_ok) { x[R - 1] = *reinterpret_cast<const double2 *>(gp + 2 * LP * (R - 1)); y[R - 1] = *reinterpret_cast<const double2 *>(gq + 2 * LP * (R - 1)); }
+                if (tail_odd) { x[R - 1].y = 0.0; y[R - 1].y = 0.0; }   // padding column of an odd dimension
+                double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
+                double gs = g0 + g1;
+#pragma unroll
+                for (int o = LP >> 1; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                const double ga = (sp.x * sq.x) * gs, ga2 = ga * ga, nn = al * be;
+                big |= valid && ga2 > tol2 * nn;
+                const bool rot = valid && ga2 > 1e-30 * nn;
+                const float gf = (float)ga, df = (float)(be - al);
+                const float g2 = gf + gf;
+                const float hh = fmaf(df, df, g2 * g2);
+                const float den = fabsf(df) + hh * rsqrt_approx(hh);
+                float tf = g2 * rcp_approx(den);
+                tf = __int_as_float(__float_as_int(tf) ^ (__float_as_int(df) & 0x80000000));
+                tf = rot ? tf : 0.0f;
+                const double t = (double)tf;
+                const double t1 = t * (sq.x * sp.y), t2 = t * (sp.x * sq.y);
+                if (valid) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        double2 u, v;
+                        u.x = fma(-t1, y[r].x, x[r].x); u.y = fma(-t1, y[r].y, x[r].y);
+                        v.x = fma(t2, x[r].x, y[r].x); v.y = fma(t2, x[r].y, y[r].y);
+                        if (r < R - 1 || tail_ok) {
+                            *reinterpret_cast<double2 *>(gp + 2 * LP * r) = u;
+                            *reinterpret_cast<double2 *>(gq + 2 * LP * r) = v;
+                        }
+                    }
+                }
+                const double w = fma(t, t, 1.0);
+                double c = (double)rsqrt_approx(fmaf(tf, tf, 1.0f));
+                c = c * fma(-0.5 * w * c, c, 1.5);
+                c = c * fma(-0.5 * w * c, c, 1.5);
+                const double wc = w * c, tg = t * ga;
+                if (lsub == 0 && valid) {
+                    dd[p] = make_double2(c * sp.x, wc * sp.y); dd[q] = make_double2(c * sq.x, wc * sq.y);
+                    nrm2[p] = al - tg; nrm2[q] = be + tg;
+                }
+            }
+            __syncthreads();
+        }
+        if (!__syncthreads_or(big ? 1 : 0)) { ++sweep; break; }
+    }
+    for (int r = warp; r < n; r += nwarp) {
+        const double d = dd[r].x;
+        for (int i = lane; i < n; i += 32) G[(size_t)r * ld + i] *= d;
+    }
+    __syncthreads();
+    return sweep;
+}
+
+// ---- large bases, blocked: the rows of G are cut into blocks of b <= bmax rows; a round-robin tournament over the blocks brings
+// two blocks at a time into the shared-memory buffer B (2 bmax rows), where one full sweep over their rows runs at shared-memory
+// latency (16 lanes per pair, same rotation as above), and writes them back.  An outer sweep visits every pair of blocks once, so
+// every pair of rows is rotated at least once (pairs inside a block once per visit of the block).  L2 traffic per outer sweep:
+// (nb - 1) reads and writes of G instead of n - 1.  Columns n <= 32 R.
+template <int R>
+__device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float tol, double *jw, double *B, int bmax) {
+    QX_ASSUME_SHARED(jw); QX_ASSUME_SHARED(B);
+    constexpr int LP = 16;
+    const int nb = (n + bmax - 1) / bmax, b = (n + nb - 1) / nb, nbe = (nb + 1) & ~1, bm1 = nbe - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = QX_NT / 32;
+    const int nslot = QX_NT / LP, slot = threadIdx.x / LP, lsub = threadIdx.x & (LP - 1);
+    double *nrm2 = jw;
+    double2 *dd = reinterpret_cast<double2 *>(jw + ((2 * b + 1) & ~1));
+    double *Bl = B + 2 * lsub;
+    const bool tail_ok = 2 * lsub + 2 * LP * (R - 1) < n;
+    const double tol2 = (double)tol * (double)tol;
+    int sweep = 0;
+    for (; sweep < 60; ++sweep) {
+        bool big = false;
+        for (int bround = 0; bround < bm1; ++bround) {
+            for (int bk = 0; bk < (nbe >> 1); ++bk) {
+                int I = bround + bk, J = bround - bk;
+                if (I >= bm1) I -= bm1;
+                if (J < 0) J += bm1;
+                if (bk == 0) I = bm1;
+                if (I >= nb || J >= nb) continue;   // bye of an odd number of blocks (uniform)
+                const int r0I = I * b, r0J = J * b;
+                const int nI = (n - r0I < b ? n - r0I : b), nJ = (n - r0J < b ? n - r0J : b), nr = nI + nJ;
+                // blocks -> shared memory, squared row norms on the way
+                for (int lr = warp; lr < nr; lr += nwarp) {
+                    const double *src = G + (size_t)(lr < nI ? r0I + lr : r0J + lr - nI) * ld;
+                    double *dst = B + (size_t)lr * ld;
+                    double acc = 0.0;
+                    for (int i = lane; i < ld; i += 32) { const double x = i < n ? src[i] : 0.0; dst[i] = x; acc = fma(x, x, acc); }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) { nrm2[lr] = acc; dd[lr] = make_double2(1.0, 1.0); }
+                }
+                __syncthreads();
+                const int mm = (nr + 1) & ~1, npair = mm >> 1, m1 = mm - 1, npass = (npair + nslot - 1) / nslot;
+                for (int round = 0; round < m1; ++round) {
+                    for (int pass = 0; pass < npass; ++pass) {
+                        if ((warp * 32) / LP + pass * nslot >= npair) continue;   // warp-uniform
+                        const int k = slot + pass * nslot;
+                        int p = round + k, q = round - k;
+                        if (p >= m1) p -= m1;
+                        if (q < 0) q += m1;
+                        if (k == 0) p = m1;
+                        const bool valid = k < npair && p < nr && q < nr;
+                        if (!valid) { p = 0; q = 0; }
+                        double *gp = Bl + p * ld, *gq = Bl + q * ld;
+                        const double2 sp = dd[p], sq = dd[q];
+                        const double al = nrm2[p], be = nrm2[q];
+                        double2 x[R], y[R];
+                        // every chunk but the last is in range for all lanes (32 (R - 1) < n); columns n .. ld-1 of B are zero
+#pragma unroll
+                        for (int r = 0; r < R - 1; ++r) {
+                            x[r] = *reinterpret_cast<const double2 *>(gp + 2 * LP * r);
+                            y[r] = *reinterpret_cast<const double2 *>(gq + 2 * LP * r);
+                        }
+                        x[R - 1] = make_double2(0.0, 0.0); y[R - 1] = make_double2(0.0, 0.0);
+                        if (tail_ok) { x[R - 1] = *reinterpret_cast<const double2 *>(gp + 2 * LP * (R - 1)); y[R - 1] = *reinterpret_cast<const double2 *>(gq + 2 * LP * (R - 1)); }
+                        double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
+                        double gs = g0 + g1;
+#pragma unroll
+                        for (int o = LP >> 1; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                        const double ga = (sp.x * sq.x) * gs, ga2 = ga * ga, nn = al * be;
+                        big |= valid && ga2 > tol2 * nn;
+                        const bool rot = valid && ga2 > 1e-30 * nn;
+                        const float gf = (float)ga, df = (float)(be - al);
+                        const float g2 = gf + gf;
+                        const float hh = fmaf(df, df, g2 * g2);
+                        const float den = fabsf(df) + hh * rsqrt_approx(hh);
+                        float tf = g2 * rcp_approx(den);
+                        tf = __int_as_float(__float_as_int(tf) ^ (__float_as_int(df) & 0x80000000));
+                        tf = rot ? tf : 0.0f;
+                        const double t = (double)tf;
+                        const double t1 = t * (sq.x * sp.y), t2 = t * (sp.x * sq.y);
+                        if (valid) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                double2 u, v;
+                                u.x = fma(-t1, y[r].x, x[r].x); u.y = fma(-t1, y[r].y, x[r].y);
+                                v.x = fma(t2, x[r].x, y[r].x); v.y = fma(t2, x[r].y, y[r].y);
+                                if (r < R - 1 || tail_ok) {
+                                    *reinterpret_cast<double2 *>(gp + 2 * LP * r) = u;
+                                    *reinterpret_cast<double2 *>(gq + 2 * LP * r) = v;
+                                }
+                            }
+                        }
+                        const double w = fma(t, t, 1.0);
+                        double c = (double)rsqrt_approx(fmaf(tf, tf, 1.0f));
+                        c = c * fma(-0.5 * w * c, c, 1.5);
+                        c = c * fma(-0.5 * w * c, c, 1.5);
+                        const double wc = w * c, tg = t * ga;
+                        if (lsub == 0 && valid) {
+                            dd[p] = make_double2(c * sp.x, wc * sp.y); dd[q] = make_double2(c * sq.x, wc * sq.y);
+                            nrm2[p] = al - tg; nrm2[q] = be + tg;
+                        }
+                    }
+                    __syncthreads();
+                }
+                // blocks back to the slab, scales applied
+                for (int lr = warp; lr < nr; lr += nwarp) {
+                    double *dst = G + (size_t)(lr < nI ? r0I + lr : r0J + lr - nI) * ld;
+                    const double *src = B + (size_t)lr * ld;
+                    const double d = dd[lr].x;
+                    for (int i = lane; i < n; i += 32) dst[i] = src[i] * d;
+                }
+                __syncthreads();
+            }
+        }
+        if (!__syncthreads_or(big ? 1 : 0)) { ++sweep; break; }
+    }
+    return sweep;
+}
+
 // generic fallback (any n): LP lanes per pair, scalar accesses
 __device__ __noinline__ int jacobi_rows_generic(int n, double *G, int ld, double *red, float tol) {
     const int mm = (n + 1) & ~1, npair = mm >> 1;
@@ -1339,7 +1582,7 @@ __device__ __noinline__ void jacobi_shift(int n, double *G, int ld, double *red)
 
 // (2) the sweeps
 template <bool SH>
-__device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *red, double *jw) {
+__device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *red, double *jw, double *jblk = nullptr, int jblock = 0) {
     const float tol = 1e-7f;  // pre-rotation ratio of the last sweep; its rotations leave O(tol^2) couplings
     const int npair = (n + 1) >> 1;
     int sweeps;
@@ -1357,6 +1600,25 @@ __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *r
             case 5: sweeps = jacobi_rows_lp8m<5>(n, G, ld, QX_JACOBI_TOL, jw); break;
             case 6: sweeps = jacobi_rows_lp8m<6>(n, G, ld, QX_JACOBI_TOL, jw); break;
             default: sweeps = jacobi_rows_lp8m<7>(n, G, ld, QX_JACOBI_TOL, jw); break;
+        }
+    } else if (!SH && jblock >= 8 && (ld & 1) == 0 && (reinterpret_cast<size_t>(G) & 15) == 0 && n <= 256) {   // global slab, blocked through shared memory
+        if (n <= 96) return jacobi_rows_generic(n, G, ld, red, tol);
+        switch ((n + 31) >> 5) {
+            case 4: sweeps = jacobi_rows_blocked<4>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
+            case 5: sweeps = jacobi_rows_blocked<5>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
+            case 6: sweeps = jacobi_rows_blocked<6>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
+            case 7: sweeps = jacobi_rows_blocked<7>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
+            default: sweeps = jacobi_rows_blocked<8>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
+        }
+    } else if (!SH && (ld & 1) == 0 && (reinterpret_cast<size_t>(G) & 15) == 0 && n <= 320) {   // global slab
+        if (n <= 96) return jacobi_rows_generic(n, G, ld, red, tol);   // (never in practice: the slab mode starts above ~110 AOs)
+        switch ((n + 31) >> 5) {   // R = ceil(n / 32) double2 per lane and row with 16 lanes per pair
+            case 4: sweeps = jacobi_rows_glob<4, 16>(n, G, ld, QX_JACOBI_TOL, jw); break;
+            case 5: sweeps = jacobi_rows_glob<5, 16>(n, G, ld, QX_JACOBI_TOL, jw); break;
+            case 6: sweeps = jacobi_rows_glob<6, 16>(n, G, ld, QX_JACOBI_TOL, jw); break;
+            case 7: sweeps = jacobi_rows_glob<7, 16>(n, G, ld, QX_JACOBI_TOL, jw); break;
+            case 8: sweeps = jacobi_rows_glob<8, 16>(n, G, ld, QX_JACOBI_TOL, jw); break;
+            default: sweeps = jacobi_rows_glob<5, 32>(n, G, ld, QX_JACOBI_TOL, jw); break;   // 256 < n <= 320: a full warp per pair
         }
     } else
         sweeps = jacobi_rows_generic(n, G, ld, red, tol);
@@ -1385,9 +1647,9 @@ __device__ __noinline__ void jacobi_finish(int n, double *G, int ld, double *emo
 
 // Eigen-decomposition of the symmetric A' held in G (n x n, ld).  Returns the number of sweeps.
 template <bool SH>
-__device__ __forceinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *emo, double *red, double *jw) {
+__device__ __forceinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *emo, double *red, double *jw, double *jblk = nullptr, int jblock = 0) {
     jacobi_shift<SH>(n, G, ld, red);
-    const int sweeps = jacobi_sweeps<SH>(n, G, ld, red, jw);
+    const int sweeps = jacobi_sweeps<SH>(n, G, ld, red, jw, jblk, jblock);
     jacobi_finish<SH>(n, G, ld, emo, red);
     return sweeps;
 }

@@ -10,6 +10,7 @@
 
 struct DevModel {
     int nat, nsh, nao, ntype, ld, ndim;  // ld: leading dimension of the shared-memory matrices (== 4 or 12 mod 16)
+    int jblock;                           // global-slab mode: rows per block of the shared-memory blocked Jacobi (0: none)
     int mat_in_global;                    // 1: the two SCC matrices do not fit shared memory and live in the per-CTA global slab
     int rows8;                            // rows of the shared-memory matrices (zero padded; multiple of 8 when the strip GEMMs apply)
     int ntask_int, ntask_grad;
