@@ -1394,9 +1394,9 @@ __device__ __noinline__ int jacobi_rows_glob(int n, double *G, int ld, float tol
 
 // ---- large bases, blocked: the rows of G are cut into blocks of b <= bmax rows; a round-robin tournament over the blocks brings
 // two blocks at a time into the shared-memory buffer B (2 bmax rows), where one full sweep over their rows runs at shared-memory
-// latency (16 lanes per pair, same rotation as above), and writes them back.  An outer sweep visits every pair of blocks once, so
-// every pair of rows is rotated at least once (pairs inside a block once per visit of the block).  L2 traffic per outer sweep:
-// (nb - 1) reads and writes of G instead of n - 1.  Columns n <= 32 R.
+// latency (16 lanes per pair, same rotation as above), and writes them back.  An outer sweep visits every pair of blocks once and
+// rotates every pair of rows exactly once.  L2 traffic per outer sweep: (nb - 1) reads and writes of G instead of n - 1.
+// Columns n <= 32 R.
 template <int R>
 __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float tol, double *jw, double *B, int bmax) {
     QX_ASSUME_SHARED(jw); QX_ASSUME_SHARED(B);
@@ -1418,9 +1418,14 @@ __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float 
                 if (I >= bm1) I -= bm1;
                 if (J < 0) J += bm1;
                 if (bk == 0) I = bm1;
-                if (I >= nb || J >= nb) continue;   // bye of an odd number of blocks (uniform)
+                // the first block round pairs every block exactly once: its visits rotate all pairs of their rows (inside the two
+                // blocks and across), the later block rounds only the pairs across the two blocks.  The bye of an odd number of
+                // blocks is a visit of one block alone in the first round and skipped later (uniform).
+                const bool full = bround == 0;
+                if (I >= nb) { const int t_ = I; I = J; J = t_; }
+                if (I >= nb || (J >= nb && !full)) continue;
                 const int r0I = I * b, r0J = J * b;
-                const int nI = (n - r0I < b ? n - r0I : b), nJ = (n - r0J < b ? n - r0J : b), nr = nI + nJ;
+                const int nI = (n - r0I < b ? n - r0I : b), nJ = J >= nb ? 0 : (n - r0J < b ? n - r0J : b), nr = nI + nJ;
                 // blocks -> shared memory, squared row norms on the way
                 for (int lr = warp; lr < nr; lr += nwarp) {
                     const double *src = G + (size_t)(lr < nI ? r0I + lr : r0J + lr - nI) * ld;
@@ -1432,16 +1437,26 @@ __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float 
                     if (lane == 0) { nrm2[lr] = acc; dd[lr] = make_double2(1.0, 1.0); }
                 }
                 __syncthreads();
-                const int mm = (nr + 1) & ~1, npair = mm >> 1, m1 = mm - 1, npass = (npair + nslot - 1) / nslot;
-                for (int round = 0; round < m1; ++round) {
+                const int mm = (nr + 1) & ~1, m1 = mm - 1, mx = nI > nJ ? nI : nJ;
+                const int npair = full ? mm >> 1 : mx, nround = full ? m1 : mx, npass = (npair + nslot - 1) / nslot;
+                for (int round = 0; round < nround; ++round) {
                     for (int pass = 0; pass < npass; ++pass) {
                         if ((warp * 32) / LP + pass * nslot >= npair) continue;   // warp-uniform
                         const int k = slot + pass * nslot;
-                        int p = round + k, q = round - k;
-                        if (p >= m1) p -= m1;
-                        if (q < 0) q += m1;
-                        if (k == 0) p = m1;
-                        const bool valid = k < npair && p < nr && q < nr;
+                        int p, q;
+                        bool valid;
+                        if (full) {   // round-robin tournament over the nr rows
+                            p = round + k; q = round - k;
+                            if (p >= m1) p -= m1;
+                            if (q < 0) q += m1;
+                            if (k == 0) p = m1;
+                            valid = k < npair && p < nr && q < nr;
+                        } else {      // row k of the first block with row (k + round) mod mx of the second
+                            int qq = k + round;
+                            if (qq >= mx) qq -= mx;
+                            p = k; q = nI + qq;
+                            valid = k < nI && qq < nJ;
+                        }
                         if (!valid) { p = 0; q = 0; }
                         double *gp = Bl + p * ld, *gq = Bl + q * ld;
                         const double2 sp = dd[p], sq = dd[q];
