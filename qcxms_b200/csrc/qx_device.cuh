@@ -703,9 +703,61 @@ __device__ __noinline__ void dmma_gemm(int n, FA loadA, FB loadB, FS store) {
     }
 }
 
-// run-time dispatch on the number of column tiles (keeps the accumulators in registers)
+// Same product for operands that live in the global slab (large bases): the B operand is staged in shared memory one group of
+// 8 MAXT columns at a time (all k), so that the inner loop reads B at shared-memory latency and B crosses L2 once instead of once
+// per strip; the row stride 8 MAXT + 4 spreads the 4 x 8 doubles of a fragment load over all banks (MAXT odd).  Ends with a barrier.
+template <int MAXT, class FA, class FB, class FS>
+__device__ __noinline__ void dmma_gemm_staged(int n, FA loadA, FB loadB, FS store, double *Bs) {
+    QX_ASSUME_SHARED(Bs);
+    constexpr int NC = 8 * MAXT, LDS = NC + 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = QX_NT / 32;
+    const int nt = (n + 7) >> 3, g = lane >> 2, tg = lane & 3, kpad = (n + 3) & ~3;
+    for (int tb = 0; tb < nt; tb += MAXT) {
+        const int j0 = tb * 8;
+        __syncthreads();   // the readers of the previous column group are done
+        for (int idx = threadIdx.x; idx < kpad * NC; idx += QX_NT) {
+            const int k = idx / NC, jj = idx - k * NC, j = j0 + jj;
+            Bs[k * LDS + jj] = (k < n && j < n) ? loadB(k, j) : 0.0;
+        }
+        __syncthreads();
+        const double *bp = Bs + tg * LDS + g;
+        for (int ti = warp; ti < nt; ti += nwarp) {
+            const int row = ti * 8 + g;
+            double acc[MAXT][2];
+#pragma unroll
+            for (int t = 0; t < MAXT; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll 4
+            for (int k0 = 0; k0 < kpad; k0 += 4) {
+                const int k = k0 + tg;
+                const double a = (row < n && k < n) ? loadA(row, k) : 0.0;
+#pragma unroll
+                for (int t = 0; t < MAXT; ++t) {
+                    const double b = bp[k0 * LDS + 8 * t];
+                    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                        : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(a), "d"(b));
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < MAXT; ++t) {
+                const int col = j0 + 8 * t + 2 * tg;
+                if (row < n && col < n) store(row, col, acc[t][0]);
+                if (row < n && col + 1 < n) store(row, col + 1, acc[t][1]);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// run-time dispatch on the number of column tiles (keeps the accumulators in registers); stage / stage_doubles: shared-memory
+// buffer for the B operand when the operands are in the global slab (null: operands are read in place)
 template <class FA, class FB, class FS>
-__device__ inline void gemm_tc(int n, FA loadA, FB loadB, FS store) {
+__device__ inline void gemm_tc(int n, FA loadA, FB loadB, FS store, double *stage = nullptr, int stage_doubles = 0) {
+    if (stage) {
+        const int kpad = (n + 3) & ~3;
+        if (kpad * (8 * 7 + 4) <= stage_doubles) { dmma_gemm_staged<7>(n, loadA, loadB, store, stage); return; }
+        if (kpad * (8 * 5 + 4) <= stage_doubles) { dmma_gemm_staged<5>(n, loadA, loadB, store, stage); return; }
+        if (kpad * (8 * 3 + 4) <= stage_doubles) { dmma_gemm_staged<3>(n, loadA, loadB, store, stage); return; }
+    }
     const int nt = (n + 7) >> 3;
     if (nt <= 4) dmma_gemm<4>(n, loadA, loadB, store);
     else if (nt <= 9) dmma_gemm<9>(n, loadA, loadB, store);

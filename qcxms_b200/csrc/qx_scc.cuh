@@ -594,6 +594,9 @@ __device__ __noinline__ void phase_gradient_pairs(const DevModel &m, Sm &s, cons
 __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, const ScratchLayout &L, double kt, EgradOut &out, double *qstart = nullptr,
                                  double *spec = nullptr) {
     const int nat = m.nat, nsh = m.nsh, nao = m.nao, ld = m.ld, ndim = m.ndim;
+    // global-slab mode: the block buffer of the Jacobi doubles as the staging buffer of the GEMMs' B operand
+    double *stg = m.mat_in_global && m.jblock > 0 ? s.jblk : nullptr;
+    const int stg_cap = 2 * m.jblock * ld;
     double *S = scratch + L.S, *H0 = scratch + L.H0, *Dt = scratch + L.Dt, *Qt = scratch + L.Qt, *T = scratch + L.T;
     double *gamma = scratch + L.gamma, *dcnp = scratch + L.dcnp, *dcnp4 = scratch + L.dcnp4, *edisp = scratch + L.edisp;
     double *c6 = scratch + L.c6, *dc6 = scratch + L.dc6, *taskout = scratch + L.taskout;
@@ -691,12 +694,13 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         } else {
             const double *Ct = s.C, *Hm = s.A;
             // Tt = Ct H1  (global scratch), then A' = Ct Tt^T back into shared memory
+            // (T is kept transposed so that the second product reads it along rows)
             gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)i * ld + k]; }, [=](int k, int j) { return Hm[(size_t)k * ld + j]; },
-                    [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; });
+                    [=](int i, int j, double v) { T[(size_t)j * nao + i] = v; }, stg, stg_cap);
             __syncthreads();
             double *Ap = s.A;
-            gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)i * ld + k]; }, [=](int k, int j) { return T[(size_t)j * nao + k]; },
-                    [=](int i, int j, double v) { Ap[(size_t)i * ld + j] = v; });
+            gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)i * ld + k]; }, [=](int k, int j) { return T[(size_t)k * nao + j]; },
+                    [=](int i, int j, double v) { Ap[(size_t)i * ld + j] = v; }, stg, stg_cap);
             __syncthreads();
         }
         QX_PH(7);
@@ -714,7 +718,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
             } else {
                 const double *Jt = s.A, *Ct = s.C;
                 gemm_tc(nao, [=](int i, int k) { return Jt[(size_t)i * ld + k]; }, [=](int k, int j) { return Ct[(size_t)k * ld + j]; },
-                        [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; });
+                        [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; }, stg, stg_cap);
                 __syncthreads();
                 for (int t = threadIdx.x; t < nao * nao; t += QX_NT) { int i = t / nao; s.C[(size_t)i * ld + (t - i * nao)] = T[t]; }
                 __syncthreads();
@@ -777,7 +781,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
             const double *Ct = s.C, *f = s.focc;
             double *Pm = s.A;
             gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)k * ld + i] * f[k]; }, [=](int k, int j) { return Ct[(size_t)k * ld + j]; },
-                    [=](int i, int j, double v) { Pm[(size_t)i * ld + j] = v; });
+                    [=](int i, int j, double v) { Pm[(size_t)i * ld + j] = v; }, stg, stg_cap);
             __syncthreads();
         }
         QX_PH(10);
@@ -845,7 +849,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         } else {
             const double *Ct = s.C, *f = s.focc;
             gemm_tc(nao, [=](int i, int k) { return Ct[(size_t)k * ld + i] * f[k]; }, [=](int k, int j) { return Ct[(size_t)k * ld + j]; },
-                    [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; });
+                    [=](int i, int j, double v) { T[(size_t)i * nao + j] = v; }, stg, stg_cap);
             __syncthreads();
             for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.C[(size_t)(t / nao) * ld + t % nao] = T[t];
             __syncthreads();
