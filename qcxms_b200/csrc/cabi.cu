@@ -572,6 +572,15 @@ struct Context {
     std::vector<int32_t> key;
 };
 
+// dynamic shared memory limit of a kernel = what the device allows next to the kernel's static shared memory
+template <class K>
+static cudaError_t allow_max_dynamic_smem(K kernel, const cudaDeviceProp &prop) {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - (int)a.sharedSizeBytes);
+}
+
 static int context_init(Context &c, int nat, const int32_t *num, const double *mass, int charge, int multiplicity, int device, int nwork) {
     CUDA_OK(cudaSetDevice(device));
     std::string why = build_host_model(c.hm, nat, num, mass, charge, multiplicity);
@@ -581,15 +590,15 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 0, c.hm.ntype) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
-    if (c.smem > (size_t)prop.sharedMemPerBlockOptin) {
+    if (c.smem + 2048 > (size_t)prop.sharedMemPerBlockOptin) {   // (2 KB: the kernels' static shared memory)
         // large basis (nao >~ 110): keep the two SCC matrices in the per-CTA global slab -- functional, slower
         c.hm.dev.mat_in_global = 1;
         c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 1, c.hm.ntype) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
-        if (c.smem > (size_t)prop.sharedMemPerBlockOptin)
+        if (c.smem + 2048 > (size_t)prop.sharedMemPerBlockOptin)
             return fail(QCXMS_B200_ERR_UNSUPPORTED, "system too large for the per-CTA working set (nat = " + std::to_string(c.hm.nat) + ")");
         // the rest of the shared memory is the block buffer of the blocked Jacobi (2 * jblock rows of the SCC matrix)
         const size_t row = (size_t)c.hm.ld * sizeof(double);
-        const size_t avail = (size_t)prop.sharedMemPerBlockOptin - c.smem - 16;
+        const size_t avail = (size_t)prop.sharedMemPerBlockOptin - c.smem - 16 - 2048;   // 2 KB: the kernels' static shared memory
         int jb = (int)(avail / (2 * row));
         if (jb > 36) jb = 36;   // 2 x 18 sixteen-lane groups: the pairs of a round of two blocks fill two passes
         if (jb >= 8 && c.hm.nao <= 256) {
@@ -600,10 +609,11 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         }
     }
     c.L = make_layout(c.hm);
-    CUDA_OK(cudaFuncSetAttribute(k_egrad_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-    CUDA_OK(cudaFuncSetAttribute(k_md_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-    CUDA_OK(cudaFuncSetAttribute(k_md_chunk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-    CUDA_OK(cudaFuncSetAttribute(k_md_chunk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    // the device maximum, not this composition's size: host threads set up different compositions concurrently
+    CUDA_OK(allow_max_dynamic_smem(k_egrad_batch, prop));
+    CUDA_OK(allow_max_dynamic_smem(k_md_init, prop));
+    CUDA_OK(allow_max_dynamic_smem(k_md_chunk<false>, prop));
+    CUDA_OK(allow_max_dynamic_smem(k_md_chunk<true>, prop));
     int per_sm = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_chunk<false>, QX_NT, c.smem));
     if (per_sm < 1) per_sm = 1;
@@ -1146,8 +1156,15 @@ extern "C" int qcxms_b200_cid_batch(const qcxms_b200_cid_config_t *cfg, int ntra
     Context ctx;
     int rc = context_init(ctx, nuc0, num0.data(), mass0.data(), cfg->mchrg, mult, device, ntraj);
     if (rc) { context_free(ctx); return rc; }
-    CUDA_OK(cudaFuncSetAttribute(k_cid_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx.smem));
-    CUDA_OK(cudaFuncSetAttribute(k_cid_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx.smem));
+    {   // the device maximum, not this composition's size: host threads set up different compositions concurrently
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        CUDA_OK(allow_max_dynamic_smem(k_cid_init, prop));
+        CUDA_OK(allow_max_dynamic_smem(k_cid_chunk, prop));
+    }
+    // own (blocking) stream: collisions of different compositions are driven from different host threads and overlap on the GPU
+    cudaStream_t strm = nullptr;
+    if (cudaStreamCreate(&strm) != cudaSuccess) { context_free(ctx); return fail(QCXMS_B200_ERR_CUDA, "cid: stream creation failed"); }
     MdConfig mc{};
     mc.mchrg = cfg->mchrg; mc.tstep = cfg->tstep;
     CidConfig cc{};
@@ -1163,7 +1180,11 @@ extern "C" int qcxms_b200_cid_batch(const qcxms_b200_cid_config_t *cfg, int ntra
         allocs.push_back(p);
         return p;
     };
-    auto cleanup = [&]() { for (void *p : allocs) cudaFree(p); context_free(ctx); };
+    auto cleanup = [&]() { cudaStreamSynchronize(strm); cudaStreamDestroy(strm); for (void *p : allocs) cudaFree(p); context_free(ctx); };
+    auto cpy = [&](void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) -> cudaError_t {
+        cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, strm);
+        return e == cudaSuccess ? cudaStreamSynchronize(strm) : e;
+    };
     CidState st{};
     double *d_rnd, *d_vcm = nullptr;
     st.xyz = (double *)dalloc(n3 * 8); st.velo = (double *)dalloc(n3 * 8); st.direc = (double *)dalloc((size_t)ntraj * 3 * 8);
@@ -1178,43 +1199,43 @@ extern "C" int qcxms_b200_cid_batch(const qcxms_b200_cid_config_t *cfg, int ntra
     std::vector<CidScalars> hsc(ntraj);
     for (int t = 0; t < ntraj; ++t) { hsc[t] = CidScalars{}; hsc[t].collided = collided[t] ? 1 : 0; }
 #define CID_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(QCXMS_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
-    CID_OK(cudaMemcpy(st.xyz, xyz, n3 * 8, cudaMemcpyHostToDevice));
-    CID_OK(cudaMemcpy(st.velo, velo, n3 * 8, cudaMemcpyHostToDevice));
-    CID_OK(cudaMemcpy(st.direc, direc, (size_t)ntraj * 3 * 8, cudaMemcpyHostToDevice));
-    CID_OK(cudaMemcpy(d_rnd, rnd, (size_t)ntraj * 9 * 8, cudaMemcpyHostToDevice));
-    if (velo_cm) CID_OK(cudaMemcpy(d_vcm, velo_cm, (size_t)ntraj * 8, cudaMemcpyHostToDevice));
-    CID_OK(cudaMemcpy(st.sc, hsc.data(), (size_t)ntraj * sizeof(CidScalars), cudaMemcpyHostToDevice));
+    CID_OK(cpy(st.xyz, xyz, n3 * 8, cudaMemcpyHostToDevice));
+    CID_OK(cpy(st.velo, velo, n3 * 8, cudaMemcpyHostToDevice));
+    CID_OK(cpy(st.direc, direc, (size_t)ntraj * 3 * 8, cudaMemcpyHostToDevice));
+    CID_OK(cpy(d_rnd, rnd, (size_t)ntraj * 9 * 8, cudaMemcpyHostToDevice));
+    if (velo_cm) CID_OK(cpy(d_vcm, velo_cm, (size_t)ntraj * 8, cudaMemcpyHostToDevice));
+    CID_OK(cpy(st.sc, hsc.data(), (size_t)ntraj * sizeof(CidScalars), cudaMemcpyHostToDevice));
     const int grid = ctx.ncta < ntraj ? ctx.ncta : ntraj;
-    CID_OK(cudaMemset(ctx.d_queue, 0, sizeof(int)));
-    k_cid_init<<<grid, QX_NT, ctx.smem>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, mc, cc, st, ntraj, nuc, icoll, ctx.d_queue);
+    CID_OK(cudaMemsetAsync(ctx.d_queue, 0, sizeof(int), strm));
+    k_cid_init<<<grid, QX_NT, ctx.smem, strm>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, mc, cc, st, ntraj, nuc, icoll, ctx.d_queue);
     CID_OK(cudaGetLastError());
     const int chunk = 32;
     for (int done = 0; done < cc.ntot + chunk; done += chunk) {
-        CID_OK(cudaMemset(ctx.d_queue, 0, sizeof(int)));
-        k_cid_chunk<<<grid, QX_NT, ctx.smem>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, mc, cc, st, ntraj, nuc, chunk, ctx.d_queue);
+        CID_OK(cudaMemsetAsync(ctx.d_queue, 0, sizeof(int), strm));
+        k_cid_chunk<<<grid, QX_NT, ctx.smem, strm>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, mc, cc, st, ntraj, nuc, chunk, ctx.d_queue);
         CID_OK(cudaGetLastError());
         if ((done / chunk) % 4 == 3 || done + chunk >= cc.ntot) {
-            CID_OK(cudaMemcpy(hsc.data(), st.sc, (size_t)ntraj * sizeof(CidScalars), cudaMemcpyDeviceToHost));
+            CID_OK(cpy(hsc.data(), st.sc, (size_t)ntraj * sizeof(CidScalars), cudaMemcpyDeviceToHost));
             bool any = false;
             for (const CidScalars &v : hsc) any = any || v.status == TRJ_RUNNING;
             if (!any) break;
         }
     }
-    CID_OK(cudaMemcpy(hsc.data(), st.sc, (size_t)ntraj * sizeof(CidScalars), cudaMemcpyDeviceToHost));
+    CID_OK(cpy(hsc.data(), st.sc, (size_t)ntraj * sizeof(CidScalars), cudaMemcpyDeviceToHost));
     // hand-back (reference src/cid.f90:1058-1105): the ion part of the collision system; set-up changes to xyz / velo stay
     // visible even when the first single point failed, as in the reference
     std::vector<double> hx(n30), hv(n30), hg(n30), hq((size_t)ntraj * nuc0), hav(n3), hst(n3);
-    CID_OK(cudaMemcpy(hx.data(), st.xyz0, n30 * 8, cudaMemcpyDeviceToHost));
-    CID_OK(cudaMemcpy(hv.data(), st.velo0, n30 * 8, cudaMemcpyDeviceToHost));
-    CID_OK(cudaMemcpy(hg.data(), st.grad0, n30 * 8, cudaMemcpyDeviceToHost));
-    CID_OK(cudaMemcpy(hq.data(), st.achrg0, (size_t)ntraj * nuc0 * 8, cudaMemcpyDeviceToHost));
-    CID_OK(cudaMemcpy(hav.data(), st.avxyz, n3 * 8, cudaMemcpyDeviceToHost));
-    CID_OK(cudaMemcpy(hst.data(), st.store, n3 * 8, cudaMemcpyDeviceToHost));
-    CID_OK(cudaMemcpy(list, st.list, (size_t)ntraj * nuc * 4, cudaMemcpyDeviceToHost));
-    CID_OK(cudaMemcpy(direc, st.direc, (size_t)ntraj * 3 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cpy(hx.data(), st.xyz0, n30 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cpy(hv.data(), st.velo0, n30 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cpy(hg.data(), st.grad0, n30 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cpy(hq.data(), st.achrg0, (size_t)ntraj * nuc0 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cpy(hav.data(), st.avxyz, n3 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cpy(hst.data(), st.store, n3 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cpy(list, st.list, (size_t)ntraj * nuc * 4, cudaMemcpyDeviceToHost));
+    CID_OK(cpy(direc, st.direc, (size_t)ntraj * 3 * 8, cudaMemcpyDeviceToHost));
     std::vector<double> sx(n3), sv(n3);
-    CID_OK(cudaMemcpy(sx.data(), st.xyz, n3 * 8, cudaMemcpyDeviceToHost));
-    CID_OK(cudaMemcpy(sv.data(), st.velo, n3 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cpy(sx.data(), st.xyz, n3 * 8, cudaMemcpyDeviceToHost));
+    CID_OK(cpy(sv.data(), st.velo, n3 * 8, cudaMemcpyDeviceToHost));
 #undef CID_OK
     for (int t = 0; t < ntraj; ++t) {
         const CidScalars &c = hsc[t];

@@ -19,9 +19,24 @@ The MD and single-point back ends are parameters so that the same driver runs on
   main.F90:1981-2128   stop rules: small fragment, low mass, slow ion / low E(COM), number of fragmentations, number of collisions
   main.F90:2133-2163   the held-back record of the charged fragment is written when a trajectory ends early
 """
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 
 from . import fragments as fr
+
+# Groups of one generation (different compositions) are independent launches: they are driven from a few host threads so that
+# their kernels, each of which fills only part of the GPU once the ensemble has fragmented into many compositions, overlap
+# (every ensemble / collision batch has its own stream; ctypes releases the GIL during the calls).
+GROUP_THREADS = 8
+
+
+def _map_groups(fn, items):
+    items = list(items)
+    if len(items) <= 1 or GROUP_THREADS <= 1:
+        return [fn(it) for it in items]
+    with ThreadPoolExecutor(max_workers=min(GROUP_THREADS, len(items))) as ex:
+        return list(ex.map(fn, items))
 
 
 def gpu_md_batch(num, mass, xyz, velo, velof, eimp, tadd, mchrg, nmax, nfragexit, isec, tstep_fs, etemp):
@@ -60,10 +75,12 @@ def run_ei(num, mass, xyz, velo, velof, eimp, tadd, mchrg=1, nmax=10000, maxsec=
                 nfe = 2 if s["isec"] > 1 else nfragexit                       # main.F90:2252
                 key = (tuple(int(a) for a in s["num"]), s["mchrg"], s["nmax"], nfe, s["isec"])
                 groups.setdefault(key, []).append(s)
-        for (_, mc, nm, nfe, isec), members in groups.items():
+        def run_group(item):
+            (_, mc, nm, nfe, isec), members = item
             g0 = members[0]
-            out = md_batch(g0["num"], g0["mass"], [s["xyz"] for s in members], [s["velo"] for s in members], [s["velof"] for s in members],
-                           [s["eimp"] for s in members], [s["tadd"] for s in members], mc, nm, nfe, isec, tstep_fs, etemp)
+            return md_batch(g0["num"], g0["mass"], [s["xyz"] for s in members], [s["velo"] for s in members], [s["velof"] for s in members],
+                            [s["eimp"] for s in members], [s["tadd"] for s in members], mc, nm, nfe, isec, tstep_fs, etemp)
+        for (_, members), out in zip(groups.items(), _map_groups(run_group, groups.items())):
             for s, r in zip(members, out):
                 _after_md(s, r, nmax0, maxsec, btf, energies)
     records = []
@@ -256,18 +273,22 @@ def run_cid(num, mass, xyz, velo, mchrg=1, gas="ar", elab=40.0, ecom=0.0, eexact
                     d = s["cm2"] - s["cm1"]
                     s["direc"] = d / np.sqrt((d * d).sum())
                 groups.setdefault((tuple(int(a) for a in s["num"]), s["mchrg"], min(s["icoll"], 2)), []).append(s)
-        for (_, mc, _), members in groups.items():
-            # trajectories of one composition with icoll == 1 (no velo_cm / direc input) or icoll > 1 run as one batch each
-            by_icoll = {}
+        # trajectories of one composition and one collision index run as one batch
+        batches = {}
+        for (comp, mc, _), members in groups.items():
             for s in members:
-                by_icoll.setdefault(s["icoll"], []).append(s)
-            for icoll, mem in by_icoll.items():
-                g0 = mem[0]
-                cfg = api.cid_config(mchrg=mc, gas=gas, tstep_fs=tstep_fs, elab=elab, ecom=ecom, eexact=eexact, manual_dist=manual_dist,
-                                     ntot=cid_ntot, etemp=max(etemp, 0.0))
-                rnd = [s["rng"].random(9) for s in mem]
-                out = cid_batch(cfg, g0["num"], g0["mass"], icoll, [s["xyz"] for s in mem], [s["velo"] for s in mem], rnd,
-                                [s["new_velo"] for s in mem], [s["direc"] for s in mem], [s["collided"] for s in mem])
+                batches.setdefault((comp, mc, s["icoll"]), []).append(s)
+
+        def run_collision(item):
+            (_, mc, icoll), mem = item
+            g0 = mem[0]
+            cfg = api.cid_config(mchrg=mc, gas=gas, tstep_fs=tstep_fs, elab=elab, ecom=ecom, eexact=eexact, manual_dist=manual_dist,
+                                 ntot=cid_ntot, etemp=max(etemp, 0.0))
+            rnd = [s["rng"].random(9) for s in mem]
+            return cid_batch(cfg, g0["num"], g0["mass"], icoll, [s["xyz"] for s in mem], [s["velo"] for s in mem], rnd,
+                             [s["new_velo"] for s in mem], [s["direc"] for s in mem], [s["collided"] for s in mem])
+        for ((_, mc, icoll), mem), out in zip(batches.items(), _map_groups(run_collision, batches.items())):
+            if True:
                 for s, r in zip(mem, out):
                     s["collided"] = int(r["collided"])
                     s["events"].append(dict(kind="cid", icoll=icoll, nat=len(s["num"]), nstep=int(r["nstep"]), nfrag=int(r["nfrag"]),
@@ -301,10 +322,12 @@ def run_cid(num, mass, xyz, velo, mchrg=1, gas="ar", elab=40.0, ecom=0.0, eexact
                 if mfp_nmax:
                     nmax = int(mfp_nmax)
                 groups.setdefault((tuple(int(a) for a in s["num"]), s["mchrg"], nmax, s["icoll"], s["isec"]), []).append(s)
-        for (_, mc, nmax, icoll, isec), mem in groups.items():
+        def run_mfp(item):
+            (_, mc, nmax, icoll, isec), mem = item
             g0 = mem[0]
-            out = mfp_batch(g0["num"], g0["mass"], [s["xyz"] for s in mem], [s["velo"] for s in mem], [s["new_velo"] for s in mem], icoll, isec,
-                            mc, nmax, tstep_fs, etemp)
+            return mfp_batch(g0["num"], g0["mass"], [s["xyz"] for s in mem], [s["velo"] for s in mem], [s["new_velo"] for s in mem], icoll, isec,
+                             mc, nmax, tstep_fs, etemp)
+        for ((_, mc, nmax, icoll, isec), mem), out in zip(groups.items(), _map_groups(run_mfp, groups.items())):
             for s, r in zip(mem, out):
                 md_ok = bool(r["mdok"]) and int(r["status"]) == 1
                 s["events"].append(dict(kind="mfp", icoll=icoll, isec=isec, nat=len(s["num"]), nstep=int(r["nstep"]), nfrag=int(r["nfrag"]),
