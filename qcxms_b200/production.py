@@ -99,8 +99,13 @@ def _after_md(s, r, nmax0, maxsec, btf, energies):
             s["records"].append(s["asave"])
         s["alive"] = False
         return
-    out = fr.manage_fragments(s["num"], s["mass"], r["axyz"], r["list"], r["achrg"], aTlast=float(r["aTlast"]), itrj=s["itrj"], isec=s["isec"],
-                              mchrg=s["mchrg"], chrgcont=s["chrgcont"], btf=btf, maxsec=maxsec, energies=energies)
+    try:
+        out = fr.manage_fragments(s["num"], s["mass"], r["axyz"], r["list"], r["achrg"], aTlast=float(r["aTlast"]), itrj=s["itrj"], isec=s["isec"],
+                                  mchrg=s["mchrg"], chrgcont=s["chrgcont"], btf=btf, maxsec=maxsec, energies=energies)
+    except RuntimeError as err:                   # the reference process of this trajectory `error stop`s (src/iniqm.f90:411-413)
+        gen.update(fatal=str(err))
+        s["alive"] = False
+        return
     gen.update(tcont=out["tcont"], fragip=None if out["fragip"] is None else [float(v) for v in out["fragip"]])
     if not out["nfrag_ok"]:                       # too many fragments: the run is not counted (main.F90:2280)
         s["alive"] = False
@@ -299,9 +304,14 @@ def run_cid(num, mass, xyz, velo, mchrg=1, gas="ar", elab=40.0, ecom=0.0, eexact
                     s["new_velo"] = float(r["velo_cm"])
                     if icoll == 1:
                         s["direc"] = np.array(r["direc"], dtype=np.float64)
-                    mf = fr.manage_fragments(s["num"], s["mass"], r["axyz"], r["list"], r["achrg"], aTlast=float(r["aTlast"]), itrj=s["itrj"],
-                                             isec=1, mchrg=s["mchrg"], chrgcont=s["chrgcont"], btf=btf, maxsec=maxsec, icoll=icoll,
-                                             energies=energies)
+                    try:
+                        mf = fr.manage_fragments(s["num"], s["mass"], r["axyz"], r["list"], r["achrg"], aTlast=float(r["aTlast"]), itrj=s["itrj"],
+                                                 isec=1, mchrg=s["mchrg"], chrgcont=s["chrgcont"], btf=btf, maxsec=maxsec, icoll=icoll,
+                                                 energies=energies)
+                    except RuntimeError as err:      # the reference process of this trajectory `error stop`s (src/iniqm.f90:411-413)
+                        s["events"].append(dict(kind="fatal", icoll=icoll, nstep=0, nfrag=0, msg=str(err)))
+                        finish(s, False)
+                        continue
                     if not mf["nfrag_ok"]:
                         finish(s, False)
                         continue
@@ -338,9 +348,14 @@ def run_cid(num, mass, xyz, velo, mchrg=1, gas="ar", elab=40.0, ecom=0.0, eexact
                 if not md_ok:
                     finish(s, False)                 # "the run is just not further counted" (main.F90:1896-1903)
                     continue
-                mf = fr.manage_fragments(s["num"], s["mass"], r["axyz"], r["list"], r["achrg"], aTlast=float(r["aTlast"]), itrj=s["itrj"],
-                                         isec=isec, mchrg=s["mchrg"], chrgcont=s["chrgcont"], btf=btf, maxsec=maxsec, icoll=icoll,
-                                         energies=energies)
+                try:
+                    mf = fr.manage_fragments(s["num"], s["mass"], r["axyz"], r["list"], r["achrg"], aTlast=float(r["aTlast"]), itrj=s["itrj"],
+                                             isec=isec, mchrg=s["mchrg"], chrgcont=s["chrgcont"], btf=btf, maxsec=maxsec, icoll=icoll,
+                                             energies=energies)
+                except RuntimeError as err:
+                    s["events"].append(dict(kind="fatal", icoll=icoll, nstep=0, nfrag=0, msg=str(err)))
+                    finish(s, False)
+                    continue
                 if not mf["nfrag_ok"]:
                     finish(s, False)
                     continue

@@ -22,6 +22,7 @@ t0 = time.perf_counter()
 res = prod.run_cid(num, ic["mass"], ic["xyz"], ic["velo"], mchrg=1, gas="ar", elab=elab, run_type="maxcoll", max_coll=max_coll, minmass=20, seed=1)
 dt = time.perf_counter() - t0
 ev = [e for t in res["per_traj"] for e in t["events"]]
+nfatal = sum(1 for e in ev if e["kind"] == "fatal")
 steps_cid = sum(e["nstep"] for e in ev if e["kind"] == "cid")
 steps_mfp = sum(e["nstep"] for e in ev if e["kind"] == "mfp")
 ncoll = [max([e["icoll"] for e in t["events"]] or [0]) for t in res["per_traj"]]
@@ -31,7 +32,7 @@ peaks = {int(i): float(spec[i]) for i in np.argsort(spec)[::-1][:8] if spec[i] >
 summary = dict(molecule=mol, ntraj=nt, elab_eV=elab, max_coll=max_coll, wall_s=dt, cid_steps=int(steps_cid), mfp_steps=int(steps_mfp),
                steps_per_s=(steps_cid + steps_mfp) / dt, cid_calls=sum(1 for e in ev if e["kind"] == "cid"), mfp_calls=sum(1 for e in ev if e["kind"] == "mfp"),
                collisions_per_traj=float(np.mean(ncoll)), fragmenting_events=int(nfragev), stopcid=sum(int(e.get("stopcid", 0)) for e in ev),
-               records=len(res["records"]), charge_sum_per_traj=float(sum(float(r[:10]) for r in res["records"]) / nt), peaks=peaks)
+               fatal_fragment_single_points=nfatal, records=len(res["records"]), charge_sum_per_traj=float(sum(float(r[:10]) for r in res["records"]) / nt), peaks=peaks)
 print(json.dumps(summary))
 if out:
     with open(out, "w") as f:
