@@ -1513,18 +1513,19 @@ __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float 
                         double *gp = Bl + p * ld, *gq = Bl + q * ld;
                         const double2 sp = dd[p], sq = dd[q];
                         const double al = nrm2[p], be = nrm2[q];
-                        double2 x[R], y[R];
-                        // every chunk but the last is in range for all lanes (32 (R - 1) < n); columns n .. ld-1 of B are zero
-#pragma unroll
-                        for (int r = 0; r < R - 1; ++r) {
-                            x[r] = *reinterpret_cast<const double2 *>(gp + 2 * LP * r);
-                            y[r] = *reinterpret_cast<const double2 *>(gq + 2 * LP * r);
-                        }
-                        x[R - 1] = make_double2(0.0, 0.0); y[R - 1] = make_double2(0.0, 0.0);
-                        if (tail_ok) { x[R - 1] = *reinterpret_cast<const double2 *>(gp + 2 * LP * (R - 1)); y[R - 1] = *reinterpret_cast<const double2 *>(gq + 2 * LP * (R - 1)); }
+                        // the rows are read twice from shared memory (dot product, then rotation) instead of being held in 4 R
+                        // registers across the rotation-parameter chain: as a __noinline__ callee this function only gets the registers
+                        // its callers leave, and holding the rows spilled them to local memory (1.0 G LDL / 0.6 G STL warp instructions
+                        // per 148 single points of C32H66, the hottest stalls of the phase)
                         double g0 = 0.0, g1 = 0.0;
 #pragma unroll
-                        for (int r = 0; r < R; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
+                        for (int r = 0; r < R; ++r) {
+                            if (r < R - 1 || tail_ok) {   // columns n .. ld-1 of B are zero
+                                const double2 x = *reinterpret_cast<const double2 *>(gp + 2 * LP * r);
+                                const double2 y = *reinterpret_cast<const double2 *>(gq + 2 * LP * r);
+                                g0 = fma(x.x, y.x, g0); g1 = fma(x.y, y.y, g1);
+                            }
+                        }
                         double gs = g0 + g1;
 #pragma unroll
                         for (int o = LP >> 1; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
@@ -1540,13 +1541,16 @@ __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float 
                         tf = rot ? tf : 0.0f;
                         const double t = (double)tf;
                         const double t1 = t * (sq.x * sp.y), t2 = t * (sp.x * sq.y);
+                        asm volatile("" ::: "memory");   // the rows are loaded again, not carried over from the dot product
                         if (valid) {
 #pragma unroll
                             for (int r = 0; r < R; ++r) {
-                                double2 u, v;
-                                u.x = fma(-t1, y[r].x, x[r].x); u.y = fma(-t1, y[r].y, x[r].y);
-                                v.x = fma(t2, x[r].x, y[r].x); v.y = fma(t2, x[r].y, y[r].y);
                                 if (r < R - 1 || tail_ok) {
+                                    const double2 x = *reinterpret_cast<const double2 *>(gp + 2 * LP * r);
+                                    const double2 y = *reinterpret_cast<const double2 *>(gq + 2 * LP * r);
+                                    double2 u, v;
+                                    u.x = fma(-t1, y.x, x.x); u.y = fma(-t1, y.y, x.y);
+                                    v.x = fma(t2, x.x, y.x); v.y = fma(t2, x.y, y.y);
                                     *reinterpret_cast<double2 *>(gp + 2 * LP * r) = u;
                                     *reinterpret_cast<double2 *>(gq + 2 * LP * r) = v;
                                 }
