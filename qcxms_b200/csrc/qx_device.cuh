@@ -1482,8 +1482,11 @@ __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float 
                 for (int lr = warp; lr < nr; lr += nwarp) {
                     const double *src = G + (size_t)(lr < nI ? r0I + lr : r0J + lr - nI) * ld;
                     double *dst = B + (size_t)lr * ld;
-                    double acc = 0.0;
-                    for (int i = lane; i < ld; i += 32) { const double x = i < n ? src[i] : 0.0; dst[i] = x; acc = fma(x, x, acc); }
+                    double acc = 0.0, xs[9];   // ld <= 268 (n <= 256): all loads of a row in flight at once, one L2 round trip per row
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) { const int i = lane + 32 * c; xs[c] = i < n ? src[i] : 0.0; }
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) { const int i = lane + 32 * c; if (i < ld) { dst[i] = xs[c]; acc = fma(xs[c], xs[c], acc); } }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                     if (lane == 0) { nrm2[lr] = acc; dd[lr] = make_double2(1.0, 1.0); }
