@@ -5,10 +5,15 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
 
 One "step" = one MD step (leapfrog + one converged cold-start GFN2-xTB energy/gradient + fragment check,
-reference src/md.f90:390-454) of EVERY trajectory of the per-GPU ensemble.  Workload (BASELINE.json configs[1]):
-caffeine cation, GFN2-xTB, EI, 1000 trajectories per GPU, synthetic initial conditions, exit
-rules disabled so every trajectory does identical work.  Trajectories are independent: ranks share nothing
-during MD (weak scaling: 1000 trajectories per GPU); the only collective is the final histogram all-reduce.
+reference src/md.f90:390-454) of EVERY trajectory of the ensemble.  Workload (BASELINE.json configs[1]):
+caffeine cation, GFN2-xTB, EI, 1000 trajectories, synthetic initial conditions, exit rules
+disabled so every trajectory does identical work.  Trajectories are independent: ranks share nothing during
+MD; the only collective is the final histogram all-reduce.
+
+--scaling strong (default; BASELINE config 2 as written): the 1000 trajectories are dealt over the N ranks
+(itrj mod N, like bin/pqcxms deals TMP.<n> directories), so the total work is fixed.  --scaling weak: 1000
+trajectories PER GPU.  With N > 1 the JSON line carries the other mode's numbers as well ("other_scaling").
+At N = 1 the two are the same run.
 """
 import argparse
 import json
@@ -102,7 +107,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ntraj", type=int, default=1000, help="trajectories per GPU")
+    ap.add_argument("--ntraj", type=int, default=1000, help="trajectories: in total (--scaling strong) or per GPU (--scaling weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--molecule", default="caffeine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--warm-start", action="store_true", help="opt-in fast mode, NOT the reference protocol (SURVEY 8f-4): SCC of a step "
@@ -116,8 +122,10 @@ def main():
     num, xyz0, _ = load_molecule(args.molecule)
     nat = len(num)
     cores = len(os.sched_getaffinity(0))
-    config = {"workload": "%s cation GFN2-xTB EI, %d trajectories per GPU, tstep 0.5 fs, etemp 5000 K, cold-start SCC acc=1.0, exit rules off"
-                          % (args.molecule, args.ntraj), "nat": nat, "ntraj_per_gpu": args.ntraj,
+    per_gpu = args.scaling == "weak"
+    config = {"workload": "%s cation GFN2-xTB EI, %d trajectories %s, tstep 0.5 fs, etemp 5000 K, cold-start SCC acc=1.0, exit rules off"
+                          % (args.molecule, args.ntraj, "per GPU" if per_gpu else "in total, dealt itrj mod N over the ranks"), "nat": nat,
+              "ntraj_total": args.ntraj * (args.gpus if per_gpu else 1),
               "l2": "per-step working set (453 KB scratch x resident CTAs + state) is re-streamed every SCC cycle; inputs are not cached between steps"}
 
     if args.warm_start:
@@ -140,7 +148,7 @@ def main():
         dt = time.perf_counter() - t0
         val = done / dt
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                            "sample": "%d trajectories x %d MD step(s) per bench step (md() incl. its initial egrad), one trajectory per host thread" % (ntraj_s, per_step)},
@@ -163,69 +171,80 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # this rank's shard of the global ensemble (weak scaling: ntraj per GPU)
-    first_id = rank * args.ntraj
-    ic = es.synthetic_initial_conditions(num, xyz0, args.ntraj, first_id=first_id)
-    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in ic.items() if k != "mass"}
+    def measure(mode):
+        """One full measurement (device-timed K steps + end-to-end leg) of this rank's shard under `mode` scaling."""
+        ids = es.shard_indices(args.ntraj, world, rank) if mode == "strong" else np.arange(rank * args.ntraj, (rank + 1) * args.ntraj)
+        ntl = len(ids)
+        ic = es.synthetic_initial_conditions(num, xyz0, ntl, ids=ids)
+        pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in ic.items() if k != "mass"}
 
-    def new_ensemble():
-        e = qx.Ensemble(num, ic["mass"], args.ntraj, mchrg=1, tstep_fs=0.5, nmax=10 ** 6, exit_rules=False, device=local_rank)
-        if args.warm_start:
-            e.set_warm_start(True)
-        e.set_all(*[pin[k].numpy() for k in ("xyz", "velo", "velof", "eimp", "tadd")])
-        return e
+        def new_ensemble():
+            e = qx.Ensemble(num, ic["mass"], ntl, mchrg=1, tstep_fs=0.5, nmax=10 ** 6, exit_rules=False, device=local_rank)
+            if args.warm_start:
+                e.set_warm_start(True)
+            e.set_all(*[pin[k].numpy() for k in ("xyz", "velo", "velof", "eimp", "tadd")])
+            return e
 
-    # ---- kernel-only throughput: inputs resident in HBM, K timed steps after W warm-up steps
-    ens = new_ensemble()
-    ens.run_md(max_steps=max(args.warmup, 3))
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    t0 = time.perf_counter()
-    steps = ens.run_md(max_steps=args.steps)
-    torch.cuda.synchronize()
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    tim = ens.last_timing()
-    dev_s = tim["kernel_ms"] * 1e-3
-    tt = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([float(steps), float(tim["scc_iterations"]), float(tim["launches"])], dtype=torch.float64, device=dev)
+        # ---- kernel-only throughput: inputs resident in HBM, K timed steps after W warm-up steps
+        ens = new_ensemble()
+        ens.run_md(max_steps=max(args.warmup, 3))
+        sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        t0 = time.perf_counter()
+        steps = ens.run_md(max_steps=args.steps)
+        torch.cuda.synchronize()
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if rank == 0 else None
+        tim = ens.last_timing()
+        dev_s = tim["kernel_ms"] * 1e-3
+        tt = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([float(steps), float(tim["scc_iterations"]), float(tim["launches"])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dev_s_max, wall_max = tt.tolist()
+        total_steps, _scc_unused, launches = cnt.tolist()
+        # mean SCC cycles per egrad over the timed steps (scc counter is cumulative over the trajectory's life)
+        res0 = ens.results()
+        n_it = float(np.mean(res0["scc_iter_total"] / (res0["nstep"] + 1.0)))
+        ens.histogram(512)
+        ens.close()
+
+        # ---- end to end through the public API with host buffers: H2D of the initial conditions, md(), D2H of the results
+        barrier()
+        t0 = time.perf_counter()
+        e2 = new_ensemble()
+        e2_steps = e2.run_md(max_steps=args.steps)
+        e2.results()
+        bins, _ = e2.histogram(512)
+        hb = torch.from_numpy(bins).to(dev)
+        es.allreduce_histogram(hb)
+        torch.cuda.synchronize()
+        barrier()
+        e2e_wall = time.perf_counter() - t0
+        e2.close()
+        t2 = torch.tensor([e2e_wall], dtype=torch.float64, device=dev)
+        c2 = torch.tensor([float(e2_steps)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c2, op=dist.ReduceOp.SUM)
+        h2d = sum(v.numel() * 8 for v in pin.values())
+        d2h = ntl * (nat * (3 * 4 + 1) * 8 + nat * 4 + 14 * 8) + 512 * 8
+        return dict(value=total_steps / dev_s_max, dev_s_max=dev_s_max, wall_max=wall_max, total_steps=total_steps, launches=launches, n_it=n_it,
+                    clocks=clocks, e2e_value=c2.item() / t2.item(), h2d=h2d, d2h=d2h, ntraj_local=ntl)
+
+    m = measure(args.scaling)
+    other = None
     if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    dev_s_max, wall_max = tt.tolist()
-    total_steps, _scc_unused, launches = cnt.tolist()
-    value = total_steps / dev_s_max
-
-    # mean SCC cycles per egrad over the timed steps (scc counter is cumulative over the trajectory's life)
-    res0 = ens.results()
-    n_it = float(np.mean(res0["scc_iter_total"] / (res0["nstep"] + 1.0)))
-    hist_bins, hist_dev = ens.histogram(512)
-    ens.close()
-
-    # ---- end to end through the public API with host buffers: H2D of the initial conditions, md(), D2H of the results
-    barrier()
-    t0 = time.perf_counter()
-    e2 = new_ensemble()
-    e2_steps = e2.run_md(max_steps=args.steps)
-    outs = e2.results()
-    bins, _ = e2.histogram(512)
-    hb = torch.from_numpy(bins).to(dev)
-    es.allreduce_histogram(hb)
-    torch.cuda.synchronize()
-    barrier()
-    e2e_wall = time.perf_counter() - t0
-    e2.close()
-    t2 = torch.tensor([e2e_wall], dtype=torch.float64, device=dev)
-    c2 = torch.tensor([float(e2_steps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        dist.all_reduce(c2, op=dist.ReduceOp.SUM)
-    e2e_value = c2.item() / t2.item()
-    h2d = sum(v.numel() * 8 for v in pin.values())
-    d2h = args.ntraj * (nat * (3 * 4 + 1) * 8 + nat * 4 + 14 * 8) + 512 * 8
+        om = measure("weak" if args.scaling == "strong" else "strong")
+        other = {"scaling": "weak" if args.scaling == "strong" else "strong", "value": om["value"], "e2e": om["e2e_value"],
+                 "ms_per_step": 1e3 * om["dev_s_max"] / args.steps, "ntraj_per_gpu": om["ntraj_local"]}
+    value, dev_s_max, wall_max, total_steps, launches, n_it, clocks = (m[k] for k in ("value", "dev_s_max", "wall_max", "total_steps", "launches", "n_it", "clocks"))
+    e2e_value, h2d, d2h = m["e2e_value"], m["h2d"], m["d2h"]
+    config["ntraj_per_gpu"] = m["ntraj_local"]
 
     if rank != 0:
         if world > 1:
@@ -248,7 +267,7 @@ def main():
         except Exception:
             traffic = None
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-           "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches / world),
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                    "note": "create + H2D initial conditions (pinned) + md() incl. its initial egrad + D2H of every trajectory's result + histogram all-reduce"},
@@ -256,6 +275,8 @@ def main():
                         "kernel": "k_md_chunk", "note": "FP64 pipe roofline; peak = cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
                                                         "achieved = SURVEY 8(d) algorithmic FLOPs, n_it = %.2f SCC cycles/step, nao = %d" % (n_it, nao)},
            "wall_s": wall_max, "scc_cycles_per_step": n_it}
+    if other:
+        out["other_scaling"] = other
     if not args.no_cpu_baseline and world == 1:
         ncpu_traj, ncpu_steps = cores, 8
         cpu_md_sample(num, xyz0, 2, 1, cores)

@@ -82,7 +82,8 @@ typedef struct {
     int32_t nmax;        /* maximum number of MD steps (reference nmax = tmax/tstep) */
     int32_t isec;        /* index of the (secondary) run, reference isec; affects the error exit */
     double tstep;        /* MD time step in atomic units (reference tstep after *fstoau) */
-    double etemp_in;     /* electronic temperature; < 0: reference setetemp() rule (5000 K + ...) */
+    double etemp_in;     /* reference etempin: >= 0 sets the electronic temperature of md()'s INITIAL single point only; the loop
+                          * calls setetemp() on every step regardless (src/md.f90:167-172, 443-445); < 0: setetemp() throughout */
     double ieetemp;      /* reference common1 ieetemp (default 0) */
     double ax;           /* reference common1 ax (0 for xtb) */
 } qcxms_b200_md_config_t;
@@ -142,6 +143,11 @@ int qcxms_b200_ensemble_get_all(qcxms_b200_ensemble_t *h, double *xyz, double *v
 /* device time (ms, CUDA events on the launching stream) and kernel launch count of the last run_md */
 int qcxms_b200_ensemble_last_timing(qcxms_b200_ensemble_t *h, double *kernel_ms, int64_t *launches,
                                     int64_t *scc_iterations);
+
+/* intenergy (reference src/md.f90:715-741): internal kinetic energy E_int [ntraj][10] (Eh) and temperature T [ntraj][10] (K) of
+ * every fragment of the current state (list / velo of the last finished step), computed on the device in the reference's
+ * summation order.  Slots beyond the number of fragments are 0. */
+int qcxms_b200_ensemble_intenergy(qcxms_b200_ensemble_t *h, double *fragT, double *e_int);
 
 /* Fragment-mass histogram of the finished trajectories of this ensemble (bins = nominal integer m/z of
  * every fragment, weight 1 per fragment); this is what one ncclAllReduce(sum) combines across GPUs in

@@ -283,7 +283,7 @@ static int md_core(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *ia
             if (nstep <= nadd && nfrag == 1) {
                 if (md_oracle_impactscale(nuc, velo, mass, velof, eimp, fadd * nstep, Ekinstart)) { res->status = 2; break; }
             }
-            if (cfg->etemp_in < 0) {
+            {   /* unconditional in the reference (src/md.f90:443-445): a user ETEMP only serves the first single point */
                 double dum = eimp - eimp * (double)(float)nstep / (double)(float)nadd;
                 etemp = md_oracle_setetemp(nfrag, dum, cfg->ax, cfg->ieetemp);
             }

@@ -150,6 +150,18 @@ def ekinet(velo, mass):
     return e.value, t.value
 
 
+def intenergy(lst, mass, velo, nfrag):
+    """intenergy (reference src/md.f90:715-741): (T[10], E_int[10])."""
+    lst = np.ascontiguousarray(lst, dtype=np.int32); mass = np.ascontiguousarray(mass, dtype=np.float64)
+    velo = np.ascontiguousarray(velo, dtype=np.float64)
+    T = np.zeros(10); e = np.zeros(10)
+    f = lib().md_oracle_intenergy
+    f.restype = None
+    f.argtypes = [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    f(len(mass), _ip(lst), _dp(mass), _dp(velo), int(nfrag), _dp(T), _dp(e))
+    return T, e
+
+
 def impactscale(velo, mass, velof, eimp, ff, e0):
     velo = np.array(velo, dtype=np.float64); mass = np.ascontiguousarray(mass, dtype=np.float64)
     velof = np.ascontiguousarray(velof, dtype=np.float64)

@@ -58,7 +58,7 @@ GASES = {"he": (2, 4.002, 2.64560263), "ne": (10, 20.18, 2.91016289), "ar": (18,
 EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_egrad_spec", "qcxms_b200_basis_size", "qcxms_b200_cid_batch", "qcxms_b200_egrad_batch", "qcxms_b200_fragment_structure", "qcxms_b200_ensemble_create",
            "qcxms_b200_ensemble_destroy", "qcxms_b200_ensemble_set_trajectory", "qcxms_b200_ensemble_set_all",
            "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_set_warm_start", "qcxms_b200_ensemble_set_mfp", "qcxms_b200_ensemble_get_new_velo", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_get_all", "qcxms_b200_ensemble_last_timing",
-           "qcxms_b200_ensemble_histogram", "qcxms_b200_last_error", "qcxms_b200_version"]
+           "qcxms_b200_ensemble_histogram", "qcxms_b200_ensemble_intenergy", "qcxms_b200_last_error", "qcxms_b200_version"]
 
 
 def lib():
@@ -88,6 +88,7 @@ def lib():
         L.qcxms_b200_ensemble_get_all.argtypes = [C.c_void_p, dp, dp, dp, ip, dp, dp, C.POINTER(MdResult)]
         L.qcxms_b200_ensemble_last_timing.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.qcxms_b200_ensemble_histogram.argtypes = [C.c_void_p, C.c_int, dp, C.POINTER(C.c_void_p)]
+        L.qcxms_b200_ensemble_intenergy.argtypes = [C.c_void_p, dp, dp]
         L.qcxms_b200_cid_batch.argtypes = [C.POINTER(CidConfig), C.c_int, C.c_int, ip, dp, C.c_int, dp, dp, dp, dp, dp, ip, dp, dp, dp, ip,
                                            C.POINTER(CidResult), C.c_int]
         L.qcxms_b200_last_error.restype = C.c_char_p
@@ -268,6 +269,12 @@ class Ensemble:
         ms, launches, scc = C.c_double(0), C.c_int64(0), C.c_int64(0)
         _check(lib().qcxms_b200_ensemble_last_timing(self._h, C.byref(ms), C.byref(launches), C.byref(scc)))
         return dict(kernel_ms=ms.value, launches=launches.value, scc_iterations=scc.value)
+
+    def intenergy(self):
+        """intenergy (reference src/md.f90:715-741) of the current state: (fragT[ntraj, 10] / K, E_int[ntraj, 10] / Eh)."""
+        T = np.zeros((self.ntraj, 10)); e = np.zeros((self.ntraj, 10))
+        _check(lib().qcxms_b200_ensemble_intenergy(self._h, _dp(T), _dp(e)))
+        return T, e
 
     def histogram(self, nbins=512):
         bins = np.zeros(nbins)

@@ -14,7 +14,7 @@
 
 #include "../../include/qcxms_b200.h"
 #include "qx_host_model.h"
-#include "qx_cid.cuh"
+#include "qx_kernels.h"
 
 using namespace qx;
 
@@ -29,520 +29,33 @@ static int fail(int code, const std::string &msg) {
         if (e__ != cudaSuccess) return fail(QCXMS_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
-// ------------------------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(QX_NT, 2) k_egrad_batch(DevModel m, ScratchLayout L, double *scratch, const double *xyz, double kt, int nsys,
-                                                       int *queue, double *energy, double *grad, double *qat, int *stat, int *niter, double *spec) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ int s_next;
-    Sm s;
-    double *my = scratch + (size_t)blockIdx.x * L.total;
-    carve(m, smem, s, my + L.matA);
-    const int nat = m.nat;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
-        __syncthreads();
-        const int t = s_next;
-        if (t >= nsys) break;
-        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.xyz[i] = xyz[(size_t)t * 3 * nat + i];
-        __syncthreads();
-        EgradOut o;
-        egrad_cta(m, s, my, L, kt, o, nullptr, spec ? spec + (size_t)t * (2 * m.nao + m.nao * nat + 1) : nullptr);
-        __syncthreads();
-        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) grad[(size_t)t * 3 * nat + i] = s.grad[i];
-        for (int i = threadIdx.x; i < nat; i += QX_NT) qat[(size_t)t * nat + i] = s.qat[i];
-        if (threadIdx.x == 0) {
-            energy[t] = o.energy;
-            stat[t] = o.stat == 0 ? 0 : -1;
-            if (niter) niter[t] = o.niter;
-        }
-    }
-}
-
+// ------------------------------------------------------------------------------------ light kernels (the heavy ones: tu_*.cu)
 __global__ void __launch_bounds__(QX_NT) k_fragments(DevModel m, const double *xyz, double rcut, int nsys, int *frag, unsigned char *conn, int *stack) {
     const int nat = m.nat;
     for (int t = blockIdx.x; t < nsys; t += gridDim.x)
         md_fragments(m, xyz + (size_t)t * 3 * nat, rcut, conn + (size_t)blockIdx.x * nat * nat, frag + (size_t)t * nat, stack + (size_t)blockIdx.x * nat);
 }
 
-// one egrad + sanity gate for trajectory t; returns Epot (0 on failure, like the reference's checkqc)
-__device__ inline double md_egrad(const DevModel &m, Sm &s, double *my, const ScratchLayout &L, const MdConfig &cfg, double etemp,
-                                  double *grad_out, double *achrg_out, int *niter_out, double *qstart = nullptr) {
+// intenergy (reference src/md.f90:715-741): one thread per trajectory, atoms in the reference's order
+__global__ void k_intenergy(DevModel m, MdState st, int ntraj, double *fragT, double *e_int) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntraj) return;
     const int nat = m.nat;
-    EgradOut o;
-    egrad_cta(m, s, my, L, etemp * QC_KTOAU, o, qstart);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        bool ok = o.stat != -2 && md_checkqc(m, o.energy, s.grad, s.qat, cfg.mchrg);
-        s.red[48] = ok ? o.energy : 0.0;
+    const int *list = st.list + (size_t)t * nat;
+    const double *velo = st.velo + (size_t)t * 3 * nat;
+    double e[10];
+    int n[10];
+    for (int i = 0; i < 10; ++i) { e[i] = 0.0; n[i] = 0; }
+    for (int i = 0; i < nat; ++i) {
+        const int j = list[i] - 1;
+        if (j < 0 || j >= 10) continue;
+        const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(velo[3 * i], velo[3 * i]), __dmul_rn(velo[3 * i + 1], velo[3 * i + 1])), __dmul_rn(velo[3 * i + 2], velo[3 * i + 2]));
+        e[j] = __dadd_rn(e[j], __dmul_rn(__dmul_rn(0.5, m.mass[i]), v2));
+        n[j] += 1;
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) grad_out[i] = s.grad[i];
-    for (int i = threadIdx.x; i < nat; i += QX_NT) achrg_out[i] = s.qat[i];
-    *niter_out = o.niter;
-    return s.red[48];
-}
-
-// steps added after a fragmentation in the mean-free-path MD (reference src/md.f90:233-235)
-__device__ inline int mfp_add_steps(int nuc) { return nuc >= 40 ? (nuc / 10) * 1000 : (nuc > 10 ? (nuc / 10) * 500 : 0); }
-
-// scalar state of the mean-free-path mode of md() (reference src/md.f90:91-116, 209-255), one per trajectory in MdState::mfp_d / mfp_i
-struct MfpScalars {
-    double old_cm[3], new_velo, new_temp, summass, ekin, pad;
-    int cnt, count_average, check_fragmented, max_steps, save_natf[10], ops, pad2;
-};
-static_assert(sizeof(MfpScalars) == 8 * sizeof(double) + 16 * sizeof(int), "MfpScalars layout");
-enum { MFP_ZERO_BEFORE = 1, MFP_ACCUM = 2, MFP_ZERO_AFTER = 4, MFP_FINAL = 8 };
-
-__device__ inline void mfp_load(const MdState &st, int t, MfpScalars &q) {
-    double *d = (double *)&q;
-    int *i = (int *)(d + 8);
-    for (int k = 0; k < 8; ++k) d[k] = __ldcg(st.mfp_d + (size_t)t * 8 + k);
-    for (int k = 0; k < 16; ++k) i[k] = __ldcg(st.mfp_i + (size_t)t * 16 + k);
-}
-__device__ inline void mfp_store(const MdState &st, int t, const MfpScalars &q) {
-    const double *d = (const double *)&q;
-    const int *i = (const int *)(d + 8);
-    for (int k = 0; k < 8; ++k) st.mfp_d[(size_t)t * 8 + k] = d[k];
-    for (int k = 0; k < 16; ++k) st.mfp_i[(size_t)t * 16 + k] = i[k];
-}
-
-// md(): everything before the loop (reference src/md.f90:155-283)
-__global__ void __launch_bounds__(QX_NT, 2) k_md_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int *queue) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ int s_next;
-    Sm s;
-    double *my = scratch + (size_t)blockIdx.x * L.total;
-    carve(m, smem, s, my + L.matA);
-    const int nat = m.nat;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
-        __syncthreads();
-        const int t = s_next;
-        if (t >= ntraj) break;
-        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.xyz[i] = st.xyz[(size_t)t * 3 * nat + i];
-        __syncthreads();
-        const double eimp = st.eimp[t];
-        const double etemp = cfg.etemp_in < 0.0 ? md_setetemp(cfg, 1, eimp) : cfg.etemp_in;
-        int nit = 0;
-        double *qw = st.qwarm ? st.qwarm + (size_t)t * (2 * m.ndim + 1) : nullptr;
-        if (qw) {   // the first single point of a trajectory has nothing to start from: zero populations == the reference's cold start
-            for (int i = threadIdx.x; i < 2 * m.ndim + 1; i += QX_NT) qw[i] = 0.0;
-            __syncthreads();
-        }
-        const double epot = md_egrad(m, s, my, L, cfg, etemp, st.grad + (size_t)t * 3 * nat, st.achrg + (size_t)t * nat, &nit, qw);
-        if (threadIdx.x == 0) {
-            st.scc_total[t] = nit;
-            const double ekin = md_ekinet_seq(nat, st.velo + (size_t)t * 3 * nat, m.mass, 0.0, nullptr);
-            const double tadd = st.tadd[t];
-            st.ekin[t] = ekin; st.ekinstart[t] = ekin; st.epot[t] = epot; st.etemp[t] = etemp;
-            if (cfg.icoll > 0) {   // mean-free-path mode: kinetic energy without the motion of the centre of mass (src/md.f90:246-255, 283)
-                MfpScalars q{};
-                q.new_velo = st.mfp_d[(size_t)t * 8 + 3];
-                cid_center_of_mass(nat, m.mass, st.xyz + (size_t)t * 3 * nat, q.old_cm);
-                for (int i = 0; i < nat; ++i) q.summass = q.summass + m.mass[i];
-                const double E_kin = 0.5 * q.summass * ((q.new_velo * QC_MSTOAU) * (q.new_velo * QC_MSTOAU));
-                const double E_kin_diff = ekin - E_kin;
-                q.new_temp = (2 * E_kin_diff) / (3 * QC_KB * nat);
-                st.ekin[t] = E_kin_diff;
-                q.check_fragmented = 1; q.max_steps = cfg.nmax;
-                mfp_store(st, t, q);
-            }
-            st.Tav[t] = 0; st.Epav[t] = 0; st.Ekav[t] = 0; st.Edum[t] = 0; st.aTlast[t] = 0; st.dtime[t] = 0; st.ttime[t] = 0;
-            st.nstep[t] = 0; st.kdump[t] = 50; st.fconst[t] = 0; st.morestep[t] = 0; st.nfrag[t] = 1;
-            st.fragstate[t] = 0; st.mdok[t] = 0;
-            st.nadd[t] = (int)((tadd + cfg.tstep) / cfg.tstep - 1.0);
-            st.fadd[t] = cfg.tstep / (tadd + cfg.tstep);
-            st.status[t] = epot == 0.0 ? TRJ_FAILED : TRJ_RUNNING;
-        }
-        for (int i = threadIdx.x; i < nat; i += QX_NT) { st.avchrg[(size_t)t * nat + i] = 0.0; st.list[(size_t)t * nat + i] = 1; }
-        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) st.avxyz[(size_t)t * 3 * nat + i] = 0.0;
-        if (cfg.icoll > 0)
-            for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) { st.avxyz2[(size_t)t * 3 * nat + i] = 0.0; st.store[(size_t)t * 3 * nat + i] = 0.0; }
-    }
-}
-
-// up to `chunk` MD steps (reference src/md.f90:285-682) for every running trajectory
-// Work items are (sub-chunk r, trajectory t), r-major, so that the last partial wave of CTAs costs a few steps and
-// not a whole chunk.  progress[t] counts the finished sub-chunks of trajectory t in this launch: item (r, t) waits
-// until (r-1, t) -- possibly still running on another resident CTA -- is done.
-// MFP = true: the mean-free-path md() of a CID run (cfg.icoll >= 1; reference global method == 3): no IEE heating, kinetic energy
-// without the centre-of-mass motion, averaged fragment structures, tmax as the only regular exit (src/md.f90:246-255, 466-621, 672).
-template <bool MFP>
-__global__ void __launch_bounds__(QX_NT, 2) k_md_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int chunk,
-                                                    int nsub, int step_limit, int *queue, int *progress, unsigned long long *steps_done) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ int s_next, s_flag;
-    __shared__ MfpScalars s_q;
-    Sm s;
-    double *my = scratch + (size_t)blockIdx.x * L.total;
-    carve(m, smem, s, my + L.matA);
-    const int nat = m.nat;
-    const double fstoau = QC_FSTOAU, kB = QC_KB;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
-        __syncthreads();
-        const int item = s_next;
-        if (item >= ntraj * nsub) break;
-        const int sub = item / ntraj, t = item - sub * ntraj;
-        if (threadIdx.x == 0) {
-            while (atomicAdd(&progress[t], 0) < sub) __nanosleep(200);
-            __threadfence();
-        }
-        __syncthreads();
-        if (__ldcg(st.status + t) != TRJ_RUNNING) {
-            if (threadIdx.x == 0) { __threadfence(); atomicAdd(&progress[t], 1); }
-            continue;
-        }
-        // per-trajectory arrays live in shared memory for the duration of the work item (read with ld.cg: the previous
-        // sub-chunk of this trajectory may have run on another SM)
-        double *velo = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global, m.ntype) + 8, *grad = velo + 3 * nat, *avxyz = grad + 3 * nat, *achrg = avxyz + 3 * nat,
-               *avchrg = achrg + nat;
-        double *gxyz = st.xyz + (size_t)t * 3 * nat, *gvelo = st.velo + (size_t)t * 3 * nat, *ggrad = st.grad + (size_t)t * 3 * nat;
-        double *gachrg = st.achrg + (size_t)t * nat, *gavchrg = st.avchrg + (size_t)t * nat, *gavxyz = st.avxyz + (size_t)t * 3 * nat;
-        const double *velof = st.velof + (size_t)t * nat;
-        int *list = st.list + (size_t)t * nat;
-        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) { s.xyz[i] = __ldcg(gxyz + i); velo[i] = __ldcg(gvelo + i); grad[i] = __ldcg(ggrad + i); avxyz[i] = __ldcg(gavxyz + i); }
-        for (int i = threadIdx.x; i < nat; i += QX_NT) { achrg[i] = __ldcg(gachrg + i); avchrg[i] = __ldcg(gavchrg + i); }
-        int scc_add = 0;
-        // scalar state, kept redundantly in every thread
-        int nstep = __ldcg(st.nstep + t), kdump = __ldcg(st.kdump + t), fconst = __ldcg(st.fconst + t), morestep = __ldcg(st.morestep + t), nfrag = __ldcg(st.nfrag + t);
-        int fragstate = 0, mdok = 0, status = TRJ_RUNNING;
-        const int nadd = __ldcg(st.nadd + t);
-        const double fadd = __ldcg(st.fadd + t), eimp = __ldcg(st.eimp + t), ekinstart = __ldcg(st.ekinstart + t);
-        double epot = __ldcg(st.epot + t), ekin = __ldcg(st.ekin + t), etemp = __ldcg(st.etemp + t), Tav = __ldcg(st.Tav + t), Epav = __ldcg(st.Epav + t),
-               Ekav = __ldcg(st.Ekav + t), Edum = __ldcg(st.Edum + t);
-        double aTlast = __ldcg(st.aTlast + t), dtime = __ldcg(st.dtime + t), ttime = __ldcg(st.ttime + t);
-        double *gavxyz2 = nullptr, *gstore = nullptr;
-        if (MFP) {
-            gavxyz2 = st.avxyz2 + (size_t)t * 3 * nat; gstore = st.store + (size_t)t * 3 * nat;
-            if (threadIdx.x == 0) mfp_load(st, t, s_q);
-        }
-        __syncthreads();
-        int done = 0;
-        for (int it = 0; it < chunk && status == TRJ_RUNNING; ++it) {
-            if (step_limit > 0 && nstep >= step_limit) break;  // pause here: the host asked for a bounded number of steps
-            nstep += 1;
-            const double T = ekin / (0.5 * 3 * nat * kB);
-            Tav += T; Epav += epot; Ekav += ekin;
-            double Eav;
-            if (nstep > nadd) { Edum += epot + ekin; Eav = Edum / (double)(float)(nstep - nadd); }
-            else Eav = epot + ekin;
-            const double Eerror = Eav - epot - ekin;
-            const bool err1 = epot == 0.0, err2 = fabs(Eerror) > (MFP ? (double)0.2f : (double)0.1f);
-            if (err1 || (err2 && cfg.exit_rules)) {
-                mdok = ((nfrag > 1 && nfrag <= 4) || cfg.isec > 1) ? 1 : 0;
-                status = TRJ_FINISHED;
-                break;
-            }
-            if (kdump > 50 - 1) {
-                kdump = 0;
-                aTlast = 0.0;
-                for (int i = threadIdx.x; i < nat; i += QX_NT) avchrg[i] = 0.0;
-                for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) avxyz[i] = 0.0;
-            }
-            for (int i = threadIdx.x; i < nat; i += QX_NT) avchrg[i] += achrg[i];
-            for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) avxyz[i] += s.xyz[i];
-            aTlast += MFP ? s_q.new_temp : T;
-            // leapfrog (reference md.f90:749-773); kinetic-energy terms summed in the reference order
-            for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) {
-                const double mass = m.mass[i / 3];
-                const double vold = velo[i];
-                const double vnew = __dsub_rn(vold, __ddiv_rn(__dmul_rn(cfg.tstep, grad[i]), mass));
-                const double vavg = __dmul_rn(0.5, __dadd_rn(vold, vnew));
-                const double x = __dadd_rn(s.xyz[i], __dmul_rn(cfg.tstep, vnew));
-                velo[i] = vnew;
-                s.xyz[i] = x;
-                s.vdp[i] = __dmul_rn(0.5, __dmul_rn(__dmul_rn(mass, vavg), vavg));
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double ke = 0.0;
-                for (int i = 0; i < 3 * nat; ++i) ke = __dadd_rn(ke, s.vdp[i]);
-                s.red[49] = ke;
-            }
-            __syncthreads();
-            ekin = s.red[49];
-            ttime += cfg.tstep / fstoau;
-            {
-                int nit = 0;
-                epot = md_egrad(m, s, my, L, cfg, etemp, grad, achrg, &nit, st.qwarm ? st.qwarm + (size_t)t * (2 * m.ndim + 1) : nullptr);
-                scc_add += nit;
-            }
-            done += 1;
-            kdump += 1;
-            if (nfrag == 1) morestep = 0;
-            if (nfrag > 1 && dtime < 1e-6) dtime = ttime / 1000.0;
-            if (!MFP) {
-                // IEE heating while the ion is intact
-                if (nstep <= nadd && nfrag == 1) {
-                    if (!md_impactscale(m, velo, velof, eimp, fadd * nstep, ekinstart, &s_flag)) { status = TRJ_FAILED; break; }
-                }
-                if (cfg.etemp_in < 0.0) {
-                    const double dum = eimp - eimp * (double)(float)nstep / (double)(float)nadd;
-                    etemp = md_setetemp(cfg, nfrag, dum);
-                }
-            }
-            md_fragments(m, s.xyz, 3.0, (unsigned char *)(my + L.taskout), list, (int *)(my + L.taskout) + (nat * nat + 3) / 4 + 4);
-            if (threadIdx.x == 0) s_flag = md_nfrag(m, list);
-            __syncthreads();
-            nfrag = s_flag;
-            if (MFP) {
-                if (nfrag > 6) { status = TRJ_FINISHED; break; }
-                if (threadIdx.x == 0) {
-                    MfpScalars &q = s_q;
-                    // kinetic energy without the centre-of-mass motion (src/md.f90:466-493)
-                    double cm[3];
-                    cid_center_of_mass(nat, m.mass, s.xyz, cm);
-                    const double d0 = cm[0] - q.old_cm[0], d1 = cm[1] - q.old_cm[1], d2 = cm[2] - q.old_cm[2];
-                    const double cm_out = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-                    q.new_velo = (cm_out / cfg.tstep) / QC_MSTOAU;
-                    q.old_cm[0] = cm[0]; q.old_cm[1] = cm[1]; q.old_cm[2] = cm[2];
-                    const double E_kin = 0.5 * q.summass * ((q.new_velo * QC_MSTOAU) * (q.new_velo * QC_MSTOAU));
-                    const double E_kin_diff = ekin - E_kin;
-                    q.new_temp = (2.0 * E_kin_diff) / (3.0 * QC_KB * nat);
-                    q.ekin = E_kin_diff;
-                    // averaged fragment structures (src/md.f90:496-621)
-                    int ops = 0;
-                    if (nfrag > q.check_fragmented) { q.count_average = 1; q.check_fragmented = nfrag; q.max_steps = nstep + mfp_add_steps(nat); }
-                    if (nfrag < q.check_fragmented && q.count_average) { q.cnt = 0; ops |= MFP_ZERO_BEFORE; q.count_average = 0; q.check_fragmented = 1; }
-                    q.pad2 = 0;
-                    if (q.count_average) {
-                        q.cnt += 1;
-                        ops |= MFP_ACCUM;
-                        q.pad2 = q.cnt;   // divisor of this step's store_avxyz
-                        int natf[10];
-                        for (int i = 0; i < 10; ++i) natf[i] = 0;
-                        for (int i = 0; i < nat; ++i) if (list[i] >= 1 && list[i] <= nfrag && list[i] <= 10) natf[list[i] - 1] += 1;
-                        for (int i = 0; i < nfrag && i < 10; ++i) {
-                            if (q.cnt == 1) q.save_natf[i] = natf[i];
-                            if (natf[i] != q.save_natf[i]) { q.cnt = 0; ops |= MFP_ZERO_AFTER; break; }
-                        }
-                        if (q.cnt == 50) { ops |= MFP_FINAL; q.cnt = 0; q.count_average = 0; }
-                    }
-                    q.ops = ops;
-                }
-                __syncthreads();
-                ekin = s_q.ekin;
-                const int ops = s_q.ops;
-                if (ops) {
-                    const double cnt = (double)s_q.pad2;
-                    for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) {
-                        double a2 = __ldcg(gavxyz2 + i), sv = __ldcg(gstore + i);
-                        if (ops & MFP_ZERO_BEFORE) { a2 = 0.0; sv = 0.0; }
-                        if (ops & MFP_ACCUM) { a2 = a2 + s.xyz[i]; sv = a2 / cnt; }
-                        if (ops & MFP_ZERO_AFTER) { a2 = 0.0; sv = 0.0; }
-                        if (ops & MFP_FINAL) a2 = 0.0;
-                        gavxyz2[i] = a2; gstore[i] = sv;
-                    }
-                }
-                const int max_steps = s_q.max_steps;
-                __syncthreads();   // thread 0 rewrites s_q in the next step
-                if (nstep >= max_steps) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
-                continue;
-            }
-            if (cfg.exit_rules) {
-                if (nfrag > 6) { status = TRJ_FINISHED; break; }
-                if (nfrag > cfg.nfragexit) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
-                fconst = nfrag >= 2 ? fconst + 1 : 0;
-                if (fconst > 1000) { fragstate = 2; mdok = 1; status = TRJ_FINISHED; break; }
-                if (nfrag >= cfg.nfragexit) {
-                    morestep += 1;
-                    if (morestep > 250) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
-                }
-            }
-            if (nstep >= cfg.nmax) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) { gxyz[i] = s.xyz[i]; gvelo[i] = velo[i]; ggrad[i] = grad[i]; gavxyz[i] = avxyz[i]; }
-        for (int i = threadIdx.x; i < nat; i += QX_NT) { gachrg[i] = achrg[i]; gavchrg[i] = avchrg[i]; }
-        if (threadIdx.x == 0) {
-            st.scc_total[t] = __ldcg(st.scc_total + t) + scc_add;
-            st.nstep[t] = nstep; st.kdump[t] = kdump; st.fconst[t] = fconst; st.morestep[t] = morestep; st.nfrag[t] = nfrag;
-            st.epot[t] = epot; st.ekin[t] = ekin; st.etemp[t] = etemp; st.Tav[t] = Tav; st.Epav[t] = Epav; st.Ekav[t] = Ekav; st.Edum[t] = Edum;
-            st.aTlast[t] = aTlast; st.dtime[t] = dtime; st.ttime[t] = ttime;
-            if (status != TRJ_RUNNING) { st.status[t] = status; st.fragstate[t] = fragstate; st.mdok[t] = mdok; }
-            if (MFP) mfp_store(st, t, s_q);
-            atomicAdd(steps_done, (unsigned long long)done);
-        }
-        __syncthreads();   // every thread's global writes of this sub-chunk are issued ...
-        if (threadIdx.x == 0) { __threadfence(); atomicAdd(&progress[t], 1); }   // ... and published before the hand-over
-    }
-}
-
-// ------------------------------------------------------------------------------------ CID (reference src/cid.f90)
-// set-up of one collision + the two single points before the loop (iniqm's is only checked, so one evaluation serves both)
-__global__ void __launch_bounds__(QX_NT, 2) k_cid_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, CidConfig cc, CidState st, int ntraj,
-                                                    int nuc, int icoll, int *queue) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ int s_next;
-    Sm s;
-    double *my = scratch + (size_t)blockIdx.x * L.total;
-    carve(m, smem, s, my + L.matA);
-    const int nuc0 = m.nat;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
-        __syncthreads();
-        const int t = s_next;
-        if (t >= ntraj) break;
-        CidScalars *sc = st.sc + t;
-        double *xyz0 = st.xyz0 + (size_t)t * 3 * nuc0, *velo0 = st.velo0 + (size_t)t * 3 * nuc0;
-        if (threadIdx.x == 0) {
-            double tinit, summass, old_cm[3];
-            cid_setup_thread0(m, cc, nuc, icoll, st.xyz + (size_t)t * 3 * nuc, st.velo + (size_t)t * 3 * nuc, st.rnd + (size_t)t * 9,
-                              st.velo_cm_in ? st.velo_cm_in[t] : 0.0, st.direc + (size_t)t * 3, xyz0, velo0, old_cm, &tinit, &summass);
-            CidScalars z{};
-            z.total_steps = cc.ntot; z.check_fragmented = 1; z.nfrag = 1; z.collided = sc->collided;
-            z.Tinit = tinit; z.summass = summass;
-            for (int k = 0; k < 3; ++k) z.old_cm[k] = old_cm[k];
-            *sc = z;
-            __threadfence_block();
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < 3 * nuc0; i += QX_NT) s.xyz[i] = xyz0[i];
-        for (int i = threadIdx.x; i < 3 * nuc; i += QX_NT) { st.avxyz[(size_t)t * 3 * nuc + i] = 0.0; st.avxyz2[(size_t)t * 3 * nuc + i] = 0.0; st.store[(size_t)t * 3 * nuc + i] = 0.0; }
-        for (int i = threadIdx.x; i < nuc; i += QX_NT) st.list[(size_t)t * nuc + i] = 1;
-        __syncthreads();
-        int nit = 0;
-        const double epot = md_egrad(m, s, my, L, cfg, cc.etemp, st.grad0 + (size_t)t * 3 * nuc0, st.achrg0 + (size_t)t * nuc0, &nit);
-        if (threadIdx.x == 0) {
-            sc->scc_total = nit; sc->epot = epot;
-            if (epot == 0.0) { sc->stopcid = 1; sc->status = TRJ_FAILED; }
-            else {
-                sc->status = TRJ_RUNNING;
-                // distance gas atom -- centre of mass of the ion as it was handed in (reference src/cid.f90:733-737)
-                double cm[3];
-                cid_center_of_mass(nuc, m.mass, st.xyz + (size_t)t * 3 * nuc, cm);
-                const int ig = nuc0 - 1;
-                const double d0 = xyz0[3 * ig] - cm[0], d1 = xyz0[3 * ig + 1] - cm[1], d2 = xyz0[3 * ig + 2] - cm[2];
-                sc->lowestCOM = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-            }
-        }
-    }
-}
-
-// up to `chunk` steps of the collision loop (reference src/cid.f90:739-1052) for every running trajectory
-__global__ void __launch_bounds__(QX_NT, 2) k_cid_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, CidConfig cc, CidState st, int ntraj,
-                                                     int nuc, int chunk, int *queue) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ int s_next, s_ops, s_cnt, s_stop;
-    __shared__ CidScalars sc;
-    Sm s;
-    double *my = scratch + (size_t)blockIdx.x * L.total;
-    carve(m, smem, s, my + L.matA);
-    const int nuc0 = m.nat;
-    const double autofs = 1.0 / QC_FSTOAU;
-    int add_steps = 0;
-    if (nuc > 10) add_steps = (nuc / 10) * 500;
-    if (nuc >= 40) add_steps = (nuc / 10) * 1000;
-    enum { OP_RESET_AV = 1, OP_ZERO_BEFORE = 2, OP_ACCUM = 4, OP_ZERO_AFTER = 8, OP_FINAL = 16 };
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
-        __syncthreads();
-        const int t = s_next;
-        if (t >= ntraj) break;
-        if (st.sc[t].status != TRJ_RUNNING) continue;
-        double *velo0 = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global, m.ntype) + 8, *grad0 = velo0 + 3 * nuc0, *achrg0 = grad0 + 3 * nuc0;
-        double *gxyz0 = st.xyz0 + (size_t)t * 3 * nuc0, *gvelo0 = st.velo0 + (size_t)t * 3 * nuc0, *ggrad0 = st.grad0 + (size_t)t * 3 * nuc0,
-               *gachrg0 = st.achrg0 + (size_t)t * nuc0;
-        double *avxyz = st.avxyz + (size_t)t * 3 * nuc, *avxyz2 = st.avxyz2 + (size_t)t * 3 * nuc, *store = st.store + (size_t)t * 3 * nuc;
-        int *list = st.list + (size_t)t * nuc;
-        for (int i = threadIdx.x; i < 3 * nuc0; i += QX_NT) { s.xyz[i] = gxyz0[i]; velo0[i] = gvelo0[i]; grad0[i] = ggrad0[i]; }
-        for (int i = threadIdx.x; i < nuc0; i += QX_NT) achrg0[i] = gachrg0[i];
-        if (threadIdx.x == 0) { sc = st.sc[t]; s_stop = 0; }
-        __syncthreads();
-        for (int it = 0; it < chunk; ++it) {
-            if (threadIdx.x == 0) {
-                sc.nstep += 1;
-                s_ops = 0;
-                if (sc.xyzavg_dump == 50) { sc.xyzavg_dump = 0; s_ops |= OP_RESET_AV; }
-                sc.ttime = sc.ttime + cc.tstep * autofs;
-                sc.distance_dump += 1; sc.xyzavg_dump += 1;
-            }
-            __syncthreads();
-            if (s_ops & OP_RESET_AV) for (int i = threadIdx.x; i < 3 * nuc; i += QX_NT) avxyz[i] = 0.0;
-            for (int i = threadIdx.x; i < 3 * nuc0; i += QX_NT) {   // leapfrog on ion + gas atom
-                const double mass = m.mass[i / 3];
-                const double vnew = __dsub_rn(velo0[i], __ddiv_rn(__dmul_rn(cc.tstep, grad0[i]), mass));
-                velo0[i] = vnew;
-                s.xyz[i] = __dadd_rn(s.xyz[i], __dmul_rn(cc.tstep, vnew));
-            }
-            __syncthreads();
-            int nit = 0;
-            const double epot = md_egrad(m, s, my, L, cfg, cc.etemp, grad0, achrg0, &nit);
-            if (threadIdx.x == 0) { sc.scc_total += nit; sc.epot = epot; }
-            if (epot == 0.0) {
-                if (threadIdx.x == 0) { sc.stopcid = 1; sc.status = TRJ_FINISHED; }
-                break;
-            }
-            md_fragments(m, s.xyz, 3.0, (unsigned char *)(my + L.taskout), list, (int *)(my + L.taskout) + (nuc * nuc + 3) / 4 + 4, nuc);
-            if (threadIdx.x == 0) {
-                double cm[3], T;
-                cid_center_of_mass(nuc, m.mass, s.xyz, cm);
-                const double dc0 = cm[0] - sc.old_cm[0], dc1 = cm[1] - sc.old_cm[1], dc2 = cm[2] - sc.old_cm[2];
-                const double cm_out = sqrt(dc0 * dc0 + dc1 * dc1 + dc2 * dc2);
-                sc.old_cm[0] = cm[0]; sc.old_cm[1] = cm[1]; sc.old_cm[2] = cm[2];
-                sc.new_velo = sc.nstep != 1 ? (cm_out / cc.tstep) / QC_MSTOAU : 0.0;
-                const double Ekin = cid_ekinet(nuc, velo0, m.mass, &T);
-                const double E_velo = 0.5 * sc.summass * ((sc.new_velo * QC_MSTOAU) * (sc.new_velo * QC_MSTOAU));
-                double new_temp = (2 * (Ekin - E_velo)) / (3 * QC_KB * nuc);
-                if (sc.nstep == 1) new_temp = sc.Tinit;
-                sc.Tav = sc.Tav + new_temp; sc.m = sc.m + 1;
-                const double avgT = sc.Tav / sc.m;
-                const int nfrag = md_nfrag(m, list, nuc);
-                sc.nfrag = nfrag;
-                if (nfrag > sc.check_fragmented) { sc.count_average = 1; sc.check_fragmented = nfrag; }
-                if (nfrag < sc.check_fragmented && sc.count_average) { sc.cnt = 0; s_ops |= OP_ZERO_BEFORE; sc.count_average = 0; sc.check_fragmented = 1; }
-                if (sc.count_average) {
-                    sc.cnt += 1;
-                    s_ops |= OP_ACCUM;
-                    s_cnt = sc.cnt;
-                    int natf[10];
-                    for (int i = 0; i < 10; ++i) natf[i] = 0;
-                    for (int i = 0; i < nuc; ++i) if (list[i] >= 1 && list[i] <= nfrag && list[i] <= 10) natf[list[i] - 1] += 1;
-                    for (int i = 0; i < nfrag && i < 10; ++i) {
-                        if (sc.cnt == 1) sc.save_natf[i] = natf[i];
-                        if (natf[i] != sc.save_natf[i]) { sc.cnt = 0; s_ops |= OP_ZERO_AFTER; break; }
-                    }
-                    if (sc.cnt == 50) { s_ops |= OP_FINAL; sc.cnt = 0; sc.count_average = 0; }
-                }
-                sc.aTlast = avgT;
-                if (sc.distance_dump == 10) {
-                    sc.distance_dump = 0;
-                    const int ig = nuc0 - 1;
-                    const double d0 = s.xyz[3 * ig] - cm[0], d1 = s.xyz[3 * ig + 1] - cm[1], d2 = s.xyz[3 * ig + 2] - cm[2];
-                    const double new_dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-                    if (new_dist < sc.lowestCOM) sc.lowestCOM = new_dist;
-                    if (sc.lowestCOM < new_dist) sc.step_counter += 1; else sc.step_counter = 0;
-                    if (sc.step_counter == 5) {
-                        sc.total_steps = sc.nstep + (int)llround(800.0 * (2 * cc.tstep * autofs));
-                        sc.collided = 1; sc.Tav = 0; sc.m = 0;
-                    }
-                }
-                if (nfrag > 1 && sc.collided && !sc.fragmented) { sc.total_steps = sc.nstep + add_steps; sc.fragmented = 1; }
-                if (sc.nstep >= sc.total_steps) { sc.stopcid = 0; sc.status = TRJ_FINISHED; s_stop = 1; }
-            }
-            __syncthreads();
-            const int ops = s_ops, stop = s_stop;
-            const double cnt = (double)s_cnt;
-            for (int i = threadIdx.x; i < 3 * nuc; i += QX_NT) {
-                avxyz[i] += s.xyz[i];
-                if (ops & OP_ZERO_BEFORE) { avxyz2[i] = 0.0; store[i] = 0.0; }
-                if (ops & OP_ACCUM) { const double v = avxyz2[i] + s.xyz[i]; avxyz2[i] = v; store[i] = v / cnt; }
-                if (ops & OP_ZERO_AFTER) { avxyz2[i] = 0.0; store[i] = 0.0; }
-                if (ops & OP_FINAL) avxyz2[i] = 0.0;
-            }
-            __syncthreads();   // thread 0 rewrites the flags at the top of the next step
-            if (stop) break;
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < 3 * nuc0; i += QX_NT) { gxyz0[i] = s.xyz[i]; gvelo0[i] = velo0[i]; ggrad0[i] = grad0[i]; }
-        for (int i = threadIdx.x; i < nuc0; i += QX_NT) gachrg0[i] = achrg0[i];
-        if (threadIdx.x == 0) st.sc[t] = sc;
+    for (int i = 0; i < 10; ++i) {
+        e_int[(size_t)t * 10 + i] = e[i];
+        fragT[(size_t)t * 10 + i] = n[i] > 0 ? e[i] / (0.5 * 3 * n[i] * QC_KB) : 0.0;
     }
 }
 
@@ -570,16 +83,10 @@ struct Context {
     double *d_scratch = nullptr;
     int *d_queue = nullptr;
     std::vector<int32_t> key;
+    const KernelSet *ks = nullptr;   // kernels compiled for the CTA width this composition runs with
 };
 
-// dynamic shared memory limit of a kernel = what the device allows next to the kernel's static shared memory
-template <class K>
-static cudaError_t allow_max_dynamic_smem(K kernel, const cudaDeviceProp &prop) {
-    cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, kernel);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - (int)a.sharedSizeBytes);
-}
+static const KernelSet KS_NT288 = QX_KERNEL_SET(nt288, 288);
 
 static int context_init(Context &c, int nat, const int32_t *num, const double *mass, int charge, int multiplicity, int device, int nwork) {
     CUDA_OK(cudaSetDevice(device));
@@ -610,12 +117,12 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
     }
     c.L = make_layout(c.hm);
     // the device maximum, not this composition's size: host threads set up different compositions concurrently
-    CUDA_OK(allow_max_dynamic_smem(k_egrad_batch, prop));
-    CUDA_OK(allow_max_dynamic_smem(k_md_init, prop));
-    CUDA_OK(allow_max_dynamic_smem(k_md_chunk<false>, prop));
-    CUDA_OK(allow_max_dynamic_smem(k_md_chunk<true>, prop));
+    c.ks = &KS_NT288;
+    CUDA_OK(c.ks->prepare_egrad(prop));
+    CUDA_OK(c.ks->prepare_md(prop));
+    CUDA_OK(c.ks->prepare_mfp(prop));
     int per_sm = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_chunk<false>, QX_NT, c.smem));
+    CUDA_OK(c.ks->md_occupancy(&per_sm, c.smem));
     if (per_sm < 1) per_sm = 1;
     // global-slab mode: the Jacobi matrix of every resident CTA has to stay in L2 (two resident CTAs per SM thrashed it for C32H66:
     // 608 instead of 778 single points/s and 0.45 GB of DRAM write-back per single point)
@@ -676,8 +183,7 @@ static int egrad_batch_impl(int nsys, int nat, const int32_t *num, const double 
     const size_t nspec = (size_t)nsys * (2 * ctx.hm.nao + (size_t)ctx.hm.nao * nat + 1);
     if (spec) CUDA_OK(cudaMalloc(&d_spec, nspec * sizeof(double)));
     if (nao_out) *nao_out = ctx.hm.nao;
-    k_egrad_batch<<<grid, QX_NT, ctx.smem>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, d_xyz, etemp * QC_KTOAU, nsys, ctx.d_queue, d_e, d_g, d_q, d_stat, d_nit, d_spec);
-    CUDA_OK(cudaGetLastError());
+    CUDA_OK(ctx.ks->egrad_batch(grid, ctx.smem, nullptr, ctx.hm.dev, ctx.L, ctx.d_scratch, d_xyz, etemp * QC_KTOAU, nsys, ctx.d_queue, d_e, d_g, d_q, d_stat, d_nit, d_spec));
     CUDA_OK(cudaDeviceSynchronize());
     if (spec) {
         spec->resize(nspec);
@@ -949,8 +455,7 @@ extern "C" int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_step
     int base_step = 0;
     if (!h->initialised) {
         CUDA_OK(cudaMemsetAsync(c.d_queue, 0, sizeof(int), h->stream));
-        k_md_init<<<grid, QX_NT, c.smem, h->stream>>>(c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, c.d_queue);
-        CUDA_OK(cudaGetLastError());
+        CUDA_OK(c.ks->md_init(grid, c.smem, h->stream, c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, c.d_queue));
         h->launches += 1;
         h->initialised = true;
     } else {
@@ -972,13 +477,8 @@ extern "C" int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_step
         CUDA_OK(cudaMemsetAsync(c.d_queue, 0, sizeof(int), h->stream));
         CUDA_OK(cudaMemsetAsync(h->d_progress, 0, h->ntraj * sizeof(int), h->stream));
         // the last sub-chunk may be shorter: the kernel bounds every sub-chunk by the launch's step limit as well
-        if (h->cfg.icoll > 0)
-            k_md_chunk<true><<<grid, QX_NT, c.smem, h->stream>>>(c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, sub_steps, nsub,
-                                                                 max_steps > 0 ? limit : 0, c.d_queue, h->d_progress, h->d_steps);
-        else
-            k_md_chunk<false><<<grid, QX_NT, c.smem, h->stream>>>(c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, sub_steps, nsub,
-                                                                  max_steps > 0 ? limit : 0, c.d_queue, h->d_progress, h->d_steps);
-        CUDA_OK(cudaGetLastError());
+        CUDA_OK((h->cfg.icoll > 0 ? c.ks->mfp_chunk : c.ks->md_chunk)(grid, c.smem, h->stream, c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, sub_steps,
+                                                                      nsub, max_steps > 0 ? limit : 0, c.d_queue, h->d_progress, h->d_steps));
         h->launches += 1;
         // poll for completion every few chunks (cheap: ntraj ints)
         if ((done / chunk) % 4 == 3 || done + chunk >= total) {
@@ -1117,6 +617,22 @@ extern "C" int qcxms_b200_ensemble_last_timing(qcxms_b200_ensemble_t *h, double 
     return 0;
 }
 
+extern "C" int qcxms_b200_ensemble_intenergy(qcxms_b200_ensemble_t *h, double *fragT, double *e_int) {
+    if (!h || !fragT || !e_int) return fail(QCXMS_B200_ERR_ARG, "null argument");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    const size_t n = (size_t)h->ntraj * 10;
+    double *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, 2 * n * sizeof(double)));
+    k_intenergy<<<(h->ntraj + 127) / 128, 128, 0, h->stream>>>(h->ctx.hm.dev, h->st, h->ntraj, d, d + n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(fragT, d, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(e_int, d + n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(QCXMS_B200_ERR_CUDA, std::string("intenergy: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int qcxms_b200_ensemble_histogram(qcxms_b200_ensemble_t *h, int nbins, double *bins_host, void **bins_device) {
     if (!h || nbins < 1) return fail(QCXMS_B200_ERR_ARG, "bad argument");
     CUDA_OK(cudaSetDevice(h->ctx.device));
@@ -1159,8 +675,7 @@ extern "C" int qcxms_b200_cid_batch(const qcxms_b200_cid_config_t *cfg, int ntra
     {   // the device maximum, not this composition's size: host threads set up different compositions concurrently
         cudaDeviceProp prop;
         CUDA_OK(cudaGetDeviceProperties(&prop, device));
-        CUDA_OK(allow_max_dynamic_smem(k_cid_init, prop));
-        CUDA_OK(allow_max_dynamic_smem(k_cid_chunk, prop));
+        CUDA_OK(ctx.ks->prepare_cid(prop));
     }
     // own (blocking) stream: collisions of different compositions are driven from different host threads and overlap on the GPU
     cudaStream_t strm = nullptr;
@@ -1207,13 +722,11 @@ extern "C" int qcxms_b200_cid_batch(const qcxms_b200_cid_config_t *cfg, int ntra
     CID_OK(cpy(st.sc, hsc.data(), (size_t)ntraj * sizeof(CidScalars), cudaMemcpyHostToDevice));
     const int grid = ctx.ncta < ntraj ? ctx.ncta : ntraj;
     CID_OK(cudaMemsetAsync(ctx.d_queue, 0, sizeof(int), strm));
-    k_cid_init<<<grid, QX_NT, ctx.smem, strm>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, mc, cc, st, ntraj, nuc, icoll, ctx.d_queue);
-    CID_OK(cudaGetLastError());
+    CID_OK(ctx.ks->cid_init(grid, ctx.smem, strm, ctx.hm.dev, ctx.L, ctx.d_scratch, mc, cc, st, ntraj, nuc, icoll, ctx.d_queue));
     const int chunk = 32;
     for (int done = 0; done < cc.ntot + chunk; done += chunk) {
         CID_OK(cudaMemsetAsync(ctx.d_queue, 0, sizeof(int), strm));
-        k_cid_chunk<<<grid, QX_NT, ctx.smem, strm>>>(ctx.hm.dev, ctx.L, ctx.d_scratch, mc, cc, st, ntraj, nuc, chunk, ctx.d_queue);
-        CID_OK(cudaGetLastError());
+        CID_OK(ctx.ks->cid_chunk(grid, ctx.smem, strm, ctx.hm.dev, ctx.L, ctx.d_scratch, mc, cc, st, ntraj, nuc, chunk, ctx.d_queue));
         if ((done / chunk) % 4 == 3 || done + chunk >= cc.ntot) {
             CID_OK(cpy(hsc.data(), st.sc, (size_t)ntraj * sizeof(CidScalars), cudaMemcpyDeviceToHost));
             bool any = false;
@@ -1267,27 +780,16 @@ extern "C" const char *qcxms_b200_version(void) { return "qcxms_b200 0.1 (sm_100
 
 // profiling builds only (-DQX_PROFILE_PHASES): read and reset the per-phase cycle counters; returns 0 counters otherwise
 extern "C" int qcxms_b200_debug_phase_cycles(double *out16) {
+    unsigned long long ph[16] = {0}, sub[16] = {0}, sh[64] = {0};
+    CUDA_OK(KS_NT288.egrad_cycles(ph, sub, sh));
+    CUDA_OK(KS_NT288.md_cycles(ph, sub, sh));
+    for (int i = 0; i < 16; ++i) out16[i] = (double)ph[i];
 #ifdef QX_PROFILE_PHASES
-    unsigned long long h[16], z[16] = {0};
-    CUDA_OK(cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof(h)));
-    CUDA_OK(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)));
-    for (int i = 0; i < 16; ++i) out16[i] = (double)h[i];
-    {
-        unsigned long long sub[16], sz[16] = {0};
-        CUDA_OK(cudaMemcpyFromSymbol(sub, g_sub_cycles, sizeof(sub)));
-        CUDA_OK(cudaMemcpyToSymbol(g_sub_cycles, sz, sizeof(sz)));
-        fprintf(stderr, "sub-phase cycles (thread 0):");
-        for (int i = 0; i < 16; ++i) if (sub[i]) fprintf(stderr, " %d:%.0f", i, (double)sub[i]);
-        fprintf(stderr, "\n");
-    }
-    unsigned long long sh[64], sz[64] = {0};
-    CUDA_OK(cudaMemcpyFromSymbol(sh, g_sweep_hist, sizeof(sh)));
-    CUDA_OK(cudaMemcpyToSymbol(g_sweep_hist, sz, sizeof(sz)));
-    fprintf(stderr, "sweeps per SCC cycle:");
+    fprintf(stderr, "sub-phase cycles (thread 0):");
+    for (int i = 0; i < 16; ++i) if (sub[i]) fprintf(stderr, " %d:%.0f", i, (double)sub[i]);
+    fprintf(stderr, "\nsweeps per SCC cycle:");
     for (int i = 0; i < 32; ++i) if (sh[32 + i]) fprintf(stderr, " %d:%.2f", i + 1, (double)sh[i] / (double)sh[32 + i]);
     fprintf(stderr, "\n");
-#else
-    for (int i = 0; i < 16; ++i) out16[i] = 0.0;
 #endif
     return 0;
 }

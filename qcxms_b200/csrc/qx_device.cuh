@@ -25,7 +25,7 @@ struct SphTerm {
     double c[3];
 };
 // real solid harmonics, index l*l + (m+l), order m = -l..l (p: y,z,x)
-__constant__ SphTerm c_sph[9] = {
+static __constant__ SphTerm c_sph[9] = {
     {1, {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, {1.0, 0, 0}},
     {1, {{0, 1, 0}, {0, 0, 0}, {0, 0, 0}}, {1.0, 0, 0}},
     {1, {{0, 0, 1}, {0, 0, 0}, {0, 0, 0}}, {1.0, 0, 0}},
@@ -37,9 +37,9 @@ __constant__ SphTerm c_sph[9] = {
     {2, {{2, 0, 0}, {0, 2, 0}, {0, 0, 0}}, {0.5 * QX_SQRT3, -0.5 * QX_SQRT3, 0}}};
 
 // quadrupole component index pairs, order xx,xy,yy,xz,yz,zz
-__constant__ int c_qa[6] = {0, 0, 1, 0, 1, 2};
-__constant__ int c_qb[6] = {0, 1, 1, 2, 2, 2};
-__constant__ double c_qscale[6] = {1.0, 2.0, 1.0, 2.0, 2.0, 1.0};
+static __constant__ int c_qa[6] = {0, 0, 1, 0, 1, 2};
+static __constant__ int c_qb[6] = {0, 1, 1, 2, 2, 2};
+static __constant__ double c_qscale[6] = {1.0, 2.0, 1.0, 2.0, 2.0, 1.0};
 
 // A pointer that is KNOWN to point into shared memory.  The phase functions are __noinline__ and take the CTA's working set
 // through `Sm &`, so plain `double *` members reach them as generic pointers and every access becomes a generic LD/ST (ncu:
@@ -126,7 +126,7 @@ __device__ inline double block_max(double v, double *red) {
 // ------------------------------------------------------------------------------------
 // coordination numbers (GFN double-exponential; D4 erf with EN weighting) + pair derivative
 // tables dcnp[i*nat+j] = (1/r) d f(r_ij)/dr, so that d cn_i/d R_i = sum_j dcnp_ij (R_i - R_j).
-__device__ __noinline__ void phase_cn(const DevModel &m, Sm &s, double *dcnp, double *dcnp4) {
+static __device__ __noinline__ void phase_cn(const DevModel &m, Sm &s, double *dcnp, double *dcnp4) {
     const int nat = m.nat;
     for (int i = threadIdx.x; i < nat; i += QX_NT) {
         double cn = 0.0, cn4 = 0.0;
@@ -163,7 +163,7 @@ __device__ __noinline__ void phase_cn(const DevModel &m, Sm &s, double *dcnp, do
 }
 
 // classical repulsion: returns the CTA-wide energy; initialises s.grad
-__device__ __noinline__ double phase_repulsion(const DevModel &m, Sm &s) {
+static __device__ __noinline__ double phase_repulsion(const DevModel &m, Sm &s) {
     const int nat = m.nat;
     double e = 0.0;
     for (int i = threadIdx.x; i < nat; i += QX_NT) {
@@ -314,7 +314,7 @@ __device__ inline void d4_c6_tables(const DevModel &m, const double *gw, const d
 
 // non-self-consistent part of D4: ATM with q = 0 weights; also fills edisp[i*nat+j] (two-body BJ kernel).
 // tmp: >= 14*nat + 5*nat*nat doubles of global scratch.
-__device__ __noinline__ double phase_d4_nonsc(const DevModel &m, Sm &s, double *edisp, double *c6, double *dc6, double *tmp) {
+static __device__ __noinline__ double phase_d4_nonsc(const DevModel &m, Sm &s, double *edisp, double *c6, double *dc6, double *tmp) {
     const int nat = m.nat;
     double *gw0 = tmp, *gwdcn0 = tmp + 7 * nat, *part = tmp + 14 * nat;
     d4_weights_all(m, s, false, gw0, gwdcn0, nullptr);
@@ -394,7 +394,7 @@ __device__ __noinline__ double phase_d4_nonsc(const DevModel &m, Sm &s, double *
 }
 
 // ------------------------------------------------------------------------------------ Coulomb set-up
-__device__ __noinline__ void phase_coulomb_setup(const DevModel &m, Sm &s, double *gamma) {
+static __device__ __noinline__ void phase_coulomb_setup(const DevModel &m, Sm &s, double *gamma) {
     const int nat = m.nat, nsh = m.nsh;
     for (int ab = threadIdx.x; ab < nsh * nsh; ab += QX_NT) {
         int a = ab / nsh, b = ab - a * nsh, i = m.sh_at[a], j = m.sh_at[b];
@@ -621,7 +621,7 @@ __device__ inline double shpoly_pair(const DevModel &m, int sa, int sb, double r
 
 // Fills the per-CTA slab: S, H0 (symmetric), Dt/Qt in "operator on the FIRST index" layout:
 //   Dt[c][b][a] = <a| (r - R_atom(b))_c |b>   (row b contiguous in a).
-__device__ __noinline__ void phase_integrals(const DevModel &m, Sm &s, double *S, double *H0, double *Dt, double *Qt) {
+static __device__ __noinline__ void phase_integrals(const DevModel &m, Sm &s, double *S, double *H0, double *Dt, double *Qt) {
     const int nao = m.nao;
     const size_t n2 = (size_t)nao * nao;
     for (int t = threadIdx.x; t < m.ntask_int; t += QX_NT) {
@@ -668,7 +668,7 @@ __device__ __noinline__ void phase_integrals(const DevModel &m, Sm &s, double *S
 // One warp owns a strip of 8 output rows and walks the column tiles, so the A fragment of a k-step is
 // reused for every tile of the strip (mma.sync.m8n8k4.f64 == DMMA.8x8x4 on sm_100a).
 template <int MAXT, class FA, class FB, class FS>
-__device__ __noinline__ void dmma_gemm(int n, FA loadA, FB loadB, FS store) {
+static __device__ __noinline__ void dmma_gemm(int n, FA loadA, FB loadB, FS store) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = QX_NT / 32;
     const int nt = (n + 7) >> 3, g = lane >> 2, tg = lane & 3;
     for (int ti = warp; ti < nt; ti += nwarp) {
@@ -707,7 +707,7 @@ __device__ __noinline__ void dmma_gemm(int n, FA loadA, FB loadB, FS store) {
 // 8 MAXT columns at a time (all k), so that the inner loop reads B at shared-memory latency and B crosses L2 once instead of once
 // per strip; the row stride 8 MAXT + 4 spreads the 4 x 8 doubles of a fragment load over all banks (MAXT odd).  Ends with a barrier.
 template <int MAXT, class FA, class FB, class FS>
-__device__ __noinline__ void dmma_gemm_staged(int n, FA loadA, FB loadB, FS store, double *Bs) {
+static __device__ __noinline__ void dmma_gemm_staged(int n, FA loadA, FB loadB, FS store, double *Bs) {
     QX_ASSUME_SHARED(Bs);
     constexpr int NC = 8 * MAXT, LDS = NC + 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = QX_NT / 32;
@@ -774,7 +774,7 @@ __device__ inline void gemm_tc(int n, FA loadA, FB loadB, FS store, double *stag
 // A' = Ct * H * Ct^T  (H symmetric in `A`, result overwrites `A`); Ct in `Ct`.  The strip of T = Ct*H is parked in the
 // warp's own rows of `A` (after a barrier: everybody has finished reading H) and read back as the A operand of the second product.
 template <int NT8>
-__device__ __noinline__ void tc_transform(int n, const double *Ct, double *A, int ld) {
+static __device__ __noinline__ void tc_transform(int n, const double *Ct, double *A, int ld) {
     QX_ASSUME_SHARED(Ct); QX_ASSUME_SHARED(A);   // the strip kernels are only used when both matrices are in shared memory
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
     double acc[NT8][2];
@@ -818,7 +818,7 @@ __device__ __noinline__ void tc_transform(int n, const double *Ct, double *A, in
 
 // Ct <- X * Ct (in place), X in `X` (row-major; here the normalised rows of the Jacobi = J^T)
 template <int NT8>
-__device__ __noinline__ void tc_left_apply(int n, const double *X, double *Ct, int ld) {
+static __device__ __noinline__ void tc_left_apply(int n, const double *X, double *Ct, int ld) {
     QX_ASSUME_SHARED(X); QX_ASSUME_SHARED(Ct);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
     double acc[NT8][2];
@@ -849,7 +849,7 @@ __device__ __noinline__ void tc_left_apply(int n, const double *X, double *Ct, i
 
 // out = Ct^T diag(w) Ct = C diag(w) C^T.  out may alias Ct (result held in registers across a barrier).
 template <int NT8>
-__device__ __noinline__ void tc_density(int n, const double *Ct, const double *w, double *out, int ld) {
+static __device__ __noinline__ void tc_density(int n, const double *Ct, const double *w, double *out, int ld) {
     QX_ASSUME_SHARED(Ct); QX_ASSUME_SHARED(w); QX_ASSUME_SHARED(out);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
     double acc[NT8][2];
@@ -890,7 +890,7 @@ __host__ __device__ inline int tc_padded_dim(int n) {   // = 8 * NT8 of the inst
 // In-place Cholesky S = L L^T on the lower triangle of A (n x n, ld), then Ct = L^{-1} (lower triangular),
 // i.e. C = L^{-T}: an S-orthonormal starting basis.  Returns false if S is not positive definite.
 template <bool SH>
-__device__ __noinline__ bool cholesky_basis(int n, double *A, double *Ct, int ld, double *red) {
+static __device__ __noinline__ bool cholesky_basis(int n, double *A, double *Ct, int ld, double *red) {
     QX_ASSUME_SHARED(red);
     if (SH) { QX_ASSUME_SHARED(A); QX_ASSUME_SHARED(Ct); }
     for (int j = 0; j < n; ++j) {
@@ -973,7 +973,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.app
 // 6 + 5, (4) is branch-free (t = 0 is an exact no-op), (5) keeps (scale, 1/scale) packed for 128-bit state accesses.
 // jw: nrm2[n] | dd[n] as double2 (scale, inverse scale), 16-byte aligned
 template <int R>
-__device__ __noinline__ int jacobi_rows_lp8t(int n, double *G, int ld, float tol, double *jw) {
+static __device__ __noinline__ int jacobi_rows_lp8t(int n, double *G, int ld, float tol, double *jw) {
     QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(jw);   // n <= 72: matrices are in shared memory
     const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
     const int k = threadIdx.x >> 3, lsub = threadIdx.x & 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1098,7 +1098,7 @@ __device__ __forceinline__ void lds_v2_if(bool p, double2 &v, const double *ptr)
 // predicated loads -- a branch around plain assignments made the compiler keep the loop-carried array in local memory
 // (65 M local loads per 1184 solves, 45 % slower than lp8t instead of 17 % faster).
 template <int R>
-__device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, float tol, double *jw) {
+static __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, float tol, double *jw) {
     QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(jw);
     const int mm = (n + 1) & ~1, K = mm >> 1, m1 = mm - 1;
     const int grp = threadIdx.x >> 3, lsub = threadIdx.x & 7;
@@ -1224,7 +1224,7 @@ __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, float tol
 // (~110 AOs, one CTA per SM): the ceil(n/2) pairs of a round are worked off in passes of QX_NT/8 groups.  Same rotation as
 // jacobi_rows_lp8t; no kept row (a group would have to keep one per pass).
 template <int R>
-__device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, float tol, double *jw) {
+static __device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, float tol, double *jw) {
     QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(jw);
     const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
     const int nslot = QX_NT / 8, slot = threadIdx.x >> 3, lsub = threadIdx.x & 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1329,7 +1329,7 @@ __device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, float tol
 // The sweep is bound by the latency of the dependent chain load -> dot -> shuffles -> rotation parameters -> store with only the
 // CTA's 9 warps to hide it: two pairs per warp (LP = 16) halve the number of passes of a round.
 template <int R, int LP>
-__device__ __noinline__ int jacobi_rows_glob(int n, double *G, int ld, float tol, double *jw) {
+static __device__ __noinline__ int jacobi_rows_glob(int n, double *G, int ld, float tol, double *jw) {
     QX_ASSUME_SHARED(jw);
     const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = QX_NT / 32;
@@ -1450,7 +1450,7 @@ __device__ __noinline__ int jacobi_rows_glob(int n, double *G, int ld, float tol
 // rotates every pair of rows exactly once.  L2 traffic per outer sweep: (nb - 1) reads and writes of G instead of n - 1.
 // Columns n <= 32 R.
 template <int R>
-__device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float tol, double *jw, double *B, int bmax) {
+static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float tol, double *jw, double *B, int bmax) {
     QX_ASSUME_SHARED(jw); QX_ASSUME_SHARED(B);
     constexpr int LP = 16;
     const int nb = (n + bmax - 1) / bmax, b = (n + nb - 1) / nb, nbe = (nb + 1) & ~1, bm1 = nbe - 1;
@@ -1587,7 +1587,7 @@ __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float 
 }
 
 // generic fallback (any n): LP lanes per pair, scalar accesses
-__device__ __noinline__ int jacobi_rows_generic(int n, double *G, int ld, double *red, float tol) {
+static __device__ __noinline__ int jacobi_rows_generic(int n, double *G, int ld, double *red, float tol) {
     const int mm = (n + 1) & ~1, npair = mm >> 1;
     int LP = 32;
     while (LP > 4 && npair * LP > QX_NT) LP >>= 1;
@@ -1636,7 +1636,7 @@ __device__ __noinline__ int jacobi_rows_generic(int n, double *G, int ld, double
 // in between was enough to make the register-hungry sweep kernels spill inside the round loop.
 // (1) Gershgorin shift: makes G positive definite, so that singular values == eigenvalues + sigma; sigma is parked in red[60]
 template <bool SH>
-__device__ __noinline__ void jacobi_shift(int n, double *G, int ld, double *red) {
+static __device__ __noinline__ void jacobi_shift(int n, double *G, int ld, double *red) {
     QX_ASSUME_SHARED(red);
     if (SH) QX_ASSUME_SHARED(G);
     double rowsum = 0.0;
@@ -1702,7 +1702,7 @@ __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *r
 // (3) eigenvalues from the row norms; normalise the rows.  On exit emo[k] = eigenvalue k and row k of G is the corresponding
 // unit eigenvector (so G holds J^T).
 template <bool SH>
-__device__ __noinline__ void jacobi_finish(int n, double *G, int ld, double *emo, const double *red) {
+static __device__ __noinline__ void jacobi_finish(int n, double *G, int ld, double *emo, const double *red) {
     QX_ASSUME_SHARED(emo); QX_ASSUME_SHARED(red);
     if (SH) QX_ASSUME_SHARED(G);
     const double sigma = red[60];

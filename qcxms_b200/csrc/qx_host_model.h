@@ -33,6 +33,7 @@ struct HostModel {
     std::vector<double> c6ref;
     std::vector<int2> task_int;
     std::vector<int> gr_ptr, gr_task;
+    std::vector<double> scal_table;
     // device copy
     void *d_blob = nullptr;
     DevModel dev{};
@@ -233,6 +234,12 @@ inline cudaError_t upload_model(HostModel &h) {
     ADD(sh_at); ADD(sh_l); ADD(sh_ao0); ADD(sh_np); ADD(sh_alpha); ADD(sh_coef); ADD(sh_level); ADD(sh_kcn); ADD(sh_poly);
     ADD(sh_refocc); ADD(sh_hub); ADD(sh_gam3); ADD(hscale); ADD(ao_at); ADD(ao_sh); ADD(ao_m); ADD(c6ref); ADD(task_int);
     ADD(gr_ptr); ADD(gr_task);
+    if (h.scal_table.empty()) {   // the reference's running sum scal = scal + 0.0002 (src/impact.f90:37)
+        h.scal_table.resize(20001);
+        volatile double scal = 0.0;
+        for (int k = 0; k <= 20000; ++k) { h.scal_table[k] = scal; scal = scal + (double)0.0002f; }
+    }
+    ADD(scal_table);
 #undef ADD
     cudaError_t err = cudaMalloc(&h.d_blob, blob.size());
     if (err != cudaSuccess) return err;
@@ -251,6 +258,7 @@ inline cudaError_t upload_model(HostModel &h) {
     PTR(sh_at, int); PTR(sh_l, int); PTR(sh_ao0, int); PTR(sh_np, int); PTR(sh_alpha, double); PTR(sh_coef, double); PTR(sh_level, double);
     PTR(sh_kcn, double); PTR(sh_poly, double); PTR(sh_refocc, double); PTR(sh_hub, double); PTR(sh_gam3, double); PTR(hscale, double);
     PTR(ao_at, int); PTR(ao_sh, int); PTR(ao_m, int); PTR(c6ref, double); PTR(task_int, int2); PTR(gr_ptr, int); PTR(gr_task, int);
+    PTR(scal_table, double);
 #undef PTR
     return cudaSuccess;
 }

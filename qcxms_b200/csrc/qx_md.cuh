@@ -104,17 +104,19 @@ __device__ inline double md_ekinet_seq(int nat, const double *velo, const double
     return __dmul_rn(e, 0.5);
 }
 
-// impactscale: first grid point (multiples of 0.0002f) whose kinetic energy reaches Esoll - 0.001f,
-// applied one grid step further, exactly like the reference loop.  Returns false on the reference's
-// 'error in impactscale' (k >= 20000).  Warp 0 evaluates 32 candidates per pass.
+// impactscale: first grid point whose kinetic energy reaches Esoll - 0.001f, applied one grid step further, exactly like the
+// reference loop.  The grid is the reference's running sum scal = scal + 0.0002 (single-precision literal, double accumulator,
+// src/impact.f90:28-37), NOT k * 0.0002: m.scal_table[k] holds the sum after k additions (host-built, 20001 entries), so the
+// candidates are bit-identical to the reference's.  Returns false on the reference's 'error in impactscale' (k >= 20000).
+// Warp 0 evaluates 32 candidates per pass.
 __device__ inline bool md_impactscale(const DevModel &m, double *velo, const double *velof, double eimp, double ff, double e0, int *flag) {
-    const double step = (double)0.0002f, tol = (double)0.001f;
+    const double tol = (double)0.001f;
     const double esoll = __dadd_rn(__dmul_rn(eimp, ff), e0);
     if (threadIdx.x < 32) {
         int found = -1;
         for (int base = 0; base < 20000 && found < 0; base += 32) {
             int c = base + threadIdx.x;  // k = c + 1
-            double scal = __dmul_rn((double)c, step);
+            double scal = m.scal_table[c < 20000 ? c : 20000];
             double e = md_ekinet_seq(m.nat, velo, m.mass, scal, velof);
             bool cont = (__dsub_rn(esoll, e) > tol) && (c + 1 < 20000);
             unsigned ball = __ballot_sync(0xffffffffu, !cont);
@@ -125,7 +127,7 @@ __device__ inline bool md_impactscale(const DevModel &m, double *velo, const dou
     __syncthreads();
     int found = *flag;
     if (found < 0 || found + 1 >= 20000) return false;
-    double scal = __dmul_rn((double)(found + 1), step);
+    double scal = m.scal_table[found + 1];
     for (int t = threadIdx.x; t < 3 * m.nat; t += QX_NT) velo[t] = __dmul_rn(velo[t], __dadd_rn(1.0, __dmul_rn(velof[t / 3], scal)));
     __syncthreads();
     return true;

@@ -6,7 +6,15 @@
 #define QX_MAXPRIM 6
 #define QX_MAXREF 7
 #define QX_MAX_ITER 250   // tblite max_iter (SCC cycles and Broyden memory)
-#define QX_NT 288         // threads per CTA; one CTA == one trajectory
+#ifndef QX_NT
+#define QX_NT 288         // threads per CTA; one CTA == one trajectory (tu_*.cu may be built for other widths, see qx_kernels.h)
+#endif
+#ifndef QX_MINB
+#define QX_MINB 2         // resident CTAs per SM the kernels are compiled for (register budget)
+#endif
+#ifndef QX_VARIANT
+#define QX_VARIANT nt288
+#endif
 
 struct DevModel {
     int nat, nsh, nao, ntype, ld, ndim;  // ld: leading dimension of the shared-memory matrices (== 4 or 12 mod 16)
@@ -35,6 +43,8 @@ struct DevModel {
     const int2 *task_int;   // all pairs incl. on-site ordered pairs
     // gradient reduction lists (CSR by atom over off-site tasks; sign +1 ket atom / -1 bra atom)
     const int *gr_ptr, *gr_task;
+    // impactscale grid: scal_table[k] = sum of k additions of 0.0002f in double (reference src/impact.f90:37), k = 0..20000
+    const double *scal_table;
 };
 
 // per-CTA scratch in global memory (stays L2 resident); offsets in doubles

@@ -10,11 +10,11 @@ namespace qx {
 
 // optional per-phase cycle accounting (profiling builds only: -DQX_PROFILE_PHASES)
 #ifdef QX_PROFILE_PHASES
-__device__ unsigned long long g_phase_cycles[16];
-__device__ unsigned long long g_sub_cycles[16];   // finer marks inside a phase (thread 0's clock, no extra barrier)
+static __device__ unsigned long long g_phase_cycles[16];
+static __device__ unsigned long long g_sub_cycles[16];   // finer marks inside a phase (thread 0's clock, no extra barrier)
 #define QX_SUB_BEGIN() long long sub_t0_ = clock64()
 #define QX_SUB(idx) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_sub_cycles[idx], (unsigned long long)(t_ - sub_t0_)); sub_t0_ = t_; } } while (0)
-__device__ unsigned long long g_sweep_hist[64];  // [iteration index (<32)] -> sweeps, [32+..] -> count
+static __device__ unsigned long long g_sweep_hist[64];  // [iteration index (<32)] -> sweeps, [32+..] -> count
 #define QX_PH_BEGIN() long long ph_t0_ = clock64()
 #define QX_PH(idx)                                                                  \
     do {                                                                            \
@@ -83,7 +83,7 @@ __device__ __forceinline__ double gamma_row_oct(const Sm &s, const double *gamma
 }
 
 // potentials from the (input) populations in s.qsh/qat/dpat/qpat -> s.vsh, vat, vdp, vqp, vao
-__device__ __noinline__ void phase_potential(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double *t7) {
+static __device__ __noinline__ void phase_potential(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double *t7) {
     const int nat = m.nat, nsh = m.nsh, nao = m.nao;
     const int oct = threadIdx.x >> 3, l8 = threadIdx.x & 7, wbase = (threadIdx.x >> 5) << 2;
     d4_weights_all(m, s, true, s.gw, nullptr, s.gwd);
@@ -148,7 +148,7 @@ __device__ __noinline__ void phase_potential(const DevModel &m, Sm &s, const dou
 }
 
 // energies of the charge-dependent terms at the (output) populations
-__device__ __noinline__ void phase_scc_energy(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double &e_es, double &e_aes, double &e_d4) {
+static __device__ __noinline__ void phase_scc_energy(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double &e_es, double &e_aes, double &e_d4) {
     const int nat = m.nat, nsh = m.nsh;
     const int oct = threadIdx.x >> 3, l8 = threadIdx.x & 7, wbase = (threadIdx.x >> 5) << 2;
     d4_weights_all(m, s, true, s.gw, nullptr, nullptr);
@@ -203,7 +203,7 @@ __device__ __noinline__ void phase_scc_energy(const DevModel &m, Sm &s, const do
 // number of bytes in flight per round trip: 128-bit loads, all 11 matrices of an element pair issued back to back.
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 template <bool SH>
-__device__ __noinline__ void phase_build_h1(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt) {
+static __device__ __noinline__ void phase_build_h1(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt) {
     const int nao = m.nao, ld = m.ld;
     double *const A = s.A;
     if (SH) QX_ASSUME_SHARED(A);
@@ -254,7 +254,7 @@ __device__ __noinline__ void phase_build_h1(const DevModel &m, Sm &s, const doub
 
 // Mulliken populations from P (in s.A, symmetric): qsh, qat, dpat, qpat and tr(P H0); pop: 11*nao doubles of scratch
 template <bool SH>
-__device__ __noinline__ double phase_mulliken(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt, double *pop) {
+static __device__ __noinline__ double phase_mulliken(const DevModel &m, Sm &s, const double *S, const double *H0, const double *Dt, const double *Qt, double *pop) {
     const int nao = m.nao, ld = m.ld, nat = m.nat, nsh = m.nsh;
     const double *const A = s.A;
     if (SH) QX_ASSUME_SHARED(A);
@@ -406,7 +406,7 @@ __device__ inline double warp_dot(const double *x, const double *y, int n) {
 }
 
 // dense solve with partial pivoting on (beta[nb x nb], c[nb]) in global scratch; CTA-cooperative
-__device__ __noinline__ bool block_solve(int nb, double *beta, double *c, double *red) {
+static __device__ __noinline__ bool block_solve(int nb, double *beta, double *c, double *red) {
     QX_ASSUME_SHARED(red);
     __shared__ int s_piv;
     for (int k = 0; k < nb; ++k) {
@@ -452,7 +452,7 @@ __device__ __noinline__ bool block_solve(int nb, double *beta, double *c, double
 // One mixer step: q_in <- next input.  dq = (output - input) of the cycle just finished must be set.
 // bsol: QX_BSOL doubles of shared memory; systems up to QX_BSOL_N unknowns (the first 14 SCC cycles) are built and solved
 // there -- the pivot search and back substitution are serial and were paying a global-memory round trip per element.
-__device__ __noinline__ bool broyden_next(Broyden &b, int n, double damp, double *red, double *bsol) {
+static __device__ __noinline__ bool broyden_next(Broyden &b, int n, double damp, double *red, double *bsol) {
     QX_ASSUME_SHARED(red); QX_ASSUME_SHARED(bsol);
     const int mem = QX_MAX_ITER;
     const double omega0 = 0.01, minw = 1.0, maxw = 100000.0, wfac = 0.01;
@@ -533,7 +533,7 @@ __device__ __noinline__ bool broyden_next(Broyden &b, int n, double damp, double
 // ------------------------------------------------------------------------------------ gradient of the AO-pair terms
 // s.A = P, s.C = W (energy weighted density); potentials in s.vao/vdp/vqp from the last SCC cycle.
 template <bool SH>
-__device__ __noinline__ void phase_gradient_pairs(const DevModel &m, Sm &s, const int2 *tasks, int ntask, double *taskout) {
+static __device__ __noinline__ void phase_gradient_pairs(const DevModel &m, Sm &s, const int2 *tasks, int ntask, double *taskout) {
     const int ld = m.ld;
     const double *const A = s.A, *const Cw = s.C;
     if (SH) { QX_ASSUME_SHARED(A); QX_ASSUME_SHARED(Cw); }

@@ -25,14 +25,17 @@ def shard_indices(ntraj, world_size, rank):
     return np.arange(rank, ntraj, world_size)
 
 
-def synthetic_initial_conditions(num, xyz_eq, ntraj, first_id=0, temperature=500.0, sigma=0.05, ieeatm=0.6, tadd_fs=400.0):
+def synthetic_initial_conditions(num, xyz_eq, ntraj, first_id=0, temperature=500.0, sigma=0.05, ieeatm=0.6, tadd_fs=400.0, ids=None):
     """Per-trajectory start geometry/velocities/IEE: counter-based RNG seeded by the GLOBAL trajectory id, so a
-    trajectory gets the same initial conditions whichever rank runs it."""
+    trajectory gets the same initial conditions whichever rank runs it.  ids: explicit global ids (a rank's shard,
+    see shard_indices); default first_id .. first_id + ntraj - 1."""
     nat = len(num)
     mass = masses_au(num)
+    ids = np.arange(first_id, first_id + ntraj) if ids is None else np.asarray(ids)
+    ntraj = len(ids)
     xyz = np.empty((ntraj, nat, 3)); velo = np.empty((ntraj, nat, 3)); eimp = np.empty(ntraj)
     for k in range(ntraj):
-        rng = np.random.Generator(np.random.Philox(key=0x5EED0000 + first_id + k))
+        rng = np.random.Generator(np.random.Philox(key=0x5EED0000 + int(ids[k])))
         xyz[k] = xyz_eq + sigma * rng.standard_normal((nat, 3))
         sign = np.where(rng.random((nat, 3)) < 0.5, -1.0, 1.0)
         velo[k] = sign * np.sqrt(KB * temperature / mass)[:, None]       # mdinitu rule, reference src/mdinit.f90:10-52

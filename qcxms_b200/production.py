@@ -202,12 +202,15 @@ def _cut_fragment(s, xyz, velo, lst, tcont):
     iatn = s["num"][sel]
     xyzn = np.asarray(xyz, dtype=np.float64)[sel]
     cema = (xyzn * iatn[:, None]).sum(0) / iatn.sum()
+    parent_mass = s["mass"]
     s["num"] = iatn.astype(np.int32)
-    s["mass"] = s["mass"][sel]
+    s["mass"] = parent_mass[sel]
     if len(sel) <= 7:
         s["small"] = True
         return False
-    if s["mass"].sum() / AMUTOAU <= s["minmass"]:
+    # sic: the reference sums the first nuc entries of the PARENT's mass array (it is re-filled with the fragment's masses only
+    # after this test, main.F90:1727, 1936), not the masses of the new fragment
+    if parent_mass[:len(sel)].sum() / AMUTOAU <= s["minmass"]:
         s["littlemass"] = True
         return False
     s["xyz"] = xyzn - cema
@@ -227,7 +230,9 @@ def run_cid(num, mass, xyz, velo, mchrg=1, gas="ar", elab=40.0, ecom=0.0, eexact
     from . import api
     num0 = np.asarray(num, dtype=np.int32)
     nt = len(xyz)
-    gas_mass = api.GASES[gas.lower()][1] * AMUTOAU * (2 if gas.lower() == "n2" else 1)
+    # sic: the mass of ONE gas atom also for N2 (gas%mIatom = 14.007, input.f90 "IATOM N2"; beta in cid.f90:347 and the E_COM stop
+    # rule of main.F90 use it as it is) -- the device side (qx_cid.cuh) does the same
+    gas_mass = api.GASES[gas.lower()][1] * AMUTOAU
     trj = []
     for t in range(nt):
         itrj = first_itrj + t

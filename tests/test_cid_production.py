@@ -94,3 +94,20 @@ def test_cid_run_is_independent_of_batching(oracle):
     second = prod.run_cid(num, ic["mass"], ic["xyz"][1:], ic["velo"][1:], first_itrj=2, **kw)
     assert both["per_traj"][1]["records"] == second["per_traj"][0]["records"]
     assert both["per_traj"][1]["events"] == second["per_traj"][0]["events"]
+
+
+def test_n2_stop_rule_uses_the_single_atom_gas_mass(oracle):
+    """E_COM = beta E_kin with beta = mIatom / (mIatom + M), mIatom = 14.007 amu also for N2 (main.F90:1993-2000, input.f90
+    'IATOM N2'): at E_lab = 5 eV a chloroethanol ion has E_COM = 0.74 eV <= 0.85 eV and the run ends after the first collision;
+    with the molecular mass (28 amu) it would be 1.29 eV and a second collision would follow."""
+    num, xyz, _ = load_molecule("chloroethanol")
+    ic = es.synthetic_initial_conditions(num, xyz, 1, first_id=320)
+    out = prod.run_cid(num, ic["mass"], ic["xyz"], ic["velo"], mchrg=1, gas="n2", elab=5.0, run_type="maxcoll", max_coll=3, minmass=20,
+                       first_itrj=1, seed=2, cid_ntot=6, mfp_nmax=4, cid_batch=oracle.cid_batch, mfp_batch=oracle.mfp_batch,
+                       energies=oracle.energies)
+    t = out["per_traj"][0]
+    assert [(e["kind"], e["icoll"]) for e in t["events"]] == [("cid", 1), ("mfp", 1)]
+    e_kin_ev = 0.5 * ic["mass"].sum() * (t["events"][-1]["new_velo"] * MSTOAU) ** 2 * 27.21138505
+    m1 = 14.007 * 1822.888486
+    assert m1 / (m1 + ic["mass"].sum()) * e_kin_ev <= 0.85 < 2 * m1 / (2 * m1 + ic["mass"].sum()) * e_kin_ev
+    assert len(t["records"]) == 1

@@ -173,3 +173,25 @@ def test_warm_start_mode_is_close_and_cheaper(qx):
     ratio = warm["scc_iter_total"].sum() / cold["scc_iter_total"].sum()
     print("warm/cold SCC cycles: %.2f" % ratio)
     assert ratio < 0.7
+
+
+def test_md_user_etemp_and_ieetemp_follow_the_reference(qx, oracle):
+    """A user ETEMP serves only the first single point of md(): the loop calls setetemp on every step regardless of it
+    (reference src/md.f90:167-172, 443-445).  Non-default ieetemp / ax make the per-step temperature step-dependent.  Also checks
+    intenergy (src/md.f90:715-741) of the final state and the accumulated impactscale grid (src/impact.f90:37)."""
+    num, ic = _ic(qx, "chloroethanol", 4, seed=40)
+    nsteps = 12
+    kw = dict(mchrg=1, nmax=nsteps, exit_rules=True, etemp=3000.0, ieetemp=1.5e4, ax=0.05)
+    ens = qx.Ensemble(num, ic["mass"], 4, **kw)
+    ens.set_all(ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+    assert ens.run_md() == 4 * nsteps
+    fragT, e_int = ens.intenergy()
+    for k in range(4):
+        got = ens.result(k)
+        ref = oracle.md(num, ic["mass"], ic["xyz"][k], ic["velo"][k], ic["velof"][k], ic["eimp"][k], ic["tadd"][k], **kw)
+        assert got["nstep"] == ref["nstep"] == nsteps and got["scc_iter_total"] == ref["scc_iter_total"]
+        assert np.abs(got["xyz"] - ref["xyz"]).max() < 1e-7 and np.abs(got["velo"] - ref["velo"]).max() < 1e-9
+        assert abs(got["Epot"] - ref["Epot"]) < 1e-7 and abs(got["Ekin"] - ref["Ekin"]) < 1e-8
+        Tr, er = oracle.intenergy(ref["list"], ic["mass"], ref["velo"], ref["nfrag"])
+        assert np.abs(e_int[k] - er).max() < 1e-9 and np.abs(fragT[k][:ref["nfrag"]] - Tr[:ref["nfrag"]]).max() < 1e-3
+    ens.close()

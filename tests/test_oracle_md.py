@@ -107,3 +107,21 @@ def test_md_golden_and_energy_conservation(oracle):
     r0 = oracle.md(num, ic["mass"], ic["xyz"][0], ic["velo"][0], ic["velof"][0], 0.0, 0.0, mchrg=1, nmax=1)
     r = oracle.md(num, ic["mass"], ic["xyz"][0], ic["velo"][0], ic["velof"][0], 0.0, 0.0, mchrg=1, nmax=40)
     assert abs((r["Epot"] + r["Ekin"]) - (r0["Epot"] + r0["Ekin"])) < 1e-3
+
+
+def test_user_etemp_serves_only_the_first_single_point(oracle):
+    """src/md.f90:167-172 vs 443-445: etempin >= 0 sets the electronic temperature of the initial egrad; inside the loop setetemp
+    is called on every step regardless, so from step 1 on the run is the default-temperature run."""
+    from qcxms_b200 import ensemble_setup as es
+    from qcxms_b200.api import load_molecule
+    num, xyz, _ = load_molecule("chloroethanol")
+    ic = es.synthetic_initial_conditions(num, xyz, 1, first_id=77)
+    a = (ic["mass"], ic["xyz"][0], ic["velo"][0], ic["velof"][0], ic["eimp"][0], ic["tadd"][0])
+    user = oracle.md(num, *a, mchrg=1, nmax=3, etemp=300.0)
+    dflt = oracle.md(num, *a, mchrg=1, nmax=3, etemp=-1.0)
+    # the first gradient (etemp 300 K vs 5000 K + IEE term) differs, so the trajectories differ slightly ...
+    assert 1e-9 < np.abs(user["xyz"] - dflt["xyz"]).max() < 1e-2
+    # ... but the last single point was evaluated at the setetemp temperature, not at 300 K
+    e5000 = oracle.egrad(num, user["xyz"], charge=1, multiplicity=2, etemp=5000.0)["energy"]
+    e300 = oracle.egrad(num, user["xyz"], charge=1, multiplicity=2, etemp=300.0)["energy"]
+    assert abs(user["Epot"] - e5000) < 1e-9 < abs(user["Epot"] - e300)

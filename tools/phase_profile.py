@@ -1,17 +1,19 @@
 #!/usr/bin/env python
 """Per-phase cycle breakdown of the fused egrad kernel (profiling build with -DQX_PROFILE_PHASES).
 Usage (on the GPU box): python tools/phase_profile.py [molecule] [nsys]
-Builds qcxms_b200/libqcxms_b200_prof.so if needed; never used by the product path."""
+Build the profiling library first (here, no GPU needed): python tools/phase_profile.py --build  -> build/libqcxms_b200_prof.so;
+never used by the product path."""
 import ctypes as C, os, subprocess, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-so = os.path.join(ROOT, "qcxms_b200", "libqcxms_b200_prof.so")
+so = os.path.join(ROOT, "build", "libqcxms_b200_prof.so")
 NAMES = ["cn+rep", "d4 nonsc/ATM", "coulomb+integrals", "cholesky basis", "broyden", "potential", "build H1", "transform C^T H C",
          "jacobi", "fermi", "density", "mulliken", "scc energy", "W matrix", "grad AO pairs", "grad rest"]
 def build(out=so, extra=()):
-    subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-DQX_PROFILE_PHASES",
-                           *extra, "-Xcompiler", "-fPIC", "-shared", "-o", out, os.path.join(ROOT, "qcxms_b200", "csrc", "cabi.cu")])
+    tag = "prof" + "".join(c if c.isalnum() else "_" for c in "".join(extra))
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "qcxms_b200", "csrc"), "-j8", "-s", "OUT=" + os.path.abspath(out),
+                           "OBJDIR=" + os.path.join(ROOT, "build", "obj_" + tag), "EXTRA=-DQX_PROFILE_PHASES " + " ".join(extra)])
 if __name__ == "__main__":
     # --so PATH: use (or with --build: write) another profiling library; -D... flags are passed to nvcc; --dump FILE: save results
     args = [a for a in sys.argv[1:]]
