@@ -1251,6 +1251,19 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
         memcpy(mix.q_in, qsh, nsh * sizeof(double));
         memcpy(mix.q_in + nsh, dpat, 3 * nat * sizeof(double));
         memcpy(mix.q_in + nsh + 3 * nat, qpat, 6 * nat * sizeof(double));
+        {   /* test hook: XTB_ORACLE_DUMP=<file> appends [nao, iscf, H1(nao^2), S(nao^2)] of every SCC cycle (eigen-solver studies) */
+            const char *dump = getenv("XTB_ORACLE_DUMP");
+            if (dump) {
+                FILE *fp = fopen(dump, "ab");
+                if (fp) {
+                    double hdr[2] = {(double)nao, (double)iscf};
+                    fwrite(hdr, sizeof(double), 2, fp);
+                    fwrite(H1, sizeof(double), n2, fp);
+                    fwrite(s.S, sizeof(double), n2, fp);
+                    fclose(fp);
+                }
+            }
+        }
         if (solve_gen(nao, H1, Linv, C, emo, work)) { stat = QC_STAT_FATAL; break; }
         memset(focc, 0, nao * sizeof(double));
         ts = 0.0;

@@ -87,6 +87,7 @@ struct Context {
 };
 
 static const KernelSet KS_NT288 = QX_KERNEL_SET(nt288, 288);
+static const KernelSet KS_NT576 = QX_KERNEL_SET(nt576, 576);   // one wide CTA per SM
 
 static int context_init(Context &c, int nat, const int32_t *num, const double *mass, int charge, int multiplicity, int device, int nwork) {
     CUDA_OK(cudaSetDevice(device));
@@ -117,7 +118,15 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
     }
     c.L = make_layout(c.hm);
     // the device maximum, not this composition's size: host threads set up different compositions concurrently
+    // Kernel set: two 288-thread CTAs per SM fill the device best when there are more trajectories than CTA slots.  An ensemble
+    // with at most one trajectory per SM (BASELINE config 2 dealt over 8 GPUs: 125 per device) is bound by the latency of a
+    // single trajectory's step instead: it runs on 576-thread CTAs, one per SM (shared-memory-resident bases only).
     c.ks = &KS_NT288;
+    {
+        const char *force = getenv("QCXMS_B200_CTA");   // test / measurement hook: 288 or 576
+        const int want = force ? atoi(force) : 0;
+        if (!c.hm.dev.mat_in_global && (want == 576 || (want == 0 && nwork > 0 && nwork <= prop.multiProcessorCount))) c.ks = &KS_NT576;
+    }
     CUDA_OK(c.ks->prepare_egrad(prop));
     CUDA_OK(c.ks->prepare_md(prop));
     CUDA_OK(c.ks->prepare_mfp(prop));

@@ -6,7 +6,7 @@ namespace qx {
 
 // ------------------------------------------------------------------------------------ CID (reference src/cid.f90)
 // set-up of one collision + the two single points before the loop (iniqm's is only checked, so one evaluation serves both)
-__global__ void __launch_bounds__(QX_NT, QX_MINB) k_cid_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, CidConfig cc, CidState st, int ntraj,
+static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_cid_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, CidConfig cc, CidState st, int ntraj,
                                                     int nuc, int icoll, int *queue) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_next;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(QX_NT, QX_MINB) k_cid_init(DevModel m, Scratch
 }
 
 // up to `chunk` steps of the collision loop (reference src/cid.f90:739-1052) for every running trajectory
-__global__ void __launch_bounds__(QX_NT, QX_MINB) k_cid_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, CidConfig cc, CidState st, int ntraj,
+static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_cid_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, CidConfig cc, CidState st, int ntraj,
                                                      int nuc, int chunk, int *queue) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_next, s_ops, s_cnt, s_stop;

@@ -4,7 +4,7 @@
 
 namespace qx {
 
-__global__ void __launch_bounds__(QX_NT, QX_MINB) k_egrad_batch(DevModel m, ScratchLayout L, double *scratch, const double *xyz, double kt, int nsys,
+static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_egrad_batch(DevModel m, ScratchLayout L, double *scratch, const double *xyz, double kt, int nsys,
                                                        int *queue, double *energy, double *grad, double *qat, int *stat, int *niter, double *spec) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_next;

@@ -31,7 +31,7 @@ __device__ inline void mfp_store(const MdState &st, int t, const MfpScalars &q) 
 
 #ifdef QX_TU_MD_INIT
 // md(): everything before the loop (reference src/md.f90:155-283)
-__global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int *queue) {
+static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_init(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int *queue) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_next;
     Sm s;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_init(DevModel m, ScratchL
 // MFP = true: the mean-free-path md() of a CID run (cfg.icoll >= 1; reference global method == 3): no IEE heating, kinetic energy
 // without the centre-of-mass motion, averaged fragment structures, tmax as the only regular exit (src/md.f90:246-255, 466-621, 672).
 template <bool MFP>
-__global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int chunk,
+static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_chunk(DevModel m, ScratchLayout L, double *scratch, MdConfig cfg, MdState st, int ntraj, int chunk,
                                                     int nsub, int step_limit, int *queue, int *progress, unsigned long long *steps_done) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_next, s_flag;

@@ -93,5 +93,6 @@ static inline cudaError_t allow_max_dynamic_smem(K kernel, const cudaDeviceProp 
      QX_CAT(tu_mfp_chunk_, V), QX_CAT(tu_cid_prepare_, V), QX_CAT(tu_cid_init_, V), QX_CAT(tu_cid_chunk_, V)}
 
 QX_DECLARE_TU_ENTRIES(nt288)
+QX_DECLARE_TU_ENTRIES(nt576)
 
 }  // namespace qx
