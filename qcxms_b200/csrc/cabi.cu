@@ -109,7 +109,7 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         const size_t avail = (size_t)prop.sharedMemPerBlockOptin - c.smem - 16 - 2048;   // 2 KB: the kernels' static shared memory
         int jb = (int)(avail / (2 * row));
         if (jb > 36) jb = 36;   // 2 x 18 sixteen-lane groups: the pairs of a round of two blocks fill two passes
-        if (jb >= 8 && c.hm.nao <= 256) {
+        if (jb >= 8 && c.hm.nao <= 316) {   // jacobi_rows_blocked: ld <= 320
             const int nb = (c.hm.nao + jb - 1) / jb;
             jb = (c.hm.nao + nb - 1) / nb;          // balanced blocks
             c.hm.dev.jblock = jb;

@@ -1482,11 +1482,11 @@ static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld,
                 for (int lr = warp; lr < nr; lr += nwarp) {
                     const double *src = G + (size_t)(lr < nI ? r0I + lr : r0J + lr - nI) * ld;
                     double *dst = B + (size_t)lr * ld;
-                    double acc = 0.0, xs[9];   // ld <= 268 (n <= 256): all loads of a row in flight at once, one L2 round trip per row
+                    double acc = 0.0, xs[10];   // ld <= 320 (n <= 316): all loads of a row in flight at once, one L2 round trip per row
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) { const int i = lane + 32 * c; xs[c] = i < n ? src[i] : 0.0; }
+                    for (int c = 0; c < 10; ++c) { const int i = lane + 32 * c; xs[c] = i < n ? src[i] : 0.0; }
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) { const int i = lane + 32 * c; if (i < ld) { dst[i] = xs[c]; acc = fma(xs[c], xs[c], acc); } }
+                    for (int c = 0; c < 10; ++c) { const int i = lane + 32 * c; if (i < ld) { dst[i] = xs[c]; acc = fma(xs[c], xs[c], acc); } }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                     if (lane == 0) { nrm2[lr] = acc; dd[lr] = make_double2(1.0, 1.0); }
@@ -1675,14 +1675,16 @@ __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *r
             case 6: sweeps = jacobi_rows_lp8m<6>(n, G, ld, QX_JACOBI_TOL, jw); break;
             default: sweeps = jacobi_rows_lp8m<7>(n, G, ld, QX_JACOBI_TOL, jw); break;
         }
-    } else if (!SH && jblock >= 8 && (ld & 1) == 0 && (reinterpret_cast<size_t>(G) & 15) == 0 && n <= 256) {   // global slab, blocked through shared memory
+    } else if (!SH && jblock >= 8 && (ld & 1) == 0 && (reinterpret_cast<size_t>(G) & 15) == 0 && n <= 316) {   // global slab, blocked through shared memory
         if (n <= 96) return jacobi_rows_generic(n, G, ld, red, tol);
         switch ((n + 31) >> 5) {
             case 4: sweeps = jacobi_rows_blocked<4>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
             case 5: sweeps = jacobi_rows_blocked<5>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
             case 6: sweeps = jacobi_rows_blocked<6>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
             case 7: sweeps = jacobi_rows_blocked<7>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
-            default: sweeps = jacobi_rows_blocked<8>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
+            case 8: sweeps = jacobi_rows_blocked<8>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
+            case 9: sweeps = jacobi_rows_blocked<9>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
+            default: sweeps = jacobi_rows_blocked<10>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;   // n <= 316 (ld <= 320)
         }
     } else if (!SH && (ld & 1) == 0 && (reinterpret_cast<size_t>(G) & 15) == 0 && n <= 320) {   // global slab
         if (n <= 96) return jacobi_rows_generic(n, G, ld, red, tol);   // (never in practice: the slab mode starts above ~110 AOs)

@@ -57,6 +57,17 @@ def test_large_basis_fallback_alkane_c32(qx, oracle):
     _compare(qx, oracle, num, x, 1, 2, 5000.0)
 
 
+def test_config5_drug_like_peptide(qx, oracle):
+    """BASELINE config 5: 98 atoms with N, O, S and Cl (d functions in the large-basis path), 152 shells / 266 AOs -- above the 256 the
+    blocked Jacobi used to be capped at.  Relaxed neutral geometry and a distorted cation."""
+    num, xyz, _ = qx.load_molecule("peptide_cl")
+    assert len(num) == 98 and set(num.tolist()) == {1, 6, 7, 8, 16, 17}
+    ref = _compare(qx, oracle, num, xyz, 0, 1, 300.0)
+    assert ref["nao"] == 266
+    rng = np.random.default_rng(5)
+    _compare(qx, oracle, num, xyz + 0.03 * rng.standard_normal(xyz.shape), 1, 2, 5000.0)
+
+
 @pytest.mark.parametrize("name", ["alkane_c14", "alkane_c17"])
 def test_medium_basis_multi_pass_jacobi(qx, oracle, name):
     """Bases between the one-pass Jacobi limit (72 AOs) and the shared-memory limit (~110): matrices in shared memory,
