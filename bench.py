@@ -27,6 +27,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL writes its banner ("NCCL version ...", NCCL_DEBUG=VERSION) to stdout, which must carry exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "trajectory_md_steps_per_s"
 UNIT = "trajectory-MD-steps/s"
@@ -171,6 +174,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the path's one collective goes through the library's own NCCL communicator (qcxms_b200_comm_*), set up outside the timed regions
+    comm = es.make_comm(local_rank)
+
     def measure(mode):
         """One full measurement (device-timed K steps + end-to-end leg) of this rank's shard under `mode` scaling."""
         ids = es.shard_indices(args.ntraj, world, rank) if mode == "strong" else np.arange(rank * args.ntraj, (rank + 1) * args.ntraj)
@@ -219,9 +225,7 @@ def main():
         e2 = new_ensemble()
         e2_steps = e2.run_md(max_steps=args.steps)
         e2.results()
-        bins, _ = e2.histogram(512)
-        hb = torch.from_numpy(bins).to(dev)
-        es.allreduce_histogram(hb)
+        comm.allreduce_histogram(e2, 512)
         torch.cuda.synchronize()
         barrier()
         e2e_wall = time.perf_counter() - t0
@@ -246,6 +250,7 @@ def main():
     e2e_value, h2d, d2h = m["e2e_value"], m["h2d"], m["d2h"]
     config["ntraj_per_gpu"] = m["ntraj_local"]
 
+    comm.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -149,11 +149,31 @@ int qcxms_b200_ensemble_last_timing(qcxms_b200_ensemble_t *h, double *kernel_ms,
  * summation order.  Slots beyond the number of fragments are 0. */
 int qcxms_b200_ensemble_intenergy(qcxms_b200_ensemble_t *h, double *fragT, double *e_int);
 
-/* Fragment-mass histogram of the finished trajectories of this ensemble (bins = nominal integer m/z of
- * every fragment, weight 1 per fragment); this is what one ncclAllReduce(sum) combines across GPUs in
- * place of concatenating every TMP.n/qcxms.res (reference bin/pqcxms:101-103).  Returns the device pointer as well so
- * the caller can hand it to NCCL without a host round trip (may be NULL). */
+/* Fragment-mass histogram of the finished trajectories of this ensemble: bin = nominal integer mass of a fragment (sum over its
+ * atoms of the mass number of the most abundant isotope, or of the atom's own mass rounded when it carries an isotope label),
+ * weight 1 per fragment.  A device-side preview of the first fragmentation generation; the spectrum proper -- statistical
+ * charges from the fragment IPs, isotope patterns -- is assembled from the qcxms.res records (qcxms_b200/spectrum.py) and combined
+ * with qcxms_b200_comm_allreduce_sum.  Returns the device pointer as well (may be NULL). */
 int qcxms_b200_ensemble_histogram(qcxms_b200_ensemble_t *h, int nbins, double *bins_host, void **bins_device);
+
+/* ---------------------------------------------------------------------------------------
+ * The one collective of the path: trajectories are dealt over the GPUs of a box (reference bin/pqcxms:88-98 deals
+ * TMP.<n> directories over processes) and only the spectrum is combined at the end, where the reference concatenates every
+ * TMP.<n>/qcxms.res (bin/pqcxms:101-103).  One process per GPU; NCCL (libnccl.so.2, loaded on first use -- set
+ * QCXMS_B200_NCCL_LIB to point at another copy) over NVLink / NVSwitch.  Bootstrap as NCCL prescribes: rank 0 calls
+ * qcxms_b200_comm_unique_id and hands the 128 bytes to the other ranks by whatever the host program has (MPI_Bcast, a file, ...);
+ * then every rank calls qcxms_b200_comm_create. */
+typedef struct qcxms_b200_comm qcxms_b200_comm_t;
+#define QCXMS_B200_UNIQUE_ID_BYTES 128
+int qcxms_b200_comm_unique_id(void *id128);
+int qcxms_b200_comm_create(const void *id128, int nranks, int rank, int device, qcxms_b200_comm_t **out);
+int qcxms_b200_comm_destroy(qcxms_b200_comm_t *c);
+/* in-place sum over the ranks of a HOST array (staged through device memory): the charge-weighted, isotope-expanded m/z
+ * intensities a rank accumulated from its qcxms.res records */
+int qcxms_b200_comm_allreduce_sum(qcxms_b200_comm_t *c, double *inout, int n);
+/* fragment-mass histogram of this rank's ensemble (qcxms_b200_ensemble_histogram), summed over the ranks on the device and
+ * returned in bins_host [nbins] */
+int qcxms_b200_ensemble_allreduce_histogram(qcxms_b200_ensemble_t *h, qcxms_b200_comm_t *c, int nbins, double *bins_host);
 
 /* ---------------------------------------------------------------------------------------
  * CID: one ion + collision-gas-atom collision MD per trajectory, replaces cid() (reference src/cid.f90:24-1111;

@@ -4,10 +4,10 @@ The product is the C-ABI shared library built from qcxms_b200/csrc (see include/
 this package is the thin host-side mirror of the reference's Fortran interface for that path.
 There is no CPU fallback: importing the API without the built CUDA library raises.
 """
-from .api import (CidConfig, CidResult, Ensemble, MdConfig, MdResult, cid, cid_config, egrad_batch, fragment_structure, get_xtb_egrad, get_xtb_egrad_spec, gfn1_xtb, gfn2_xtb,
+from .api import (CidConfig, CidResult, Comm, Ensemble, MdConfig, MdResult, cid, cid_config, egrad_batch, fragment_structure, get_xtb_egrad, get_xtb_egrad_spec, gfn1_xtb, gfn2_xtb,
                   ipea1_xtb, lib, load_molecule, version)
 
-from . import fragments  # noqa: E402,F401
+from . import fragments, spectrum  # noqa: E402,F401
 
-__all__ = ["fragments", "CidConfig", "CidResult", "cid", "cid_config", "Ensemble", "MdConfig", "MdResult", "egrad_batch", "fragment_structure", "get_xtb_egrad", "get_xtb_egrad_spec", "gfn1_xtb",
+__all__ = ["fragments", "spectrum", "CidConfig", "CidResult", "Comm", "cid", "cid_config", "Ensemble", "MdConfig", "MdResult", "egrad_batch", "fragment_structure", "get_xtb_egrad", "get_xtb_egrad_spec", "gfn1_xtb",
            "gfn2_xtb", "ipea1_xtb", "lib", "load_molecule", "version"]

@@ -58,7 +58,9 @@ GASES = {"he": (2, 4.002, 2.64560263), "ne": (10, 20.18, 2.91016289), "ar": (18,
 EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_egrad_spec", "qcxms_b200_basis_size", "qcxms_b200_cid_batch", "qcxms_b200_egrad_batch", "qcxms_b200_fragment_structure", "qcxms_b200_ensemble_create",
            "qcxms_b200_ensemble_destroy", "qcxms_b200_ensemble_set_trajectory", "qcxms_b200_ensemble_set_all",
            "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_set_warm_start", "qcxms_b200_ensemble_set_mfp", "qcxms_b200_ensemble_get_new_velo", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_get_all", "qcxms_b200_ensemble_last_timing",
-           "qcxms_b200_ensemble_histogram", "qcxms_b200_ensemble_intenergy", "qcxms_b200_last_error", "qcxms_b200_version"]
+           "qcxms_b200_ensemble_histogram", "qcxms_b200_ensemble_intenergy", "qcxms_b200_last_error", "qcxms_b200_version",
+           "qcxms_b200_comm_unique_id", "qcxms_b200_comm_create", "qcxms_b200_comm_destroy", "qcxms_b200_comm_allreduce_sum",
+           "qcxms_b200_ensemble_allreduce_histogram"]
 
 
 def lib():
@@ -91,6 +93,11 @@ def lib():
         L.qcxms_b200_ensemble_intenergy.argtypes = [C.c_void_p, dp, dp]
         L.qcxms_b200_cid_batch.argtypes = [C.POINTER(CidConfig), C.c_int, C.c_int, ip, dp, C.c_int, dp, dp, dp, dp, dp, ip, dp, dp, dp, ip,
                                            C.POINTER(CidResult), C.c_int]
+        L.qcxms_b200_comm_unique_id.argtypes = [C.c_void_p]
+        L.qcxms_b200_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.qcxms_b200_comm_destroy.argtypes = [C.c_void_p]
+        L.qcxms_b200_comm_allreduce_sum.argtypes = [C.c_void_p, dp, C.c_int]
+        L.qcxms_b200_ensemble_allreduce_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp]
         L.qcxms_b200_last_error.restype = C.c_char_p
         L.qcxms_b200_version.restype = C.c_char_p
         _LIB = L
@@ -314,6 +321,40 @@ def cid(cfg, num, mass, icoll, xyz, velo, rnd, velo_cm=None, direc=None, collide
         if k != "direc":
             out[k] = np.array([getattr(r, k) for r in res])
     return out
+
+
+class Comm:
+    """The path's one collective through the C ABI (qcxms_b200_comm_*: NCCL over NVLink / NVSwitch, one process per GPU).
+    Rank 0 draws `Comm.unique_id()` and hands the 128 bytes to the other ranks (any transport the host has); every rank then
+    constructs Comm(id, nranks, rank, device)."""
+
+    def __init__(self, unique_id, nranks, rank, device=0):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._c = C.c_void_p()
+        _check(lib().qcxms_b200_comm_create(buf, int(nranks), int(rank), int(device), C.byref(self._c)))
+        self.nranks, self.rank = int(nranks), int(rank)
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * 128)()
+        _check(lib().qcxms_b200_comm_unique_id(buf))
+        return bytes(buf.raw)
+
+    def allreduce_sum(self, arr):
+        """in-place sum over the ranks of a host float64 array (e.g. spectrum.spectrum(records))"""
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        _check(lib().qcxms_b200_comm_allreduce_sum(self._c, _dp(a), int(a.size)))
+        return a
+
+    def allreduce_histogram(self, ensemble, nbins=512):
+        bins = np.zeros(int(nbins))
+        _check(lib().qcxms_b200_ensemble_allreduce_histogram(ensemble._h, self._c, int(nbins), _dp(bins)))
+        return bins
+
+    def close(self):
+        if self._c:
+            lib().qcxms_b200_comm_destroy(self._c)
+            self._c = C.c_void_p()
 
 
 def load_molecule(name):

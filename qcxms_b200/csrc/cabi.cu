@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -59,18 +61,24 @@ __global__ void k_intenergy(DevModel m, MdState st, int ntraj, double *fragT, do
     }
 }
 
+// mass number of the most abundant isotope, H .. Ar
+__constant__ int c_nominal_mass[19] = {0, 1, 4, 7, 9, 11, 12, 14, 16, 19, 20, 23, 24, 27, 28, 31, 32, 35, 40};
+
 __global__ void k_histogram(DevModel m, MdState st, int ntraj, int nbins, double *bins) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntraj || st.status[t] != TRJ_FINISHED || !st.mdok[t]) return;
     const int *list = st.list + (size_t)t * m.nat;
     for (int f = 1; f <= 10; ++f) {
-        double mass = 0.0;
-        for (int i = 0; i < m.nat; ++i)
-            if (list[i] == f) mass += m.mass[i];
-        if (mass > 0.0) {
-            int bin = (int)llrint(mass * QC_AUTOAMU);
-            if (bin >= 0 && bin < nbins) atomicAdd(&bins[bin], 1.0);
+        int nominal = 0, natoms = 0;
+        for (int i = 0; i < m.nat; ++i) {
+            if (list[i] != f) continue;
+            const double amu = m.mass[i] * QC_AUTOAMU;
+            const int z = m.num[i], std_mass = z <= 18 ? c_nominal_mass[z] : (int)llrint(amu);
+            // an isotope label (reference imass) shows as a mass far from the element's natural average
+            nominal += fabs(amu - std_mass) > 1.6 ? (int)llrint(amu) : std_mass;
+            natoms += 1;
         }
+        if (natoms > 0 && nominal < nbins) atomicAdd(&bins[nominal], 1.0);
     }
 }
 
@@ -656,6 +664,125 @@ extern "C" int qcxms_b200_ensemble_histogram(qcxms_b200_ensemble_t *h, int nbins
     CUDA_OK(cudaStreamSynchronize(h->stream));
     if (bins_host) CUDA_OK(cudaMemcpy(bins_host, h->d_bins, nbins * sizeof(double), cudaMemcpyDeviceToHost));
     if (bins_device) *bins_device = h->d_bins;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ the collective (NCCL, loaded on first use)
+namespace {
+struct NcclUniqueId { char internal[QCXMS_B200_UNIQUE_ID_BYTES]; };
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+NcclApi &nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *env = getenv("QCXMS_B200_NCCL_LIB");
+        const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            if (!n || !*n) continue;
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+            api.why = dlerror();
+        }
+        if (!api.handle) return;
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.handle, "ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
+        api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
+        if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString) {
+            api.why = "NCCL entry points missing";
+            api.handle = nullptr;
+        }
+    });
+    return api;
+}
+constexpr int kNcclDouble = 8, kNcclSum = 0;   // ncclFloat64, ncclSum (nccl.h)
+}  // namespace
+
+struct qcxms_b200_comm {
+    void *comm = nullptr;
+    int nranks = 0, rank = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    double *d_buf = nullptr;
+    size_t cap = 0;
+};
+
+#define NCCL_OK(expr)                                                                                              \
+    do {                                                                                                           \
+        int r__ = (expr);                                                                                          \
+        if (r__ != 0) return fail(QCXMS_B200_ERR_CUDA, std::string(#expr) + ": " + nccl_api().GetErrorString(r__)); \
+    } while (0)
+
+extern "C" int qcxms_b200_comm_unique_id(void *id128) {
+    if (!id128) return fail(QCXMS_B200_ERR_ARG, "null argument");
+    NcclApi &api = nccl_api();
+    if (!api.handle) return fail(QCXMS_B200_ERR_UNSUPPORTED, "NCCL is not available: " + api.why);
+    NcclUniqueId id;
+    NCCL_OK(api.GetUniqueId(&id));
+    memcpy(id128, id.internal, sizeof(id.internal));
+    return 0;
+}
+
+extern "C" int qcxms_b200_comm_create(const void *id128, int nranks, int rank, int device, qcxms_b200_comm_t **out) {
+    if (!id128 || !out || nranks < 1 || rank < 0 || rank >= nranks) return fail(QCXMS_B200_ERR_ARG, "bad argument");
+    NcclApi &api = nccl_api();
+    if (!api.handle) return fail(QCXMS_B200_ERR_UNSUPPORTED, "NCCL is not available: " + api.why);
+    CUDA_OK(cudaSetDevice(device));
+    qcxms_b200_comm *c = new qcxms_b200_comm;
+    c->nranks = nranks; c->rank = rank; c->device = device;
+    NcclUniqueId id;
+    memcpy(id.internal, id128, sizeof(id.internal));
+    int r = api.CommInitRank(&c->comm, nranks, id, rank);
+    if (r != 0) { delete c; return fail(QCXMS_B200_ERR_CUDA, std::string("ncclCommInitRank: ") + api.GetErrorString(r)); }
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { api.CommDestroy(c->comm); delete c; return fail(QCXMS_B200_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = c;
+    return 0;
+}
+
+extern "C" int qcxms_b200_comm_destroy(qcxms_b200_comm_t *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->comm) nccl_api().CommDestroy(c->comm);
+    if (c->d_buf) cudaFree(c->d_buf);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int qcxms_b200_comm_allreduce_sum(qcxms_b200_comm_t *c, double *inout, int n) {
+    if (!c || !inout || n < 1) return fail(QCXMS_B200_ERR_ARG, "bad argument");
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->cap < (size_t)n) {
+        if (c->d_buf) cudaFree(c->d_buf);
+        c->d_buf = nullptr; c->cap = 0;
+        CUDA_OK(cudaMalloc(&c->d_buf, (size_t)n * sizeof(double)));
+        c->cap = n;
+    }
+    CUDA_OK(cudaMemcpyAsync(c->d_buf, inout, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCCL_OK(nccl_api().AllReduce(c->d_buf, c->d_buf, (size_t)n, kNcclDouble, kNcclSum, c->comm, c->stream));
+    CUDA_OK(cudaMemcpyAsync(inout, c->d_buf, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qcxms_b200_ensemble_allreduce_histogram(qcxms_b200_ensemble_t *h, qcxms_b200_comm_t *c, int nbins, double *bins_host) {
+    if (!h || !c || !bins_host) return fail(QCXMS_B200_ERR_ARG, "bad argument");
+    if (c->device != h->ctx.device) return fail(QCXMS_B200_ERR_ARG, "communicator and ensemble live on different devices");
+    void *d_bins = nullptr;
+    int rc = qcxms_b200_ensemble_histogram(h, nbins, nullptr, &d_bins);   // synchronises the ensemble's stream
+    if (rc) return rc;
+    NCCL_OK(nccl_api().AllReduce(d_bins, d_bins, (size_t)nbins, kNcclDouble, kNcclSum, c->comm, c->stream));
+    CUDA_OK(cudaMemcpyAsync(bins_host, d_bins, (size_t)nbins * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

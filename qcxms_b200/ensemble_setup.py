@@ -54,6 +54,18 @@ def allreduce_histogram(bins):
     return bins
 
 
+def make_comm(device=0):
+    """The C-ABI communicator (qcxms_b200_comm_*, NCCL) for this process: bootstrapped through torch.distributed when a process
+    group exists (rank 0's unique id is broadcast), a one-rank communicator otherwise."""
+    from .api import Comm
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        box = [Comm.unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return Comm(box[0], dist.get_world_size(), dist.get_rank(), device)
+    return Comm(Comm.unique_id(), 1, 0, device)
+
+
 def spectrum_from_histogram(bins):
     """Normalised stick spectrum (base peak = 100) from the summed fragment-mass histogram."""
     bins = np.asarray(bins, dtype=np.float64)
