@@ -27,9 +27,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL writes its banner ("NCCL version ...", NCCL_DEBUG=VERSION) to stdout, which must carry exactly one JSON line
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL writes its banner ("NCCL version ...", NCCL_DEBUG=VERSION or WARN) to stdout, which must carry exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "trajectory_md_steps_per_s"
 UNIT = "trajectory-MD-steps/s"
@@ -70,7 +69,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_md_sample(num, xyz0, ntraj, nsteps, threads):
+def cpu_md_sample(num, xyz0, ntraj, nsteps, threads, method=2):
     """The oracle's md() on the host cores: ntraj trajectories x nsteps steps, one trajectory per thread (ctypes drops the GIL)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle as po
@@ -79,7 +78,7 @@ def cpu_md_sample(num, xyz0, ntraj, nsteps, threads):
     ic = es.synthetic_initial_conditions(num, xyz0, ntraj)
 
     def run(k):
-        r = po.md(num, ic["mass"], ic["xyz"][k], ic["velo"][k], ic["velof"][k], ic["eimp"][k], ic["tadd"][k], mchrg=1, nmax=nsteps, exit_rules=False)
+        r = po.md(num, ic["mass"], ic["xyz"][k], ic["velo"][k], ic["velof"][k], ic["eimp"][k], ic["tadd"][k], mchrg=1, nmax=nsteps, exit_rules=False, method=method)
         return r["nstep"]
 
     t0 = time.perf_counter()
@@ -113,6 +112,7 @@ def main():
     ap.add_argument("--ntraj", type=int, default=1000, help="trajectories: in total (--scaling strong) or per GPU (--scaling weak)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--molecule", default="caffeine")
+    ap.add_argument("--method", default="gfn2", choices=["gfn2", "gfn1"], help="gfn1: BASELINE config 3 (same molecule, GFN1-xTB Hamiltonian)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--warm-start", action="store_true", help="opt-in fast mode, NOT the reference protocol (SURVEY 8f-4): SCC of a step "
                     "starts from the previous step's converged populations; never the headline number")
@@ -123,11 +123,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from qcxms_b200.api import load_molecule
     num, xyz0, _ = load_molecule(args.molecule)
+    method_id = {"gfn2": 2, "gfn1": 1}[args.method]
     nat = len(num)
     cores = len(os.sched_getaffinity(0))
     per_gpu = args.scaling == "weak"
-    config = {"workload": "%s cation GFN2-xTB EI, %d trajectories %s, tstep 0.5 fs, etemp 5000 K, cold-start SCC acc=1.0, exit rules off"
-                          % (args.molecule, args.ntraj, "per GPU" if per_gpu else "in total, dealt itrj mod N over the ranks"), "nat": nat,
+    config = {"workload": "%s cation %s-xTB EI, %d trajectories %s, tstep 0.5 fs, etemp 5000 K, cold-start SCC acc=1.0, exit rules off"
+                          % (args.molecule, args.method.upper(), args.ntraj, "per GPU" if per_gpu else "in total, dealt itrj mod N over the ranks"), "nat": nat,
               "ntraj_total": args.ntraj * (args.gpus if per_gpu else 1),
               "l2": "per-step working set (453 KB scratch x resident CTAs + state) is re-streamed every SCC cycle; inputs are not cached between steps"}
 
@@ -142,11 +143,11 @@ def main():
         from oracle import pyoracle  # noqa: F401
         ntraj_s, per_step = cores, 8
         for _ in range(max(args.warmup, 1)):
-            cpu_md_sample(num, xyz0, min(ntraj_s, 4), 1, cores)
+            cpu_md_sample(num, xyz0, min(ntraj_s, 4), 1, cores, method_id)
         t0 = time.perf_counter()
         done = 0
         for _ in range(args.steps):
-            d, _dt = cpu_md_sample(num, xyz0, ntraj_s, per_step, cores)
+            d, _dt = cpu_md_sample(num, xyz0, ntraj_s, per_step, cores, method_id)
             done += d + ntraj_s          # md() starts with one egrad before its first step: same work as a step
         dt = time.perf_counter() - t0
         val = done / dt
@@ -185,7 +186,7 @@ def main():
         pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in ic.items() if k != "mass"}
 
         def new_ensemble():
-            e = qx.Ensemble(num, ic["mass"], ntl, mchrg=1, tstep_fs=0.5, nmax=10 ** 6, exit_rules=False, device=local_rank)
+            e = qx.Ensemble(num, ic["mass"], ntl, mchrg=1, tstep_fs=0.5, nmax=10 ** 6, exit_rules=False, device=local_rank, method=method_id)
             if args.warm_start:
                 e.set_warm_start(True)
             e.set_all(*[pin[k].numpy() for k in ("xyz", "velo", "velof", "eimp", "tadd")])
@@ -257,10 +258,10 @@ def main():
         return
 
     fp64_peak = measure_fp64_peak(torch, dev)
-    nsh, nao = {"caffeine": (38, 66)}.get(args.molecule, (None, None))
+    nsh, nao = {("caffeine", 2): (38, 66), ("caffeine", 1): (48, 76)}.get((args.molecule, method_id), (None, None))
     if nao is None:
         from oracle import pyoracle
-        nsh, nao = pyoracle.dims(num)
+        nsh, nao = pyoracle.dims(num, method_id)
     flops = algorithmic_flops_per_traj_step(nao, n_it) * (total_steps / world)   # per GPU
     achieved = flops / dev_s_max / 1e12
     traffic = None
@@ -284,8 +285,8 @@ def main():
         out["other_scaling"] = other
     if not args.no_cpu_baseline and world == 1:
         ncpu_traj, ncpu_steps = cores, 8
-        cpu_md_sample(num, xyz0, 2, 1, cores)
-        done, dt = cpu_md_sample(num, xyz0, ncpu_traj, ncpu_steps, cores)
+        cpu_md_sample(num, xyz0, 2, 1, cores, method_id)
+        done, dt = cpu_md_sample(num, xyz0, ncpu_traj, ncpu_steps, cores, method_id)
         out["cpu_baseline"] = {"value": (done + ncpu_traj) / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": "%d trajectories x %d MD steps (+1 initial egrad each) of the same workload, oracle md(), one trajectory per host thread" % (ncpu_traj, ncpu_steps)}
     print(json.dumps(out))

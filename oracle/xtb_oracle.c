@@ -26,9 +26,11 @@
 #include "../qcxms_b200/csrc/params/d4_refdata.h"
 #include "../qcxms_b200/csrc/params/elem_tables.h"
 #include "../qcxms_b200/csrc/params/gfn2_params.h"
+#include "../qcxms_b200/csrc/params/gfn1_params.h"
+#include "../qcxms_b200/csrc/params/d3_refdata.h"
 #include "../qcxms_b200/csrc/params/stong_table.h"
 
-#define MAXPRIM 6
+#define MAXPRIM 8 /* GFN1: the orthogonalised H 2s carries the 1s primitives as well (3 + 4) */
 #define MAX_ITER 250
 #define SQRT3 1.7320508075688772935
 #define PI 3.14159265358979323846264338327950288
@@ -54,6 +56,10 @@ static const double *trafo_row(int l, int m) {
 
 typedef struct {
     int nat, nsh, nao, charge;
+    int method;                 /* QC_METHOD_GFN2 or QC_METHOD_GFN1 */
+    const gfn2_elem_t *elem;    /* element table of the method */
+    int *sh_val;                /* [nsh] GFN1: 0 marks a diffuse shell */
+    double *at_gam3;            /* [nat] GFN1: atom-resolved third-order parameter */
     double kt;
     const int32_t *num;
     const double *xyz;
@@ -83,11 +89,13 @@ static const stong_entry_t *stong_find(int n, int l, int ng) {
 }
 
 int xtb_oracle_dims(int nat, const int32_t *num, int method_id, int *nsh, int *nao) {
-    if (method_id != QC_METHOD_GFN2) return QC_STAT_UNKNOWN_METHOD;
+    if (method_id != QC_METHOD_GFN2 && method_id != QC_METHOD_GFN1) return QC_STAT_UNKNOWN_METHOD;
+    if (method_id == QC_METHOD_GFN1) gfn1_ensure_loaded();
     int ns = 0, na = 0;
     for (int i = 0; i < nat; ++i) {
         if (num[i] < 1 || num[i] > GFN2_MAXZ) return QC_STAT_FATAL;
-        const gfn2_elem_t *e = &GFN2_ELEM[num[i]];
+        if (method_id == QC_METHOD_GFN1 && !GFN1_EXTRA[num[i]].supported) return QC_STAT_FATAL;
+        const gfn2_elem_t *e = method_id == QC_METHOD_GFN1 ? &GFN1_ELEM[num[i]] : &GFN2_ELEM[num[i]];
         ns += e->nshell;
         for (int k = 0; k < e->nshell; ++k) na += NSPH[e->ang[k]];
     }
@@ -98,7 +106,8 @@ int xtb_oracle_dims(int nat, const int32_t *num, int method_id, int *nsh, int *n
 
 static int setup_basis(sys_t *s) {
     int nat = s->nat;
-    if (xtb_oracle_dims(nat, s->num, QC_METHOD_GFN2, &s->nsh, &s->nao)) return -1;
+    if (xtb_oracle_dims(nat, s->num, s->method, &s->nsh, &s->nao)) return -1;
+    const int gfn1 = s->method == QC_METHOD_GFN1;
     int nsh = s->nsh, nao = s->nao;
     s->at_sh0 = xcalloc(nat, sizeof(int));
     s->at_nsh = xcalloc(nat, sizeof(int));
@@ -117,9 +126,12 @@ static int setup_basis(sys_t *s) {
     s->sh_hub = xcalloc(nsh, sizeof(double));
     s->sh_gam3 = xcalloc(nsh, sizeof(double));
     s->sh_zeta = xcalloc(nsh, sizeof(double));
+    s->sh_val = xcalloc(nsh, sizeof(int));
+    s->at_gam3 = xcalloc(nat, sizeof(double));
     int ish = 0, iao = 0;
     for (int i = 0; i < nat; ++i) {
-        const gfn2_elem_t *e = &GFN2_ELEM[s->num[i]];
+        const gfn2_elem_t *e = &s->elem[s->num[i]];
+        if (gfn1) s->at_gam3[i] = e->hubbard_deriv;
         s->at_sh0[i] = ish;
         s->at_nsh[i] = e->nshell;
         for (int k = 0; k < e->nshell; ++k, ++ish) {
@@ -130,10 +142,15 @@ static int setup_basis(sys_t *s) {
             s->sh_np[ish] = e->nprim[k];
             s->sh_level[ish] = e->selfenergy[k] * GFN2_EVTOAU;
             s->sh_kcn[ish] = e->kcn[k] * GFN2_EVTOAU;
+            s->sh_val[ish] = 1;
+            if (gfn1) {   /* h = level (1 + kcn_l CN) written as level - kcn CN */
+                s->sh_kcn[ish] = -e->selfenergy[k] * GFN2_EVTOAU * GFN1_KCN_L[l];
+                s->sh_val[ish] = GFN1_EXTRA[s->num[i]].valence[k];
+            }
             s->sh_poly[ish] = e->shpoly[k];
             s->sh_refocc[ish] = e->refocc[k];
             s->sh_hub[ish] = e->hubbard * e->shell_hubbard[l];
-            s->sh_gam3[ish] = e->hubbard_deriv * GFN2_KSHELL3[l];
+            s->sh_gam3[ish] = gfn1 ? 0.0 : e->hubbard_deriv * GFN2_KSHELL3[l];
             s->sh_zeta[ish] = e->slater[k];
             const stong_entry_t *t = stong_find(e->pqn[k], l, e->nprim[k]);
             if (!t) return -1;
@@ -148,6 +165,26 @@ static int setup_basis(sys_t *s) {
                 s->ao_at[iao] = i;
                 s->ao_sh[iao] = ish;
             }
+            /* GFN1: a second shell of the same angular momentum (H 2s) is Schmidt-orthogonalised to the first one and renormalised:
+             * chi' = (chi_2 - <1|2>/<1|1> chi_1) / |...|, so it carries the primitives of both (s functions only) */
+            if (gfn1 && k > 0 && l == 0) {
+                int first = -1;
+                for (int kk = 0; kk < k; ++kk) if (e->ang[kk] == l) first = s->at_sh0[i] + kk;
+                if (first >= 0) {
+                    double *a1 = s->sh_alpha + first * MAXPRIM, *c1 = s->sh_coef + first * MAXPRIM;
+                    double *a2 = s->sh_alpha + ish * MAXPRIM, *c2 = s->sh_coef + ish * MAXPRIM;
+                    int n1 = s->sh_np[first], n2 = s->sh_np[ish];
+                    if (n1 + n2 > MAXPRIM) return -1;
+                    double s11 = 0, s12 = 0, s22 = 0;
+                    for (int p = 0; p < n1; ++p) for (int q = 0; q < n1; ++q) s11 += c1[p] * c1[q] * pow(PI / (a1[p] + a1[q]), 1.5);
+                    for (int p = 0; p < n1; ++p) for (int q = 0; q < n2; ++q) s12 += c1[p] * c2[q] * pow(PI / (a1[p] + a2[q]), 1.5);
+                    for (int p = 0; p < n2; ++p) for (int q = 0; q < n2; ++q) s22 += c2[p] * c2[q] * pow(PI / (a2[p] + a2[q]), 1.5);
+                    double f = s12 / s11, nrm = 1.0 / sqrt(s22 - s12 * s12 / s11);
+                    for (int q = 0; q < n2; ++q) c2[q] *= nrm;
+                    for (int p = 0; p < n1; ++p) { a2[n2 + p] = a1[p]; c2[n2 + p] = -f * nrm * c1[p]; }
+                    s->sh_np[ish] = n1 + n2;
+                }
+            }
         }
     }
     return 0;
@@ -157,6 +194,34 @@ static int setup_basis(sys_t *s) {
 static double d3_rcov(int z) { return 4.0 / 3.0 * COVRAD2009_AA[z] * TB_AATOAU; }
 
 /* GFN2 double-exponential counting function: ka = 10, kb = 20, r_shift = 2, cutoff 25 bohr */
+/* GFN1 / D3: exponential counting function, k1 = 16, covalent radii x 4/3 (reference src/dftd3.f90:607-642 ncoord, cn_thr = 1000 bohr^2) */
+static void exp_cn(sys_t *s) {
+    int nat = s->nat;
+    const double k1 = 16.0, cn_thr = 1000.0;
+    memset(s->cn, 0, nat * sizeof(double));
+    memset(s->dcndr, 0, (size_t)nat * nat * 3 * sizeof(double));
+    for (int i = 0; i < nat; ++i)
+        for (int j = 0; j < i; ++j) {
+            double v[3] = {s->xyz[3 * i] - s->xyz[3 * j], s->xyz[3 * i + 1] - s->xyz[3 * j + 1],
+                           s->xyz[3 * i + 2] - s->xyz[3 * j + 2]};
+            double r2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+            if (r2 > cn_thr) continue;
+            double r = sqrt(r2), rco = D3_RCOV[s->num[i]] + D3_RCOV[s->num[j]];
+            double ex = exp(-k1 * (rco / r - 1.0));
+            double f = 1.0 / (1.0 + ex);
+            double df = -k1 * rco / r2 * ex * f * f;
+            s->cn[i] += f;
+            s->cn[j] += f;
+            for (int c = 0; c < 3; ++c) {
+                double g = df * v[c] / r;
+                s->dcndr[(i * nat + i) * 3 + c] += g;
+                s->dcndr[(j * nat + i) * 3 + c] -= g;
+                s->dcndr[(j * nat + j) * 3 + c] -= g;
+                s->dcndr[(i * nat + j) * 3 + c] += g;
+            }
+        }
+}
+
 static void gfn_cn(sys_t *s) {
     int nat = s->nat;
     const double ka = 10.0, kb = 20.0, rshift = 2.0, cutoff2 = 25.0 * 25.0;
@@ -384,13 +449,25 @@ static void shift_operator(const double vec[3], double s, const double di[3], co
 static double gfn2_hscale(const sys_t *s, int ish, int jsh) {
     static const double kdiag[3] = {GFN2_KDIAG_S, GFN2_KDIAG_P, GFN2_KDIAG_D};
     int li = s->sh_l[ish], lj = s->sh_l[jsh];
+    if (s->method == QC_METHOD_GFN1) {
+        static const double k1[3] = {GFN1_KDIAG_S, GFN1_KDIAG_P, GFN1_KDIAG_D};
+        int zi = s->num[s->sh_at[ish]], zj = s->num[s->sh_at[jsh]];
+        if (s->sh_val[ish] && s->sh_val[jsh]) {
+            double kll = (li + lj == 1) ? GFN1_K_SP : 0.5 * (k1[li] + k1[lj]);
+            double den = s->elem[zi].en - s->elem[zj].en;
+            return gfn1_kpair(zi, zj) * kll * (1.0 + GFN1_ENSCALE * den * den);
+        }
+        if (s->sh_val[ish]) return 0.5 * (k1[li] + GFN1_KDIFF);
+        if (s->sh_val[jsh]) return 0.5 * (k1[lj] + GFN1_KDIFF);
+        return GFN1_KDIFF;
+    }
     double k;
     if (li == lj) k = kdiag[li];
     else if (li == 2 || lj == 2) k = (li + lj == 2) ? GFN2_K_SD : GFN2_K_PD;
     else k = 0.5 * (kdiag[li] + kdiag[lj]);
     double zi = s->sh_zeta[ish], zj = s->sh_zeta[jsh];
     double zij = pow(2.0 * sqrt(zi * zj) / (zi + zj), GFN2_WEXP);
-    double den = GFN2_ELEM[s->num[s->sh_at[ish]]].en - GFN2_ELEM[s->num[s->sh_at[jsh]]].en;
+    double den = s->elem[s->num[s->sh_at[ish]]].en - s->elem[s->num[s->sh_at[jsh]]].en;
     return zij * k * (1.0 + GFN2_ENSCALE * den * den);
 }
 
@@ -408,7 +485,7 @@ static void build_integrals(sys_t *s) {
             double vec[3] = {s->xyz[3 * iat] - s->xyz[3 * jat], s->xyz[3 * iat + 1] - s->xyz[3 * jat + 1],
                              s->xyz[3 * iat + 2] - s->xyz[3 * jat + 2]};
             double r2 = vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2];
-            double radsum = (GFN2_ELEM[s->num[iat]].atomic_rad + GFN2_ELEM[s->num[jat]].atomic_rad) * TB_AATOAU;
+            double radsum = (s->elem[s->num[iat]].atomic_rad + s->elem[s->num[jat]].atomic_rad) * TB_AATOAU;
             double rr = sqrt(sqrt(r2) / radsum);
             for (int is = 0; is < s->at_nsh[iat]; ++is)
                 for (int js = 0; js < s->at_nsh[jat]; ++js) {
@@ -899,11 +976,11 @@ static double repulsion(const sys_t *s, double *grad) {
     double e = 0.0;
     for (int i = 0; i < s->nat; ++i)
         for (int j = 0; j < i; ++j) {
-            const gfn2_elem_t *ei = &GFN2_ELEM[s->num[i]], *ej = &GFN2_ELEM[s->num[j]];
+            const gfn2_elem_t *ei = &s->elem[s->num[i]], *ej = &s->elem[s->num[j]];
             double v[3], r2 = 0;
             for (int k = 0; k < 3; ++k) { v[k] = s->xyz[3 * i + k] - s->xyz[3 * j + k]; r2 += v[k] * v[k]; }
             double r = sqrt(r2);
-            double kexp = (s->num[i] <= 2 && s->num[j] <= 2) ? GFN2_REP_KEXP_LIGHT : GFN2_REP_KEXP;
+            double kexp = s->method == QC_METHOD_GFN1 ? GFN1_REP_KEXP : ((s->num[i] <= 2 && s->num[j] <= 2) ? GFN2_REP_KEXP_LIGHT : GFN2_REP_KEXP);
             double alpha = sqrt(ei->rep_alpha * ej->rep_alpha), zz = ei->rep_zeff * ej->rep_zeff;
             double rk = pow(r, kexp);
             double ex = exp(-alpha * rk);
@@ -923,7 +1000,8 @@ static void coulomb_setup(const sys_t *s, cache_t *c) {
     for (int a = 0; a < nsh; ++a)
         for (int b = 0; b < nsh; ++b) {
             int i = s->sh_at[a], j = s->sh_at[b];
-            double gam = 0.5 * (s->sh_hub[a] + s->sh_hub[b]);
+            double gam = s->method == QC_METHOD_GFN1 ? 2.0 / (1.0 / s->sh_hub[a] + 1.0 / s->sh_hub[b])   /* harmonic average */
+                                                     : 0.5 * (s->sh_hub[a] + s->sh_hub[b]);
             if (i == j)
                 c->gamma[a * nsh + b] = gam;
             else {
@@ -932,9 +1010,10 @@ static void coulomb_setup(const sys_t *s, cache_t *c) {
                 c->gamma[a * nsh + b] = 1.0 / sqrt(r2 + 1.0 / (gam * gam)); /* gexp = 2 */
             }
         }
+    if (s->method == QC_METHOD_GFN1) return;   /* no multipole electrostatics */
     /* multipole damping radii from the GFN CN */
     for (int i = 0; i < nat; ++i) {
-        const gfn2_elem_t *e = &GFN2_ELEM[s->num[i]];
+        const gfn2_elem_t *e = &s->elem[s->num[i]];
         double arg = s->cn[i] - e->mp_vcn - GFN2_MP_SHIFT;
         double t1 = exp(-GFN2_MP_KEXP * arg);
         double t2 = (GFN2_MP_RMAX - e->mp_rad) / (1.0 + t1);
@@ -981,9 +1060,14 @@ static void build_potential(const sys_t *s, const cache_t *c, const double *qsh,
         for (int b = 0; b < nsh; ++b) v += c->gamma[a * nsh + b] * qsh[b];
         p->vsh[a] += v + qsh[a] * qsh[a] * s->sh_gam3[a];
     }
+    if (s->method == QC_METHOD_GFN1) {   /* atom-resolved third order; no multipoles, no self-consistent dispersion */
+        for (int i = 0; i < nat; ++i) p->vat[i] += qat[i] * qat[i] * s->at_gam3[i];
+        for (int mu = 0; mu < s->nao; ++mu) p->vao[mu] = p->vsh[s->ao_sh[mu]] + p->vat[s->ao_at[mu]];
+        return;
+    }
     /* anisotropic electrostatics + multipole XC kernels */
     for (int d = 0; d < nat; ++d) {
-        const gfn2_elem_t *e = &GFN2_ELEM[s->num[d]];
+        const gfn2_elem_t *e = &s->elem[s->num[d]];
         for (int q = 0; q < nat; ++q) {
             if (q == d) continue;
             size_t pq = (size_t)d * nat + q;
@@ -1023,8 +1107,13 @@ static void scc_energies(const sys_t *s, cache_t *c, const double *qsh, const do
         e2 += 0.5 * v * qsh[a];
         e3 += qsh[a] * qsh[a] * qsh[a] * s->sh_gam3[a] / 3.0;
     }
+    if (s->method == QC_METHOD_GFN1) {
+        for (int i = 0; i < nat; ++i) e3 += qat[i] * qat[i] * qat[i] * s->at_gam3[i] / 3.0;
+        *es2 = e2; *es3 = e3; *eaes = 0.0; *ed4 = 0.0;
+        return;
+    }
     for (int d = 0; d < nat; ++d) {
-        const gfn2_elem_t *e = &GFN2_ELEM[s->num[d]];
+        const gfn2_elem_t *e = &s->elem[s->num[d]];
         double vd[3] = {0, 0, 0}, vq[6] = {0, 0, 0, 0, 0, 0};
         for (int q = 0; q < nat; ++q) {
             if (q == d) continue;
@@ -1143,16 +1232,128 @@ static int broyden_next(broyden_t *m) {
 
 /* The reference hard-codes accuracy = 1.0 (src/tblite.f90:46).  Tests may tighten it to
  * separate SCC-threshold noise from genuine disagreement (finite-difference checks). */
+/* ------------------------------------------------------------ GFN1: D3(BJ) --- */
+/* C6(i,j) interpolated over the reference systems with Gaussian weights in CN space and its derivatives with respect to both
+ * coordination numbers (reference src/dftd3.f90:334-405 get_dC6_dCNij, k3 = -4). */
+static void d3_c6(int zi, int zj, double cni, double cnj, double *c6, double *dc6i, double *dc6j) {
+    const double k3 = -4.0;
+    double c6mem = -1.e99, r_save = 9999.0, zaehler = 0, nenner = 0, dzi = 0, dni = 0, dzj = 0, dnj = 0;
+    for (int a = 0; a < D3_MXC[zi]; ++a)
+        for (int b = 0; b < D3_MXC[zj]; ++b) {
+            double c6ref = D3_C6AB[zi][zj][a][b][0];
+            if (c6ref > 0) {
+                double cn_refi = D3_C6AB[zi][zj][a][b][1], cn_refj = D3_C6AB[zi][zj][a][b][2];
+                double r = (cn_refi - cni) * (cn_refi - cni) + (cn_refj - cnj) * (cn_refj - cnj);
+                if (r < r_save) { r_save = r; c6mem = c6ref; }
+                double expterm = exp(k3 * r);
+                zaehler += c6ref * expterm;
+                nenner += expterm;
+                expterm = expterm * 2.0 * k3;
+                double term = expterm * (cni - cn_refi);
+                dzi += c6ref * term; dni += term;
+                term = expterm * (cnj - cn_refj);
+                dzj += c6ref * term; dnj += term;
+            }
+        }
+    if (nenner > 1.0e-99) {
+        *c6 = zaehler / nenner;
+        *dc6i = ((dzi * nenner) - (dni * zaehler)) / (nenner * nenner);
+        *dc6j = ((dzj * nenner) - (dnj * zaehler)) / (nenner * nenner);
+    } else {
+        *c6 = c6mem; *dc6i = 0.0; *dc6j = 0.0;
+    }
+}
+
+/* two-body D3 with Becke-Johnson damping (reference src/dftd3.f90:107-186, BJ variant, no three-body term):
+ * E = - sum_{i>j} C6 (s6 / (r^6 + R0^6) + 3 s8 r42 / (r^8 + R0^8)), R0 = a1 sqrt(3 r42) + a2, r42 = r2r4_i r2r4_j.
+ * Adds dE/dR at fixed CN to grad and dE/dCN to dEdcn (the CN is the exponential one the Hamiltonian uses). */
+static double d3_bj(const sys_t *s, double *grad, double *dEdcn) {
+    const double rthr = 4000.0;
+    double disp = 0.0;
+    for (int i = 0; i < s->nat; ++i)
+        for (int j = 0; j < i; ++j) {
+            double v[3], r2 = 0;
+            for (int k = 0; k < 3; ++k) { v[k] = s->xyz[3 * i + k] - s->xyz[3 * j + k]; r2 += v[k] * v[k]; }
+            if (r2 > rthr) continue;
+            double c6, dc6i, dc6j;
+            d3_c6(s->num[i], s->num[j], s->cn[i], s->cn[j], &c6, &dc6i, &dc6j);
+            double r42 = D3_R2R4[s->num[i]] * D3_R2R4[s->num[j]];
+            double r = sqrt(r2), r4 = r2 * r2, r6 = r4 * r2, r8 = r6 * r2;
+            double R0 = GFN1_D3_A1 * sqrt(3.0 * r42) + GFN1_D3_A2;
+            double t6 = r6 + pow(R0, 6), t8 = r8 + pow(R0, 8);
+            double rest = GFN1_D3_S6 / t6 + 3.0 * GFN1_D3_S8 * r42 / t8;
+            disp -= rest * c6;
+            /* (1/r) dE/dr at fixed C6 */
+            double dedr = c6 * (GFN1_D3_S6 * 6.0 * r4 * r / (t6 * t6) + GFN1_D3_S8 * 24.0 * r42 * r6 * r / (t8 * t8)) / r;
+            for (int k = 0; k < 3; ++k) { grad[3 * i + k] += dedr * v[k]; grad[3 * j + k] -= dedr * v[k]; }
+            dEdcn[i] -= rest * dc6i;
+            dEdcn[j] -= rest * dc6j;
+        }
+    return disp;
+}
+
+/* ------------------------------------------------- GFN1: halogen-bond correction --- */
+/* For every halogen X with its nearest neighbour K and every acceptor A (N, O, P, S) within 20 bohr:
+ * E = c_X (1/2 - 1/4 cos(A-X-K))^6 (t^12 - damp t^6) / (1 + t^12), t = xbrad (R_A + R_X) / r_AX (atomic radii as in the
+ * H0 polynomial).  Restated from the published GFN1-xTB definition (tblite classical/halogen.f90 is not available). */
+static double halogen_bond(const sys_t *s, double *grad) {
+    double exb = 0.0;
+    for (int x = 0; x < s->nat; ++x) {
+        if (!gfn1_xb_donor(s->num[x])) continue;
+        int kn = -1;
+        double best = 1e300;
+        for (int k = 0; k < s->nat; ++k) {
+            if (k == x) continue;
+            double d2 = 0;
+            for (int c = 0; c < 3; ++c) { double d = s->xyz[3 * k + c] - s->xyz[3 * x + c]; d2 += d * d; }
+            if (d2 < best) { best = d2; kn = k; }
+        }
+        if (kn < 0) continue;
+        for (int a = 0; a < s->nat; ++a) {
+            if (a == x || a == kn || !gfn1_xb_acceptor(s->num[a])) continue;
+            double u[3], w[3], ru2 = 0, rw2 = 0, uw = 0;
+            for (int c = 0; c < 3; ++c) {
+                u[c] = s->xyz[3 * a + c] - s->xyz[3 * x + c];
+                w[c] = s->xyz[3 * kn + c] - s->xyz[3 * x + c];
+                ru2 += u[c] * u[c]; rw2 += w[c] * w[c]; uw += u[c] * w[c];
+            }
+            if (ru2 > 400.0) continue;
+            double ru = sqrt(ru2), rw = sqrt(rw2), cosv = uw / (ru * rw);
+            double r0 = GFN1_XB_RAD * (s->elem[s->num[a]].atomic_rad + s->elem[s->num[x]].atomic_rad) * TB_AATOAU;
+            double t = r0 / ru, t6 = pow(t, 6), t12 = t6 * t6;
+            double lj = (t12 - GFN1_XB_DAMP * t6) / (1.0 + t12);
+            double dt6 = -6.0 * t6 / ru, dt12 = -12.0 * t12 / ru;
+            double dlj = ((dt12 - GFN1_XB_DAMP * dt6) * (1.0 + t12) - (t12 - GFN1_XB_DAMP * t6) * dt12) / ((1.0 + t12) * (1.0 + t12));
+            double base = 0.5 - 0.25 * cosv, at = pow(base, 6), dat = 6.0 * pow(base, 5) * (-0.25);
+            double cx = GFN1_EXTRA[s->num[x]].xbond;
+            exb += cx * at * lj;
+            for (int c = 0; c < 3; ++c) {
+                double dcos_a = (w[c] / rw - cosv * u[c] / ru) / ru, dcos_k = (u[c] / ru - cosv * w[c] / rw) / rw;
+                double ga = cx * (at * dlj * u[c] / ru + dat * lj * dcos_a), gk = cx * dat * lj * dcos_k;
+                grad[3 * a + c] += ga;
+                grad[3 * kn + c] += gk;
+                grad[3 * x + c] -= ga + gk;
+            }
+        }
+    }
+    return exb;
+}
+
 static double g_accuracy = 1.0;
 void xtb_oracle_set_accuracy(double acc) { g_accuracy = acc; }
 
 int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge, int multiplicity, int method_id,
                      double etemp, double *qat_out, double *energy_out, double *grad_out,
                      xtb_oracle_detail_t *detail) {
-    if (method_id != QC_METHOD_GFN2) return QC_STAT_UNKNOWN_METHOD; /* GFN1/IPEA1: not yet restated */
+    /* IPEA1 (method id 11) shares the GFN1 model with another element table that is not reconstructed here */
+    if (method_id != QC_METHOD_GFN2 && method_id != QC_METHOD_GFN1) return QC_STAT_UNKNOWN_METHOD;
+    const int gfn1 = method_id == QC_METHOD_GFN1;
+    if (gfn1) gfn1_ensure_loaded();
     int stat = QC_STAT_OK;
     sys_t s;
     memset(&s, 0, sizeof s);
+    s.method = method_id;
+    s.elem = gfn1 ? GFN1_ELEM : GFN2_ELEM;
     s.nat = nat; s.num = num; s.xyz = xyz; s.charge = charge;
     s.kt = etemp * QC_KTOAU;
     if (setup_basis(&s)) return QC_STAT_FATAL;
@@ -1186,11 +1387,18 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
     c.gwdq = xcalloc(nd, sizeof(double));
 
     /* --- geometry-dependent set-up ------------------------------------------------ */
-    gfn_cn(&s);
-    d4_cn(&s);
-    double e_rep = repulsion(&s, grad);
-    d4_setup(&s, &c);
-    double e_atm = d4_atm(&s, &c, grad, dEdcn4);
+    double e_rep, e_atm;   /* e_atm: the dispersion (+ halogen bond) energy that does not depend on the charges */
+    if (gfn1) {
+        exp_cn(&s);
+        e_rep = repulsion(&s, grad);
+        e_atm = d3_bj(&s, grad, dEdcn) + halogen_bond(&s, grad);
+    } else {
+        gfn_cn(&s);
+        d4_cn(&s);
+        e_rep = repulsion(&s, grad);
+        d4_setup(&s, &c);
+        e_atm = d4_atm(&s, &c, grad, dEdcn4);
+    }
     coulomb_setup(&s, &c);
     build_integrals(&s);
 
@@ -1214,7 +1422,7 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
     double *emo = xcalloc(nao, sizeof(double)), *focc = xcalloc(nao, sizeof(double)), *ftmp = xcalloc(nao, sizeof(double));
     broyden_t mix;
     memset(&mix, 0, sizeof mix);
-    mix.ndim = nsh + 9 * nat; mix.memory = MAX_ITER; mix.damp = 0.4;
+    mix.ndim = gfn1 ? nsh : nsh + 9 * nat; mix.memory = MAX_ITER; mix.damp = 0.4;   /* GFN1 mixes the shell charges only */
     mix.q_in = xcalloc(mix.ndim, sizeof(double)); mix.qlast_in = xcalloc(mix.ndim, sizeof(double));
     mix.dq = xcalloc(mix.ndim, sizeof(double)); mix.dqlast = xcalloc(mix.ndim, sizeof(double));
     mix.df = xcalloc((size_t)MAX_ITER * mix.ndim, sizeof(double)); mix.u = xcalloc((size_t)MAX_ITER * mix.ndim, sizeof(double));
@@ -1229,8 +1437,10 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
         if (iscf > 0) {
             if (broyden_next(&mix)) { stat = QC_STAT_FATAL; break; }
             memcpy(qsh, mix.q_in, nsh * sizeof(double));
-            memcpy(dpat, mix.q_in + nsh, 3 * nat * sizeof(double));
-            memcpy(qpat, mix.q_in + nsh + 3 * nat, 6 * nat * sizeof(double));
+            if (!gfn1) {
+                memcpy(dpat, mix.q_in + nsh, 3 * nat * sizeof(double));
+                memcpy(qpat, mix.q_in + nsh + 3 * nat, 6 * nat * sizeof(double));
+            }
             memset(qat, 0, nat * sizeof(double));
             for (int a = 0; a < nsh; ++a) qat[s.sh_at[a]] += qsh[a];
         }
@@ -1249,8 +1459,10 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
             }
         /* mixer input of this cycle */
         memcpy(mix.q_in, qsh, nsh * sizeof(double));
-        memcpy(mix.q_in + nsh, dpat, 3 * nat * sizeof(double));
-        memcpy(mix.q_in + nsh + 3 * nat, qpat, 6 * nat * sizeof(double));
+        if (!gfn1) {
+            memcpy(mix.q_in + nsh, dpat, 3 * nat * sizeof(double));
+            memcpy(mix.q_in + nsh + 3 * nat, qpat, 6 * nat * sizeof(double));
+        }
         {   /* test hook: XTB_ORACLE_DUMP=<file> appends [nao, iscf, H1(nao^2), S(nao^2)] of every SCC cycle (eigen-solver studies) */
             const char *dump = getenv("XTB_ORACLE_DUMP");
             if (dump) {
@@ -1294,16 +1506,20 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
                 double p = P[ab];
                 qsh[s.ao_sh[b]] -= p * s.S[ab];
                 int ib = s.ao_at[b];
-                for (int k = 0; k < 3; ++k) dpat[3 * ib + k] -= p * s.D[k * n2 + ab];
-                for (int k = 0; k < 6; ++k) qpat[6 * ib + k] -= p * s.Q[k * n2 + ab];
+                if (!gfn1) {
+                    for (int k = 0; k < 3; ++k) dpat[3 * ib + k] -= p * s.D[k * n2 + ab];
+                    for (int k = 0; k < 6; ++k) qpat[6 * ib + k] -= p * s.Q[k * n2 + ab];
+                }
                 e_el += p * s.H0[ab];
             }
         memset(qat, 0, nat * sizeof(double));
         for (int a = 0; a < nsh; ++a) qat[s.sh_at[a]] += qsh[a];
         /* mixer difference (output - input) */
         for (int i = 0; i < nsh; ++i) mix.dq[i] = qsh[i] - mix.q_in[i];
-        for (int i = 0; i < 3 * nat; ++i) mix.dq[nsh + i] = dpat[i] - mix.q_in[nsh + i];
-        for (int i = 0; i < 6 * nat; ++i) mix.dq[nsh + 3 * nat + i] = qpat[i] - mix.q_in[nsh + 3 * nat + i];
+        if (!gfn1) {
+            for (int i = 0; i < 3 * nat; ++i) mix.dq[nsh + i] = dpat[i] - mix.q_in[nsh + i];
+            for (int i = 0; i < 6 * nat; ++i) mix.dq[nsh + 3 * nat + i] = qpat[i] - mix.q_in[nsh + 3 * nat + i];
+        }
         scc_energies(&s, &c, qsh, qat, dpat, qpat, &e_es2, &e_es3, &e_aes, &e_d4);
         eelec = ts + e_el + e_es2 + e_es3 + e_aes + e_d4;
         double err = 0.0;
@@ -1328,7 +1544,7 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
                 for (int k = 0; k < 3; ++k) grad[3 * i + k] += f * (xyz[3 * i + k] - xyz[3 * j + k]);
             }
         /* anisotropic ES */
-        for (int i = 0; i < nat; ++i)
+        for (int i = 0; i < (gfn1 ? 0 : nat); ++i)
             for (int j = 0; j < i; ++j) {
                 double v[3], r2 = 0;
                 for (int k = 0; k < 3; ++k) { v[k] = xyz[3 * j + k] - xyz[3 * i + k]; r2 += v[k] * v[k]; }
@@ -1365,7 +1581,7 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
                 dEdcn[j] += 0.5 * dER0 * c.dmrdcn[j];
             }
         /* two-body D4 with the final charges */
-        {
+        if (!gfn1) {
             double *c6 = xcalloc((size_t)nat * nat, sizeof(double)), *dc6 = xcalloc((size_t)nat * nat, sizeof(double));
             d4_weights(&s, c.ngw, s.cnd4, qat, c.gw, c.gwdcn, NULL);
             d4_atomic_c6(&s, &c, c.gw, c.gwdcn, c6, dc6);
@@ -1410,7 +1626,7 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
             for (int jat = 0; jat < iat; ++jat) {
                 double vec[3] = {xyz[3 * iat] - xyz[3 * jat], xyz[3 * iat + 1] - xyz[3 * jat + 1], xyz[3 * iat + 2] - xyz[3 * jat + 2]};
                 double r2 = vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2], r = sqrt(r2);
-                double radsum = (GFN2_ELEM[num[iat]].atomic_rad + GFN2_ELEM[num[jat]].atomic_rad) * TB_AATOAU;
+                double radsum = (s.elem[num[iat]].atomic_rad + s.elem[num[jat]].atomic_rad) * TB_AATOAU;
                 double rr = sqrt(r / radsum);
                 double dG[3] = {0, 0, 0};
                 for (int is = 0; is < s.at_nsh[iat]; ++is)
@@ -1494,7 +1710,7 @@ int xtb_oracle_egrad(int nat, const int32_t *num, const double *xyz, int charge,
 
     free(s.at_sh0); free(s.at_nsh); free(s.sh_at); free(s.sh_l); free(s.sh_ao0); free(s.sh_np); free(s.ao_at); free(s.ao_sh);
     free(s.sh_alpha); free(s.sh_coef); free(s.sh_level); free(s.sh_kcn); free(s.sh_poly); free(s.sh_refocc);
-    free(s.sh_hub); free(s.sh_gam3); free(s.sh_zeta); free(s.cn); free(s.dcndr); free(s.cnd4); free(s.dcnd4dr);
+    free(s.sh_hub); free(s.sh_gam3); free(s.sh_zeta); free(s.sh_val); free(s.at_gam3); free(s.cn); free(s.dcndr); free(s.cnd4); free(s.dcnd4dr);
     free(s.S); free(s.H0); free(s.D); free(s.Q); free(s.selfen); free(grad); free(dEdcn); free(dEdcn4);
     free(c.gamma); free(c.mrad); free(c.dmrdcn); free(c.sd); free(c.dd); free(c.sq); free(c.c6ref); free(c.dispmat);
     free(c.gw); free(c.gwdcn); free(c.gwdq);

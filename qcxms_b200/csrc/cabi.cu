@@ -97,9 +97,9 @@ struct Context {
 static const KernelSet KS_NT288 = QX_KERNEL_SET(nt288, 288);
 static const KernelSet KS_NT576 = QX_KERNEL_SET(nt576, 576);   // one wide CTA per SM
 
-static int context_init(Context &c, int nat, const int32_t *num, const double *mass, int charge, int multiplicity, int device, int nwork) {
+static int context_init(Context &c, int nat, const int32_t *num, const double *mass, int charge, int multiplicity, int device, int nwork, int method = QCXMS_B200_GFN2) {
     CUDA_OK(cudaSetDevice(device));
-    std::string why = build_host_model(c.hm, nat, num, mass, charge, multiplicity);
+    std::string why = build_host_model(c.hm, nat, num, mass, charge, multiplicity, method);
     if (!why.empty()) return fail(QCXMS_B200_ERR_UNSUPPORTED, why);
     CUDA_OK(upload_model(c.hm));
     c.device = device;
@@ -164,8 +164,9 @@ static int egrad_batch_impl(int nsys, int nat, const int32_t *num, const double 
                             double etemp, double *qat, double *energy, double *gradient, int32_t *stat, int32_t *niter,
                             std::vector<double> *spec, int *nao_out) {
     if (nsys < 1 || nat < 1 || !num || !xyz || !qat || !energy || !gradient || !stat) return fail(QCXMS_B200_ERR_ARG, "null or empty argument");
-    if (method_id != QCXMS_B200_GFN2) {
-        // reference: unknown method -> stat = 5, outputs untouched (src/tblite.f90:114-120).  GFN1/IPEA1 are not built yet.
+    if (method_id != QCXMS_B200_GFN2 && method_id != QCXMS_B200_GFN1) {
+        // reference: unknown method -> stat = 5, outputs untouched (src/tblite.f90:114-120).  IPEA1 (id 11) shares the GFN1 model with
+        // another element table that is not reconstructed: it reports "unknown method" as well.
         for (int i = 0; i < nsys; ++i) stat[i] = QCXMS_B200_STAT_UNKNOWN_METHOD;
         return 0;
     }
@@ -174,13 +175,13 @@ static int egrad_batch_impl(int nsys, int nat, const int32_t *num, const double 
     static Context ctx;
     std::lock_guard<std::mutex> lock(mtx);
     std::vector<int32_t> key(num, num + nat);
-    key.push_back(charge); key.push_back(multiplicity); key.push_back(nsys > 1 ? 1 << 20 : 1);
+    key.push_back(charge); key.push_back(multiplicity); key.push_back(nsys > 1 ? 1 << 20 : 1); key.push_back(method_id);
     int dev = 0;
     cudaGetDevice(&dev);
     if (key != ctx.key || ctx.device != dev) {
         context_free(ctx);
         ctx.key.clear();
-        int rc = context_init(ctx, nat, num, nullptr, charge, multiplicity, dev, nsys > 1 ? 0 : 1);
+        int rc = context_init(ctx, nat, num, nullptr, charge, multiplicity, dev, nsys > 1 ? 0 : 1, method_id);
         if (rc) { context_free(ctx); return rc; }
         ctx.key = key;
     }
@@ -228,11 +229,13 @@ extern "C" int qcxms_b200_egrad(int nat, const int32_t *num, const double *xyz, 
 
 extern "C" int qcxms_b200_basis_size(int nat, const int32_t *num, int method_id, int32_t *nao) {
     if (nat < 1 || !num || !nao) return fail(QCXMS_B200_ERR_ARG, "null or empty argument");
-    if (method_id != QCXMS_B200_GFN2) return fail(QCXMS_B200_ERR_UNSUPPORTED, "only GFN2-xTB (method id 2) is implemented");
+    if (method_id != QCXMS_B200_GFN2 && method_id != QCXMS_B200_GFN1) return fail(QCXMS_B200_ERR_UNSUPPORTED, "GFN2-xTB (method id 2) and GFN1-xTB (1) are implemented");
+    if (method_id == QCXMS_B200_GFN1) gfn1_ensure_loaded();
     int n = 0;
     for (int i = 0; i < nat; ++i) {
-        if (num[i] < 1 || num[i] > GFN2_MAXZ) return fail(QCXMS_B200_ERR_UNSUPPORTED, "GFN2-xTB parameters are available for H-Ar");
-        const gfn2_elem_t &e = GFN2_ELEM[num[i]];
+        if (num[i] < 1 || num[i] > GFN2_MAXZ) return fail(QCXMS_B200_ERR_UNSUPPORTED, "parameters are available for H-Ar");
+        if (method_id == QCXMS_B200_GFN1 && !GFN1_EXTRA[num[i]].supported) return fail(QCXMS_B200_ERR_UNSUPPORTED, "no GFN1-xTB parameters for this element");
+        const gfn2_elem_t &e = method_id == QCXMS_B200_GFN1 ? GFN1_ELEM[num[i]] : GFN2_ELEM[num[i]];
         for (int k = 0; k < e.nshell; ++k) n += 2 * e.ang[k] + 1;
     }
     *nao = n;
@@ -327,14 +330,14 @@ static cudaError_t ens_alloc(qcxms_b200_ensemble *h, T **p, size_t n) {
 extern "C" int qcxms_b200_ensemble_create(const qcxms_b200_md_config_t *cfg, int ntraj, int nat, const int32_t *num, const double *mass, int device,
                                           qcxms_b200_ensemble_t **out) {
     if (!cfg || !num || !out || ntraj < 1 || nat < 1) return fail(QCXMS_B200_ERR_ARG, "null or empty argument");
-    if (cfg->method_id != QCXMS_B200_GFN2) return fail(QCXMS_B200_ERR_UNSUPPORTED, "only GFN2-xTB (method id 2) is implemented");
+    if (cfg->method_id != QCXMS_B200_GFN2 && cfg->method_id != QCXMS_B200_GFN1) return fail(QCXMS_B200_ERR_UNSUPPORTED, "GFN2-xTB (method id 2) and GFN1-xTB (1) are implemented");
     auto *h = new qcxms_b200_ensemble();
     // multiplicity as the reference's getspin() would pass it (src/utility.f90:449-464); tblite discards it anyway
     int zsum = 0;
     for (int i = 0; i < nat; ++i) zsum += num[i];
     int j = zsum - std::abs(cfg->mchrg);
     int mult = j < 1 ? -1 : 1 + j % 2;
-    int rc = context_init(h->ctx, nat, num, mass, cfg->mchrg, mult, device, ntraj);
+    int rc = context_init(h->ctx, nat, num, mass, cfg->mchrg, mult, device, ntraj, cfg->method_id);
     if (rc) { context_free(h->ctx); delete h; return rc; }
     h->ntraj = ntraj;
     h->cfg.mchrg = cfg->mchrg; h->cfg.nfragexit = cfg->nfragexit; h->cfg.exit_rules = cfg->exit_rules; h->cfg.nmax = cfg->nmax; h->cfg.isec = cfg->isec;
@@ -793,7 +796,7 @@ extern "C" int qcxms_b200_cid_batch(const qcxms_b200_cid_config_t *cfg, int ntra
     if (!cfg || ntraj < 1 || nuc < 1 || !num || !mass || !xyz || !velo || !rnd || !direc || !collided || !grad || !achrg || !axyz || !list || !res)
         return fail(QCXMS_B200_ERR_ARG, "null or empty argument");
     if (icoll < 1 || (icoll > 1 && !velo_cm)) return fail(QCXMS_B200_ERR_ARG, "icoll >= 1; later collisions need velo_cm");
-    if (cfg->method_id != QCXMS_B200_GFN2) return fail(QCXMS_B200_ERR_UNSUPPORTED, "only GFN2-xTB (method id 2) is implemented");
+    if (cfg->method_id != QCXMS_B200_GFN2 && cfg->method_id != QCXMS_B200_GFN1) return fail(QCXMS_B200_ERR_UNSUPPORTED, "GFN2-xTB (method id 2) and GFN1-xTB (1) are implemented");
     if (cfg->gas_z != 2 && cfg->gas_z != 10 && cfg->gas_z != 18 && cfg->gas_z != 7)
         return fail(QCXMS_B200_ERR_UNSUPPORTED, "collision gas must be He, Ne, Ar or N2");
     const int ngas = cfg->gas_z == 7 ? 2 : 1;   // N2: two atoms of mass gas_mass each (reference src/cid.f90:179-180)
@@ -806,7 +809,7 @@ extern "C" int qcxms_b200_cid_batch(const qcxms_b200_cid_config_t *cfg, int ntra
     const int j = zsum - std::abs(cfg->mchrg);
     const int mult = j < 1 ? -1 : 1 + j % 2;
     Context ctx;
-    int rc = context_init(ctx, nuc0, num0.data(), mass0.data(), cfg->mchrg, mult, device, ntraj);
+    int rc = context_init(ctx, nuc0, num0.data(), mass0.data(), cfg->mchrg, mult, device, ntraj, cfg->method_id);
     if (rc) { context_free(ctx); return rc; }
     {   // the device maximum, not this composition's size: host threads set up different compositions concurrently
         cudaDeviceProp prop;

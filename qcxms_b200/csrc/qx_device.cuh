@@ -12,6 +12,7 @@
 #include <math.h>
 
 #include "params/gfn2_params.h"
+#include "params/gfn1_params.h"
 #include "qx_model.h"
 
 namespace qx {
@@ -128,6 +129,30 @@ __device__ inline double block_max(double v, double *red) {
 // tables dcnp[i*nat+j] = (1/r) d f(r_ij)/dr, so that d cn_i/d R_i = sum_j dcnp_ij (R_i - R_j).
 static __device__ __noinline__ void phase_cn(const DevModel &m, Sm &s, double *dcnp, double *dcnp4) {
     const int nat = m.nat;
+    if (m.method == 1) {   // GFN1 / D3: exponential counting function, k1 = 16 (reference src/dftd3.f90:607-642), cn_thr = 1000 bohr^2
+        for (int i = threadIdx.x; i < nat; i += QX_NT) {
+            double cn = 0.0;
+            const double xi = s.xyz[3 * i], yi = s.xyz[3 * i + 1], zi = s.xyz[3 * i + 2], rci = m.at_rcov[i];
+            for (int j = 0; j < nat; ++j) {
+                double g = 0.0;
+                if (j != i) {
+                    const double vx = xi - s.xyz[3 * j], vy = yi - s.xyz[3 * j + 1], vz = zi - s.xyz[3 * j + 2];
+                    const double r2 = vx * vx + vy * vy + vz * vz, r = sqrt(r2), rco = rci + m.at_rcov[j];
+                    if (r2 <= 1000.0) {
+                        const double ex = exp(-16.0 * (rco / r - 1.0)), f = 1.0 / (1.0 + ex);
+                        cn += f;
+                        g = -16.0 * rco / r2 * ex * f * f / r;
+                    }
+                }
+                dcnp[i * nat + j] = g;
+                dcnp4[i * nat + j] = 0.0;
+            }
+            s.cn[i] = cn;
+            s.cn4[i] = 0.0;
+        }
+        __syncthreads();
+        return;
+    }
     for (int i = threadIdx.x; i < nat; i += QX_NT) {
         double cn = 0.0, cn4 = 0.0;
         double xi = s.xyz[3 * i], yi = s.xyz[3 * i + 1], zi = s.xyz[3 * i + 2];
@@ -172,7 +197,7 @@ static __device__ __noinline__ double phase_repulsion(const DevModel &m, Sm &s) 
             if (j == i) continue;
             double vx = s.xyz[3 * i] - s.xyz[3 * j], vy = s.xyz[3 * i + 1] - s.xyz[3 * j + 1], vz = s.xyz[3 * i + 2] - s.xyz[3 * j + 2];
             double r2 = vx * vx + vy * vy + vz * vz, r = sqrt(r2);
-            bool light = m.num[i] <= 2 && m.num[j] <= 2;
+            bool light = m.method != 1 && m.num[i] <= 2 && m.num[j] <= 2;   // GFN1: kexp = 1.5 for every pair
             double kexp = light ? GFN2_REP_KEXP_LIGHT : GFN2_REP_KEXP;
             double alpha = sqrt(m.at_repa[i] * m.at_repa[j]), zz = m.at_repz[i] * m.at_repz[j];
             double rk = light ? r : r * sqrt(r);
@@ -393,12 +418,110 @@ static __device__ __noinline__ double phase_d4_nonsc(const DevModel &m, Sm &s, d
     return block_sum(e3, s.red);
 }
 
+// ------------------------------------------------------------------------------------ GFN1: D3(BJ) and the halogen-bond correction
+// C6(i,j) from the reference systems with Gaussian weights in CN space, and dC6/dCN_i (reference src/dftd3.f90:334-405, k3 = -4)
+__device__ inline void d3_c6_pair(const DevModel &m, int i, int j, double cni, double cnj, double &c6, double &dc6i) {
+    const double *ref = m.d3ref + ((size_t)m.type[i] * m.ntype + m.type[j]) * 75;
+    double c6mem = -1.e99, r_save = 9999.0, zaehler = 0.0, nenner = 0.0, dz = 0.0, dn = 0.0;
+    for (int a = 0; a < m.at_mxc[i]; ++a)
+        for (int b = 0; b < m.at_mxc[j]; ++b) {
+            const double c6ref = ref[(a * 5 + b) * 3];
+            if (c6ref > 0.0) {
+                const double ci = ref[(a * 5 + b) * 3 + 1], cj = ref[(a * 5 + b) * 3 + 2];
+                const double r = (ci - cni) * (ci - cni) + (cj - cnj) * (cj - cnj);
+                if (r < r_save) { r_save = r; c6mem = c6ref; }
+                double expterm = exp(-4.0 * r);
+                zaehler += c6ref * expterm;
+                nenner += expterm;
+                expterm = expterm * 2.0 * -4.0;
+                const double term = expterm * (cni - ci);
+                dz += c6ref * term;
+                dn += term;
+            }
+        }
+    if (nenner > 1.0e-99) { c6 = zaehler / nenner; dc6i = ((dz * nenner) - (dn * zaehler)) / (nenner * nenner); }
+    else { c6 = c6mem; dc6i = 0.0; }
+}
+
+// E = - sum_{i>j} C6 (s6 / (r^6 + R0^6) + 3 s8 r42 / (r^8 + R0^8)), R0 = a1 sqrt(3 r42) + a2 (reference src/dftd3.f90:107-186, BJ variant,
+// no three-body term).  Thread i sums over all partners j: half the pair energy, the full gradient of atom i at fixed CN and
+// dE/dCN_i.  Followed by the halogen-bond correction (a handful of X...A contacts: one thread, fixed order).
+static __device__ __noinline__ double phase_d3_xb(const DevModel &m, Sm &s) {
+    const int nat = m.nat;
+    double e = 0.0;
+    for (int i = threadIdx.x; i < nat; i += QX_NT) {
+        double gx = 0, gy = 0, gz = 0, dcn = 0;
+        for (int j = 0; j < nat; ++j) {
+            if (j == i) continue;
+            const double vx = s.xyz[3 * i] - s.xyz[3 * j], vy = s.xyz[3 * i + 1] - s.xyz[3 * j + 1], vz = s.xyz[3 * i + 2] - s.xyz[3 * j + 2];
+            const double r2 = vx * vx + vy * vy + vz * vz;
+            if (r2 > 4000.0) continue;
+            double c6, dc6i;
+            d3_c6_pair(m, i, j, s.cn[i], s.cn[j], c6, dc6i);
+            const double r42 = m.at_r2r4d3[i] * m.at_r2r4d3[j], r = sqrt(r2), r4 = r2 * r2, r6 = r4 * r2, r8 = r6 * r2;
+            const double R0 = GFN1_D3_A1 * sqrt(3.0 * r42) + GFN1_D3_A2, R02 = R0 * R0, R06 = R02 * R02 * R02;
+            const double t6 = r6 + R06, t8 = r8 + R06 * R02;
+            const double rest = GFN1_D3_S6 / t6 + 3.0 * GFN1_D3_S8 * r42 / t8;
+            e -= 0.5 * rest * c6;
+            const double dedr = c6 * (GFN1_D3_S6 * 6.0 * r4 * r / (t6 * t6) + GFN1_D3_S8 * 24.0 * r42 * r6 * r / (t8 * t8)) / r;
+            gx += dedr * vx; gy += dedr * vy; gz += dedr * vz;
+            dcn -= rest * dc6i;
+        }
+        s.grad[3 * i] += gx; s.grad[3 * i + 1] += gy; s.grad[3 * i + 2] += gz;
+        s.dEdcn[i] += dcn;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // halogen bond: donors X (with strength), nearest neighbour K, acceptors A = N, O, P, S within 20 bohr
+        for (int x = 0; x < nat; ++x) {
+            const double cx = m.at_xb[x];
+            if (cx == 0.0) continue;
+            int kn = -1;
+            double best = 1e300;
+            for (int k = 0; k < nat; ++k) {
+                if (k == x) continue;
+                const double dx = s.xyz[3 * k] - s.xyz[3 * x], dy = s.xyz[3 * k + 1] - s.xyz[3 * x + 1], dz = s.xyz[3 * k + 2] - s.xyz[3 * x + 2];
+                const double d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 < best) { best = d2; kn = k; }
+            }
+            if (kn < 0) continue;
+            for (int a = 0; a < nat; ++a) {
+                const int za = m.num[a];
+                if (a == x || a == kn || !(za == 7 || za == 8 || za == 15 || za == 16)) continue;
+                double u[3], w[3], ru2 = 0, rw2 = 0, uw = 0;
+                for (int c = 0; c < 3; ++c) {
+                    u[c] = s.xyz[3 * a + c] - s.xyz[3 * x + c];
+                    w[c] = s.xyz[3 * kn + c] - s.xyz[3 * x + c];
+                    ru2 += u[c] * u[c]; rw2 += w[c] * w[c]; uw += u[c] * w[c];
+                }
+                if (ru2 > 400.0) continue;
+                const double ru = sqrt(ru2), rw = sqrt(rw2), cosv = uw / (ru * rw);
+                const double r0 = GFN1_XB_RAD * (m.at_rad[a] + m.at_rad[x]);
+                const double t = r0 / ru, t2 = t * t, t6 = t2 * t2 * t2, t12 = t6 * t6;
+                const double lj = (t12 - GFN1_XB_DAMP * t6) / (1.0 + t12);
+                const double dt6 = -6.0 * t6 / ru, dt12 = -12.0 * t12 / ru;
+                const double dlj = ((dt12 - GFN1_XB_DAMP * dt6) * (1.0 + t12) - (t12 - GFN1_XB_DAMP * t6) * dt12) / ((1.0 + t12) * (1.0 + t12));
+                const double base = 0.5 - 0.25 * cosv, b2 = base * base, b5 = b2 * b2 * base, at = b5 * base, dat = 6.0 * b5 * (-0.25);
+                e += cx * at * lj;
+                for (int c = 0; c < 3; ++c) {
+                    const double dcos_a = (w[c] / rw - cosv * u[c] / ru) / ru, dcos_k = (u[c] / ru - cosv * w[c] / rw) / rw;
+                    const double ga = cx * (at * dlj * u[c] / ru + dat * lj * dcos_a), gk = cx * dat * lj * dcos_k;
+                    s.grad[3 * a + c] += ga;
+                    s.grad[3 * kn + c] += gk;
+                    s.grad[3 * x + c] -= ga + gk;
+                }
+            }
+        }
+    }
+    return block_sum(e, s.red);
+}
+
 // ------------------------------------------------------------------------------------ Coulomb set-up
 static __device__ __noinline__ void phase_coulomb_setup(const DevModel &m, Sm &s, double *gamma) {
     const int nat = m.nat, nsh = m.nsh;
     for (int ab = threadIdx.x; ab < nsh * nsh; ab += QX_NT) {
         int a = ab / nsh, b = ab - a * nsh, i = m.sh_at[a], j = m.sh_at[b];
-        double gam = 0.5 * (m.sh_hub[a] + m.sh_hub[b]);
+        double gam = m.method == 1 ? 2.0 / (1.0 / m.sh_hub[a] + 1.0 / m.sh_hub[b])   // GFN1: harmonic average
+                                   : 0.5 * (m.sh_hub[a] + m.sh_hub[b]);
         if (i != j) {
             double vx = s.xyz[3 * i] - s.xyz[3 * j], vy = s.xyz[3 * i + 1] - s.xyz[3 * j + 1], vz = s.xyz[3 * i + 2] - s.xyz[3 * j + 2];
             gam = 1.0 / sqrt(vx * vx + vy * vy + vz * vz + 1.0 / (gam * gam));

@@ -15,6 +15,8 @@
 #include "params/d4_refdata.h"
 #include "params/elem_tables.h"
 #include "params/gfn2_params.h"
+#include "params/gfn1_params.h"
+#include "params/d3_refdata.h"
 #include "params/stong_table.h"
 #include "qx_model.h"
 
@@ -31,6 +33,9 @@ struct HostModel {
     std::vector<double> sh_alpha, sh_coef, sh_level, sh_kcn, sh_poly, sh_refocc, sh_hub, sh_gam3, sh_zeta, hscale;
     std::vector<int> ao_at, ao_sh, ao_m;
     std::vector<double> c6ref;
+    int method = 2;
+    std::vector<double> at_gam3, at_xb, at_r2r4d3, d3ref;
+    std::vector<int> at_mxc;
     std::vector<int2> task_int;
     std::vector<int> gr_ptr, gr_task;
     std::vector<double> scal_table;
@@ -44,20 +49,30 @@ inline double d4_zeta_h(double a, double c, double qref, double qmod) {
 }
 
 // returns empty string on success, otherwise the reason
-inline std::string build_host_model(HostModel &h, int nat, const int32_t *num, const double *mass, int charge, int multiplicity) {
+inline std::string build_host_model(HostModel &h, int nat, const int32_t *num, const double *mass, int charge, int multiplicity, int method = 2) {
     h = HostModel();
     h.nat = nat;
     h.charge = charge;
+    h.method = method;
+    const bool gfn1 = method == 1;
+    if (gfn1) gfn1_ensure_loaded();
     std::vector<int> types;
     for (int i = 0; i < nat; ++i) {
         int z = num[i];
         if (z < 1 || z > GFN2_MAXZ) return "element Z=" + std::to_string(z) + " is outside the parametrised range (H..Ar)";
+        if (gfn1 && !GFN1_EXTRA[z].supported)
+            return "no GFN1-xTB parameters for Z=" + std::to_string(z) + " (built-in: H, C, N, O, F, Cl; others through QCXMS_B200_GFN1_PARAM)";
         int t = (int)(std::find(types.begin(), types.end(), z) - types.begin());
         if (t == (int)types.size()) types.push_back(z);
-        const gfn2_elem_t &e = GFN2_ELEM[z];
+        const gfn2_elem_t &e = gfn1 ? GFN1_ELEM[z] : GFN2_ELEM[z];
         h.num.push_back(z);
         h.type.push_back(t);
-        h.at_rcov.push_back(4.0 / 3.0 * COVRAD2009_AA[z] * TB_AATOAU);
+        h.at_gam3.push_back(gfn1 ? e.hubbard_deriv : 0.0);
+        h.at_xb.push_back(gfn1 ? GFN1_EXTRA[z].xbond : 0.0);
+        h.at_r2r4d3.push_back(D3_R2R4[z]);
+        h.at_mxc.push_back(D3_MXC[z]);
+        // the exponential CN of GFN1 / D3 uses the in-tree D3 radii (reference src/copyc6.f90 setrcov), like the oracle
+        h.at_rcov.push_back(gfn1 ? D3_RCOV[z] : 4.0 / 3.0 * COVRAD2009_AA[z] * TB_AATOAU);
         h.at_rad.push_back(e.atomic_rad * TB_AATOAU);
         h.at_repa.push_back(e.rep_alpha);
         h.at_repz.push_back(e.rep_zeff);
@@ -86,11 +101,12 @@ inline std::string build_host_model(HostModel &h, int nat, const int32_t *num, c
             h.sh_ao0.push_back(h.nao + nao_at);
             h.sh_np.push_back(e.nprim[k]);
             h.sh_level.push_back(e.selfenergy[k] * GFN2_EVTOAU);
-            h.sh_kcn.push_back(e.kcn[k] * GFN2_EVTOAU);
+            // GFN1: h = level (1 + kcn_l CN) written as level - kcn CN
+            h.sh_kcn.push_back(gfn1 ? -e.selfenergy[k] * GFN2_EVTOAU * GFN1_KCN_L[l] : e.kcn[k] * GFN2_EVTOAU);
             h.sh_poly.push_back(e.shpoly[k]);
             h.sh_refocc.push_back(e.refocc[k]);
             h.sh_hub.push_back(e.hubbard * e.shell_hubbard[l]);
-            h.sh_gam3.push_back(e.hubbard_deriv * GFN2_KSHELL3[l]);
+            h.sh_gam3.push_back(gfn1 ? 0.0 : e.hubbard_deriv * GFN2_KSHELL3[l]);
             h.sh_zeta.push_back(e.slater[k]);
             const double dfact = l == 2 ? 3.0 : 1.0;
             for (int p = 0; p < QX_MAXPRIM; ++p) {
@@ -101,6 +117,25 @@ inline std::string build_host_model(HostModel &h, int nat, const int32_t *num, c
                 }
                 h.sh_alpha.push_back(a);
                 h.sh_coef.push_back(c);
+            }
+            // GFN1: a second s shell on the atom (H 2s) is Schmidt-orthogonalised to the first and renormalised (see the oracle's setup_basis)
+            if (gfn1 && k > 0 && l == 0) {
+                int first = -1;
+                for (int kk = 0; kk < k; ++kk) if (e.ang[kk] == l) first = h.at_sh0[i] + kk;
+                if (first >= 0) {
+                    double *a1 = &h.sh_alpha[(size_t)first * QX_MAXPRIM], *c1 = &h.sh_coef[(size_t)first * QX_MAXPRIM];
+                    double *a2 = &h.sh_alpha[(size_t)h.nsh * QX_MAXPRIM], *c2 = &h.sh_coef[(size_t)h.nsh * QX_MAXPRIM];
+                    const int n1 = h.sh_np[first], n2 = h.sh_np[h.nsh];
+                    if (n1 + n2 > QX_MAXPRIM) return "too many primitives in an orthogonalised shell";
+                    double s11 = 0, s12 = 0, s22 = 0;
+                    for (int p = 0; p < n1; ++p) for (int q = 0; q < n1; ++q) s11 += c1[p] * c1[q] * std::pow(M_PI / (a1[p] + a1[q]), 1.5);
+                    for (int p = 0; p < n1; ++p) for (int q = 0; q < n2; ++q) s12 += c1[p] * c2[q] * std::pow(M_PI / (a1[p] + a2[q]), 1.5);
+                    for (int p = 0; p < n2; ++p) for (int q = 0; q < n2; ++q) s22 += c2[p] * c2[q] * std::pow(M_PI / (a2[p] + a2[q]), 1.5);
+                    const double f = s12 / s11, nrm = 1.0 / std::sqrt(s22 - s12 * s12 / s11);
+                    for (int q = 0; q < n2; ++q) c2[q] *= nrm;
+                    for (int p = 0; p < n1; ++p) { a2[n2 + p] = a1[p]; c2[n2 + p] = -f * nrm * c1[p]; }
+                    h.sh_np[h.nsh] = n1 + n2;
+                }
             }
             for (int m = 0; m < 2 * l + 1; ++m) {
                 h.ao_at.push_back(i);
@@ -119,7 +154,7 @@ inline std::string build_host_model(HostModel &h, int nat, const int32_t *num, c
     h.rows8 = tc_padded_dim(h.nao) ? tc_padded_dim(h.nao) : h.nao;
     h.ld = h.nao;
     while (h.ld % 16 != 4 && h.ld % 16 != 12) h.ld += 1;
-    h.ndim = h.nsh + 9 * nat;
+    h.ndim = gfn1 ? h.nsh : h.nsh + 9 * nat;   // GFN1 mixes the shell charges only (no multipoles)
     // occupation numbers (tblite get_occupation / get_alpha_beta_occupation; uhf = min(mult-1, 0), tblite.f90:111)
     double nocc = -(double)charge;
     for (double v : h.sh_refocc) nocc += v;
@@ -136,6 +171,21 @@ inline std::string build_host_model(HostModel &h, int nat, const int32_t *num, c
     for (int a = 0; a < h.nsh; ++a)
         for (int b = 0; b < h.nsh; ++b) {
             int la = h.sh_l[a], lb = h.sh_l[b];
+            if (gfn1) {
+                static const double k1[3] = {GFN1_KDIAG_S, GFN1_KDIAG_P, GFN1_KDIAG_D};
+                const int ia = h.sh_at[a], ib = h.sh_at[b], za = h.num[ia], zb = h.num[ib];
+                const bool va = GFN1_EXTRA[za].valence[a - h.at_sh0[ia]] != 0, vb = GFN1_EXTRA[zb].valence[b - h.at_sh0[ib]] != 0;
+                double km;
+                if (va && vb) {
+                    const double kll = (la + lb == 1) ? GFN1_K_SP : 0.5 * (k1[la] + k1[lb]);
+                    const double den = GFN1_ELEM[za].en - GFN1_ELEM[zb].en;
+                    km = gfn1_kpair(za, zb) * kll * (1.0 + GFN1_ENSCALE * den * den);
+                } else if (va) km = 0.5 * (k1[la] + GFN1_KDIFF);
+                else if (vb) km = 0.5 * (k1[lb] + GFN1_KDIFF);
+                else km = GFN1_KDIFF;
+                h.hscale[(size_t)a * h.nsh + b] = km;
+                continue;
+            }
             double k;
             if (la == lb) k = kdiag[la];
             else if (la == 2 || lb == 2) k = (la + lb == 2) ? GFN2_K_SD : GFN2_K_PD;
@@ -180,6 +230,14 @@ inline std::string build_host_model(HostModel &h, int nat, const int32_t *num, c
                     for (int k = 0; k < D4_NFREQ - 1; ++k) acc += 0.5 * (freq[k + 1] - freq[k]) * (ai[k + 1] * aj[k + 1] + ai[k] * aj[k]);
                     h.c6ref[(((size_t)ti * h.ntype + tj) * QX_MAXREF + ri) * QX_MAXREF + rj] = 3.0 / M_PI * acc;
                 }
+    // GFN1: D3 reference table per type pair (in-tree data, reference include/pars.fh via src/copyc6.f90)
+    h.d3ref.assign((size_t)h.ntype * h.ntype * D3_MAXC * D3_MAXC * 3, -1.0);
+    for (int ti = 0; ti < h.ntype; ++ti)
+        for (int tj = 0; tj < h.ntype; ++tj)
+            for (int a = 0; a < D3_MAXC; ++a)
+                for (int b = 0; b < D3_MAXC; ++b)
+                    for (int c = 0; c < 3; ++c)
+                        h.d3ref[((((size_t)ti * h.ntype + tj) * D3_MAXC + a) * D3_MAXC + b) * 3 + c] = D3_C6AB[types[ti]][types[tj]][a][b][c];
     for (int i = 0; i < nat; ++i) {
         int z = h.num[i];
         h.at_nref.push_back(D4_REFN[z]);
@@ -233,7 +291,7 @@ inline cudaError_t upload_model(HostModel &h) {
     ADD(at_r4r2); ADD(at_zeff); ADD(at_gam); ADD(at_qcrad); ADD(mass); ADD(at_refcn); ADD(at_refq);
     ADD(sh_at); ADD(sh_l); ADD(sh_ao0); ADD(sh_np); ADD(sh_alpha); ADD(sh_coef); ADD(sh_level); ADD(sh_kcn); ADD(sh_poly);
     ADD(sh_refocc); ADD(sh_hub); ADD(sh_gam3); ADD(hscale); ADD(ao_at); ADD(ao_sh); ADD(ao_m); ADD(c6ref); ADD(task_int);
-    ADD(gr_ptr); ADD(gr_task);
+    ADD(gr_ptr); ADD(gr_task); ADD(at_gam3); ADD(at_xb); ADD(at_r2r4d3); ADD(at_mxc); ADD(d3ref);
     if (h.scal_table.empty()) {   // the reference's running sum scal = scal + 0.0002 (src/impact.f90:37)
         h.scal_table.resize(20001);
         volatile double scal = 0.0;
@@ -247,6 +305,7 @@ inline cudaError_t upload_model(HostModel &h) {
     if (err != cudaSuccess) return err;
     char *base = (char *)h.d_blob;
     DevModel &d = h.dev;
+    d.method = h.method;
     d.nat = h.nat; d.nsh = h.nsh; d.nao = h.nao; d.ntype = h.ntype; d.ld = h.ld; d.ndim = h.ndim; d.rows8 = h.rows8; d.mat_in_global = 0;
     d.ntask_int = (int)h.task_int.size(); d.ntask_grad = 0;
     d.nel[0] = h.nel[0]; d.nel[1] = h.nel[1];
@@ -259,6 +318,7 @@ inline cudaError_t upload_model(HostModel &h) {
     PTR(sh_kcn, double); PTR(sh_poly, double); PTR(sh_refocc, double); PTR(sh_hub, double); PTR(sh_gam3, double); PTR(hscale, double);
     PTR(ao_at, int); PTR(ao_sh, int); PTR(ao_m, int); PTR(c6ref, double); PTR(task_int, int2); PTR(gr_ptr, int); PTR(gr_task, int);
     PTR(scal_table, double);
+    PTR(at_gam3, double); PTR(at_xb, double); PTR(at_r2r4d3, double); PTR(at_mxc, int); PTR(d3ref, double);
 #undef PTR
     return cudaSuccess;
 }

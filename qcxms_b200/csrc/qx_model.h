@@ -3,7 +3,7 @@
 #pragma once
 #include <cstdint>
 
-#define QX_MAXPRIM 6
+#define QX_MAXPRIM 8   // GFN1: the orthogonalised H 2s carries the 1s primitives as well (3 + 4)
 #define QX_MAXREF 7
 #define QX_MAX_ITER 250   // tblite max_iter (SCC cycles and Broyden memory)
 #ifndef QX_NT
@@ -18,6 +18,7 @@
 
 struct DevModel {
     int nat, nsh, nao, ntype, ld, ndim;  // ld: leading dimension of the shared-memory matrices (== 4 or 12 mod 16)
+    int method;                           // 2: GFN2-xTB, 1: GFN1-xTB (exp CN, D3(BJ), halogen bond, atomic third order, no multipoles)
     int jblock;                           // global-slab mode: rows per block of the shared-memory blocked Jacobi (0: none)
     int mat_in_global;                    // 1: the two SCC matrices do not fit shared memory and live in the per-CTA global slab
     int rows8;                            // rows of the shared-memory matrices (zero padded; multiple of 8 when the strip GEMMs apply)
@@ -39,6 +40,11 @@ struct DevModel {
     const int *ao_at, *ao_sh, *ao_m;
     // type-pair D4 reference C6 [ntype][ntype][QX_MAXREF][QX_MAXREF]
     const double *c6ref;
+    // GFN1: atomic third-order parameter, halogen-bond strength (0: no donor), D3 sqrt(0.5 r4/r2 sqrt(Z)), number of D3 reference
+    // systems per atom and the type-pair D3 reference table [ntype][ntype][5][5][3] = (C6, CN_ref(i), CN_ref(j)) (-1: none)
+    const double *at_gam3, *at_xb, *at_r2r4d3;
+    const int *at_mxc;
+    const double *d3ref;
     // work lists: AO pairs (a on the bra atom, b on the ket atom; atom(a) <= atom(b))
     const int2 *task_int;   // all pairs incl. on-site ordered pairs
     // gradient reduction lists (CSR by atom over off-site tasks; sign +1 ket atom / -1 bra atom)

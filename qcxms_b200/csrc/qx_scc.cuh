@@ -86,13 +86,22 @@ __device__ __forceinline__ double gamma_row_oct(const Sm &s, const double *gamma
 static __device__ __noinline__ void phase_potential(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double *t7) {
     const int nat = m.nat, nsh = m.nsh, nao = m.nao;
     const int oct = threadIdx.x >> 3, l8 = threadIdx.x & 7, wbase = (threadIdx.x >> 5) << 2;
-    d4_weights_all(m, s, true, s.gw, nullptr, s.gwd);
+    if (m.method != 1) d4_weights_all(m, s, true, s.gw, nullptr, s.gwd);
     for (int base = 0; base < nsh; base += QX_NT / 8) {
         if (base + wbase >= nsh) continue;
         const bool active = base + oct < nsh;
         const int a = active ? base + oct : 0;
         const double v = gamma_row_oct(s, gamma, nsh, a);
         if (active && l8 == 0) s.vsh[a] = v + s.qsh[a] * s.qsh[a] * m.sh_gam3[a];
+    }
+    if (m.method == 1) {   // GFN1: atom-resolved third order; no multipole electrostatics, no self-consistent dispersion
+        for (int i = threadIdx.x; i < nat; i += QX_NT) s.vat[i] = s.qat[i] * s.qat[i] * m.at_gam3[i];
+        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.vdp[i] = 0.0;
+        for (int i = threadIdx.x; i < 6 * nat; i += QX_NT) s.vqp[i] = 0.0;
+        __syncthreads();
+        for (int mu = threadIdx.x; mu < nao; mu += QX_NT) s.vao[mu] = s.vsh[m.ao_sh[mu]] + s.vat[m.ao_at[mu]];
+        __syncthreads();
+        return;
     }
     // anisotropic electrostatics: one group per atom i, lanes over the partners j
     for (int base = 0; base < nat; base += QX_NT / 8) {
@@ -151,7 +160,7 @@ static __device__ __noinline__ void phase_potential(const DevModel &m, Sm &s, co
 static __device__ __noinline__ void phase_scc_energy(const DevModel &m, Sm &s, const double *gamma, const double *edisp, double &e_es, double &e_aes, double &e_d4) {
     const int nat = m.nat, nsh = m.nsh;
     const int oct = threadIdx.x >> 3, l8 = threadIdx.x & 7, wbase = (threadIdx.x >> 5) << 2;
-    d4_weights_all(m, s, true, s.gw, nullptr, nullptr);
+    if (m.method != 1) d4_weights_all(m, s, true, s.gw, nullptr, nullptr);
     double es = 0.0, ea = 0.0, ed = 0.0;
     for (int base = 0; base < nsh; base += QX_NT / 8) {
         if (base + wbase >= nsh) continue;
@@ -159,6 +168,13 @@ static __device__ __noinline__ void phase_scc_energy(const DevModel &m, Sm &s, c
         const int a = active ? base + oct : 0;
         const double v = gamma_row_oct(s, gamma, nsh, a);
         if (active && l8 == 0) es += 0.5 * v * s.qsh[a] + s.qsh[a] * s.qsh[a] * s.qsh[a] * m.sh_gam3[a] / 3.0;
+    }
+    if (m.method == 1) {   // GFN1: + atomic third order, nothing else depends on the charges
+        for (int i = threadIdx.x; i < nat; i += QX_NT) es += s.qat[i] * s.qat[i] * s.qat[i] * m.at_gam3[i] / 3.0;
+        e_es = block_sum(es, s.red);
+        e_aes = 0.0;
+        e_d4 = 0.0;
+        return;
     }
     for (int base = 0; base < nat; base += QX_NT / 8) {
         if (base + wbase >= nat) continue;
@@ -617,7 +633,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     phase_cn(m, s, dcnp, dcnp4);
     out.e_rep = phase_repulsion(m, s);
     QX_PH(0);
-    out.e_atm = phase_d4_nonsc(m, s, edisp, c6, dc6, taskout);
+    out.e_atm = m.method == 1 ? phase_d3_xb(m, s) : phase_d4_nonsc(m, s, edisp, c6, dc6, taskout);
     QX_PH(1);
     phase_coulomb_setup(m, s, gamma);
     phase_integrals(m, s, S, H0, Dt, Qt);
@@ -882,17 +898,20 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     }
     __syncthreads();
     // D4 two-body with the final charges
-    double *gwq = taskout, *gwdcnq = taskout + 7 * nat;
-    d4_weights_all(m, s, true, gwq, gwdcnq, nullptr);
-    __syncthreads();
-    d4_c6_tables(m, gwq, gwdcnq, c6, dc6);
-    __syncthreads();
+    const bool gfn1 = m.method == 1;
+    if (!gfn1) {
+        double *gwq = taskout, *gwdcnq = taskout + 7 * nat;
+        d4_weights_all(m, s, true, gwq, gwdcnq, nullptr);
+        __syncthreads();
+        d4_c6_tables(m, gwq, gwdcnq, c6, dc6);
+        __syncthreads();
+    }
     for (int i = threadIdx.x >> 5; i < nat; i += QX_NT / 32) {   // one warp per atom, lanes over the partners
         const int lane = threadIdx.x & 31;
         double gx = 0, gy = 0, gz = 0, dcn = 0, dcn4 = 0;
         const double *mi = s.dpat + 3 * i, *ti = s.qpat + 6 * i;
         const double qi = s.qat[i];
-        for (int j = lane; j < nat; j += 32) {
+        for (int j = lane; j < (gfn1 ? 0 : nat); j += 32) {   // GFN1: D3 and no multipoles -- both handled before the SCC / absent
             if (j == i) continue;
             // --- dispersion
             {

@@ -47,6 +47,49 @@ def test_unknown_method_sets_stat_5(qx):
     num, xyz, _ = qx.load_molecule("chloroethanol")
     _, _, _, stat = qx.get_xtb_egrad(num, xyz, 0, 1, 99, 300.0)
     assert stat == 5
+    _, _, _, stat = qx.get_xtb_egrad(num, xyz, 0, 1, qx.ipea1_xtb, 300.0)   # IPEA1: GFN1 model, element table not reconstructed
+    assert stat == 5
+
+
+@pytest.mark.parametrize("name,charge,mult,etemp", [
+    ("monoethanolamine", 0, 1, 300.0), ("monoethanolamine", 1, 2, 5000.0), ("caffeine", 1, 2, 5000.0), ("caffeine", 0, 1, 300.0),
+    ("chloroethanol", 1, 2, 5000.0), ("xb", 0, 1, 300.0)])
+def test_gfn1_egrad_matches_oracle(qx, oracle, name, charge, mult, etemp):
+    """GFN1-xTB (method id 1; BASELINE config 3): exponential CN, two s shells on H, D3(BJ), halogen bond, atomic third order."""
+    if name == "xb":
+        from test_oracle_gfn1 import XB_NUM as num, XB_XYZ as xyz
+    else:
+        num, xyz, _ = qx.load_molecule(name)
+        xyz = xyz + 0.04 * np.random.default_rng(11).standard_normal(xyz.shape)
+    q, e, g, stat = qx.get_xtb_egrad(num, xyz, charge, mult, qx.gfn1_xtb, etemp)
+    ref = oracle.egrad(num, xyz, charge=charge, multiplicity=mult, method=1, etemp=etemp, detail=True)
+    assert stat == ref["stat"] == 0
+    assert abs(e - ref["energy"]) < E_TOL, (e, ref["energy"])
+    assert np.abs(g - ref["gradient"]).max() < G_TOL
+    assert np.abs(q - ref["qat"]).max() < Q_TOL
+
+
+def test_gfn1_batch_niter_and_md(qx, oracle):
+    from qcxms_b200 import ensemble_setup as es
+    num, xyz, _ = qx.load_molecule("monoethanolamine")
+    geoms = xyz[None] + 0.08 * np.random.default_rng(7).standard_normal((8,) + xyz.shape)
+    out = qx.egrad_batch(num, geoms, 1, 2, qx.gfn1_xtb, 5000.0)
+    for k in range(len(geoms)):
+        ref = oracle.egrad(num, geoms[k], charge=1, multiplicity=2, method=1, etemp=5000.0, detail=True)
+        assert out["stat"][k] == 0 and out["niter"][k] == ref["niter"]
+        assert abs(out["energy"][k] - ref["energy"]) < E_TOL and np.abs(out["gradient"][k] - ref["gradient"]).max() < G_TOL
+    # md() with the GFN1 calculator: a short EI run against the oracle's md
+    ic = es.synthetic_initial_conditions(num, xyz, 3)
+    ens = qx.Ensemble(num, ic["mass"], 3, mchrg=1, nmax=12, exit_rules=True, method=qx.gfn1_xtb)
+    ens.set_all(ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+    assert ens.run_md() == 3 * 12
+    for k in range(3):
+        got = ens.result(k)
+        ref = oracle.md(num, ic["mass"], ic["xyz"][k], ic["velo"][k], ic["velof"][k], ic["eimp"][k], ic["tadd"][k], mchrg=1, nmax=12, method=1)
+        assert got["nstep"] == ref["nstep"] == 12 and got["scc_iter_total"] == ref["scc_iter_total"]
+        assert np.abs(got["xyz"] - ref["xyz"]).max() < 1e-7 and abs(got["Epot"] - ref["Epot"]) < 1e-7
+        assert np.array_equal(got["list"], ref["list"])
+    ens.close()
 
 
 def test_large_basis_fallback_alkane_c32(qx, oracle):

@@ -113,6 +113,8 @@ def guess(n, l, ng):
 
 CASES = [(n, l, ng) for (n, l) in [(1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (2, 1), (3, 1), (4, 1), (5, 1),
                                      (3, 2), (4, 2), (5, 2)] for ng in (3, 4)]
+# GFN1-xTB expands the s/p valence shells of the elements beyond He in six primitives
+CASES += [(2, 0, 6), (2, 1, 6), (3, 0, 6), (3, 1, 6)]
 
 KAT = {
     (1, 0, 3): ([2.227660584, 0.4057711562, 0.1098175104], [0.1543289673, 0.5353281423, 0.4446345422]),
