@@ -135,6 +135,20 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         const int want = force ? atoi(force) : 0;
         if (!c.hm.dev.mat_in_global && (want == 576 || (want == 0 && nwork > 0 && nwork <= prop.multiProcessorCount))) c.ks = &KS_NT576;
     }
+    // The wide CTAs have the SM to themselves: three more shared-memory matrices fit, and with them the GEMM-based eigenpair
+    // refinement (qx_oa.cuh) that takes the one-sided Jacobi's latency chain out of the SCC (QCXMS_B200_OA=0 keeps the Jacobi).
+    if (c.ks == &KS_NT576 && oa_supported(c.hm.nat, c.hm.nao, c.hm.ntype, 576)) {
+        const char *off = getenv("QCXMS_B200_OA");
+        const size_t smem_oa = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 0, c.hm.ntype, 1) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
+        if (!(off && atoi(off) == 0) && smem_oa + 2048 <= (size_t)prop.sharedMemPerBlockOptin) {
+            c.hm.dev.oa = 1;
+            const char *stop = getenv("QCXMS_B200_OA_STOP");   // measurement hook
+            c.hm.dev.oa_stop = stop ? atof(stop) : QX_OA_STOP;
+            const char *kap = getenv("QCXMS_B200_OA_KAPPA");
+            c.hm.dev.oa_kappa = kap ? atof(kap) : QX_OA_KAPPA;
+            c.smem = smem_oa;
+        }
+    }
     CUDA_OK(c.ks->prepare_egrad(prop));
     CUDA_OK(c.ks->prepare_md(prop));
     CUDA_OK(c.ks->prepare_mfp(prop));
@@ -352,6 +366,10 @@ extern "C" int qcxms_b200_ensemble_create(const qcxms_b200_md_config_t *cfg, int
     EA(nstep, nt); EA(kdump, nt); EA(fconst, nt); EA(morestep, nt); EA(nfrag, nt); EA(status, nt); EA(fragstate, nt); EA(mdok, nt); EA(nadd, nt);
     EA(list, n1); EA(scc_total, nt);
 #undef EA
+    if (e == cudaSuccess && h->ctx.hm.dev.oa) {   // eigenvector seeds of the eigenpair refinement, per trajectory
+        const size_t per = (size_t)QX_OA_NSTORE * h->ctx.hm.nao * h->ctx.hm.nao + 1;
+        e = ens_alloc(h, &s.eigseed, (size_t)ntraj * per);
+    }
     if (e == cudaSuccess) e = ens_alloc(h, &h->d_steps, 1);
     if (e == cudaSuccess) e = ens_alloc(h, &h->d_progress, nt);
     if (e == cudaSuccess) e = cudaStreamCreate(&h->stream);
@@ -922,6 +940,8 @@ extern "C" int qcxms_b200_debug_phase_cycles(double *out16) {
     unsigned long long ph[16] = {0}, sub[16] = {0}, sh[64] = {0};
     CUDA_OK(KS_NT288.egrad_cycles(ph, sub, sh));
     CUDA_OK(KS_NT288.md_cycles(ph, sub, sh));
+    CUDA_OK(KS_NT576.egrad_cycles(ph, sub, sh));
+    CUDA_OK(KS_NT576.md_cycles(ph, sub, sh));
     for (int i = 0; i < 16; ++i) out16[i] = (double)ph[i];
 #ifdef QX_PROFILE_PHASES
     fprintf(stderr, "sub-phase cycles (thread 0):");

@@ -61,13 +61,14 @@ struct SmPtr {
 
 struct Sm {
     double *A, *C;   // shared memory, or the CTA's global slab when the basis is too large (DevModel::mat_in_global)
+    double *X3, *X4, *S5;   // DevModel::oa: work matrices of the eigenpair refinement (C^T H C / E, C^T S C) and the overlap, shared memory
     double *jblk;    // global-slab mode: shared-memory buffer of 2 * DevModel::jblock rows for the blocked Jacobi
     SmPtr xyz, cn, cn4, mrad, dmr, qat, vat, dpat, vdp, qpat, vqp;
     SmPtr qsh, vsh, selfen, vao, emo, focc, gw, gwd, dEdcn, dEdcn4, grad, red, jw, bsol, pop, d4u;
 };
 
-__host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld, int rows8, int mat_in_global, int ntype) {
-    return (mat_in_global ? 0 : 2 * (size_t)rows8 * ld) + 3 * nat + 6 * nat /*cn cn4 mrad dmr qat vat*/ + 6 * nat /*dpat vdp*/ + 12 * nat /*qpat vqp*/
+__host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld, int rows8, int mat_in_global, int ntype, int oa = 0) {
+    return (mat_in_global ? 0 : (oa ? 5 : 2) * (size_t)rows8 * ld) + 3 * nat + 6 * nat /*cn cn4 mrad dmr qat vat*/ + 6 * nat /*dpat vdp*/ + 12 * nat /*qpat vqp*/
            + 3 * nsh + 3 * nao + 8 + 14 * nat /*gw gwd*/ + 2 * nat + 3 * nat /*grad*/ + 64 + 3 * nao + 8 /*jw*/ + QX_BSOL /*Broyden solve*/ + 11 * nao + (nao & 1) /*pop*/ + 7 * nat * ntype /*d4u*/;
 }
 
@@ -79,6 +80,12 @@ __device__ inline void carve(const DevModel &m, double *base, Sm &s, double *gma
     } else {
         s.A = p; p += (size_t)m.rows8 * m.ld;
         s.C = p; p += (size_t)m.rows8 * m.ld;
+        s.X3 = s.X4 = s.S5 = nullptr;
+        if (m.oa) {
+            s.X3 = p; p += (size_t)m.rows8 * m.ld;
+            s.X4 = p; p += (size_t)m.rows8 * m.ld;
+            s.S5 = p; p += (size_t)m.rows8 * m.ld;
+        }
     }
     s.xyz = p; p += 3 * nat;
     s.cn = p; p += nat; s.cn4 = p; p += nat; s.mrad = p; p += nat; s.dmr = p; p += nat;
@@ -95,7 +102,7 @@ __device__ inline void carve(const DevModel &m, double *base, Sm &s, double *gma
     s.bsol = p; p += QX_BSOL;
     s.pop = p; p += 11 * nao + (nao & 1);
     s.d4u = p;
-    s.jblk = base + ((smem_doubles(nat, nsh, nao, m.ld, m.rows8, m.mat_in_global, m.ntype) + 11 * (size_t)nat + 16 + 1) & ~(size_t)1);
+    s.jblk = base + ((smem_doubles(nat, nsh, nao, m.ld, m.rows8, m.mat_in_global, m.ntype, m.oa) + 11 * (size_t)nat + 16 + 1) & ~(size_t)1);
 }
 
 __device__ inline double block_sum(double v, double *red) {
@@ -896,45 +903,64 @@ __device__ inline void gemm_tc(int n, FA loadA, FB loadB, FS store, double *stag
 // of ld are predicated (only the last one does).
 // A' = Ct * H * Ct^T  (H symmetric in `A`, result overwrites `A`); Ct in `Ct`.  The strip of T = Ct*H is parked in the
 // warp's own rows of `A` (after a barrier: everybody has finished reading H) and read back as the A operand of the second product.
+// WPS warps share one strip (each takes a contiguous range of its column tiles): 1 for the 288-thread kernels (9 warps, 9 strips),
+// 2 for the wide CTAs, whose 18 warps would otherwise leave half of the tensor pipe's issue slots unused.
+#define QX_WPS ((QX_NT / 32) >= 18 ? 2 : 1)
+// Explicit shared-state-space accesses (32-bit shared-window addresses): with generic pointers the compiler emitted generic LD for
+// some of the fragment loads of these kernels despite QX_ASSUME_SHARED (ncu: long-scoreboard stalls on the DMMA lines).
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(x), "d"(y) : "memory"); }
+
 template <int NT8>
 static __device__ __noinline__ void tc_transform(int n, const double *Ct, double *A, int ld) {
-    QX_ASSUME_SHARED(Ct); QX_ASSUME_SHARED(A);   // the strip kernels are only used when both matrices are in shared memory
+    constexpr int WPS = QX_WPS, TH = (NT8 + WPS - 1) / WPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
-    double acc[NT8][2];
-    bool okb[NT8], oks[NT8];
+    const int strip = warp / WPS, t0 = (warp % WPS) * TH;
+    const bool act = strip < NT8;
+    const unsigned ct = smem_addr(Ct), am = smem_addr(A), ld8 = 8u * (unsigned)ld;
+    double acc[TH][2];
+    bool okb[TH], oks[TH];
 #pragma unroll
-    for (int t = 0; t < NT8; ++t) { okb[t] = 8 * t + g < ld; oks[t] = 8 * t + 2 * tg + 1 < ld; acc[t][0] = acc[t][1] = 0.0; }
-    double *myrow = A + (warp * 8 + g) * ld;
-    if (warp < NT8) {
-        const double *arow = Ct + (warp * 8 + g) * ld + tg;   // A fragment: Ct[row][k0 + tg]
-        const double *bcol = A + tg * ld + g;                  // B fragment: H[k0 + tg][8 t + g]
+    for (int t = 0; t < TH; ++t) {
+        okb[t] = t0 + t < NT8 && 8 * (t0 + t) + g < ld; oks[t] = t0 + t < NT8 && 8 * (t0 + t) + 2 * tg + 1 < ld;
+        acc[t][0] = acc[t][1] = 0.0;
+    }
+    const unsigned myrow = am + (unsigned)(strip * 8 + g) * ld8;
+    if (act) {
+        const unsigned arow = ct + (unsigned)(strip * 8 + g) * ld8 + 8u * tg;   // A fragment: Ct[row][k0 + tg]
+        const unsigned bcol = am + (unsigned)tg * ld8 + 8u * (g + 8 * t0);      // B fragment: H[k0 + tg][8 t + g]
 #pragma unroll 2
         for (int k0 = 0; k0 < kmax; k0 += 4) {
-            const double a = arow[k0];
+            const double a = lds_f64(arow + 8u * k0);
 #pragma unroll
-            for (int t = 0; t < NT8; ++t) { const double b = okb[t] ? bcol[k0 * ld + 8 * t] : 0.0; QX_DMMA(acc[t], a, b); }
+            for (int t = 0; t < TH; ++t) { const double b = okb[t] ? lds_f64(bcol + (unsigned)k0 * ld8 + 64u * t) : 0.0; QX_DMMA(acc[t], a, b); }
         }
     }
     __syncthreads();   // every warp has finished reading H
-    if (warp < NT8) {
+    if (act) {
 #pragma unroll
-        for (int t = 0; t < NT8; ++t) {
-            if (oks[t]) *reinterpret_cast<double2 *>(myrow + 8 * t + 2 * tg) = make_double2(acc[t][0], acc[t][1]);
+        for (int t = 0; t < TH; ++t) {
+            if (oks[t]) sts_v2f64(myrow + 8u * (8 * (t0 + t) + 2 * tg), acc[t][0], acc[t][1]);
             acc[t][0] = acc[t][1] = 0.0;
         }
-        __syncwarp();
+    }
+    if (WPS == 1) __syncwarp(); else __syncthreads();   // the strip of T = Ct H is complete
+    if (act) {
         // second product: A'[strip][col] = sum_k T[strip][k] Ct[col][k]
-        const double *bct = Ct + g * ld + tg;                  // B fragment: Ct[8 t + g][k0 + tg]
+        const unsigned bct = ct + (unsigned)(g + 8 * t0) * ld8 + 8u * tg;      // B fragment: Ct[8 t + g][k0 + tg]
 #pragma unroll 2
         for (int k0 = 0; k0 < kmax; k0 += 4) {
-            const double a = myrow[k0 + tg];
+            const double a = lds_f64(myrow + 8u * (k0 + tg));
 #pragma unroll
-            for (int t = 0; t < NT8; ++t) { const double b = bct[8 * t * ld + k0]; QX_DMMA(acc[t], a, b); }
+            for (int t = 0; t < TH; ++t) { const double b = t0 + t < NT8 ? lds_f64(bct + 8u * t * ld8 + 8u * k0) : 0.0; QX_DMMA(acc[t], a, b); }
         }
-        __syncwarp();
+    }
+    if (WPS == 1) __syncwarp(); else __syncthreads();   // everybody has read the strip of T before it is overwritten
+    if (act) {
 #pragma unroll
-        for (int t = 0; t < NT8; ++t)
-            if (oks[t]) *reinterpret_cast<double2 *>(myrow + 8 * t + 2 * tg) = make_double2(acc[t][0], acc[t][1]);
+        for (int t = 0; t < TH; ++t)
+            if (oks[t]) sts_v2f64(myrow + 8u * (8 * (t0 + t) + 2 * tg), acc[t][0], acc[t][1]);
     }
     __syncthreads();
 }
@@ -942,30 +968,34 @@ static __device__ __noinline__ void tc_transform(int n, const double *Ct, double
 // Ct <- X * Ct (in place), X in `X` (row-major; here the normalised rows of the Jacobi = J^T)
 template <int NT8>
 static __device__ __noinline__ void tc_left_apply(int n, const double *X, double *Ct, int ld) {
-    QX_ASSUME_SHARED(X); QX_ASSUME_SHARED(Ct);
+    constexpr int WPS = QX_WPS, TH = (NT8 + WPS - 1) / WPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
-    double acc[NT8][2];
-    bool okb[NT8], oks[NT8];
+    const int strip = warp / WPS, t0 = (warp % WPS) * TH;
+    const bool act = strip < NT8;
+    const unsigned xm = smem_addr(X), ct = smem_addr(Ct), ld8 = 8u * (unsigned)ld;
+    double acc[TH][2];
+    bool okb[TH], oks[TH];
 #pragma unroll
-    for (int t = 0; t < NT8; ++t) { okb[t] = 8 * t + g < ld; oks[t] = 8 * t + 2 * tg + 1 < ld; }
-    if (warp < NT8) {
-#pragma unroll
-        for (int t = 0; t < NT8; ++t) acc[t][0] = acc[t][1] = 0.0;
-        const double *arow = X + (warp * 8 + g) * ld + tg;
-        const double *bcol = Ct + tg * ld + g;
+    for (int t = 0; t < TH; ++t) {
+        okb[t] = t0 + t < NT8 && 8 * (t0 + t) + g < ld; oks[t] = t0 + t < NT8 && 8 * (t0 + t) + 2 * tg + 1 < ld;
+        acc[t][0] = acc[t][1] = 0.0;
+    }
+    if (act) {
+        const unsigned arow = xm + (unsigned)(strip * 8 + g) * ld8 + 8u * tg;
+        const unsigned bcol = ct + (unsigned)tg * ld8 + 8u * (g + 8 * t0);
 #pragma unroll 2
         for (int k0 = 0; k0 < kmax; k0 += 4) {
-            const double a = arow[k0];
+            const double a = lds_f64(arow + 8u * k0);
 #pragma unroll
-            for (int t = 0; t < NT8; ++t) { const double b = okb[t] ? bcol[k0 * ld + 8 * t] : 0.0; QX_DMMA(acc[t], a, b); }
+            for (int t = 0; t < TH; ++t) { const double b = okb[t] ? lds_f64(bcol + (unsigned)k0 * ld8 + 64u * t) : 0.0; QX_DMMA(acc[t], a, b); }
         }
     }
     __syncthreads();
-    if (warp < NT8) {
-        double *orow = Ct + (warp * 8 + g) * ld + 2 * tg;
+    if (act) {
+        const unsigned orow = ct + (unsigned)(strip * 8 + g) * ld8 + 8u * (2 * tg + 8 * t0);
 #pragma unroll
-        for (int t = 0; t < NT8; ++t)
-            if (oks[t]) *reinterpret_cast<double2 *>(orow + 8 * t) = make_double2(acc[t][0], acc[t][1]);
+        for (int t = 0; t < TH; ++t)
+            if (oks[t]) sts_v2f64(orow + 64u * t, acc[t][0], acc[t][1]);
     }
     __syncthreads();
 }
@@ -973,31 +1003,35 @@ static __device__ __noinline__ void tc_left_apply(int n, const double *X, double
 // out = Ct^T diag(w) Ct = C diag(w) C^T.  out may alias Ct (result held in registers across a barrier).
 template <int NT8>
 static __device__ __noinline__ void tc_density(int n, const double *Ct, const double *w, double *out, int ld) {
-    QX_ASSUME_SHARED(Ct); QX_ASSUME_SHARED(w); QX_ASSUME_SHARED(out);
+    constexpr int WPS = QX_WPS, TH = (NT8 + WPS - 1) / WPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
-    double acc[NT8][2];
-    bool okb[NT8], oks[NT8];
+    const int strip = warp / WPS, t0 = (warp % WPS) * TH;
+    const bool act = strip < NT8;
+    const unsigned ct = smem_addr(Ct), wv = smem_addr(w), om = smem_addr(out), ld8 = 8u * (unsigned)ld;
+    double acc[TH][2];
+    bool okb[TH], oks[TH];
 #pragma unroll
-    for (int t = 0; t < NT8; ++t) { okb[t] = 8 * t + g < ld; oks[t] = 8 * t + 2 * tg + 1 < ld; }
-    if (warp < NT8) {
-#pragma unroll
-        for (int t = 0; t < NT8; ++t) acc[t][0] = acc[t][1] = 0.0;
-        const bool oka = warp * 8 + g < ld;
-        const double *acol = Ct + tg * ld + (oka ? warp * 8 + g : 0);   // A fragment: (Ct^T)[row][k] = Ct[k0 + tg][row]
-        const double *bcol = Ct + tg * ld + g;                          // B fragment: Ct[k0 + tg][8 t + g]
+    for (int t = 0; t < TH; ++t) {
+        okb[t] = t0 + t < NT8 && 8 * (t0 + t) + g < ld; oks[t] = t0 + t < NT8 && 8 * (t0 + t) + 2 * tg + 1 < ld;
+        acc[t][0] = acc[t][1] = 0.0;
+    }
+    if (act) {
+        const bool oka = strip * 8 + g < ld;
+        const unsigned acol = ct + (unsigned)tg * ld8 + 8u * (oka ? strip * 8 + g : 0);   // A fragment: (Ct^T)[row][k] = Ct[k0 + tg][row]
+        const unsigned bcol = ct + (unsigned)tg * ld8 + 8u * (g + 8 * t0);                // B fragment: Ct[k0 + tg][8 t + g]
 #pragma unroll 2
         for (int k0 = 0; k0 < kmax; k0 += 4) {
-            const double a = oka ? acol[k0 * ld] * w[k0 + tg] : 0.0;
+            const double a = oka ? lds_f64(acol + (unsigned)k0 * ld8) * lds_f64(wv + 8u * (k0 + tg)) : 0.0;
 #pragma unroll
-            for (int t = 0; t < NT8; ++t) { const double b = okb[t] ? bcol[k0 * ld + 8 * t] : 0.0; QX_DMMA(acc[t], a, b); }
+            for (int t = 0; t < TH; ++t) { const double b = okb[t] ? lds_f64(bcol + (unsigned)k0 * ld8 + 64u * t) : 0.0; QX_DMMA(acc[t], a, b); }
         }
     }
     __syncthreads();
-    if (warp < NT8) {
-        double *orow = out + (warp * 8 + g) * ld + 2 * tg;
+    if (act) {
+        const unsigned orow = om + (unsigned)(strip * 8 + g) * ld8 + 8u * (2 * tg + 8 * t0);
 #pragma unroll
-        for (int t = 0; t < NT8; ++t)
-            if (oks[t]) *reinterpret_cast<double2 *>(orow + 8 * t) = make_double2(acc[t][0], acc[t][1]);
+        for (int t = 0; t < TH; ++t)
+            if (oks[t]) sts_v2f64(orow + 64u * t, acc[t][0], acc[t][1]);
     }
     __syncthreads();
 }

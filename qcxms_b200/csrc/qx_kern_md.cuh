@@ -54,7 +54,10 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_init(DevModel m, S
             for (int i = threadIdx.x; i < 2 * m.ndim + 1; i += QX_NT) qw[i] = 0.0;
             __syncthreads();
         }
-        const double epot = md_egrad(m, s, my, L, cfg, etemp, st.grad + (size_t)t * 3 * nat, st.achrg + (size_t)t * nat, &nit, qw);
+        double *es = st.eigseed ? st.eigseed + (size_t)t * ((size_t)QX_OA_NSTORE * m.nao * m.nao + 1) : nullptr;
+        if (es && threadIdx.x == 0) es[(size_t)QX_OA_NSTORE * m.nao * m.nao] = 0.0;   // no seeds before the first single point
+        __syncthreads();
+        const double epot = md_egrad(m, s, my, L, cfg, etemp, st.grad + (size_t)t * 3 * nat, st.achrg + (size_t)t * nat, &nit, qw, es);
         if (threadIdx.x == 0) {
             st.scc_total[t] = nit;
             const double ekin = md_ekinet_seq(nat, st.velo + (size_t)t * 3 * nat, m.mass, 0.0, nullptr);
@@ -122,7 +125,7 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_chunk(DevModel m, 
         }
         // per-trajectory arrays live in shared memory for the duration of the work item (read with ld.cg: the previous
         // sub-chunk of this trajectory may have run on another SM)
-        double *velo = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global, m.ntype) + 8, *grad = velo + 3 * nat, *avxyz = grad + 3 * nat, *achrg = avxyz + 3 * nat,
+        double *velo = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global, m.ntype, m.oa) + 8, *grad = velo + 3 * nat, *avxyz = grad + 3 * nat, *achrg = avxyz + 3 * nat,
                *avchrg = achrg + nat;
         double *gxyz = st.xyz + (size_t)t * 3 * nat, *gvelo = st.velo + (size_t)t * 3 * nat, *ggrad = st.grad + (size_t)t * 3 * nat;
         double *gachrg = st.achrg + (size_t)t * nat, *gavchrg = st.avchrg + (size_t)t * nat, *gavxyz = st.avxyz + (size_t)t * 3 * nat;
@@ -192,7 +195,8 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_chunk(DevModel m, 
             ttime += cfg.tstep / fstoau;
             {
                 int nit = 0;
-                epot = md_egrad(m, s, my, L, cfg, etemp, grad, achrg, &nit, st.qwarm ? st.qwarm + (size_t)t * (2 * m.ndim + 1) : nullptr);
+                epot = md_egrad(m, s, my, L, cfg, etemp, grad, achrg, &nit, st.qwarm ? st.qwarm + (size_t)t * (2 * m.ndim + 1) : nullptr,
+                                st.eigseed ? st.eigseed + (size_t)t * ((size_t)QX_OA_NSTORE * m.nao * m.nao + 1) : nullptr);
                 scc_add += nit;
             }
             done += 1;

@@ -33,6 +33,7 @@ struct MdState {
     double *mfp_d, *avxyz2, *store;
     int *mfp_i;
     double *qwarm;    // [ntraj][2 ndim + 1] converged populations of the last two steps + count; null unless the opt-in warm start is on
+    double *eigseed;  // [ntraj][QX_OA_NSTORE nao^2 + 1] eigenvector seeds of the eigenpair refinement (DevModel::oa), null otherwise
 };
 
 enum { TRJ_RUNNING = 0, TRJ_FINISHED = 1, TRJ_FAILED = 2 };

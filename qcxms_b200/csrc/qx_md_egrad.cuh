@@ -6,10 +6,10 @@ namespace qx {
 
 // one egrad + sanity gate for trajectory t; returns Epot (0 on failure, like the reference's checkqc)
 __device__ inline double md_egrad(const DevModel &m, Sm &s, double *my, const ScratchLayout &L, const MdConfig &cfg, double etemp,
-                                  double *grad_out, double *achrg_out, int *niter_out, double *qstart = nullptr) {
+                                  double *grad_out, double *achrg_out, int *niter_out, double *qstart = nullptr, double *eigseed = nullptr) {
     const int nat = m.nat;
     EgradOut o;
-    egrad_cta(m, s, my, L, etemp * QC_KTOAU, o, qstart);
+    egrad_cta(m, s, my, L, etemp * QC_KTOAU, o, qstart, nullptr, eigseed);
     __syncthreads();
     if (threadIdx.x == 0) {
         bool ok = o.stat != -2 && md_checkqc(m, o.energy, s.grad, s.qat, cfg.mchrg);

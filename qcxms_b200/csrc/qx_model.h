@@ -18,6 +18,9 @@
 
 struct DevModel {
     int nat, nsh, nao, ntype, ld, ndim;  // ld: leading dimension of the shared-memory matrices (== 4 or 12 mod 16)
+    double oa_kappa;                      // pairs with |coupling| > kappa |gap| go into exactly diagonalised clusters
+    double oa_stop;                       // convergence threshold of the refinement (max |E_ij| of the last pass)
+    int oa;                               // 1: GEMM-based eigenpair refinement (qx_oa.cuh) with three more shared-memory matrices (wide-CTA kernels)
     int method;                           // 2: GFN2-xTB, 1: GFN1-xTB (exp CN, D3(BJ), halogen bond, atomic third order, no multipoles)
     int jblock;                           // global-slab mode: rows per block of the shared-memory blocked Jacobi (0: none)
     int mat_in_global;                    // 1: the two SCC matrices do not fit shared memory and live in the per-CTA global slab

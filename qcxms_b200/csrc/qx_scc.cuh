@@ -33,6 +33,10 @@ static __device__ unsigned long long g_sweep_hist[64];  // [iteration index (<32
 #define QX_SUB(idx) do {} while (0)
 #endif
 
+}  // namespace qx
+#include "qx_oa.cuh"   // (after the profiling macros it uses)
+namespace qx {
+
 struct EgradOut {
     double energy;
     double e_rep, e_atm, e_el, e_es, e_aes, e_d4, e_ts;
@@ -607,8 +611,11 @@ static __device__ __noinline__ void phase_gradient_pairs(const DevModel &m, Sm &
 // spec (may be null): the reference's spec_calc output (src/tblite.f90:152-164, src/mo_energ.f90:31-43) -- [nao] orbital energies,
 // [nao] occupations, [nao][nat] raw Mulliken population of every orbital on every atom (orbitals in solver order: the host sorts
 // and normalises), [1] HOMO index of the alpha channel.
+// eigseed (may be null; DevModel::oa only): [QX_OA_NSTORE nao^2 + 1] eigenvectors (transposed, dense nao x nao) of the first SCC cycles of
+// the previous call for this trajectory + the number of valid entries.  They seed the eigenpair refinement of the same cycles of
+// this call; the SCC protocol (zero start, iterates, stop test) is untouched -- only the eigen-solver's starting guess changes.
 __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, const ScratchLayout &L, double kt, EgradOut &out, double *qstart = nullptr,
-                                 double *spec = nullptr) {
+                                 double *spec = nullptr, double *eigseed = nullptr) {
     const int nat = m.nat, nsh = m.nsh, nao = m.nao, ld = m.ld, ndim = m.ndim;
     // global-slab mode: the block buffer of the Jacobi doubles as the staging buffer of the GEMMs' B operand
     double *stg = m.mat_in_global && m.jblock > 0 ? s.jblk : nullptr;
@@ -642,10 +649,23 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     // S-orthonormal start basis: C = L^{-T}.  Padding columns of the shared matrices are zeroed once: the
     // 128-bit row accesses of the Jacobi read (and rewrite) them.
     for (int t = threadIdx.x; t < m.rows8 * ld; t += QX_NT) { s.A[t] = 0.0; s.C[t] = 0.0; }
+    int nseed = 0;           // eigenvector seeds of the previous call (eigenpair refinement only)
+    bool c_valid = false;    // s.C holds an S-orthonormal basis (Cholesky start basis or the eigenvectors of the previous cycle)
+    if (m.oa) {
+        for (int t = threadIdx.x; t < m.rows8 * ld; t += QX_NT) { s.X3[t] = 0.0; s.X4[t] = 0.0; s.S5[t] = 0.0; }
+        if (eigseed) nseed = (int)__ldcg(eigseed + (size_t)QX_OA_NSTORE * nao * nao);
+    }
     __syncthreads();
-    for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.A[(size_t)(t / nao) * ld + t % nao] = S[t];
+    for (int t = threadIdx.x; t < nao * nao; t += QX_NT) {
+        const double v = S[t];
+        s.A[(size_t)(t / nao) * ld + t % nao] = v;
+        if (m.oa) s.S5[(size_t)(t / nao) * ld + t % nao] = v;
+    }
     __syncthreads();
-    if (!(m.mat_in_global ? cholesky_basis<false>(nao, s.A, s.C, ld, s.red) : cholesky_basis<true>(nao, s.A, s.C, ld, s.red))) { out.stat = -2; out.energy = 0.0; return; }  // hard failure: S not positive definite
+    if (!(m.oa && nseed > 0)) {   // (with a seed for the first cycle the Cholesky start basis is only built if the refinement fails)
+        if (!(m.mat_in_global ? cholesky_basis<false>(nao, s.A, s.C, ld, s.red) : cholesky_basis<true>(nao, s.A, s.C, ld, s.red))) { out.stat = -2; out.energy = 0.0; return; }  // hard failure: S not positive definite
+        c_valid = true;
+    }
 
     if (qstart) {   // warm start (opt-in): linear extrapolation of the converged populations of the last two steps of this trajectory
         const bool two = __ldcg(qstart + 2 * ndim) >= 2.0;
@@ -703,7 +723,48 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         // A' = C^T H1 C in the current S-orthonormal basis (s.C holds C transposed), then Jacobi (C <- C J)
         const int npad = tc_padded_dim(nao);
         const bool strip = npad != 0 && npad / 8 <= QX_NT / 32;
-        if (strip) {
+        bool refined = false;
+        if (m.oa) {
+            // ---- eigenpair refinement (qx_oa.cuh): seed = the same cycle of the previous call (first cycles) or the previous cycle
+            const int kc = iscf - 1;
+            const size_t n2 = (size_t)nao * nao;
+            if (c_valid) {   // keep the orthonormal basis for the fall-back
+                for (int t = threadIdx.x; t < nao * nao; t += QX_NT) T[t] = s.C[(size_t)(t / nao) * ld + t % nao];
+            }
+            const bool from_seed = eigseed && kc < QX_OA_NSTORE && kc < nseed;
+            if (from_seed) {
+                __syncthreads();
+                for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.C[(size_t)(t / nao) * ld + t % nao] = __ldcg(eigseed + kc * n2 + t);
+            }
+            __syncthreads();
+            int passes = 0;
+            if (from_seed || (c_valid && kc > 0)) {
+                const bool bid = !from_seed;
+                passes = npad == 32 ? oa_refine<4>(m, s, bid) : (npad == 64 ? oa_refine<8>(m, s, bid) : oa_refine<9>(m, s, bid));
+            }
+            refined = passes > 0;
+            out.sweeps += passes;
+            if (!refined) {
+                if (c_valid) {   // back to the orthonormal basis of the previous cycle (or the Cholesky basis)
+                    __syncthreads();
+                    for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.C[(size_t)(t / nao) * ld + t % nao] = T[t];
+                    __syncthreads();
+                } else {         // first cycle, seed not good enough: Cholesky start basis now (it needs s.A: H1 is rebuilt afterwards)
+                    for (int t = threadIdx.x; t < m.rows8 * ld; t += QX_NT) { s.A[t] = 0.0; s.C[t] = 0.0; }
+                    __syncthreads();
+                    for (int t = threadIdx.x; t < nao * nao; t += QX_NT) s.A[(size_t)(t / nao) * ld + t % nao] = S[t];
+                    __syncthreads();
+                    if (!cholesky_basis<true>(nao, s.A, s.C, ld, s.red)) { out.stat = -2; break; }
+                    for (int t = threadIdx.x; t < m.rows8 * ld; t += QX_NT) s.A[t] = 0.0;
+                    __syncthreads();
+                    phase_build_h1<true>(m, s, S, H0, Dt, Qt);
+                }
+            }
+            c_valid = true;
+        }
+        if (refined) {
+            // eigenvalues are in s.emo, eigenvectors in s.C
+        } else if (strip) {
             if (npad == 32) tc_transform<4>(nao, s.C, s.A, ld);
             else if (npad == 64) tc_transform<8>(nao, s.C, s.A, ld);
             else tc_transform<9>(nao, s.C, s.A, ld);
@@ -720,7 +781,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
             __syncthreads();
         }
         QX_PH(7);
-        {
+        if (!refined) {
             int sw_ = m.mat_in_global ? jacobi_eigh_rows<false>(nao, s.A, ld, s.emo, s.red, s.jw, s.jblk, m.jblock) : jacobi_eigh_rows<true>(nao, s.A, ld, s.emo, s.red, s.jw);
             out.sweeps += sw_;
 #ifdef QX_PROFILE_PHASES
@@ -739,6 +800,10 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
                 for (int t = threadIdx.x; t < nao * nao; t += QX_NT) { int i = t / nao; s.C[(size_t)i * ld + (t - i * nao)] = T[t]; }
                 __syncthreads();
             }
+        }
+        if (m.oa && eigseed && iscf <= QX_OA_NSTORE) {   // seed for the same cycle of the next call
+            const size_t n2 = (size_t)nao * nao;
+            for (int t = threadIdx.x; t < nao * nao; t += QX_NT) eigseed[(iscf - 1) * n2 + t] = s.C[(size_t)(t / nao) * ld + t % nao];
         }
         QX_PH(8);
         // order statistics needed for the Fermi-level start value
@@ -820,6 +885,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
     }
     out.niter = iscf;
     out.energy = out.e_rep + out.e_atm + eelec;
+    if (m.oa && eigseed && threadIdx.x == 0) eigseed[(size_t)QX_OA_NSTORE * nao * nao] = out.stat == -2 ? 0.0 : (double)(iscf < QX_OA_NSTORE ? iscf : QX_OA_NSTORE);
     if (out.stat == -2) return;
     if (qstart && converged) {   // hand the converged populations to the next step of this trajectory: [latest | previous | count]
         for (int i = threadIdx.x; i < ndim; i += QX_NT) {
