@@ -174,6 +174,16 @@ static void context_free(Context &c) {
     c.d_scratch = nullptr; c.d_queue = nullptr; c.hm.d_blob = nullptr;
 }
 
+// a cached calculator of the level-1 entry points with its device I/O block and stream
+#define QX_EGRAD_SLOTS 6
+struct EgradSlot {
+    Context ctx;
+    void *d_io = nullptr;
+    size_t cap = 0;
+    cudaStream_t stream = nullptr;
+    unsigned long long used = 0;
+};
+
 static int egrad_batch_impl(int nsys, int nat, const int32_t *num, const double *xyz, int charge, int multiplicity, int method_id,
                             double etemp, double *qat, double *energy, double *gradient, int32_t *stat, int32_t *niter,
                             std::vector<double> *spec, int *nao_out) {
@@ -184,50 +194,61 @@ static int egrad_batch_impl(int nsys, int nat, const int32_t *num, const double 
         for (int i = 0; i < nsys; ++i) stat[i] = QCXMS_B200_STAT_UNKNOWN_METHOD;
         return 0;
     }
-    // cache the model of the last composition: the reference calls this entry point once per MD step
+    // The reference calls this entry point once per MD step and, in between, for the fragments of analyse() (src/iniqm.f90:393):
+    // the calculators of the last few compositions stay alive (least recently used one is replaced), each with its own device
+    // I/O buffers (grown on demand, never freed per call) and stream.
     static std::mutex mtx;
-    static Context ctx;
+    static EgradSlot slots[QX_EGRAD_SLOTS];
+    static unsigned long long tick = 0;
     std::lock_guard<std::mutex> lock(mtx);
     std::vector<int32_t> key(num, num + nat);
     key.push_back(charge); key.push_back(multiplicity); key.push_back(nsys > 1 ? 1 << 20 : 1); key.push_back(method_id);
     int dev = 0;
     cudaGetDevice(&dev);
-    if (key != ctx.key || ctx.device != dev) {
-        context_free(ctx);
-        ctx.key.clear();
-        int rc = context_init(ctx, nat, num, nullptr, charge, multiplicity, dev, nsys > 1 ? 0 : 1, method_id);
-        if (rc) { context_free(ctx); return rc; }
-        ctx.key = key;
+    EgradSlot *sl = nullptr;
+    for (auto &c : slots)
+        if (c.ctx.key == key && c.ctx.device == dev) sl = &c;
+    if (!sl) {
+        sl = &slots[0];
+        for (auto &c : slots)
+            if (c.used < sl->used) sl = &c;
+        context_free(sl->ctx);
+        sl->ctx.key.clear();
+        int rc = context_init(sl->ctx, nat, num, nullptr, charge, multiplicity, dev, nsys > 1 ? 0 : 1, method_id);
+        if (rc) { context_free(sl->ctx); return rc; }
+        sl->ctx.key = key;
+        if (!sl->stream) CUDA_OK(cudaStreamCreateWithFlags(&sl->stream, cudaStreamNonBlocking));
     }
-    const size_t n3 = (size_t)nsys * nat * 3;
-    double *d_xyz = nullptr, *d_e = nullptr, *d_g = nullptr, *d_q = nullptr;
-    int *d_stat = nullptr, *d_nit = nullptr;
-    CUDA_OK(cudaMalloc(&d_xyz, n3 * sizeof(double)));
-    CUDA_OK(cudaMalloc(&d_g, n3 * sizeof(double)));
-    CUDA_OK(cudaMalloc(&d_q, (size_t)nsys * nat * sizeof(double)));
-    CUDA_OK(cudaMalloc(&d_e, nsys * sizeof(double)));
-    CUDA_OK(cudaMalloc(&d_stat, nsys * sizeof(int)));
-    CUDA_OK(cudaMalloc(&d_nit, nsys * sizeof(int)));
-    CUDA_OK(cudaMemcpy(d_xyz, xyz, n3 * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemset(ctx.d_queue, 0, sizeof(int)));
-    int grid = ctx.ncta < nsys ? ctx.ncta : nsys;
-    double *d_spec = nullptr;
-    const size_t nspec = (size_t)nsys * (2 * ctx.hm.nao + (size_t)ctx.hm.nao * nat + 1);
-    if (spec) CUDA_OK(cudaMalloc(&d_spec, nspec * sizeof(double)));
+    sl->used = ++tick;
+    Context &ctx = sl->ctx;
+    const size_t n3 = (size_t)nsys * nat * 3, n1 = (size_t)nsys * nat;
+    const size_t nspec = spec ? (size_t)nsys * (2 * ctx.hm.nao + (size_t)ctx.hm.nao * nat + 1) : 0;
+    // one device block: xyz | grad | qat | energy | spec | stat | niter
+    const size_t ndbl = 2 * n3 + n1 + nsys + nspec, bytes = ndbl * sizeof(double) + 2 * (size_t)nsys * sizeof(int);
+    if (sl->cap < bytes) {
+        if (sl->d_io) cudaFree(sl->d_io);
+        sl->d_io = nullptr; sl->cap = 0;
+        CUDA_OK(cudaMalloc(&sl->d_io, bytes));
+        sl->cap = bytes;
+    }
+    double *d_xyz = reinterpret_cast<double *>(sl->d_io), *d_g = d_xyz + n3, *d_q = d_g + n3, *d_e = d_q + n1, *d_spec = spec ? d_e + nsys : nullptr;
+    int *d_stat = reinterpret_cast<int *>(d_xyz + ndbl), *d_nit = d_stat + nsys;
+    cudaStream_t st = sl->stream;
+    CUDA_OK(cudaMemcpyAsync(d_xyz, xyz, n3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemsetAsync(ctx.d_queue, 0, sizeof(int), st));
+    const int grid = ctx.ncta < nsys ? ctx.ncta : nsys;
     if (nao_out) *nao_out = ctx.hm.nao;
-    CUDA_OK(ctx.ks->egrad_batch(grid, ctx.smem, nullptr, ctx.hm.dev, ctx.L, ctx.d_scratch, d_xyz, etemp * QC_KTOAU, nsys, ctx.d_queue, d_e, d_g, d_q, d_stat, d_nit, d_spec));
-    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(ctx.ks->egrad_batch(grid, ctx.smem, st, ctx.hm.dev, ctx.L, ctx.d_scratch, d_xyz, etemp * QC_KTOAU, nsys, ctx.d_queue, d_e, d_g, d_q, d_stat, d_nit, d_spec));
     if (spec) {
         spec->resize(nspec);
-        CUDA_OK(cudaMemcpy(spec->data(), d_spec, nspec * sizeof(double), cudaMemcpyDeviceToHost));
-        cudaFree(d_spec);
+        CUDA_OK(cudaMemcpyAsync(spec->data(), d_spec, nspec * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
-    CUDA_OK(cudaMemcpy(energy, d_e, nsys * sizeof(double), cudaMemcpyDeviceToHost));
-    CUDA_OK(cudaMemcpy(gradient, d_g, n3 * sizeof(double), cudaMemcpyDeviceToHost));
-    CUDA_OK(cudaMemcpy(qat, d_q, (size_t)nsys * nat * sizeof(double), cudaMemcpyDeviceToHost));
-    CUDA_OK(cudaMemcpy(stat, d_stat, nsys * sizeof(int), cudaMemcpyDeviceToHost));
-    if (niter) CUDA_OK(cudaMemcpy(niter, d_nit, nsys * sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(d_xyz); cudaFree(d_g); cudaFree(d_q); cudaFree(d_e); cudaFree(d_stat); cudaFree(d_nit);
+    CUDA_OK(cudaMemcpyAsync(energy, d_e, nsys * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(gradient, d_g, n3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(qat, d_q, n1 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(stat, d_stat, nsys * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (niter) CUDA_OK(cudaMemcpyAsync(niter, d_nit, nsys * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -294,22 +315,24 @@ extern "C" int qcxms_b200_fragment_structure(int nsys, int nat, const int32_t *n
     }
     DevModel m{};
     m.nat = nat;
-    double *d_rad, *d_xyz;
-    int *d_frag, *d_stack;
-    unsigned char *d_conn;
-    int grid = nsys < 1024 ? nsys : 1024;
-    CUDA_OK(cudaMalloc(&d_rad, nat * sizeof(double)));
-    CUDA_OK(cudaMalloc(&d_xyz, (size_t)nsys * nat * 3 * sizeof(double)));
-    CUDA_OK(cudaMalloc(&d_frag, (size_t)nsys * nat * sizeof(int)));
-    CUDA_OK(cudaMalloc(&d_stack, (size_t)grid * nat * sizeof(int)));
-    CUDA_OK(cudaMalloc(&d_conn, (size_t)grid * nat * nat));
-    CUDA_OK(cudaMemcpy(d_rad, qcrad.data(), nat * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(d_xyz, xyz, (size_t)nsys * nat * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    const int grid = nsys < 1024 ? nsys : 1024;
+    // one device block (freed on every path): radii | xyz | frag | stack | conn
+    const size_t b_rad = nat * sizeof(double), b_xyz = (size_t)nsys * nat * 3 * sizeof(double), b_frag = (size_t)nsys * nat * sizeof(int),
+                 b_stack = (size_t)grid * nat * sizeof(int), b_conn = (size_t)grid * nat * nat;
+    struct Block {
+        char *p = nullptr;
+        ~Block() { if (p) cudaFree(p); }
+    } blk;
+    CUDA_OK(cudaMalloc(&blk.p, b_rad + b_xyz + b_frag + b_stack + b_conn));
+    double *d_rad = reinterpret_cast<double *>(blk.p), *d_xyz = reinterpret_cast<double *>(blk.p + b_rad);
+    int *d_frag = reinterpret_cast<int *>(blk.p + b_rad + b_xyz), *d_stack = reinterpret_cast<int *>(blk.p + b_rad + b_xyz + b_frag);
+    unsigned char *d_conn = reinterpret_cast<unsigned char *>(blk.p + b_rad + b_xyz + b_frag + b_stack);
+    CUDA_OK(cudaMemcpy(d_rad, qcrad.data(), b_rad, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_xyz, xyz, b_xyz, cudaMemcpyHostToDevice));
     m.at_qcrad = d_rad;
     k_fragments<<<grid, QX_NT>>>(m, d_xyz, rcut, nsys, d_frag, d_conn, d_stack);
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaMemcpy(frag, d_frag, (size_t)nsys * nat * sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(d_rad); cudaFree(d_xyz); cudaFree(d_frag); cudaFree(d_stack); cudaFree(d_conn);
+    CUDA_OK(cudaMemcpy(frag, d_frag, b_frag, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -323,6 +346,7 @@ struct qcxms_b200_ensemble {
     unsigned long long *d_steps = nullptr;
     int *d_progress = nullptr;
     double *d_bins = nullptr;
+    double *qwarm_buf = nullptr;
     int nbins = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -430,8 +454,11 @@ extern "C" int qcxms_b200_ensemble_set_warm_start(qcxms_b200_ensemble_t *h, int 
     if (!h) return fail(QCXMS_B200_ERR_ARG, "null handle");
     CUDA_OK(cudaSetDevice(h->ctx.device));
     if (on && !h->st.qwarm) {
-        cudaError_t e = ens_alloc(h, &h->st.qwarm, (size_t)h->ntraj * (2 * h->ctx.hm.ndim + 1));
-        if (e != cudaSuccess) return fail(QCXMS_B200_ERR_CUDA, std::string("warm-start buffer: ") + cudaGetErrorString(e));
+        if (!h->qwarm_buf) {   // allocated once per handle; switching the mode off and on again reuses it
+            cudaError_t e = ens_alloc(h, &h->qwarm_buf, (size_t)h->ntraj * (2 * h->ctx.hm.ndim + 1));
+            if (e != cudaSuccess) return fail(QCXMS_B200_ERR_CUDA, std::string("warm-start buffer: ") + cudaGetErrorString(e));
+        }
+        h->st.qwarm = h->qwarm_buf;
         h->initialised = false;   // the populations are seeded by the initial single point of md()
     } else if (!on)
         h->st.qwarm = nullptr;    // (buffer stays owned by the handle)
