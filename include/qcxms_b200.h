@@ -131,6 +131,15 @@ int qcxms_b200_ensemble_set_mfp(qcxms_b200_ensemble_t *h, int icoll, const doubl
 /* new_velo [ntraj] after run_md (mean-free-path mode only) */
 int qcxms_b200_ensemble_get_new_velo(qcxms_b200_ensemble_t *h, double *new_velo);
 
+/* The two ground-state runs that precede the production runs (reference src/main.F90:545-567): md() with it = -1 (equilibration:
+ * velocities rescaled towards tsoll when the running mean temperature is more than 5 % off, src/md.f90:402-410; no energy test)
+ * and it = 0 (NVE sampling: positions and velocities of EVERY step are recorded -- the lines of qcxms.gs, src/md.f90:380-385).  Both
+ * keep the electronic temperature at etemp_in (>= 0 required), add no impact energy, look for no fragments and end after nmax
+ * steps.  it = 1 returns to production mode.  Call before run_md. */
+int qcxms_b200_ensemble_set_gs_mode(qcxms_b200_ensemble_t *h, int it, double tsoll);
+/* it = 0: records first .. first + count - 1 of trajectory itrj, [count][nat][6] = (x, y, z, vx, vy, vz) per atom in a.u. */
+int qcxms_b200_ensemble_get_gs(qcxms_b200_ensemble_t *h, int itrj, int first, int count, double *xyzvelo);
+
 int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_steps, int64_t *steps_done);
 
 int qcxms_b200_ensemble_get_result(qcxms_b200_ensemble_t *h, int itrj, double *xyz, double *velo, double *grad,

@@ -348,6 +348,50 @@ static int md_core(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *ia
     return 0;
 }
 
+/* md() for it = -1 (equilibration) and it = 0 (sampling) -- reference src/md.f90:34-708 with it <= 0: etemp = etempin on every step
+ * (:290-297), nadd = 0 and velof = 1 (:270-274), Eerror = 0 for it < 0 (:318), qcxms.gs record before the step for it == 0
+ * (:380-385), velocity rescaling towards Tsoll for it < 0 (:402-410), no fragment section (:416), tmax as the exit (:672).
+ * gs (may be NULL): [nmax][nuc][6] records. */
+int md_oracle_md_gs(const qcxms_b200_md_config_t *cfg, int it, double Tsoll, int nuc, const int32_t *iat, const double *mass, double *xyz,
+                    double *velo, double *grad, double *achrg, double *gs, qcxms_b200_md_result_t *res) {
+    const double tstep = cfg->tstep, etemp = cfg->etemp_in;
+    double Ekin, T, Epot;
+    int niter = 0, scc_total = 0, mdok = 0, nstep = 0;
+    md_oracle_ekinet(nuc, velo, mass, &Ekin, &T);
+    md_oracle_egrad(nuc, xyz, iat, cfg->mchrg, etemp, cfg->method_id, &Epot, grad, achrg, &niter);
+    scc_total += niter;
+    memset(res, 0, sizeof *res);
+    if (Epot == 0) { res->status = 2; return 0; }
+    double Tav = 0, Epav = 0, Ekav = 0, Edum = 0, Eav, Eerror, ttime = 0;
+    const int nadd = 0;
+    for (;;) {
+        nstep = nstep + 1;
+        T = Ekin / (0.5 * 3 * nuc * QC_KB);
+        Tav = Tav + T; Epav = Epav + Epot; Ekav = Ekav + Ekin;
+        if (nstep > nadd) { Edum = Edum + Epot + Ekin; Eav = Edum / (double)(float)(nstep - nadd); }
+        else Eav = Epot + Ekin;
+        Eerror = Eav - Epot - Ekin;
+        if (it < 0) Eerror = 0;
+        if (Epot == 0 || (fabs(Eerror) > (double)0.1f && cfg->exit_rules)) { mdok = cfg->isec > 1; break; }
+        if (it == 0 && gs)
+            for (int i = 0; i < nuc; ++i)
+                for (int j = 0; j < 3; ++j) { gs[((size_t)(nstep - 1) * nuc + i) * 6 + j] = xyz[3 * i + j]; gs[((size_t)(nstep - 1) * nuc + i) * 6 + 3 + j] = velo[3 * i + j]; }
+        md_oracle_leapfrog(nuc, grad, mass, tstep, xyz, velo, &Ekin);
+        ttime = ttime + tstep / QC_FSTOAU;
+        md_oracle_egrad(nuc, xyz, iat, cfg->mchrg, etemp, cfg->method_id, &Epot, grad, achrg, &niter);
+        scc_total += niter;
+        double dum = 100. * fabs(Tav / nstep - Tsoll) / Tsoll;
+        if (dum > 5.0 && it < 0 && nstep > 50) {
+            double f = sqrt(Tav / nstep / Tsoll);
+            for (int i = 0; i < 3 * nuc; ++i) velo[i] = velo[i] / f;
+        }
+        if (nstep >= cfg->nmax) { mdok = 1; break; }
+    }
+    res->mdok = mdok; res->fragstate = mdok ? 1 : 0; res->nstep = nstep; res->nfrag = 1; res->status = 1; res->scc_iter_total = scc_total;
+    res->Tav = Tav / nstep; res->Epav = Epav / nstep; res->Ekav = Ekav / nstep; res->ttime = ttime; res->Epot = Epot; res->Ekin = Ekin;
+    return 0;
+}
+
 int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
                  const double *velof, double eimp, double tadd, int step_limit, double *grad, int32_t *list, double *achrg, double *axyz,
                  qcxms_b200_md_result_t *res) {

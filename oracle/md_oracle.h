@@ -27,6 +27,9 @@ int md_oracle_egrad(int nuc, const double *xyz, const int32_t *iat, int mchrg, d
 int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
                  const double *velof, double eimp, double tadd, int max_steps, double *grad, int32_t *list, double *achrg, double *axyz,
                  qcxms_b200_md_result_t *res);
+/* md() for it = -1 / 0: the ground-state equilibration and sampling runs (src/md.f90 with it <= 0, called from src/main.F90:545-567) */
+int md_oracle_md_gs(const qcxms_b200_md_config_t *cfg, int it, double Tsoll, int nuc, const int32_t *iat, const double *mass, double *xyz,
+                    double *velo, double *grad, double *achrg, double *gs, qcxms_b200_md_result_t *res);
 /* md() for it > 0 as the mean-free-path MD of a CID run (method 3, icoll >= 1; called from src/main.F90:1860-1866); new_velo in/out, m/s */
 int md_oracle_md_mfp(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
                      int icoll, double *new_velo, int step_limit, double *grad, int32_t *list, double *achrg, double *axyz,

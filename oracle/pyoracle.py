@@ -238,6 +238,24 @@ def md(num, mass, xyz, velo, velof, eimp, tadd, mchrg=1, tstep_fs=0.5, nmax=1000
     return out
 
 
+def md_gs(num, mass, xyz, velo, it, tsoll, etemp, mchrg=0, tstep_fs=0.5, nmax=100, method=2, exit_rules=True):
+    """md() of the reference for it = -1 (equilibration) / it = 0 (sampling).  Adds gs [nmax, nat, 6] (records of qcxms.gs) for it = 0."""
+    num = np.ascontiguousarray(num, dtype=np.int32); nat = len(num)
+    mass = np.ascontiguousarray(mass, dtype=np.float64)
+    xyz = np.array(xyz, dtype=np.float64).reshape(nat, 3); velo = np.array(velo, dtype=np.float64).reshape(nat, 3)
+    cfg = MdConfig(int(method), int(mchrg), 3, int(bool(exit_rules)), int(nmax), 1, float(tstep_fs) * 41.3413733365614, float(etemp), 0.0, 0.0)
+    grad = np.zeros((nat, 3)); achrg = np.zeros(nat); gs = np.zeros((int(nmax), nat, 6))
+    res = MdResult()
+    f = lib().md_oracle_md_gs
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    f.argtypes = [C.POINTER(MdConfig), C.c_int, C.c_double, C.c_int, ip, dp, dp, dp, dp, dp, dp, C.POINTER(MdResult)]
+    f(C.byref(cfg), int(it), float(tsoll), nat, _ip(num), _dp(mass), _dp(xyz), _dp(velo), _dp(grad), _dp(achrg), _dp(gs), C.byref(res))
+    out = dict(xyz=xyz, velo=velo, grad=grad, achrg=achrg, gs=gs)
+    for k, _ in MdResult._fields_:
+        out[k] = getattr(res, k)
+    return out
+
+
 def md_mfp(num, mass, xyz, velo, icoll, new_velo, mchrg=1, tstep_fs=0.5, nmax=1000, method=2, etemp=-1.0, ieetemp=0.0, ax=0.0, isec=2,
            max_steps=0, exit_rules=True):
     """md() of the reference as the mean-free-path MD of a CID run (method 3, icoll >= 1).  Adds new_velo (m/s) to the result."""

@@ -60,7 +60,7 @@ EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_egrad_spec", "qcxms_b200_basis_size",
            "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_set_warm_start", "qcxms_b200_ensemble_set_mfp", "qcxms_b200_ensemble_get_new_velo", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_get_all", "qcxms_b200_ensemble_last_timing",
            "qcxms_b200_ensemble_histogram", "qcxms_b200_ensemble_intenergy", "qcxms_b200_last_error", "qcxms_b200_version",
            "qcxms_b200_comm_unique_id", "qcxms_b200_comm_create", "qcxms_b200_comm_destroy", "qcxms_b200_comm_allreduce_sum",
-           "qcxms_b200_ensemble_allreduce_histogram"]
+           "qcxms_b200_ensemble_allreduce_histogram", "qcxms_b200_ensemble_set_gs_mode", "qcxms_b200_ensemble_get_gs"]
 
 
 def lib():
@@ -98,6 +98,8 @@ def lib():
         L.qcxms_b200_comm_destroy.argtypes = [C.c_void_p]
         L.qcxms_b200_comm_allreduce_sum.argtypes = [C.c_void_p, dp, C.c_int]
         L.qcxms_b200_ensemble_allreduce_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp]
+        L.qcxms_b200_ensemble_set_gs_mode.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.qcxms_b200_ensemble_get_gs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp]
         L.qcxms_b200_last_error.restype = C.c_char_p
         L.qcxms_b200_version.restype = C.c_char_p
         _LIB = L
@@ -229,6 +231,17 @@ class Ensemble:
     def set_warm_start(self, on=True):
         """Opt-in fast mode (not the reference protocol): SCC of each step starts from the previous step's converged populations."""
         _check(lib().qcxms_b200_ensemble_set_warm_start(self._h, int(bool(on))))
+
+    def set_gs_mode(self, it, tsoll=0.0):
+        """md() with it = -1 (ground-state equilibration towards tsoll K) or it = 0 (NVE sampling, every step recorded); 1: production."""
+        _check(lib().qcxms_b200_ensemble_set_gs_mode(self._h, int(it), float(tsoll)))
+
+    def gs_records(self, itrj=0, first=0, count=None):
+        """The records of qcxms.gs for trajectory itrj: [count, nat, 6] = xyz | velo of every step of the sampling run."""
+        count = self.cfg.nmax - first if count is None else count
+        out = np.zeros((count, self.nat, 6))
+        _check(lib().qcxms_b200_ensemble_get_gs(self._h, int(itrj), int(first), int(count), _dp(out)))
+        return out
 
     def set_mfp(self, icoll, new_velo):
         """Mean-free-path MD of a CID run: md() with the reference's method == 3, icoll >= 1; new_velo [ntraj] in m/s as cid() returned it."""

@@ -347,6 +347,7 @@ struct qcxms_b200_ensemble {
     int *d_progress = nullptr;
     double *d_bins = nullptr;
     double *qwarm_buf = nullptr;
+    double *gs_buf = nullptr;
     int nbins = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -380,6 +381,7 @@ extern "C" int qcxms_b200_ensemble_create(const qcxms_b200_md_config_t *cfg, int
     h->ntraj = ntraj;
     h->cfg.mchrg = cfg->mchrg; h->cfg.nfragexit = cfg->nfragexit; h->cfg.exit_rules = cfg->exit_rules; h->cfg.nmax = cfg->nmax; h->cfg.isec = cfg->isec;
     h->cfg.tstep = cfg->tstep; h->cfg.etemp_in = cfg->etemp_in; h->cfg.ieetemp = cfg->ieetemp; h->cfg.ax = cfg->ax;
+    h->cfg.it_mode = 1; h->cfg.tsoll = 0.0;
     const size_t n1 = (size_t)ntraj * nat, n3 = n1 * 3, nt = ntraj;
     MdState &s = h->st;
     cudaError_t e = cudaSuccess;
@@ -462,6 +464,39 @@ extern "C" int qcxms_b200_ensemble_set_warm_start(qcxms_b200_ensemble_t *h, int 
         h->initialised = false;   // the populations are seeded by the initial single point of md()
     } else if (!on)
         h->st.qwarm = nullptr;    // (buffer stays owned by the handle)
+    return 0;
+}
+
+// md() with it = -1 (equilibration) or it = 0 (sampling, every step recorded) -- the two ground-state runs the reference does before
+// the production runs (src/main.F90:545-567)
+extern "C" int qcxms_b200_ensemble_set_gs_mode(qcxms_b200_ensemble_t *h, int it, double tsoll) {
+    if (!h || (it != 0 && it != -1 && it != 1)) return fail(QCXMS_B200_ERR_ARG, "it must be -1 (equilibration), 0 (sampling) or 1 (production)");
+    if (it < 0 && !(tsoll > 0.0)) return fail(QCXMS_B200_ERR_ARG, "the equilibration needs a target temperature");
+    if (it <= 0 && h->cfg.etemp_in < 0.0) return fail(QCXMS_B200_ERR_ARG, "ground-state runs need an explicit electronic temperature (etemp_in)");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    h->cfg.it_mode = it;
+    h->cfg.tsoll = tsoll;
+    h->st.gsdump = nullptr;
+    if (it == 0) {
+        const size_t n = (size_t)h->ntraj * h->cfg.nmax * 6 * h->ctx.hm.nat;
+        if (n * sizeof(double) > ((size_t)16 << 30)) return fail(QCXMS_B200_ERR_ARG, "ground-state record buffer would exceed 16 GB: fewer steps or trajectories");
+        if (!h->gs_buf) {
+            cudaError_t e = ens_alloc(h, &h->gs_buf, n);
+            if (e != cudaSuccess) return fail(QCXMS_B200_ERR_CUDA, std::string("ground-state record buffer: ") + cudaGetErrorString(e));
+        }
+        h->st.gsdump = h->gs_buf;
+    }
+    h->initialised = false;
+    return 0;
+}
+
+// records first .. first + count - 1 (0-based steps) of trajectory itrj: [count][nat][6] = xyz, velo of every atom (the lines of qcxms.gs)
+extern "C" int qcxms_b200_ensemble_get_gs(qcxms_b200_ensemble_t *h, int itrj, int first, int count, double *xyzvelo) {
+    if (!h || !xyzvelo || itrj < 0 || itrj >= h->ntraj || first < 0 || count < 1 || first + count > h->cfg.nmax) return fail(QCXMS_B200_ERR_ARG, "bad argument");
+    if (!h->gs_buf || h->cfg.it_mode != 0) return fail(QCXMS_B200_ERR_ARG, "the ensemble is not in ground-state sampling mode");
+    CUDA_OK(cudaSetDevice(h->ctx.device));
+    const size_t rec = (size_t)6 * h->ctx.hm.nat;
+    CUDA_OK(cudaMemcpy(xyzvelo, h->gs_buf + ((size_t)itrj * h->cfg.nmax + first) * rec, (size_t)count * rec * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -47,7 +47,7 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_init(DevModel m, S
         for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) s.xyz[i] = st.xyz[(size_t)t * 3 * nat + i];
         __syncthreads();
         const double eimp = st.eimp[t];
-        const double etemp = cfg.etemp_in < 0.0 ? md_setetemp(cfg, 1, eimp) : cfg.etemp_in;
+        const double etemp = (cfg.etemp_in < 0.0 && cfg.it_mode > 0) ? md_setetemp(cfg, 1, eimp) : cfg.etemp_in;
         int nit = 0;
         double *qw = st.qwarm ? st.qwarm + (size_t)t * (2 * m.ndim + 1) : nullptr;
         if (qw) {   // the first single point of a trajectory has nothing to start from: zero populations == the reference's cold start
@@ -78,7 +78,7 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_init(DevModel m, S
             st.Tav[t] = 0; st.Epav[t] = 0; st.Ekav[t] = 0; st.Edum[t] = 0; st.aTlast[t] = 0; st.dtime[t] = 0; st.ttime[t] = 0;
             st.nstep[t] = 0; st.kdump[t] = 50; st.fconst[t] = 0; st.morestep[t] = 0; st.nfrag[t] = 1;
             st.fragstate[t] = 0; st.mdok[t] = 0;
-            st.nadd[t] = (int)((tadd + cfg.tstep) / cfg.tstep - 1.0);
+            st.nadd[t] = cfg.it_mode > 0 ? (int)((tadd + cfg.tstep) / cfg.tstep - 1.0) : 0;   // ground-state runs: nadd = 0 (src/md.f90:270-274)
             st.fadd[t] = cfg.tstep / (tadd + cfg.tstep);
             st.status[t] = epot == 0.0 ? TRJ_FAILED : TRJ_RUNNING;
         }
@@ -153,11 +153,12 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_chunk(DevModel m, 
             if (step_limit > 0 && nstep >= step_limit) break;  // pause here: the host asked for a bounded number of steps
             nstep += 1;
             const double T = ekin / (0.5 * 3 * nat * kB);
+            if (!MFP && cfg.it_mode <= 0) etemp = cfg.etemp_in;   // src/md.f90:290-297
             Tav += T; Epav += epot; Ekav += ekin;
             double Eav;
             if (nstep > nadd) { Edum += epot + ekin; Eav = Edum / (double)(float)(nstep - nadd); }
             else Eav = epot + ekin;
-            const double Eerror = Eav - epot - ekin;
+            const double Eerror = (!MFP && cfg.it_mode < 0) ? 0.0 : Eav - epot - ekin;   // no energy-conservation test while equilibrating (:318)
             const bool err1 = epot == 0.0, err2 = fabs(Eerror) > (MFP ? (double)0.2f : (double)0.1f);
             if (err1 || (err2 && cfg.exit_rules)) {
                 mdok = ((nfrag > 1 && nfrag <= 4) || cfg.isec > 1) ? 1 : 0;
@@ -173,6 +174,10 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_chunk(DevModel m, 
             for (int i = threadIdx.x; i < nat; i += QX_NT) avchrg[i] += achrg[i];
             for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) avxyz[i] += s.xyz[i];
             aTlast += MFP ? s_q.new_temp : T;
+            if (!MFP && cfg.it_mode == 0 && st.gsdump) {   // the record of this step in qcxms.gs (src/md.f90:380-385)
+                double *rec = st.gsdump + ((size_t)t * cfg.nmax + (nstep - 1)) * 6 * nat;
+                for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) { const int a = i / 3, c = i - 3 * a; rec[6 * a + c] = s.xyz[i]; rec[6 * a + 3 + c] = velo[i]; }
+            }
             // leapfrog (reference md.f90:749-773); kinetic-energy terms summed in the reference order
             for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) {
                 const double mass = m.mass[i / 3];
@@ -203,6 +208,20 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_chunk(DevModel m, 
             kdump += 1;
             if (nfrag == 1) morestep = 0;
             if (nfrag > 1 && dtime < 1e-6) dtime = ttime / 1000.0;
+            if (!MFP && cfg.it_mode <= 0) {
+                // ground-state runs: rescale towards Tsoll while equilibrating (src/md.f90:402-410); no IEE, no fragment check, tmax is the only exit
+                if (cfg.it_mode < 0) {
+                    const double dum = 100.0 * fabs(Tav / nstep - cfg.tsoll) / cfg.tsoll;
+                    if (dum > 5.0 && nstep > 50) {
+                        const double f = sqrt(Tav / nstep / cfg.tsoll);
+                        __syncthreads();
+                        for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) velo[i] = velo[i] / f;
+                        __syncthreads();
+                    }
+                }
+                if (nstep >= cfg.nmax) { fragstate = 1; mdok = 1; status = TRJ_FINISHED; break; }
+                continue;
+            }
             if (!MFP) {
                 // IEE heating while the ion is intact
                 if (nstep <= nadd && nfrag == 1) {

@@ -19,6 +19,9 @@ namespace qx {
 struct MdConfig {
     int mchrg, nfragexit, exit_rules, nmax, isec;
     double tstep, etemp_in, ieetemp, ax;
+    int it_mode; // reference argument `it` of md(): > 0 production run (default 1); 0: ground-state sampling (NVE, every step dumped, qcxms.gs);
+                 // -1: ground-state equilibration (velocities rescaled towards tsoll).  src/md.f90:128-131, 290-297, 380-385, 402-410
+    double tsoll; // target temperature of the equilibration (reference Tsoll = Tinit)
     int icoll;   // 0: EI md(); >= 1: mean-free-path md() of a CID run (reference global method == 3, src/main.F90:1860-1866)
 };
 
@@ -33,6 +36,7 @@ struct MdState {
     double *mfp_d, *avxyz2, *store;
     int *mfp_i;
     double *qwarm;    // [ntraj][2 ndim + 1] converged populations of the last two steps + count; null unless the opt-in warm start is on
+    double *gsdump;   // it_mode == 0: [ntraj][nmax][nat][6] positions and velocities of every step (the records of qcxms.gs), null otherwise
     double *eigseed;  // [ntraj][QX_OA_NSTORE nao^2 + 1] eigenvector seeds of the eigenpair refinement (DevModel::oa), null otherwise
 };
 
