@@ -128,6 +128,12 @@ int qcxms_b200_ensemble_set_warm_start(qcxms_b200_ensemble_t *h, int on);
  * new_velo [ntraj]: the reference's in/out argument new_velo (velocity of the ion's centre of mass, m/s) as cid() returned it.
  * Call after set_all / set_trajectory and before run_md. */
 int qcxms_b200_ensemble_set_mfp(qcxms_b200_ensemble_t *h, int icoll, const double *new_velo);
+/* Switches the ensemble to the heating MD that precedes the first collision of an ESI/CID run: md() with the global method == 3,
+ * icoll = 0 and starting_md = .true. (call site src/main.F90:1357-1362): Berendsen scaling of the velocities towards tscale (K)
+ * during the first nadd steps while the ion is intact (src/md.f90:428-434), no IEE heating, error threshold and fragment
+ * averaging of the method-3 branch, kinetic energy with the centre-of-mass motion.  eimp = E_Scale and tadd = pretadd are
+ * the per-trajectory values given to set_all / set_trajectory.  Call after them and before run_md. */
+int qcxms_b200_ensemble_set_esi(qcxms_b200_ensemble_t *h, double tscale);
 /* new_velo [ntraj] after run_md (mean-free-path mode only) */
 int qcxms_b200_ensemble_get_new_velo(qcxms_b200_ensemble_t *h, double *new_velo);
 

@@ -213,11 +213,16 @@ static void natf_count(int nuc, const int32_t *list, int nfrag, int *natf);
  *               fragment-structure averaging over 50 steps after a fragmentation (:496-621) with max_steps = nstep + add_steps (:507),
  *               tmax as the only regular exit (:672), error threshold 0.2 (:325), axyz from the averaged fragments (:694-699).
  *               new_velo (m/s) is in/out (:252, :474). */
+/*   esi_tsoll > 0: the pre-collision heating MD of an ESI/CID run (global method 3, icoll = 0, starting_md = .true.; called from
+ *               src/main.F90:1357-1362 with Tsoll = tscale, tadd = pretadd, eimp = E_Scale): Berendsen scaling of the velocities towards
+ *               Tsoll during the first nadd steps while the ion is intact (:428-434); everything else as in the mean-free-path mode
+ *               except that the kinetic energy keeps the centre-of-mass motion (:254, :466 need icoll >= 1). */
 static int md_core(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
                    const double *velof, double eimp, double tadd, int icoll, double *new_velo_io, int step_limit, double *grad,
-                   int32_t *list, double *achrg, double *axyz, qcxms_b200_md_result_t *res) {
+                   int32_t *list, double *achrg, double *axyz, qcxms_b200_md_result_t *res, double esi_tsoll) {
     const double tstep = cfg->tstep;
-    const int cid = icoll > 0;
+    const int com = icoll > 0;                      /* kinetic energy without the centre-of-mass motion */
+    const int cid = icoll > 0 || esi_tsoll > 0;     /* global method == 3 */
     double Ekin, T, Epot, etemp;
     int mdok = 0, nfrag = 1, fragstate = 0, scc_total = 0, niter = 0;
     md_oracle_ekinet(nuc, velo, mass, &Ekin, &T);
@@ -247,7 +252,7 @@ static int md_core(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *ia
         double E_kin = 0.5 * summass * ((new_velo * QC_MSTOAU) * (new_velo * QC_MSTOAU));
         double E_kin_diff = Ekin - E_kin;
         new_temp = (2 * E_kin_diff) / (3 * QC_KB * nuc);
-        if (cid) Ekin = E_kin_diff;
+        if (com) Ekin = E_kin_diff;
     }
     int max_steps = cfg->nmax;
     for (;;) {
@@ -271,7 +276,7 @@ static int md_core(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *ia
         }
         for (int i = 0; i < nuc; ++i) avchrg[i] += achrg[i];
         for (int i = 0; i < 3 * nuc; ++i) avxyz[i] += xyz[i];
-        aTlast = aTlast + (cid ? new_temp : T);
+        aTlast = aTlast + (com ? new_temp : T);
         md_oracle_leapfrog(nuc, grad, mass, tstep, xyz, velo, &Ekin);
         ttime = ttime + tstep / QC_FSTOAU;
         md_oracle_egrad(nuc, xyz, iat, cfg->mchrg, etemp, cfg->method_id, &Epot, grad, achrg, &niter);
@@ -279,6 +284,10 @@ static int md_core(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *ia
         kdump = kdump + 1;
         if (nfrag == 1) morestep = 0;
         if (nfrag > 1 && dtime < 1e-6) dtime = ttime / 1000.;
+        if (cid && !com && nfrag == 1 && nstep <= nadd) {   /* Berendsen thermostat of the heating MD, md.f90:428-434 */
+            double sca = sqrt(1.0 + ((tstep / QC_FSTOAU) / 150) * (esi_tsoll / T - 1.0));
+            for (int i = 0; i < 3 * nuc; ++i) velo[i] = sca * velo[i];
+        }
         if (!cid) {
             if (nstep <= nadd && nfrag == 1) {
                 if (md_oracle_impactscale(nuc, velo, mass, velof, eimp, fadd * nstep, Ekinstart)) { res->status = 2; break; }
@@ -292,16 +301,18 @@ static int md_core(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *ia
         md_oracle_fragmass(nuc, iat, list, mass, NULL, &nfrag, NULL, NULL);
         if (cid) {
             if (nfrag > 6) break;
-            /* kinetic energy without the centre-of-mass motion, md.f90:466-493 */
-            md_oracle_center_of_mass(nuc, mass, xyz, cm);
-            double d0 = cm[0] - old_cm[0], d1 = cm[1] - old_cm[1], d2 = cm[2] - old_cm[2];
-            double cm_out = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-            new_velo = (cm_out / tstep) / QC_MSTOAU;
-            for (int k = 0; k < 3; ++k) old_cm[k] = cm[k];
-            double E_kin = 0.5 * summass * ((new_velo * QC_MSTOAU) * (new_velo * QC_MSTOAU));
-            double E_kin_diff = Ekin - E_kin;
-            new_temp = (2.0 * E_kin_diff) / (3.0 * QC_KB * nuc);
-            Ekin = E_kin_diff;
+            if (com) {
+                /* kinetic energy without the centre-of-mass motion, md.f90:466-493 */
+                md_oracle_center_of_mass(nuc, mass, xyz, cm);
+                double d0 = cm[0] - old_cm[0], d1 = cm[1] - old_cm[1], d2 = cm[2] - old_cm[2];
+                double cm_out = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                new_velo = (cm_out / tstep) / QC_MSTOAU;
+                for (int k = 0; k < 3; ++k) old_cm[k] = cm[k];
+                double E_kin = 0.5 * summass * ((new_velo * QC_MSTOAU) * (new_velo * QC_MSTOAU));
+                double E_kin_diff = Ekin - E_kin;
+                new_temp = (2.0 * E_kin_diff) / (3.0 * QC_KB * nuc);
+                Ekin = E_kin_diff;
+            }
             /* averaged fragment structures, md.f90:496-621 */
             if (nfrag > check_fragmented) { count_average = 1; check_fragmented = nfrag; max_steps = nstep + add_steps; }
             if (nfrag < check_fragmented && count_average) {
@@ -395,14 +406,23 @@ int md_oracle_md_gs(const qcxms_b200_md_config_t *cfg, int it, double Tsoll, int
 int md_oracle_md(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
                  const double *velof, double eimp, double tadd, int step_limit, double *grad, int32_t *list, double *achrg, double *axyz,
                  qcxms_b200_md_result_t *res) {
-    return md_core(cfg, nuc, iat, mass, xyz, velo, velof, eimp, tadd, 0, NULL, step_limit, grad, list, achrg, axyz, res);
+    return md_core(cfg, nuc, iat, mass, xyz, velo, velof, eimp, tadd, 0, NULL, step_limit, grad, list, achrg, axyz, res, 0.0);
 }
 
 int md_oracle_md_mfp(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
                      int icoll, double *new_velo, int step_limit, double *grad, int32_t *list, double *achrg, double *axyz,
                      qcxms_b200_md_result_t *res) {
     if (icoll < 1 || !new_velo) return 1;
-    return md_core(cfg, nuc, iat, mass, xyz, velo, NULL, 0.0, 0.0, icoll, new_velo, step_limit, grad, list, achrg, axyz, res);
+    return md_core(cfg, nuc, iat, mass, xyz, velo, NULL, 0.0, 0.0, icoll, new_velo, step_limit, grad, list, achrg, axyz, res, 0.0);
+}
+
+/* md() as the heating MD before the first collision of an ESI/CID run (method 3, icoll = 0, starting_md; src/main.F90:1357-1362) */
+int md_oracle_md_esi(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
+                     double tsoll, double eimp, double tadd, int step_limit, double *grad, int32_t *list, double *achrg, double *axyz,
+                     qcxms_b200_md_result_t *res) {
+    if (!(tsoll > 0.0)) return 1;
+    double new_velo = 0.0;
+    return md_core(cfg, nuc, iat, mass, xyz, velo, NULL, eimp, tadd, 0, &new_velo, step_limit, grad, list, achrg, axyz, res, tsoll);
 }
 
 /* ======================================================================================== CID

@@ -34,6 +34,10 @@ int md_oracle_md_gs(const qcxms_b200_md_config_t *cfg, int it, double Tsoll, int
 int md_oracle_md_mfp(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
                      int icoll, double *new_velo, int step_limit, double *grad, int32_t *list, double *achrg, double *axyz,
                      qcxms_b200_md_result_t *res);
+/* md() as the pre-collision heating MD of an ESI/CID run (method 3, icoll = 0, starting_md = .true.) */
+int md_oracle_md_esi(const qcxms_b200_md_config_t *cfg, int nuc, const int32_t *iat, const double *mass, double *xyz, double *velo,
+                     double tsoll, double eimp, double tadd, int step_limit, double *grad, int32_t *list, double *achrg, double *axyz,
+                     qcxms_b200_md_result_t *res);
 /* cid() pieces (src/rotation.f90, src/diag3x3.f90, src/boxmuller.f90, src/cid.f90) */
 void md_oracle_eigvec3x3(double a[3][3], double w[3], double q[3][3]);
 void md_oracle_euler_rotation(int nuc, double *xyz, double *velo, double a, double b, double c);

@@ -238,6 +238,25 @@ def md(num, mass, xyz, velo, velof, eimp, tadd, mchrg=1, tstep_fs=0.5, nmax=1000
     return out
 
 
+def md_esi(num, mass, xyz, velo, tscale, eimp, tadd, mchrg=1, tstep_fs=0.5, nmax=1000, method=2, etemp=-1.0, isec=1, exit_rules=True):
+    """md() of the reference as the heating MD before the first collision of an ESI/CID run (method 3, icoll = 0, starting_md)."""
+    num = np.ascontiguousarray(num, dtype=np.int32); nat = len(num)
+    mass = np.ascontiguousarray(mass, dtype=np.float64)
+    xyz = np.array(xyz, dtype=np.float64).reshape(nat, 3); velo = np.array(velo, dtype=np.float64).reshape(nat, 3)
+    cfg = MdConfig(int(method), int(mchrg), 3, int(bool(exit_rules)), int(nmax), int(isec), float(tstep_fs) * 41.3413733365614, float(etemp), 0.0, 0.0)
+    grad = np.zeros((nat, 3)); lst = np.zeros(nat, dtype=np.int32); achrg = np.zeros(nat); axyz = np.zeros((nat, 3))
+    res = MdResult()
+    f = lib().md_oracle_md_esi
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    f.argtypes = [C.POINTER(MdConfig), C.c_int, ip, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int, dp, ip, dp, dp, C.POINTER(MdResult)]
+    f(C.byref(cfg), nat, _ip(num), _dp(mass), _dp(xyz), _dp(velo), float(tscale), float(eimp), float(tadd), 0, _dp(grad), _ip(lst), _dp(achrg), _dp(axyz),
+      C.byref(res))
+    out = dict(xyz=xyz, velo=velo, grad=grad, list=lst, achrg=achrg, axyz=axyz)
+    for k, _ in MdResult._fields_:
+        out[k] = getattr(res, k)
+    return out
+
+
 def md_gs(num, mass, xyz, velo, it, tsoll, etemp, mchrg=0, tstep_fs=0.5, nmax=100, method=2, exit_rules=True):
     """md() of the reference for it = -1 (equilibration) / it = 0 (sampling).  Adds gs [nmax, nat, 6] (records of qcxms.gs) for it = 0."""
     num = np.ascontiguousarray(num, dtype=np.int32); nat = len(num)
@@ -378,6 +397,12 @@ def md_batch(num, mass, xyz, velo, velof, eimp, tadd, mchrg, nmax, nfragexit, is
 def cid_batch(cfg, num, mass, icoll, xyz, velo, rnd, velo_cm, direc, collided):
     """cid back end for qcxms_b200.production.run_cid (CPU oracle instead of qcxms_b200_cid_batch)"""
     return [cid(cfg, num, mass, icoll, xyz[k], velo[k], rnd[k], velo_cm=velo_cm[k], direc=direc[k], collided=collided[k])
+            for k in range(len(xyz))]
+
+
+def esi_batch(num, mass, xyz, velo, tscale, e_scale, pretadd, mchrg, nmax, tstep_fs, etemp):
+    """heating-MD back end for qcxms_b200.production.run_cid (CPU oracle instead of the CUDA ensemble)"""
+    return [md_esi(num, mass, xyz[k], velo[k], tscale, e_scale, pretadd, mchrg=mchrg, tstep_fs=tstep_fs, nmax=nmax, etemp=etemp, isec=1)
             for k in range(len(xyz))]
 
 

@@ -60,7 +60,7 @@ EXPORTS = ["qcxms_b200_egrad", "qcxms_b200_egrad_spec", "qcxms_b200_basis_size",
            "qcxms_b200_ensemble_run_md", "qcxms_b200_ensemble_set_warm_start", "qcxms_b200_ensemble_set_mfp", "qcxms_b200_ensemble_get_new_velo", "qcxms_b200_ensemble_get_result", "qcxms_b200_ensemble_get_all", "qcxms_b200_ensemble_last_timing",
            "qcxms_b200_ensemble_histogram", "qcxms_b200_ensemble_intenergy", "qcxms_b200_last_error", "qcxms_b200_version",
            "qcxms_b200_comm_unique_id", "qcxms_b200_comm_create", "qcxms_b200_comm_destroy", "qcxms_b200_comm_allreduce_sum",
-           "qcxms_b200_ensemble_allreduce_histogram", "qcxms_b200_ensemble_set_gs_mode", "qcxms_b200_ensemble_get_gs"]
+           "qcxms_b200_ensemble_allreduce_histogram", "qcxms_b200_ensemble_set_gs_mode", "qcxms_b200_ensemble_get_gs", "qcxms_b200_ensemble_set_esi"]
 
 
 def lib():
@@ -98,6 +98,7 @@ def lib():
         L.qcxms_b200_comm_destroy.argtypes = [C.c_void_p]
         L.qcxms_b200_comm_allreduce_sum.argtypes = [C.c_void_p, dp, C.c_int]
         L.qcxms_b200_ensemble_allreduce_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp]
+        L.qcxms_b200_ensemble_set_esi.argtypes = [C.c_void_p, C.c_double]
         L.qcxms_b200_ensemble_set_gs_mode.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.qcxms_b200_ensemble_get_gs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp]
         L.qcxms_b200_last_error.restype = C.c_char_p
@@ -231,6 +232,11 @@ class Ensemble:
     def set_warm_start(self, on=True):
         """Opt-in fast mode (not the reference protocol): SCC of each step starts from the previous step's converged populations."""
         _check(lib().qcxms_b200_ensemble_set_warm_start(self._h, int(bool(on))))
+
+    def set_esi(self, tscale):
+        """Heating MD before the first collision of an ESI/CID run (reference md() with method 3, icoll 0, starting_md): Berendsen scaling
+        towards tscale (K) during the first nadd steps; eimp = E_Scale and tadd = pretadd as given to set_all."""
+        _check(lib().qcxms_b200_ensemble_set_esi(self._h, float(tscale)))
 
     def set_gs_mode(self, it, tsoll=0.0):
         """md() with it = -1 (ground-state equilibration towards tsoll K) or it = 0 (NVE sampling, every step recorded); 1: production."""

@@ -381,7 +381,7 @@ extern "C" int qcxms_b200_ensemble_create(const qcxms_b200_md_config_t *cfg, int
     h->ntraj = ntraj;
     h->cfg.mchrg = cfg->mchrg; h->cfg.nfragexit = cfg->nfragexit; h->cfg.exit_rules = cfg->exit_rules; h->cfg.nmax = cfg->nmax; h->cfg.isec = cfg->isec;
     h->cfg.tstep = cfg->tstep; h->cfg.etemp_in = cfg->etemp_in; h->cfg.ieetemp = cfg->ieetemp; h->cfg.ax = cfg->ax;
-    h->cfg.it_mode = 1; h->cfg.tsoll = 0.0;
+    h->cfg.it_mode = 1; h->cfg.tsoll = 0.0; h->cfg.method3 = 0; h->cfg.starting_md = 0;
     const size_t n1 = (size_t)ntraj * nat, n3 = n1 * 3, nt = ntraj;
     MdState &s = h->st;
     cudaError_t e = cudaSuccess;
@@ -515,7 +515,22 @@ extern "C" int qcxms_b200_ensemble_set_mfp(qcxms_b200_ensemble_t *h, int icoll, 
     for (size_t t = 0; t < nt; ++t) d[t * 8 + 3] = new_velo[t];   // picked up by the initial single point of md()
     CUDA_OK(cudaMemcpy(h->st.mfp_d, d.data(), d.size() * sizeof(double), cudaMemcpyHostToDevice));
     h->cfg.icoll = icoll;
+    h->cfg.method3 = 1;
+    h->cfg.starting_md = 0;
     h->initialised = false;
+    return 0;
+}
+
+// md() as the heating MD before the first collision of an ESI/CID run: reference global method == 3, icoll = 0, starting_md = .true.,
+// Tsoll = tscale (src/main.F90:1330-1362; md.f90:428-434).  eimp (E_Scale) and tadd (pretadd) come in through set_all / set_trajectory.
+extern "C" int qcxms_b200_ensemble_set_esi(qcxms_b200_ensemble_t *h, double tscale) {
+    if (!h || !(tscale > 0.0)) return fail(QCXMS_B200_ERR_ARG, "tscale (K) > 0 required");
+    std::vector<double> zero(h->ntraj, 0.0);
+    int rc = qcxms_b200_ensemble_set_mfp(h, 1, zero.data());   // allocates and clears the buffers of the method-3 branch of md()
+    if (rc) return rc;
+    h->cfg.icoll = 0;
+    h->cfg.starting_md = 1;
+    h->cfg.tsoll = tscale;
     return 0;
 }
 
@@ -531,7 +546,7 @@ extern "C" int qcxms_b200_ensemble_get_new_velo(qcxms_b200_ensemble_t *h, double
 
 // mean-free-path mode: axyz is the averaged fragment structure once a fragmentation was counted (reference src/md.f90:694-699)
 static cudaError_t mfp_fix_axyz(qcxms_b200_ensemble_t *h, size_t t0, size_t nt, double *axyz) {
-    if (h->cfg.icoll <= 0 || !axyz) return cudaSuccess;
+    if (!h->cfg.method3 || !axyz) return cudaSuccess;
     const size_t n3 = (size_t)h->ctx.hm.nat * 3;
     std::vector<int> mi(nt * 16);
     std::vector<double> st(nt * n3);
@@ -568,7 +583,7 @@ extern "C" int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_step
     const int limit = max_steps > 0 ? base_step + max_steps : 0;
     // mean-free-path mode: every counted fragmentation moves the end to nstep + add_steps (src/md.f90:507); the loop ends when no
     // trajectory is running any more, the bound is a safety net only
-    const int total = max_steps > 0 ? max_steps : (h->cfg.icoll > 0 ? h->cfg.nmax + 64 * (h->ctx.hm.nat / 10 + 1) * 1000 : h->cfg.nmax);
+    const int total = max_steps > 0 ? max_steps : (h->cfg.method3 ? h->cfg.nmax + 64 * (h->ctx.hm.nat / 10 + 1) * 1000 : h->cfg.nmax);
     const int chunk = 64, sub_steps = 8;
     std::vector<int> status(h->ntraj);
     for (int done = 0; done < total; done += chunk) {
@@ -577,7 +592,7 @@ extern "C" int qcxms_b200_ensemble_run_md(qcxms_b200_ensemble_t *h, int max_step
         CUDA_OK(cudaMemsetAsync(c.d_queue, 0, sizeof(int), h->stream));
         CUDA_OK(cudaMemsetAsync(h->d_progress, 0, h->ntraj * sizeof(int), h->stream));
         // the last sub-chunk may be shorter: the kernel bounds every sub-chunk by the launch's step limit as well
-        CUDA_OK((h->cfg.icoll > 0 ? c.ks->mfp_chunk : c.ks->md_chunk)(grid, c.smem, h->stream, c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, sub_steps,
+        CUDA_OK((h->cfg.method3 ? c.ks->mfp_chunk : c.ks->md_chunk)(grid, c.smem, h->stream, c.hm.dev, c.L, c.d_scratch, h->cfg, h->st, h->ntraj, sub_steps,
                                                                       nsub, max_steps > 0 ? limit : 0, c.d_queue, h->d_progress, h->d_steps));
         h->launches += 1;
         // poll for completion every few chunks (cheap: ntraj ints)

@@ -63,7 +63,7 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_init(DevModel m, S
             const double ekin = md_ekinet_seq(nat, st.velo + (size_t)t * 3 * nat, m.mass, 0.0, nullptr);
             const double tadd = st.tadd[t];
             st.ekin[t] = ekin; st.ekinstart[t] = ekin; st.epot[t] = epot; st.etemp[t] = etemp;
-            if (cfg.icoll > 0) {   // mean-free-path mode: kinetic energy without the motion of the centre of mass (src/md.f90:246-255, 283)
+            if (cfg.method3) {   // mean-free-path mode: kinetic energy without the motion of the centre of mass (src/md.f90:246-255, 283)
                 MfpScalars q{};
                 q.new_velo = st.mfp_d[(size_t)t * 8 + 3];
                 cid_center_of_mass(nat, m.mass, st.xyz + (size_t)t * 3 * nat, q.old_cm);
@@ -71,7 +71,7 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_init(DevModel m, S
                 const double E_kin = 0.5 * q.summass * ((q.new_velo * QC_MSTOAU) * (q.new_velo * QC_MSTOAU));
                 const double E_kin_diff = ekin - E_kin;
                 q.new_temp = (2 * E_kin_diff) / (3 * QC_KB * nat);
-                st.ekin[t] = E_kin_diff;
+                if (cfg.icoll > 0) st.ekin[t] = E_kin_diff;   // (the heating MD before the first collision keeps the full kinetic energy, :254)
                 q.check_fragmented = 1; q.max_steps = cfg.nmax;
                 mfp_store(st, t, q);
             }
@@ -84,7 +84,7 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_init(DevModel m, S
         }
         for (int i = threadIdx.x; i < nat; i += QX_NT) { st.avchrg[(size_t)t * nat + i] = 0.0; st.list[(size_t)t * nat + i] = 1; }
         for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) st.avxyz[(size_t)t * 3 * nat + i] = 0.0;
-        if (cfg.icoll > 0)
+        if (cfg.method3)
             for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) { st.avxyz2[(size_t)t * 3 * nat + i] = 0.0; st.store[(size_t)t * 3 * nat + i] = 0.0; }
     }
 }
@@ -173,7 +173,7 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_chunk(DevModel m, 
             }
             for (int i = threadIdx.x; i < nat; i += QX_NT) avchrg[i] += achrg[i];
             for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) avxyz[i] += s.xyz[i];
-            aTlast += MFP ? s_q.new_temp : T;
+            aTlast += (MFP && cfg.icoll > 0) ? s_q.new_temp : T;
             if (!MFP && cfg.it_mode == 0 && st.gsdump) {   // the record of this step in qcxms.gs (src/md.f90:380-385)
                 double *rec = st.gsdump + ((size_t)t * cfg.nmax + (nstep - 1)) * 6 * nat;
                 for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) { const int a = i / 3, c = i - 3 * a; rec[6 * a + c] = s.xyz[i]; rec[6 * a + 3 + c] = velo[i]; }
@@ -232,6 +232,11 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_chunk(DevModel m, 
                     etemp = md_setetemp(cfg, nfrag, dum);
                 }
             }
+            if (MFP && cfg.icoll == 0 && cfg.starting_md && nfrag == 1 && nstep <= nadd) {   // Berendsen thermostat of the heating MD (src/md.f90:428-434)
+                const double sca = sqrt(1.0 + ((cfg.tstep / fstoau) / 150) * (cfg.tsoll / T - 1.0));
+                for (int i = threadIdx.x; i < 3 * nat; i += QX_NT) velo[i] = sca * velo[i];
+                __syncthreads();
+            }
             md_fragments(m, s.xyz, 3.0, (unsigned char *)(my + L.taskout), list, (int *)(my + L.taskout) + (nat * nat + 3) / 4 + 4);
             if (threadIdx.x == 0) s_flag = md_nfrag(m, list);
             __syncthreads();
@@ -240,17 +245,20 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_chunk(DevModel m, 
                 if (nfrag > 6) { status = TRJ_FINISHED; break; }
                 if (threadIdx.x == 0) {
                     MfpScalars &q = s_q;
-                    // kinetic energy without the centre-of-mass motion (src/md.f90:466-493)
-                    double cm[3];
-                    cid_center_of_mass(nat, m.mass, s.xyz, cm);
-                    const double d0 = cm[0] - q.old_cm[0], d1 = cm[1] - q.old_cm[1], d2 = cm[2] - q.old_cm[2];
-                    const double cm_out = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-                    q.new_velo = (cm_out / cfg.tstep) / QC_MSTOAU;
-                    q.old_cm[0] = cm[0]; q.old_cm[1] = cm[1]; q.old_cm[2] = cm[2];
-                    const double E_kin = 0.5 * q.summass * ((q.new_velo * QC_MSTOAU) * (q.new_velo * QC_MSTOAU));
-                    const double E_kin_diff = ekin - E_kin;
-                    q.new_temp = (2.0 * E_kin_diff) / (3.0 * QC_KB * nat);
-                    q.ekin = E_kin_diff;
+                    q.ekin = ekin;
+                    if (cfg.icoll > 0) {
+                        // kinetic energy without the centre-of-mass motion (src/md.f90:466-493)
+                        double cm[3];
+                        cid_center_of_mass(nat, m.mass, s.xyz, cm);
+                        const double d0 = cm[0] - q.old_cm[0], d1 = cm[1] - q.old_cm[1], d2 = cm[2] - q.old_cm[2];
+                        const double cm_out = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                        q.new_velo = (cm_out / cfg.tstep) / QC_MSTOAU;
+                        q.old_cm[0] = cm[0]; q.old_cm[1] = cm[1]; q.old_cm[2] = cm[2];
+                        const double E_kin = 0.5 * q.summass * ((q.new_velo * QC_MSTOAU) * (q.new_velo * QC_MSTOAU));
+                        const double E_kin_diff = ekin - E_kin;
+                        q.new_temp = (2.0 * E_kin_diff) / (3.0 * QC_KB * nat);
+                        q.ekin = E_kin_diff;
+                    }
                     // averaged fragment structures (src/md.f90:496-621)
                     int ops = 0;
                     if (nfrag > q.check_fragmented) { q.count_average = 1; q.check_fragmented = nfrag; q.max_steps = nstep + mfp_add_steps(nat); }

@@ -22,6 +22,9 @@ struct MdConfig {
     int it_mode; // reference argument `it` of md(): > 0 production run (default 1); 0: ground-state sampling (NVE, every step dumped, qcxms.gs);
                  // -1: ground-state equilibration (velocities rescaled towards tsoll).  src/md.f90:128-131, 290-297, 380-385, 402-410
     double tsoll; // target temperature of the equilibration (reference Tsoll = Tinit)
+    int method3;     // 1: md() inside a CID run (reference global method == 3): mean-free-path MD (icoll >= 1) or the heating MD before the
+                     // first collision (icoll == 0 with starting_md: Berendsen scaling towards tsoll, src/md.f90:428-434, main.F90:1357-1362)
+    int starting_md;
     int icoll;   // 0: EI md(); >= 1: mean-free-path md() of a CID run (reference global method == 3, src/main.F90:1860-1866)
 };
 

@@ -137,6 +137,8 @@ def _after_md(s, r, nmax0, maxsec, btf, energies):
 # ------------------------------------------------------------------------------------------------------------------- CID
 AATOAU = 1.0 / 0.52917726                 # reference src/xtb_mctc_convert.f90 (aatoau = 1 / autoaa)
 MSTOAU = 1.0 / 2.18769126364e+06
+KB = 3.166808578545117e-06
+FSTOAU = 41.3413733365614
 AUTOEV = 27.21138505
 AMUTOAU = 1.660539040e-27 * (1.0 / 9.10938356e-31)
 
@@ -193,6 +195,21 @@ def gpu_mfp_batch(num, mass, xyz, velo, new_velo, icoll, isec, mchrg, nmax, tste
     return [{k: (v[i] if isinstance(v, np.ndarray) else v) for k, v in res.items()} for i in range(nt)]
 
 
+def gpu_esi_batch(num, mass, xyz, velo, tscale, e_scale, pretadd, mchrg, nmax, tstep_fs, etemp):
+    """heating MD before the first collision (md() with method 3, icoll 0, starting_md) for ions of one composition and one length"""
+    from . import api
+    nt = len(xyz)
+    ens = api.Ensemble(num, mass, nt, mchrg=mchrg, tstep_fs=tstep_fs, nmax=nmax, nfragexit=3, exit_rules=True, etemp=etemp, isec=1)
+    try:
+        ens.set_all(np.asarray(xyz), np.asarray(velo), np.ones((nt, len(num))), np.full(nt, float(e_scale)), np.full(nt, float(pretadd)))
+        ens.set_esi(tscale)
+        ens.run_md()
+        res = ens.results()
+    finally:
+        ens.close()
+    return [{k: (v[i] if isinstance(v, np.ndarray) else v) for k, v in res.items()} for i in range(nt)]
+
+
 def _cut_fragment(s, xyz, velo, lst, tcont):
     """Atoms of fragment tcont (all atoms for tcont == 0), recentred on sum(Z r) / sum(Z) (sic) -- main.F90:1672-1754, 1911-1963.
     Returns False when the rest is too small / too light to continue."""
@@ -221,9 +238,12 @@ def _cut_fragment(s, xyz, velo, lst, tcont):
 def run_cid(num, mass, xyz, velo, mchrg=1, gas="ar", elab=40.0, ecom=0.0, eexact=False, manual_dist=0, tstep_fs=0.5, etemp=-1.0, btf=1.0,
             maxsec=7, run_type="fullauto", set_coll=10, max_coll=0, collno=(0, 0, 0), collsec=(0, 0, 0), tgas=300.0, pgas=0.132, lchamb=0.2,
             minmass=45, first_itrj=1, seed=0, cid_ntot=15000, mfp_nmax=None, cid_batch=gpu_cid_batch, mfp_batch=gpu_mfp_batch,
-            energies=fr._gpu_energies):
-    """CID production run for ntraj ions given as arrays with a leading [ntraj] axis (the ESI pre-heating MD is the caller's business:
-    `noesi` of the reference).  run_type: "fullauto" | "collauto" | "maxcoll" | "collno" | "collsec" (main.F90:1490-1592).
+            energies=fr._gpu_energies, esi_ev=0.0, esi_nmax=None, esi_batch=gpu_esi_batch):
+    """CID production run for ntraj ions given as arrays with a leading [ntraj] axis.  esi_ev = 0: the reference's `noesi`; esi_ev > 0
+    (keyword `esi <eV>`): every ion whose internal energy is below esi_ev is first heated to it by the thermostatted MD of
+    main.F90:1243-1362 (md() with method 3, icoll 0, starting_md; nmax = nint(2.5 (T_target - T)), pretadd = 3/4 of its length).  An ion that
+    fragments while being heated goes on with its charged fragment straight to the collisions (the reference runs further heating MDs
+    with isec > 1 first: not reproduced).  run_type: "fullauto" | "collauto" | "maxcoll" | "collno" | "collsec" (main.F90:1490-1592).
     Random numbers (9 per cid() call, 2 per vary_collisions, 1 per collauto redraw) come from one numpy Generator per trajectory seeded
     with (seed, itrj), so a trajectory does not depend on how the ensemble is batched.  mfp_nmax / cid_ntot shorten the runs (tests).
     Returns dict(records = qcxms_cid.res lines, per_traj = [dict(itrj, events, records)])."""
@@ -271,6 +291,49 @@ def run_cid(num, mass, xyz, velo, mchrg=1, gas="ar", elab=40.0, ecom=0.0, eexact
             finish(s, True)                      # small / littlemass: main.F90:2133-2155
             return False
         return True
+
+    # ---- ESI: heat the ions to the requested internal energy before the first collision (main.F90:1243-1362)
+    if esi_ev > 0.0:
+        groups = {}
+        for s in trj:
+            if s["phase"] != "cid":
+                continue
+            nuc = len(s["num"])
+            ekin = 0.5 * (s["mass"][:, None] * s["velo"] ** 2).sum()
+            temp = ekin / (0.5 * 3 * nuc * KB)
+            ene1 = temp * (0.5 * 3 * nuc * KB) * AUTOEV
+            e_scale = esi_ev if esi_ev - ene1 > 0 else 0.0
+            if e_scale <= 0:
+                continue                                          # "! No Scaling !"
+            tscale = (e_scale * 2.0 / 3.0) / (nuc * KB * AUTOEV)
+            nmax = int(np.floor((tscale - temp) * 2.5 + 0.5)) if not esi_nmax else int(esi_nmax)
+            pretadd = float(nmax) * FSTOAU * tstep_fs * 0.75
+            groups.setdefault((tuple(int(a) for a in s["num"]), s["mchrg"], nmax), []).append((s, tscale, e_scale / AUTOEV, pretadd))
+
+        def run_esi(item):
+            (_, mc, nmax), mem = item
+            g0 = mem[0][0]
+            return esi_batch(g0["num"], g0["mass"], [m[0]["xyz"] for m in mem], [m[0]["velo"] for m in mem], mem[0][1], mem[0][2], mem[0][3], mc, nmax,
+                             tstep_fs, etemp)
+        for ((_, mc, nmax), mem), out in zip(groups.items(), _map_groups(run_esi, groups.items())):
+            for (s, tscale, _, _), r in zip(mem, out):
+                md_ok = bool(r["mdok"]) and int(r["status"]) == 1
+                s["events"].append(dict(kind="esi", icoll=0, isec=1, nat=len(s["num"]), nstep=int(r["nstep"]), nfrag=int(r["nfrag"]), md_ok=md_ok,
+                                        tscale=float(tscale)))
+                if not md_ok:
+                    finish(s, False)                 # the reference process stops here (main.F90:1398)
+                    continue
+                try:
+                    mf = fr.manage_fragments(s["num"], s["mass"], r["axyz"], r["list"], r["achrg"], aTlast=float(r["aTlast"]), itrj=s["itrj"],
+                                             isec=1, mchrg=s["mchrg"], chrgcont=s["chrgcont"], btf=btf, maxsec=maxsec, icoll=0, energies=energies)
+                except RuntimeError as err:
+                    s["events"].append(dict(kind="fatal", icoll=0, nstep=0, nfrag=0, msg=str(err)))
+                    finish(s, False)
+                    continue
+                if not mf["nfrag_ok"]:
+                    finish(s, False)
+                    continue
+                after_fragments(s, mf, r["xyz"], r["velo"], r["list"])
 
     while any(s["phase"] != "done" for s in trj):
         # ---- collisions

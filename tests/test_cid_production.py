@@ -111,3 +111,27 @@ def test_n2_stop_rule_uses_the_single_atom_gas_mass(oracle):
     m1 = 14.007 * 1822.888486
     assert m1 / (m1 + ic["mass"].sum()) * e_kin_ev <= 0.85 < 2 * m1 / (2 * m1 + ic["mass"].sum()) * e_kin_ev
     assert len(t["records"]) == 1
+
+
+def test_esi_preheating_before_the_collisions(oracle):
+    """keyword `esi <eV>` (main.F90:1243-1362): ions colder than the requested internal energy are heated by the thermostatted MD
+    (md() with method 3, icoll 0, starting_md) before the first collision; ions that are already hotter are left alone."""
+    num, xyz, _ = load_molecule("chloroethanol")
+    ic = es.synthetic_initial_conditions(num, xyz, 2, first_id=330, temperature=300.0)
+    nuc = len(num)
+    e_int = [0.5 * (ic["mass"][:, None] * ic["velo"][k] ** 2).sum() * 27.21138505 for k in range(2)]
+    kw = dict(mchrg=1, gas="ar", elab=40.0, run_type="maxcoll", max_coll=1, minmass=20, seed=5, cid_ntot=5, mfp_nmax=4, cid_batch=oracle.cid_batch,
+              mfp_batch=oracle.mfp_batch, esi_batch=oracle.esi_batch, energies=oracle.energies)
+    out = prod.run_cid(num, ic["mass"], ic["xyz"], ic["velo"], esi_ev=2.0 * max(e_int), esi_nmax=12, **kw)
+    for t in out["per_traj"]:
+        kinds = [(e["kind"], e["icoll"]) for e in t["events"]]
+        assert kinds == [("esi", 0), ("cid", 1), ("mfp", 1)] and t["events"][0]["nstep"] == 12 and t["events"][0]["md_ok"]
+        tscale = t["events"][0]["tscale"]
+        assert abs(tscale - (2.0 * max(e_int) * 2.0 / 3.0) / (nuc * 3.166808578545117e-06 * 27.21138505)) < 1e-9
+    # length of the heating run when it is not overridden: nint(2.5 (T_target - T)), main.F90:1335
+    cold = prod.run_cid(num, ic["mass"], ic["xyz"][:1], ic["velo"][:1], esi_ev=1.02 * e_int[0], **kw)
+    t0 = e_int[0] / 27.21138505 / (1.5 * nuc * 3.166808578545117e-06)
+    assert cold["per_traj"][0]["events"][0]["nstep"] == int(np.floor(0.02 * t0 * 2.5 + 0.5))
+    # "! No Scaling !": the ion already holds more than the requested energy
+    none = prod.run_cid(num, ic["mass"], ic["xyz"][:1], ic["velo"][:1], esi_ev=0.5 * e_int[0], **kw)
+    assert [e["kind"] for e in none["per_traj"][0]["events"]] == ["cid", "mfp"]

@@ -160,3 +160,43 @@ def test_cid_production_run_matches_oracle_backend(qx, oracle):
         va = [e.get("velo_cm", e.get("new_velo")) for e in a["events"]]
         vb = [e.get("velo_cm", e.get("new_velo")) for e in b["events"]]
         assert np.allclose(va, vb, rtol=1e-6, atol=1e-3)
+
+
+def test_esi_heating_md_matches_oracle(qx, oracle):
+    """md() as the heating MD before the first collision of an ESI/CID run (reference md() with method 3, icoll = 0, starting_md;
+    src/md.f90:428-434, call site main.F90:1357-1362): Berendsen scaling towards tscale during the first nadd steps."""
+    num, xyz, _ = qx.load_molecule("thf_h")
+    nt = 3
+    ic = es.synthetic_initial_conditions(num, xyz, nt, first_id=40, temperature=300.0)
+    mass, nmax = ic["mass"], 40
+    tscale = 900.0
+    e_scale = 1.5 * len(num) * 3.166808578545117e-06 * tscale          # inner energy for tscale (Eh)
+    pretadd = nmax * 41.3413733365614 * 0.5 * 0.75                      # main.F90:1336 with tstep 0.5 fs
+    ens = qx.Ensemble(num, mass, nt, mchrg=1, nmax=nmax, isec=1)
+    ens.set_all(ic["xyz"], ic["velo"], np.ones((nt, len(num))), np.full(nt, e_scale), np.full(nt, pretadd))
+    ens.set_esi(tscale)
+    assert ens.run_md() == nt * nmax
+    got = ens.results()
+    ens.close()
+    for k in range(nt):
+        ref = oracle.md_esi(num, mass, ic["xyz"][k], ic["velo"][k], tscale, e_scale, pretadd, nmax=nmax, isec=1)
+        assert got["nstep"][k] == ref["nstep"] == nmax and got["mdok"][k] == ref["mdok"] == 1 and got["scc_iter_total"][k] == ref["scc_iter_total"]
+        assert np.abs(got["xyz"][k] - ref["xyz"]).max() < 1e-7 and np.abs(got["velo"][k] - ref["velo"]).max() < 1e-9
+        assert abs(got["Epot"][k] - ref["Epot"]) < 1e-7 and abs(got["Ekin"][k] - ref["Ekin"]) < 1e-9
+        assert abs(got["aTlast"][k] - ref["aTlast"]) < 1e-3 and abs(got["Tav"][k] - ref["Tav"]) < 1e-3
+        # the thermostat heats: the last temperatures are well above the 300 K start
+        assert ref["aTlast"] > 350.0
+
+
+@pytest.mark.parametrize("name,elab", [("thf_h", 40.0), ("dichlorobenzamide_h", 60.0)])
+def test_cid_on_the_reference_cid_examples(qx, oracle, name, elab):
+    """The reference's own CID inputs (share/examples/CID: protonated THF, elab 40; protonated dichlorobenzamide, elab 60; Ar): the first
+    collision against the oracle."""
+    num, xyz, _ = qx.load_molecule(name)
+    nt = 3
+    ic = es.synthetic_initial_conditions(num, xyz, nt, first_id=5, temperature=300.0)
+    rnd = np.random.default_rng(17).random((nt, 9))
+    cfg = qx.cid_config(mchrg=1, gas="ar", elab=elab, ntot=14)
+    got = qx.cid(cfg, num, ic["mass"], 1, ic["xyz"], ic["velo"], rnd)
+    for k in range(nt):
+        _compare(got, oracle.cid(cfg, num, ic["mass"], 1, ic["xyz"][k], ic["velo"][k], rnd[k]), k)
