@@ -129,6 +129,51 @@ module qcxms_tblite
          integer(c_int32_t), intent(out) :: list(nuc, *)
          type(cid_result), intent(out) :: res(*)
       end function cid_batch
+      ! ---- round 2: ground-state md() modes, ESI heating MD, the C-ABI collective (include/qcxms_b200.h)
+      integer(c_int) function ensemble_set_gs_mode(handle, it, tsoll) bind(c, name="qcxms_b200_ensemble_set_gs_mode")
+         import :: c_int, c_double, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: it               ! -1 equilibration, 0 sampling (src/main.F90:545-567), 1 production
+         real(c_double), value :: tsoll
+      end function ensemble_set_gs_mode
+
+      integer(c_int) function ensemble_get_gs(handle, itrj, first, count, xyzvelo) bind(c, name="qcxms_b200_ensemble_get_gs")
+         import :: c_int, c_double, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: itrj, first, count
+         real(c_double), intent(out) :: xyzvelo(6, *)      ! (x,y,z,vx,vy,vz) per atom and step: the records of qcxms.gs
+      end function ensemble_get_gs
+
+      integer(c_int) function ensemble_set_esi(handle, tscale) bind(c, name="qcxms_b200_ensemble_set_esi")
+         import :: c_int, c_double, c_ptr
+         type(c_ptr), value :: handle
+         real(c_double), value :: tscale           ! Tsoll of md(..., starting_md = .true.) (src/main.F90:1357-1362)
+      end function ensemble_set_esi
+
+      integer(c_int) function comm_unique_id(id128) bind(c, name="qcxms_b200_comm_unique_id")
+         import :: c_int, c_char
+         character(kind=c_char), intent(out) :: id128(128)
+      end function comm_unique_id
+
+      integer(c_int) function comm_create(id128, nranks, rank, device, comm) bind(c, name="qcxms_b200_comm_create")
+         import :: c_int, c_char, c_ptr
+         character(kind=c_char), intent(in) :: id128(128)
+         integer(c_int), value :: nranks, rank, device
+         type(c_ptr), intent(out) :: comm
+      end function comm_create
+
+      integer(c_int) function comm_allreduce_sum(comm, inout, n) bind(c, name="qcxms_b200_comm_allreduce_sum")
+         import :: c_int, c_double, c_ptr
+         type(c_ptr), value :: comm
+         real(c_double), intent(inout) :: inout(*)
+         integer(c_int), value :: n
+      end function comm_allreduce_sum
+
+      integer(c_int) function comm_destroy(comm) bind(c, name="qcxms_b200_comm_destroy")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: comm
+      end function comm_destroy
+
    end interface
 
 contains
