@@ -117,6 +117,12 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         const size_t avail = (size_t)prop.sharedMemPerBlockOptin - c.smem - 16 - 2048;   // 2 KB: the kernels' static shared memory
         int jb = (int)(avail / (2 * row));
         if (jb > 36) jb = 36;   // 2 x 18 sixteen-lane groups: the pairs of a round of two blocks fill two passes
+        else if (jb > 18 && jb < 36) {
+            // between 18 and 36 rows the second pass of every round runs half empty; 18 rows fill exactly one pass (22 % fewer
+            // pass-rounds per sweep for the 266-AO peptide, a few more block copies).  QCXMS_B200_JBLOCK overrides (measurement hook).
+            const char *force = getenv("QCXMS_B200_JBLOCK");
+            jb = force ? atoi(force) : 18;
+        }
         if (jb >= 8 && c.hm.nao <= 316) {   // jacobi_rows_blocked: ld <= 320
             const int nb = (c.hm.nao + jb - 1) / jb;
             jb = (c.hm.nao + nb - 1) / nb;          // balanced blocks

@@ -845,9 +845,18 @@ static __device__ __noinline__ void dmma_gemm_staged(int n, FA loadA, FB loadB, 
     for (int tb = 0; tb < nt; tb += MAXT) {
         const int j0 = tb * 8;
         __syncthreads();   // the readers of the previous column group are done
-        for (int idx = threadIdx.x; idx < kpad * NC; idx += QX_NT) {
-            const int k = idx / NC, jj = idx - k * NC, j = j0 + jj;
-            Bs[k * LDS + jj] = (k < n && j < n) ? loadB(k, j) : 0.0;
+        for (int base = 0; base < kpad * NC; base += 4 * QX_NT) {   // four independent L2 loads in flight per thread
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * QX_NT + threadIdx.x, k = idx / NC, j = j0 + idx - k * NC;
+                v[u] = (idx < kpad * NC && k < n && j < n) ? loadB(k, j) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * QX_NT + threadIdx.x, k = idx / NC, jj = idx - k * NC;
+                if (idx < kpad * NC) Bs[k * LDS + jj] = v[u];
+            }
         }
         __syncthreads();
         const double *bp = Bs + tg * LDS + g;
@@ -856,16 +865,29 @@ static __device__ __noinline__ void dmma_gemm_staged(int n, FA loadA, FB loadB, 
             double acc[MAXT][2];
 #pragma unroll
             for (int t = 0; t < MAXT; ++t) acc[t][0] = acc[t][1] = 0.0;
-#pragma unroll 4
-            for (int k0 = 0; k0 < kpad; k0 += 4) {
-                const int k = k0 + tg;
-                const double a = (row < n && k < n) ? loadA(row, k) : 0.0;
+            // The A operand comes straight from L2 (~600 cycles): its fragments are fetched KB k-steps ahead, one batch in flight while the
+            // previous one feeds the tensor pipe (KB x MAXT DMMA of 16 cycles each per scheduler cover the round trip).
+            constexpr int KB = 8;
+            double a_cur[KB], a_nxt[KB];
 #pragma unroll
-                for (int t = 0; t < MAXT; ++t) {
-                    const double b = bp[k0 * LDS + 8 * t];
-                    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                        : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(a), "d"(b));
+            for (int u = 0; u < KB; ++u) { const int k = 4 * u + tg; a_cur[u] = (row < n && k < n) ? loadA(row, k) : 0.0; }
+            for (int kb = 0; kb < kpad; kb += 4 * KB) {
+#pragma unroll
+                for (int u = 0; u < KB; ++u) { const int k = kb + 4 * KB + 4 * u + tg; a_nxt[u] = (row < n && k < n) ? loadA(row, k) : 0.0; }
+#pragma unroll
+                for (int u = 0; u < KB; ++u) {
+                    const int k0 = kb + 4 * u;
+                    if (k0 < kpad) {
+#pragma unroll
+                        for (int t = 0; t < MAXT; ++t) {
+                            const double b = bp[k0 * LDS + 8 * t];
+                            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(a_cur[u]), "d"(b));
+                        }
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < KB; ++u) a_cur[u] = a_nxt[u];
             }
 #pragma unroll
             for (int t = 0; t < MAXT; ++t) {
