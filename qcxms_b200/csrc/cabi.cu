@@ -112,24 +112,32 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         c.smem = (smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 1, c.hm.ntype) + 11 * (size_t)c.hm.nat + 16) * sizeof(double) + 64;
         if (c.smem + 2048 > (size_t)prop.sharedMemPerBlockOptin)
             return fail(QCXMS_B200_ERR_UNSUPPORTED, "system too large for the per-CTA working set (nat = " + std::to_string(c.hm.nat) + ")");
-        // the rest of the shared memory is the block buffer of the blocked Jacobi (2 * jblock rows of the SCC matrix)
-        const size_t row = (size_t)c.hm.ld * sizeof(double);
-        const size_t avail = (size_t)prop.sharedMemPerBlockOptin - c.smem - 16 - 2048;   // 2 KB: the kernels' static shared memory
-        int jb = (int)(avail / (2 * row));
-        if (jb > 36) jb = 36;   // 2 x 18 sixteen-lane groups: the pairs of a round of two blocks fill two passes
-        else if (jb > 18 && jb < 36) {
-            // between 18 and 36 rows the second pass of every round runs half empty; 18 rows fill exactly one pass (22 % fewer
-            // pass-rounds per sweep for the 266-AO peptide, a few more block copies).  QCXMS_B200_JBLOCK overrides (measurement hook).
-            const char *force = getenv("QCXMS_B200_JBLOCK");
-            jb = force ? atoi(force) : 18;
-        }
+        // The rest of the shared memory -- and, underneath it, the phase-local scratch vectors bsol/pop/d4u, dead while the
+        // eigensolver or a GEMM runs (carve(), qx_device.cuh) -- is the block buffer of the blocked Jacobi: 2 * jblock rows of the SCC
+        // matrix.  The MD/CID kernels' per-trajectory vectors follow the buffer (DevModel::extras_off).
+        const size_t vec = smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 1, c.hm.ntype);
+        const size_t extras = 11 * (size_t)c.hm.nat + 16;
+        const size_t jblk_off = (vec - smem_tail_doubles(c.hm.nat, c.hm.nao, c.hm.ntype) + 1) & ~(size_t)1;
+        const size_t limit = ((size_t)prop.sharedMemPerBlockOptin - 2048 - 64) / sizeof(double);   // 2 KB: the kernels' static shared memory
+        const size_t cap = limit - jblk_off - extras - 4;
+        const char *force_cta = getenv("QCXMS_B200_CTA");
+        const int slots = force_cta && atoi(force_cta) == 288 ? 18 : 36;   // sixteen-lane groups of the CTA (wide CTA, below)
+        int jb = (int)(cap / (2 * (size_t)c.hm.ld));
+        if (jb > 36) jb = 36;   // 36 rows per block: the pairs of a round of two blocks fill one pass of the wide CTA (two of the narrow one)
+        else if (jb > 18 && jb < 36 && slots == 18) jb = 18;   // a half-empty second pass every round costs more than the extra block copies
+        if (const char *force = getenv("QCXMS_B200_JBLOCK")) { const int f = atoi(force); if (f >= 8 && f <= jb) jb = f; }   // measurement hook
+        c.hm.dev.extras_off = (int)(vec + 8);
         if (jb >= 8 && c.hm.nao <= 316) {   // jacobi_rows_blocked: ld <= 320
             const int nb = (c.hm.nao + jb - 1) / jb;
             jb = (c.hm.nao + nb - 1) / nb;          // balanced blocks
             c.hm.dev.jblock = jb;
-            c.smem += 16 + 2 * (size_t)jb * row;
+            size_t end = jblk_off + 2 * (size_t)jb * c.hm.ld;
+            if (end < vec) end = vec;
+            c.hm.dev.extras_off = (int)((end + 3) & ~(size_t)1);
+            c.smem = ((size_t)c.hm.dev.extras_off + extras) * sizeof(double) + 64;
         }
-    }
+    } else
+        c.hm.dev.extras_off = (int)(smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 0, c.hm.ntype) + 8);
     c.L = make_layout(c.hm);
     // the device maximum, not this composition's size: host threads set up different compositions concurrently
     // Kernel set: two 288-thread CTAs per SM fill the device best when there are more trajectories than CTA slots.  An ensemble
@@ -140,6 +148,9 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         const char *force = getenv("QCXMS_B200_CTA");   // test / measurement hook: 288 or 576
         const int want = force ? atoi(force) : 0;
         if (!c.hm.dev.mat_in_global && (want == 576 || (want == 0 && nwork > 0 && nwork <= prop.multiProcessorCount))) c.ks = &KS_NT576;
+        // large bases run one CTA per SM anyway (L2 residency of the SCC matrices, below): the wide CTA rotates 36 row pairs per pass
+        // of the blocked Jacobi instead of 18 and gives the staged GEMMs twice the warps
+        if (c.hm.dev.mat_in_global && c.hm.dev.jblock > 0 && want != 288) c.ks = &KS_NT576;
     }
     // The wide CTAs have the SM to themselves: three more shared-memory matrices fit, and with them the GEMM-based eigenpair
     // refinement (qx_oa.cuh) that takes the one-sided Jacobi's latency chain out of the SCC (QCXMS_B200_OA=0 keeps the Jacobi).
@@ -153,6 +164,7 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
             const char *kap = getenv("QCXMS_B200_OA_KAPPA");
             c.hm.dev.oa_kappa = kap ? atof(kap) : QX_OA_KAPPA;
             c.smem = smem_oa;
+            c.hm.dev.extras_off = (int)(smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 0, c.hm.ntype, 1) + 8);
         }
     }
     CUDA_OK(c.ks->prepare_egrad(prop));

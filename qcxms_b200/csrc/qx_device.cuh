@@ -67,6 +67,9 @@ struct Sm {
     SmPtr qsh, vsh, selfen, vao, emo, focc, gw, gwd, dEdcn, dEdcn4, grad, red, jw, bsol, pop, d4u;
 };
 
+// doubles of the phase-local tail (bsol, pop, d4u) the global-slab mode's block buffer may overlay
+__host__ __device__ inline size_t smem_tail_doubles(int nat, int nao, int ntype) { return QX_BSOL + 11 * (size_t)nao + (nao & 1) + 7 * (size_t)nat * ntype; }
+
 __host__ __device__ inline size_t smem_doubles(int nat, int nsh, int nao, int ld, int rows8, int mat_in_global, int ntype, int oa = 0) {
     return (mat_in_global ? 0 : (oa ? 5 : 2) * (size_t)rows8 * ld) + 3 * nat + 6 * nat /*cn cn4 mrad dmr qat vat*/ + 6 * nat /*dpat vdp*/ + 12 * nat /*qpat vqp*/
            + 3 * nsh + 3 * nao + 8 + 14 * nat /*gw gwd*/ + 2 * nat + 3 * nat /*grad*/ + 64 + 3 * nao + 8 /*jw*/ + QX_BSOL /*Broyden solve*/ + 11 * nao + (nao & 1) /*pop*/ + 7 * nat * ntype /*d4u*/;
@@ -102,7 +105,10 @@ __device__ inline void carve(const DevModel &m, double *base, Sm &s, double *gma
     s.bsol = p; p += QX_BSOL;
     s.pop = p; p += 11 * nao + (nao & 1);
     s.d4u = p;
-    s.jblk = base + ((smem_doubles(nat, nsh, nao, m.ld, m.rows8, m.mat_in_global, m.ntype, m.oa) + 11 * (size_t)nat + 16 + 1) & ~(size_t)1);
+    // global-slab mode: the block buffer of the blocked Jacobi (and the staging buffer of the staged GEMMs) starts ON TOP of the
+    // phase-local scratch vectors bsol/pop/d4u -- none of them is live while the eigensolver or a GEMM runs -- and extends to the
+    // MD/CID kernels' vectors at DevModel::extras_off
+    s.jblk = m.jblock > 0 ? base + (((size_t)(s.bsol.ptr() - base) + 1) & ~(size_t)1) : nullptr;
 }
 
 __device__ inline double block_sum(double v, double *red) {
@@ -1623,6 +1629,7 @@ static __device__ __noinline__ int jacobi_rows_glob(int n, double *G, int ld, fl
     return sweep;
 }
 
+#define QX_JB_LANES 16
 // ---- large bases, blocked: the rows of G are cut into blocks of b <= bmax rows; a round-robin tournament over the blocks brings
 // two blocks at a time into the shared-memory buffer B (2 bmax rows), where one full sweep over their rows runs at shared-memory
 // latency (16 lanes per pair, same rotation as above), and writes them back.  An outer sweep visits every pair of blocks once and
@@ -1631,7 +1638,7 @@ static __device__ __noinline__ int jacobi_rows_glob(int n, double *G, int ld, fl
 template <int R>
 static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float tol, double *jw, double *B, int bmax) {
     QX_ASSUME_SHARED(jw); QX_ASSUME_SHARED(B);
-    constexpr int LP = 16;
+    constexpr int LP = QX_JB_LANES;   // lanes per row pair: a pass rotates 18 pairs on the 288-thread CTA, 36 on the 576-thread one
     const int nb = (n + bmax - 1) / bmax, b = (n + nb - 1) / nb, nbe = (nb + 1) & ~1, bm1 = nbe - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = QX_NT / 32;
     const int nslot = QX_NT / LP, slot = threadIdx.x / LP, lsub = threadIdx.x & (LP - 1);
@@ -1856,7 +1863,9 @@ __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *r
         }
     } else if (!SH && jblock >= 8 && (ld & 1) == 0 && (reinterpret_cast<size_t>(G) & 15) == 0 && n <= 316) {   // global slab, blocked through shared memory
         if (n <= 96) return jacobi_rows_generic(n, G, ld, red, tol);
-        switch ((n + 31) >> 5) {
+        switch ((n + 2 * QX_JB_LANES - 1) / (2 * QX_JB_LANES)) {   // R = double2 chunks per lane and row
+            case 2: sweeps = jacobi_rows_blocked<2>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
+            case 3: sweeps = jacobi_rows_blocked<3>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
             case 4: sweeps = jacobi_rows_blocked<4>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
             case 5: sweeps = jacobi_rows_blocked<5>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
             case 6: sweeps = jacobi_rows_blocked<6>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;

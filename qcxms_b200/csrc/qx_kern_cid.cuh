@@ -78,7 +78,7 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_cid_chunk(DevModel m,
         const int t = s_next;
         if (t >= ntraj) break;
         if (st.sc[t].status != TRJ_RUNNING) continue;
-        double *velo0 = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global, m.ntype, m.oa) + 8, *grad0 = velo0 + 3 * nuc0, *achrg0 = grad0 + 3 * nuc0;
+        double *velo0 = smem + m.extras_off, *grad0 = velo0 + 3 * nuc0, *achrg0 = grad0 + 3 * nuc0;
         double *gxyz0 = st.xyz0 + (size_t)t * 3 * nuc0, *gvelo0 = st.velo0 + (size_t)t * 3 * nuc0, *ggrad0 = st.grad0 + (size_t)t * 3 * nuc0,
                *gachrg0 = st.achrg0 + (size_t)t * nuc0;
         double *avxyz = st.avxyz + (size_t)t * 3 * nuc, *avxyz2 = st.avxyz2 + (size_t)t * 3 * nuc, *store = st.store + (size_t)t * 3 * nuc;

@@ -125,7 +125,7 @@ static __global__ void __launch_bounds__(QX_NT, QX_MINB) k_md_chunk(DevModel m, 
         }
         // per-trajectory arrays live in shared memory for the duration of the work item (read with ld.cg: the previous
         // sub-chunk of this trajectory may have run on another SM)
-        double *velo = smem + smem_doubles(m.nat, m.nsh, m.nao, m.ld, m.rows8, m.mat_in_global, m.ntype, m.oa) + 8, *grad = velo + 3 * nat, *avxyz = grad + 3 * nat, *achrg = avxyz + 3 * nat,
+        double *velo = smem + m.extras_off, *grad = velo + 3 * nat, *avxyz = grad + 3 * nat, *achrg = avxyz + 3 * nat,
                *avchrg = achrg + nat;
         double *gxyz = st.xyz + (size_t)t * 3 * nat, *gvelo = st.velo + (size_t)t * 3 * nat, *ggrad = st.grad + (size_t)t * 3 * nat;
         double *gachrg = st.achrg + (size_t)t * nat, *gavchrg = st.avchrg + (size_t)t * nat, *gavxyz = st.avxyz + (size_t)t * 3 * nat;

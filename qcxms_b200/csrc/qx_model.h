@@ -23,6 +23,7 @@ struct DevModel {
     int oa;                               // 1: GEMM-based eigenpair refinement (qx_oa.cuh) with three more shared-memory matrices (wide-CTA kernels)
     int method;                           // 2: GFN2-xTB, 1: GFN1-xTB (exp CN, D3(BJ), halogen bond, atomic third order, no multipoles)
     int jblock;                           // global-slab mode: rows per block of the shared-memory blocked Jacobi (0: none)
+    int extras_off;                       // offset (doubles) of the MD/CID kernels' per-trajectory vectors in the CTA's shared memory
     int mat_in_global;                    // 1: the two SCC matrices do not fit shared memory and live in the per-CTA global slab
     int rows8;                            // rows of the shared-memory matrices (zero padded; multiple of 8 when the strip GEMMs apply)
     int ntask_int, ntask_grad;
