@@ -177,7 +177,8 @@ int qcxms_b200_ensemble_histogram(qcxms_b200_ensemble_t *h, int nbins, double *b
  * TMP.<n>/qcxms.res (bin/pqcxms:101-103).  One process per GPU; NCCL (libnccl.so.2, loaded on first use -- set
  * QCXMS_B200_NCCL_LIB to point at another copy) over NVLink / NVSwitch.  Bootstrap as NCCL prescribes: rank 0 calls
  * qcxms_b200_comm_unique_id and hands the 128 bytes to the other ranks by whatever the host program has (MPI_Bcast, a file, ...);
- * then every rank calls qcxms_b200_comm_create. */
+ * then every rank calls qcxms_b200_comm_create (collective: it ends with a one-element all-reduce, so that NCCL's lazy channel
+ * set-up is paid here and not in the first spectrum reduction). */
 typedef struct qcxms_b200_comm qcxms_b200_comm_t;
 #define QCXMS_B200_UNIQUE_ID_BYTES 128
 int qcxms_b200_comm_unique_id(void *id128);

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqcxms_b200.so")
+LIB_PATH = os.environ.get("QCXMS_B200_LIB") or os.path.join(_HERE, "libqcxms_b200.so")   # (the override is a measurement hook)
 _LIB = None
 
 # method selectors (reference src/tblite.f90:34-40)

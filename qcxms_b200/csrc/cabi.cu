@@ -861,7 +861,12 @@ extern "C" int qcxms_b200_comm_create(const void *id128, int nranks, int rank, i
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { api.CommDestroy(c->comm); delete c; return fail(QCXMS_B200_ERR_CUDA, cudaGetErrorString(e)); }
     *out = c;
-    return 0;
+    // NCCL connects its channels lazily, at the first collective (22 ms on one B200, more over NVLink): pay that here, in the set-up
+    // call every rank makes together, not in the first spectrum reduction of the run
+    double one = 1.0;
+    const int rc = qcxms_b200_comm_allreduce_sum(c, &one, 1);
+    if (rc != 0) { qcxms_b200_comm_destroy(c); *out = nullptr; }
+    return rc;
 }
 
 extern "C" int qcxms_b200_comm_destroy(qcxms_b200_comm_t *c) {
