@@ -96,6 +96,7 @@ struct Context {
 
 static const KernelSet KS_NT288 = QX_KERNEL_SET(nt288, 288);
 static const KernelSet KS_NT576 = QX_KERNEL_SET(nt576, 576);   // one wide CTA per SM
+static const KernelSet KS_NT512 = QX_KERNEL_SET(nt512, 512);   // one CTA per SM with 128 registers per thread: large bases
 
 static int context_init(Context &c, int nat, const int32_t *num, const double *mass, int charge, int multiplicity, int device, int nwork, int method = QCXMS_B200_GFN2) {
     CUDA_OK(cudaSetDevice(device));
@@ -121,10 +122,13 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         const size_t limit = ((size_t)prop.sharedMemPerBlockOptin - 2048 - 64) / sizeof(double);   // 2 KB: the kernels' static shared memory
         const size_t cap = limit - jblk_off - extras - 4;
         const char *force_cta = getenv("QCXMS_B200_CTA");
-        const int slots = force_cta && atoi(force_cta) == 288 ? 18 : 36;   // sixteen-lane groups of the CTA (wide CTA, below)
+        const int wide = force_cta ? atoi(force_cta) : 512;                        // kernel set of this path (chosen below)
+        const int slots = (wide == 288 || wide == 576 ? wide : 512) / 16;          // sixteen-lane groups of the CTA
         int jb = (int)(cap / (2 * (size_t)c.hm.ld));
-        if (jb > 36) jb = 36;   // 36 rows per block: the pairs of a round of two blocks fill one pass of the wide CTA (two of the narrow one)
-        else if (jb > 18 && jb < 36 && slots == 18) jb = 18;   // a half-empty second pass every round costs more than the extra block copies
+        // the pairs of a round of two blocks (jb of them, jb - 1/2 in the first block round) should fill whole passes of `slots` groups:
+        // a half-empty second pass every round costs more than the extra block copies of smaller blocks
+        if (slots == 18) jb = jb >= 36 ? 36 : (jb > 18 ? 18 : jb);
+        else if (jb > slots) jb = slots;
         if (const char *force = getenv("QCXMS_B200_JBLOCK")) { const int f = atoi(force); if (f >= 8 && f <= jb) jb = f; }   // measurement hook
         c.hm.dev.extras_off = (int)(vec + 8);
         if (jb >= 8 && c.hm.nao <= 316) {   // jacobi_rows_blocked: ld <= 320
@@ -148,9 +152,9 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         const char *force = getenv("QCXMS_B200_CTA");   // test / measurement hook: 288 or 576
         const int want = force ? atoi(force) : 0;
         if (!c.hm.dev.mat_in_global && (want == 576 || (want == 0 && nwork > 0 && nwork <= prop.multiProcessorCount))) c.ks = &KS_NT576;
-        // large bases run one CTA per SM anyway (L2 residency of the SCC matrices, below): the wide CTA rotates 36 row pairs per pass
-        // of the blocked Jacobi instead of 18 and gives the staged GEMMs twice the warps
-        if (c.hm.dev.mat_in_global && c.hm.dev.jblock > 0 && want != 288) c.ks = &KS_NT576;
+        // large bases run one CTA per SM anyway (L2 residency of the SCC matrices, below): the 512-thread CTA rotates 32 row pairs per
+        // pass of the blocked Jacobi instead of 18, holds them in its 128 registers per thread, and gives the staged GEMMs 16 warps
+        if (c.hm.dev.mat_in_global && c.hm.dev.jblock > 0 && want != 288) c.ks = want == 576 ? &KS_NT576 : &KS_NT512;
     }
     // The wide CTAs have the SM to themselves: three more shared-memory matrices fit, and with them the GEMM-based eigenpair
     // refinement (qx_oa.cuh) that takes the one-sided Jacobi's latency chain out of the SCC (QCXMS_B200_OA=0 keeps the Jacobi).
@@ -1042,6 +1046,8 @@ extern "C" int qcxms_b200_debug_phase_cycles(double *out16) {
     CUDA_OK(KS_NT288.md_cycles(ph, sub, sh));
     CUDA_OK(KS_NT576.egrad_cycles(ph, sub, sh));
     CUDA_OK(KS_NT576.md_cycles(ph, sub, sh));
+    CUDA_OK(KS_NT512.egrad_cycles(ph, sub, sh));
+    CUDA_OK(KS_NT512.md_cycles(ph, sub, sh));
     for (int i = 0; i < 16; ++i) out16[i] = (double)ph[i];
 #ifdef QX_PROFILE_PHASES
     fprintf(stderr, "sub-phase cycles (thread 0):");

@@ -1638,6 +1638,9 @@ static __device__ __noinline__ int jacobi_rows_glob(int n, double *G, int ld, fl
 template <int R>
 static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float tol, double *jw, double *B, int bmax) {
     QX_ASSUME_SHARED(jw); QX_ASSUME_SHARED(B);
+    // 512-thread CTAs have 128 registers per thread: the row pair stays in registers between dot product and rotation (two passes
+    // over shared memory per rotation instead of three; at 96 registers this spills and is slower: 486 vs 672 peptide single points/s)
+    constexpr bool HOLD = QX_NT == 512;
     constexpr int LP = QX_JB_LANES;   // lanes per row pair: a pass rotates 18 pairs on the 288-thread CTA, 36 on the 576-thread one
     const int nb = (n + bmax - 1) / bmax, b = (n + nb - 1) / nb, nbe = (nb + 1) & ~1, bm1 = nbe - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = QX_NT / 32;
@@ -1707,12 +1710,14 @@ static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld,
                         // its callers leave, and holding the rows spilled them to local memory (1.0 G LDL / 0.6 G STL warp instructions
                         // per 148 single points of C32H66, the hottest stalls of the phase)
                         double g0 = 0.0, g1 = 0.0;
+                        double2 xh[HOLD ? R : 1], yh[HOLD ? R : 1];
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             if (r < R - 1 || tail_ok) {   // columns n .. ld-1 of B are zero
                                 const double2 x = *reinterpret_cast<const double2 *>(gp + 2 * LP * r);
                                 const double2 y = *reinterpret_cast<const double2 *>(gq + 2 * LP * r);
                                 g0 = fma(x.x, y.x, g0); g1 = fma(x.y, y.y, g1);
+                                if (HOLD) { xh[r] = x; yh[r] = y; }
                             }
                         }
                         double gs = g0 + g1;
@@ -1730,13 +1735,13 @@ static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld,
                         tf = rot ? tf : 0.0f;
                         const double t = (double)tf;
                         const double t1 = t * (sq.x * sp.y), t2 = t * (sp.x * sq.y);
-                        asm volatile("" ::: "memory");   // the rows are loaded again, not carried over from the dot product
+                        if (!HOLD) asm volatile("" ::: "memory");   // the rows are loaded again, not carried over from the dot product
                         if (valid) {
 #pragma unroll
                             for (int r = 0; r < R; ++r) {
                                 if (r < R - 1 || tail_ok) {
-                                    const double2 x = *reinterpret_cast<const double2 *>(gp + 2 * LP * r);
-                                    const double2 y = *reinterpret_cast<const double2 *>(gq + 2 * LP * r);
+                                    const double2 x = HOLD ? xh[r] : *reinterpret_cast<const double2 *>(gp + 2 * LP * r);
+                                    const double2 y = HOLD ? yh[r] : *reinterpret_cast<const double2 *>(gq + 2 * LP * r);
                                     double2 u, v;
                                     u.x = fma(-t1, y.x, x.x); u.y = fma(-t1, y.y, x.y);
                                     v.x = fma(t2, x.x, y.x); v.y = fma(t2, x.y, y.y);

@@ -94,5 +94,6 @@ static inline cudaError_t allow_max_dynamic_smem(K kernel, const cudaDeviceProp 
 
 QX_DECLARE_TU_ENTRIES(nt288)
 QX_DECLARE_TU_ENTRIES(nt576)
+QX_DECLARE_TU_ENTRIES(nt512)
 
 }  // namespace qx
