@@ -94,7 +94,7 @@ struct Context {
     const KernelSet *ks = nullptr;   // kernels compiled for the CTA width this composition runs with
 };
 
-static const KernelSet KS_NT288 = QX_KERNEL_SET(nt288, 288);
+static const KernelSet KS_NT320 = QX_KERNEL_SET(nt320, 320);   // two CTAs per SM: the default
 static const KernelSet KS_NT576 = QX_KERNEL_SET(nt576, 576);   // one wide CTA per SM
 static const KernelSet KS_NT512 = QX_KERNEL_SET(nt512, 512);   // one CTA per SM with 128 registers per thread: large bases
 
@@ -123,11 +123,11 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         const size_t cap = limit - jblk_off - extras - 4;
         const char *force_cta = getenv("QCXMS_B200_CTA");
         const int wide = force_cta ? atoi(force_cta) : 512;                        // kernel set of this path (chosen below)
-        const int slots = (wide == 288 || wide == 576 ? wide : 512) / 16;          // sixteen-lane groups of the CTA
+        const int slots = (wide == 288 || wide == 320 ? 320 : wide == 576 ? 576 : 512) / 16;          // sixteen-lane groups of the CTA
         int jb = (int)(cap / (2 * (size_t)c.hm.ld));
         // the pairs of a round of two blocks (jb of them, jb - 1/2 in the first block round) should fill whole passes of `slots` groups:
         // a half-empty second pass every round costs more than the extra block copies of smaller blocks
-        if (slots == 18) jb = jb >= 36 ? 36 : (jb > 18 ? 18 : jb);
+        if (slots == 20) jb = jb >= 40 ? 40 : (jb > 20 ? 20 : jb);
         else if (jb > slots) jb = slots;
         if (const char *force = getenv("QCXMS_B200_JBLOCK")) { const int f = atoi(force); if (f >= 8 && f <= jb) jb = f; }   // measurement hook
         c.hm.dev.extras_off = (int)(vec + 8);
@@ -144,17 +144,18 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         c.hm.dev.extras_off = (int)(smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 0, c.hm.ntype) + 8);
     c.L = make_layout(c.hm);
     // the device maximum, not this composition's size: host threads set up different compositions concurrently
-    // Kernel set: two 288-thread CTAs per SM fill the device best when there are more trajectories than CTA slots.  An ensemble
+    // Kernel set: two 320-thread CTAs per SM fill the device best when there are more trajectories than CTA slots.  An ensemble
     // with at most one trajectory per SM (BASELINE config 2 dealt over 8 GPUs: 125 per device) is bound by the latency of a
     // single trajectory's step instead: it runs on 576-thread CTAs, one per SM (shared-memory-resident bases only).
-    c.ks = &KS_NT288;
+    c.ks = &KS_NT320;
     {
-        const char *force = getenv("QCXMS_B200_CTA");   // test / measurement hook: 288 or 576
-        const int want = force ? atoi(force) : 0;
+        const char *force = getenv("QCXMS_B200_CTA");   // test / measurement hook: 320 (or 288: the narrow set), 512, 576
+        int want = force ? atoi(force) : 0;
+        if (want == 288) want = 320;
         if (!c.hm.dev.mat_in_global && (want == 576 || (want == 0 && nwork > 0 && nwork <= prop.multiProcessorCount))) c.ks = &KS_NT576;
         // large bases run one CTA per SM anyway (L2 residency of the SCC matrices, below): the 512-thread CTA rotates 32 row pairs per
         // pass of the blocked Jacobi instead of 18, holds them in its 128 registers per thread, and gives the staged GEMMs 16 warps
-        if (c.hm.dev.mat_in_global && c.hm.dev.jblock > 0 && want != 288) c.ks = want == 576 ? &KS_NT576 : &KS_NT512;
+        if (c.hm.dev.mat_in_global && c.hm.dev.jblock > 0 && want != 320) c.ks = want == 576 ? &KS_NT576 : &KS_NT512;
     }
     // The wide CTAs have the SM to themselves: three more shared-memory matrices fit, and with them the GEMM-based eigenpair
     // refinement (qx_oa.cuh) that takes the one-sided Jacobi's latency chain out of the SCC (QCXMS_B200_OA=0 keeps the Jacobi).
@@ -1042,8 +1043,8 @@ extern "C" const char *qcxms_b200_version(void) { return "qcxms_b200 0.1 (sm_100
 // profiling builds only (-DQX_PROFILE_PHASES): read and reset the per-phase cycle counters; returns 0 counters otherwise
 extern "C" int qcxms_b200_debug_phase_cycles(double *out16) {
     unsigned long long ph[16] = {0}, sub[16] = {0}, sh[64] = {0};
-    CUDA_OK(KS_NT288.egrad_cycles(ph, sub, sh));
-    CUDA_OK(KS_NT288.md_cycles(ph, sub, sh));
+    CUDA_OK(KS_NT320.egrad_cycles(ph, sub, sh));
+    CUDA_OK(KS_NT320.md_cycles(ph, sub, sh));
     CUDA_OK(KS_NT576.egrad_cycles(ph, sub, sh));
     CUDA_OK(KS_NT576.md_cycles(ph, sub, sh));
     CUDA_OK(KS_NT512.egrad_cycles(ph, sub, sh));

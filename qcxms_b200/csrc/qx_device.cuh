@@ -931,7 +931,7 @@ __device__ inline void gemm_tc(int n, FA loadA, FB loadB, FS store, double *stag
 // of ld are predicated (only the last one does).
 // A' = Ct * H * Ct^T  (H symmetric in `A`, result overwrites `A`); Ct in `Ct`.  The strip of T = Ct*H is parked in the
 // warp's own rows of `A` (after a barrier: everybody has finished reading H) and read back as the A operand of the second product.
-// WPS warps share one strip (each takes a contiguous range of its column tiles): 1 for the 288-thread kernels (9 warps, 9 strips),
+// WPS warps share one strip (each takes a contiguous range of its column tiles): 1 for the 320-thread kernels (10 warps, 9 strips),
 // 2 for the wide CTAs, whose 18 warps would otherwise leave half of the tensor pipe's issue slots unused.
 #define QX_WPS ((QX_NT / 32) >= 18 ? 2 : 1)
 // Explicit shared-state-space accesses (32-bit shared-window addresses): with generic pointers the compiler emitted generic LD for
@@ -1641,7 +1641,7 @@ static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld,
     // 512-thread CTAs have 128 registers per thread: the row pair stays in registers between dot product and rotation (two passes
     // over shared memory per rotation instead of three; at 96 registers this spills and is slower: 486 vs 672 peptide single points/s)
     constexpr bool HOLD = QX_NT == 512;
-    constexpr int LP = QX_JB_LANES;   // lanes per row pair: a pass rotates 18 pairs on the 288-thread CTA, 36 on the 576-thread one
+    constexpr int LP = QX_JB_LANES;   // lanes per row pair: a pass rotates QX_NT / 16 pairs
     const int nb = (n + bmax - 1) / bmax, b = (n + nb - 1) / nb, nbe = (nb + 1) & ~1, bm1 = nbe - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = QX_NT / 32;
     const int nslot = QX_NT / LP, slot = threadIdx.x / LP, lsub = threadIdx.x & (LP - 1);

@@ -66,7 +66,7 @@ static inline cudaError_t allow_max_dynamic_smem(K kernel, const cudaDeviceProp 
     cudaError_t name(unsigned long long *, unsigned long long *, unsigned long long *) { return cudaSuccess; }
 #endif
 
-// entry points of the translation units; V = QX_VARIANT of the build (nt288: the default two-CTAs-per-SM kernels)
+// entry points of the translation units; V = QX_VARIANT of the build (nt320: the default two-CTAs-per-SM kernels)
 #define QX_DECLARE_TU_ENTRIES(V)                                                                                                              \
     cudaError_t QX_CAT(tu_egrad_prepare_, V)(const cudaDeviceProp &);                                                                         \
     cudaError_t QX_CAT(tu_egrad_launch_, V)(int, size_t, cudaStream_t, DevModel, ScratchLayout, double *, const double *, double, int, int *, \
@@ -92,7 +92,7 @@ static inline cudaError_t allow_max_dynamic_smem(K kernel, const cudaDeviceProp 
      QX_CAT(tu_md_occupancy_, V), QX_CAT(tu_md_init_, V), QX_CAT(tu_md_chunk_, V), QX_CAT(tu_md_cycles_, V), QX_CAT(tu_mfp_prepare_, V),        \
      QX_CAT(tu_mfp_chunk_, V), QX_CAT(tu_cid_prepare_, V), QX_CAT(tu_cid_init_, V), QX_CAT(tu_cid_chunk_, V)}
 
-QX_DECLARE_TU_ENTRIES(nt288)
+QX_DECLARE_TU_ENTRIES(nt320)
 QX_DECLARE_TU_ENTRIES(nt576)
 QX_DECLARE_TU_ENTRIES(nt512)
 

@@ -7,13 +7,13 @@
 #define QX_MAXREF 7
 #define QX_MAX_ITER 250   // tblite max_iter (SCC cycles and Broyden memory)
 #ifndef QX_NT
-#define QX_NT 288         // threads per CTA; one CTA == one trajectory (tu_*.cu may be built for other widths, see qx_kernels.h)
+#define QX_NT 320         // threads per CTA; one CTA == one trajectory (tu_*.cu may be built for other widths, see qx_kernels.h)
 #endif
 #ifndef QX_MINB
 #define QX_MINB 2         // resident CTAs per SM the kernels are compiled for (register budget)
 #endif
 #ifndef QX_VARIANT
-#define QX_VARIANT nt288
+#define QX_VARIANT nt320
 #endif
 
 struct DevModel {
