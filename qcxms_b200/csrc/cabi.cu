@@ -152,7 +152,17 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         const char *force = getenv("QCXMS_B200_CTA");   // test / measurement hook: 320 (or 288: the narrow set), 512, 576
         int want = force ? atoi(force) : 0;
         if (want == 288) want = 320;
-        if (!c.hm.dev.mat_in_global && (want == 576 || (want == 0 && nwork > 0 && nwork <= prop.multiProcessorCount))) c.ks = &KS_NT576;
+        if (!c.hm.dev.mat_in_global) {
+            // medium bases (72 < nao <~ 110): the working set allows one CTA per SM whatever its width, so it is a wide one with 128
+            // registers per thread (the 43 - 52 row pairs of a Jacobi round in one pass of eight-lane groups instead of two, more warps
+            // for everything else).  C14H30, 86 AOs: 12.5 k -> 19.1 k, C17H36, 104 AOs: 8.5 k -> 12.9 k single points/s; 576 threads
+            // with their 96 registers: 17.7 / 10.6 k
+            const bool medium = 2 * (c.smem + 1024) > (size_t)prop.sharedMemPerMultiprocessor;
+            if (want == 576) c.ks = &KS_NT576;
+            else if (want == 512) c.ks = &KS_NT512;
+            else if (want == 0 && medium) c.ks = &KS_NT512;
+            else if (want == 0 && nwork > 0 && nwork <= prop.multiProcessorCount) c.ks = &KS_NT576;
+        }
         // large bases run one CTA per SM anyway (L2 residency of the SCC matrices, below): the 512-thread CTA rotates 32 row pairs per
         // pass of the blocked Jacobi instead of 18, holds them in its 128 registers per thread, and gives the staged GEMMs 16 warps
         if (c.hm.dev.mat_in_global && c.hm.dev.jblock > 0 && want != 320) c.ks = want == 576 ? &KS_NT576 : &KS_NT512;
