@@ -1268,12 +1268,24 @@ static __device__ __noinline__ int jacobi_rows_lp8t(int n, double *G, int ld, fl
     return sweep;
 }
 
-#ifndef QX_JACOBI_NOKEEP   // default; -DQX_JACOBI_NOKEEP selects jacobi_rows_lp8t
 // predicated 128-bit shared-memory load into an existing value
 __device__ __forceinline__ void lds_v2_if(bool p, double2 &v, const double *ptr) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(ptr);
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.shared.v2.f64 {%0, %1}, [%2];\n\t}" : "+d"(v.x), "+d"(v.y) : "r"(a), "r"((int)p));
 }
+// predicated 64-bit / 128-bit shared-memory loads of the sweep's scale state.  Idle groups (no pair in this round) used to do dummy
+// loads from row 0 while its owner rotated it -- harmless, their values are never used, but a read/write hazard for
+// compute-sanitizer's racecheck; predicated loads touch nothing.
+__device__ __forceinline__ double lds_f64_if(bool p, double dflt, const double *ptr) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(ptr);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.f64 %0, [%1];\n\t}" : "+d"(dflt) : "r"(a), "r"((int)p));
+    return dflt;
+}
+__device__ __forceinline__ double2 lds_v2_or(bool p, double2 dflt, const double2 *ptr) {
+    lds_v2_if(p, dflt, reinterpret_cast<const double *>(ptr));
+    return dflt;
+}
+#ifndef QX_JACOBI_NOKEEP   // default; -DQX_JACOBI_NOKEEP selects jacobi_rows_lp8t
 // ---- "kept row" variant of the trimmed kernel (default).  Group g plays slot k = (g - round) mod K, whose "plus" player (round + k)
 // is the plus player of slot k - 1 in the next round, so the plus row stays in registers; only the "minus" rows (and both
 // rows of slot 0, which wraps to slot K - 1) travel through shared memory: half the row traffic of jacobi_rows_lp8t, whose
@@ -1328,15 +1340,17 @@ static __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, fl
                     // assignments): with a conditionally assigned loop-carried array the compiler keeps x[] in local memory.
                     const bool fresh = round == 0 || k == K - 1;
 #pragma unroll
-                    for (int r = 0; r < R - 1; ++r) lds_v2_if(fresh, x[r], gp + 16 * r);
-                    lds_v2_if(fresh && tail_ok, x[R - 1], gp + 16 * (R - 1));
+                    for (int r = 0; r < R - 1; ++r) lds_v2_if(fresh && va, x[r], gp + 16 * r);
+                    lds_v2_if(fresh && va && tail_ok, x[R - 1], gp + 16 * (R - 1));
                 }
 #pragma unroll
-                for (int r = 0; r < R - 1; ++r) y[r] = *reinterpret_cast<const double2 *>(gq + 16 * r);
-                y[R - 1] = make_double2(0.0, 0.0);
-                if (tail_ok) y[R - 1] = *reinterpret_cast<const double2 *>(gq + 16 * (R - 1));
-                const double2 sx = dd[ra], sq = dd[rb];
-                const double al = nrm2[ra], be = nrm2[rb];
+                for (int r = 0; r < R; ++r) y[r] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int r = 0; r < R - 1; ++r) lds_v2_if(vb, y[r], gq + 16 * r);
+                lds_v2_if(vb && tail_ok, y[R - 1], gq + 16 * (R - 1));
+                const double2 one2 = make_double2(1.0, 1.0);
+                const double2 sx = lds_v2_or(va, one2, dd + ra), sq = lds_v2_or(vb, one2, dd + rb);
+                const double al = lds_f64_if(va, 1.0, nrm2 + ra), be = lds_f64_if(vb, 1.0, nrm2 + rb);
                 double g0 = 0.0, g1 = 0.0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
@@ -1379,6 +1393,7 @@ static __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, fl
                     c = c * fma(-0.5 * w * c, c, 1.5);
                     c = c * fma(-0.5 * w * c, c, 1.5);
                     const double wc = w * c, tg = t * ga;
+                    __syncwarp();   // the eight lanes of the group have read the scale state that lane 0 replaces
                     if (lsub == 0 && valid) {
                         dd[ra] = make_double2(c * sx.x, wc * sx.y); dd[rb] = make_double2(c * sq.x, wc * sq.y);
                         nrm2[ra] = al - tg; nrm2[rb] = be + tg;
@@ -1445,16 +1460,19 @@ static __device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, fl
                 const bool valid = k < npair && p < n && q < n;
                 if (!valid) { p = 0; q = 0; }
                 double *gp = Gl + p * ld, *gq = Gl + q * ld;
-                const double2 sp = dd[p], sq = dd[q];
-                const double al = nrm2[p], be = nrm2[q];
+                const double2 one2 = make_double2(1.0, 1.0);
+                const double2 sp = lds_v2_or(valid, one2, dd + p), sq = lds_v2_or(valid, one2, dd + q);
+                const double al = lds_f64_if(valid, 1.0, nrm2 + p), be = lds_f64_if(valid, 1.0, nrm2 + q);
                 double2 x[R], y[R];
 #pragma unroll
+                for (int r = 0; r < R; ++r) { x[r] = make_double2(0.0, 0.0); y[r] = make_double2(0.0, 0.0); }
+#pragma unroll
                 for (int r = 0; r < R - 1; ++r) {
-                    x[r] = *reinterpret_cast<const double2 *>(gp + 16 * r);
-                    y[r] = *reinterpret_cast<const double2 *>(gq + 16 * r);
+                    lds_v2_if(valid, x[r], gp + 16 * r);
+                    lds_v2_if(valid, y[r], gq + 16 * r);
                 }
-                x[R - 1] = make_double2(0.0, 0.0); y[R - 1] = make_double2(0.0, 0.0);
-                if (tail_ok) { x[R - 1] = *reinterpret_cast<const double2 *>(gp + 16 * (R - 1)); y[R - 1] = *reinterpret_cast<const double2 *>(gq + 16 * (R - 1)); }
+                lds_v2_if(valid && tail_ok, x[R - 1], gp + 16 * (R - 1));
+                lds_v2_if(valid && tail_ok, y[R - 1], gq + 16 * (R - 1));
                 double g0 = 0.0, g1 = 0.0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
@@ -1491,6 +1509,7 @@ static __device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, fl
                 c = c * fma(-0.5 * w * c, c, 1.5);
                 c = c * fma(-0.5 * w * c, c, 1.5);
                 const double wc = w * c, tg = t * ga;
+                __syncwarp();   // the eight lanes of the group have read the scale state that lane 0 replaces
                 if (lsub == 0 && valid) {
                     dd[p] = make_double2(c * sp.x, wc * sp.y); dd[q] = make_double2(c * sq.x, wc * sq.y);
                     nrm2[p] = al - tg; nrm2[q] = be + tg;
@@ -1703,8 +1722,9 @@ static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld,
                         }
                         if (!valid) { p = 0; q = 0; }
                         double *gp = Bl + p * ld, *gq = Bl + q * ld;
-                        const double2 sp = dd[p], sq = dd[q];
-                        const double al = nrm2[p], be = nrm2[q];
+                        const double2 one2 = make_double2(1.0, 1.0);
+                        const double2 sp = lds_v2_or(valid, one2, dd + p), sq = lds_v2_or(valid, one2, dd + q);
+                        const double al = lds_f64_if(valid, 1.0, nrm2 + p), be = lds_f64_if(valid, 1.0, nrm2 + q);
                         // the rows are read twice from shared memory (dot product, then rotation) instead of being held in 4 R
                         // registers across the rotation-parameter chain: as a __noinline__ callee this function only gets the registers
                         // its callers leave, and holding the rows spilled them to local memory (1.0 G LDL / 0.6 G STL warp instructions
@@ -1714,8 +1734,9 @@ static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld,
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             if (r < R - 1 || tail_ok) {   // columns n .. ld-1 of B are zero
-                                const double2 x = *reinterpret_cast<const double2 *>(gp + 2 * LP * r);
-                                const double2 y = *reinterpret_cast<const double2 *>(gq + 2 * LP * r);
+                                double2 x = make_double2(0.0, 0.0), y = x;   // (idle groups load nothing)
+                                lds_v2_if(valid, x, gp + 2 * LP * r);
+                                lds_v2_if(valid, y, gq + 2 * LP * r);
                                 g0 = fma(x.x, y.x, g0); g1 = fma(x.y, y.y, g1);
                                 if (HOLD) { xh[r] = x; yh[r] = y; }
                             }
@@ -1755,6 +1776,7 @@ static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld,
                         c = c * fma(-0.5 * w * c, c, 1.5);
                         c = c * fma(-0.5 * w * c, c, 1.5);
                         const double wc = w * c, tg = t * ga;
+                        __syncwarp();   // the lanes of the group have read the scale state that lane 0 replaces
                         if (lsub == 0 && valid) {
                             dd[p] = make_double2(c * sp.x, wc * sp.y); dd[q] = make_double2(c * sq.x, wc * sq.y);
                             nrm2[p] = al - tg; nrm2[q] = be + tg;
