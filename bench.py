@@ -63,6 +63,10 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)   # gone before the end-to-end leg starts
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -224,17 +228,21 @@ def main():
         # ---- end to end through the public API with host buffers: H2D of the initial conditions, md(), D2H of the results.
         # Three full repetitions (each one creates its ensemble, uploads, runs, reads back and reduces); the median is reported and
         # all three are kept in the JSON line (box-to-box the first repetition moves by several per cent: allocator and NCCL state)
-        e2e_runs = []
+        e2e_runs, e2e_parts = [], []
         for _rep in range(E2E_REPS):
             barrier()
             t0 = time.perf_counter()
             e2 = new_ensemble()
+            t1 = time.perf_counter()
             e2_steps = e2.run_md(max_steps=args.steps)
+            t2_ = time.perf_counter()
             e2.results()
             comm.allreduce_histogram(e2, 512)
             torch.cuda.synchronize()
             barrier()
             e2e_wall = time.perf_counter() - t0
+            e2e_parts.append({"create_upload_ms": 1e3 * (t1 - t0), "md_ms": 1e3 * (t2_ - t1), "kernel_ms": e2.last_timing()["kernel_ms"],
+                              "results_reduce_ms": 1e3 * (t0 + e2e_wall - t2_)})
             e2.close()
             t2 = torch.tensor([e2e_wall], dtype=torch.float64, device=dev)
             c2 = torch.tensor([float(e2_steps)], dtype=torch.float64, device=dev)
@@ -245,7 +253,7 @@ def main():
         h2d = sum(v.numel() * 8 for v in pin.values())
         d2h = ntl * (nat * (3 * 4 + 1) * 8 + nat * 4 + 14 * 8) + 512 * 8
         return dict(value=total_steps / dev_s_max, dev_s_max=dev_s_max, wall_max=wall_max, total_steps=total_steps, launches=launches, n_it=n_it,
-                    clocks=clocks, e2e_value=float(np.median(e2e_runs)), e2e_runs=e2e_runs, h2d=h2d, d2h=d2h, ntraj_local=ntl)
+                    clocks=clocks, e2e_value=float(np.median(e2e_runs)), e2e_runs=e2e_runs, e2e_parts=e2e_parts, h2d=h2d, d2h=d2h, ntraj_local=ntl)
 
     m = measure(args.scaling)
     other = None
@@ -282,7 +290,7 @@ def main():
            "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches / world),
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-                   "runs": m["e2e_runs"],
+                   "runs": m["e2e_runs"], "parts_rank0": m["e2e_parts"],
                    "note": "median of %d full repetitions of: create + H2D initial conditions (pinned) + md() incl. its initial egrad + D2H of every trajectory's result + histogram all-reduce" % E2E_REPS},
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic,
                         "kernel": "k_md_chunk", "note": "FP64 pipe roofline; peak = cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
