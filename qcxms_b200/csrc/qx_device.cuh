@@ -1158,7 +1158,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.app
 // 6 + 5, (4) is branch-free (t = 0 is an exact no-op), (5) keeps (scale, 1/scale) packed for 128-bit state accesses.
 // jw: nrm2[n] | dd[n] as double2 (scale, inverse scale), 16-byte aligned
 template <int R>
-static __device__ __noinline__ int jacobi_rows_lp8t(int n, double *G, int ld, float tol, double *jw) {
+static __device__ __noinline__ int jacobi_rows_lp8t(int n, double *G, int ld, float tol, double *jw, float = 0.0f) {
     QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(jw);   // n <= 72: matrices are in shared memory
     const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
     const int k = threadIdx.x >> 3, lsub = threadIdx.x & 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1295,7 +1295,9 @@ __device__ __forceinline__ double2 lds_v2_or(bool p, double2 dflt, const double2
 // predicated loads -- a branch around plain assignments made the compiler keep the loop-carried array in local memory
 // (65 M local loads per 1184 solves, 45 % slower than lp8t instead of 17 % faster).
 template <int R>
-static __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, float tol, double *jw) {
+// gate > 0: a sweep whose largest pre-rotation coupling stayed below `gate` (but not below tol) ends the call with -(sweeps): the
+// caller then checks convergence on the Gram matrix and applies the last, tiny rotations as three DMMA products (jacobi_polish).
+static __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, float tol, double *jw, float gate = 0.0f) {
     QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(jw);
     const int mm = (n + 1) & ~1, K = mm >> 1, m1 = mm - 1;
     const int grp = threadIdx.x >> 3, lsub = threadIdx.x & 7;
@@ -1306,6 +1308,8 @@ static __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, fl
     const bool tail_ok = 2 * lsub + 16 * (R - 1) < n;
     const bool gact = grp < K, wact = ((threadIdx.x >> 5) << 2) < K;   // wact is warp-uniform
     int sweep = 0;
+    bool early = false;
+    const double gate2 = (double)gate * (double)gate;
     for (; sweep < 60; ++sweep) {
         {   // fold the scales into the rows and refresh the norms
             const int lane = threadIdx.x & 31;
@@ -1320,7 +1324,7 @@ static __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, fl
             }
         }
         __syncthreads();
-        bool big = false;
+        bool big = false, mid = false;
         double2 x[R], y[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) x[r] = make_double2(0.0, 0.0);   // lanes beyond the row end keep zeros in the tail chunk
@@ -1361,6 +1365,7 @@ static __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, fl
                 const double ga = (sx.x * sq.x) * gs, ga2 = ga * ga, nn = al * be;
                 const bool valid = va && vb;
                 big |= valid && ga2 > ((double)tol * (double)tol) * nn;
+                mid |= valid && ga2 > gate2 * nn;
                 const bool rot = valid && ga2 > 1e-30 * nn;
                 const float gf = (float)ga, df = (float)(be - al);
                 const float g2 = gf + gf;
@@ -1404,6 +1409,7 @@ static __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, fl
             __syncthreads();
         }
         if (!__syncthreads_or(big ? 1 : 0)) { ++sweep; break; }
+        if (gate > 0.0f && !__syncthreads_or(mid ? 1 : 0)) { ++sweep; early = true; break; }
     }
     {   // fold the remaining scales
         const int lane = threadIdx.x & 31;
@@ -1413,7 +1419,7 @@ static __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, fl
         }
     }
     __syncthreads();
-    return sweep;
+    return early ? -sweep : sweep;
 }
 #define QX_JROWS jacobi_rows_lp8r
 #else
@@ -1867,20 +1873,242 @@ static __device__ __noinline__ void jacobi_shift(int n, double *G, int ld, doubl
     __syncthreads();
 }
 
+
+// ------------------------------------------------------------------------------------ the last sweep as three DMMA products
+// Every eigen-decomposition ends with a sweep whose pre-rotation couplings are all below QX_JACOBI_TOL: it confirms convergence and
+// applies rotations of <= 1e-4 rad.  Both are cheaper on the tensor pipe: the couplings are the off-diagonal elements of the Gram
+// matrix M = G G^T (one product), and the rotations, to second order in the antisymmetric Theta_ij = -t_ij (t_ij: the tangent the sweep
+// would use, from M_ij, M_ii, M_jj), are G <- G + Theta (G + Theta G / 2) (two products; what they leave is O(theta^3)).  Pairs with a
+// larger angle -- near-degenerate rows -- are left out of Theta and rotated exactly afterwards (a short list).  Numerical study on the
+// SCC matrices of a distorted caffeine cation (all 12 cycles): eigenvalues to 1e-14, eigenvector residuals <= 5e-13, orthogonality
+// <= 3e-12 -- the figures of the sweep it replaces.  Needs one shared-memory matrix besides G: the caller's C^T is parked in the
+// CTA's global slab meanwhile.
+#ifdef QX_PROFILE_PHASES
+static __device__ unsigned long long g_sub_cycles[16];
+#define QX_PSUB_BEGIN() long long psub_t0_ = clock64()
+#define QX_PSUB(idx) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_sub_cycles[idx], (unsigned long long)(t_ - psub_t0_)); psub_t0_ = t_; } } while (0)
+#define QX_PCOUNT(idx) do { if (threadIdx.x == 0) atomicAdd(&g_sub_cycles[idx], 1ull); } while (0)
+#else
+#define QX_PSUB_BEGIN() do {} while (0)
+#define QX_PSUB(idx) do {} while (0)
+#define QX_PCOUNT(idx) do {} while (0)
+#endif
+#ifndef QX_POLISH_GATE
+#define QX_POLISH_GATE 1e-3f   // try the Gram check after a sweep whose couplings all stayed below this
+#endif
+#define QX_POLISH_TBIG 1e-4    // tangents above this are rotated exactly, one after the other
+#define QX_POLISH_CAP 32       // at most this many of them (otherwise: back to the sweeps)
+#define QX_POLISH_T2 1e-6      // all tangents below this: the second-order term (<= 1e-12) is dropped, one product instead of two
+
+// Mg (global, row stride ld) = G G^T
+template <int NT8>
+static __device__ __noinline__ void tc_gram(int n, const double *G, double *Mg, int ld) {
+    constexpr int WPS = QX_WPS, TH = (NT8 + WPS - 1) / WPS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
+    const int strip = warp / WPS, t0 = (warp % WPS) * TH;
+    const bool act = strip < NT8;
+    const unsigned gm = smem_addr(G), ld8 = 8u * (unsigned)ld;
+    double acc[TH][2];
+#pragma unroll
+    for (int t = 0; t < TH; ++t) acc[t][0] = acc[t][1] = 0.0;
+    if (act) {
+        const unsigned arow = gm + (unsigned)(strip * 8 + g) * ld8 + 8u * tg;   // A fragment: G[row][k0 + tg]
+        const unsigned brow = gm + (unsigned)(g + 8 * t0) * ld8 + 8u * tg;      // B fragment: G[8 t + g][k0 + tg]
+#pragma unroll 2
+        for (int k0 = 0; k0 < kmax; k0 += 4) {
+            const double a = lds_f64(arow + 8u * k0);
+#pragma unroll
+            for (int t = 0; t < TH; ++t) { const double b = t0 + t < NT8 ? lds_f64(brow + 8u * t * ld8 + 8u * k0) : 0.0; QX_DMMA(acc[t], a, b); }
+        }
+        double *orow = Mg + (size_t)(strip * 8 + g) * ld + 2 * tg + 8 * t0;
+#pragma unroll
+        for (int t = 0; t < TH; ++t)
+            if (t0 + t < NT8 && 8 * (t0 + t) + 2 * tg + 1 < ld) *reinterpret_cast<double2 *>(orow + 8 * t) = make_double2(acc[t][0], acc[t][1]);
+    }
+    __syncthreads();
+}
+
+// MODE 0: Out = G + (Th B) / 2 with B = G (Out: another matrix);  MODE 1: G += Th B with B = X;  MODE 2: G += Th G in place (first
+// order only: the products of all warps are complete before anybody stores).  Th: global, row stride ld.
+template <int NT8, int MODE>
+static __device__ __noinline__ void tc_polish_apply(int n, const double *Th, const double *B, double *G, double *Out, int ld) {
+    constexpr int WPS = QX_WPS, TH = (NT8 + WPS - 1) / WPS, KS = 2 * NT8;   // k-steps of the padded dimension
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
+    const int strip = warp / WPS, t0 = (warp % WPS) * TH;
+    const bool act = strip < NT8;
+    const unsigned bm = smem_addr(B), gm = smem_addr(G), om = smem_addr(Out), ld8 = 8u * (unsigned)ld;
+    double acc[TH][2];
+    bool okb[TH], oks[TH];
+#pragma unroll
+    for (int t = 0; t < TH; ++t) {
+        okb[t] = t0 + t < NT8 && 8 * (t0 + t) + g < ld; oks[t] = t0 + t < NT8 && 8 * (t0 + t) + 2 * tg + 1 < ld;
+        acc[t][0] = acc[t][1] = 0.0;
+    }
+    if (act) {
+        const double *arow = Th + (size_t)(strip * 8 + g) * ld + tg;            // A fragment: Th[row][k0 + tg]
+        const unsigned bcol = bm + (unsigned)tg * ld8 + 8u * (g + 8 * t0);      // B fragment: B[k0 + tg][8 t + g]
+        double av[KS];   // the warp's strip of Theta is 8 x n: all of its k-steps are fetched from L2 at once
+#pragma unroll
+        for (int u = 0; u < KS; ++u) av[u] = 4 * u < kmax ? __ldcg(arow + 4 * u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < KS; ++u) {
+            const int k0 = 4 * u;
+            if (k0 < kmax) {
+#pragma unroll
+                for (int t = 0; t < TH; ++t) { const double b = okb[t] ? lds_f64(bcol + (unsigned)k0 * ld8 + 64u * t) : 0.0; QX_DMMA(acc[t], av[u], b); }
+            }
+        }
+    }
+    if (MODE == 2) __syncthreads();   // everybody has finished reading G
+    if (act) {
+        const unsigned grow = gm + (unsigned)(strip * 8 + g) * ld8 + 8u * (2 * tg + 8 * t0);
+        const unsigned orow = om + (unsigned)(strip * 8 + g) * ld8 + 8u * (2 * tg + 8 * t0);
+#pragma unroll
+        for (int t = 0; t < TH; ++t)
+            if (oks[t]) {
+                const double g0 = lds_f64(grow + 64u * t), g1 = lds_f64(grow + 64u * t + 8u);
+                if (MODE == 0) sts_v2f64(orow + 64u * t, fma(0.5, acc[t][0], g0), fma(0.5, acc[t][1], g1));
+                else sts_v2f64(orow + 64u * t, g0 + acc[t][0], g1 + acc[t][1]);
+            }
+    }
+    __syncthreads();
+}
+
+// G: rows after a sweep with couplings < QX_POLISH_GATE (scales folded in); X: the other shared-memory matrix (contents preserved);
+// gs: 2 * rows8 * ld doubles of the CTA's global slab; jw: the sweep's (now idle) state vector.  Returns true if the rows are
+// orthogonal to tol afterwards (the job of the last sweep is done), false if the couplings are not yet below tol (G unchanged).
+template <int NT8>
+static __device__ __noinline__ bool jacobi_polish(int n, double *G, double *X, int ld, double *gs, double *jw, float tol) {
+    QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(X); QX_ASSUME_SHARED(jw);
+    constexpr int U = (64 * NT8 * NT8 + QX_NT - 1) / QX_NT;   // elements of M per thread
+    const int nfull = 8 * NT8 * ld;
+    double *Mg = gs, *park = gs + nfull;
+    int *cnt = reinterpret_cast<int *>(jw), *list = cnt + 2;
+    double *dg = jw + 18;                                      // diagonal of M (jw: 3 n + 8 doubles, n >= 16)
+    if (threadIdx.x == 0) *cnt = 0;
+    QX_PSUB_BEGIN();
+    tc_gram<NT8>(n, G, Mg, ld);   // (ends with a barrier)
+    QX_PSUB(8);
+    for (int i = threadIdx.x; i < n; i += QX_NT) dg[i] = __ldcg(Mg + (size_t)i * ld + i);
+    // Every element (i, j) of M is handled where it lies -- its thread derives the tangent of the pair (min, max) from M_ij and the two
+    // diagonal elements, and M_ij == M_ji bitwise (same products, same order) -- so all loads and stores are coalesced.
+    double mv[U];
+    const int i0 = threadIdx.x / n, j0 = threadIdx.x - i0 * n, di = QX_NT / n, dj = QX_NT - di * n;
+    {
+        int i = i0, j = j0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {   // all of this thread's couplings in flight at once: one L2 round trip
+            mv[u] = i < n && i != j ? __ldcg(Mg + (size_t)i * ld + j) : 0.0;
+            i += di; j += dj;
+            if (j >= n) { j -= n; ++i; }
+        }
+    }
+    __syncthreads();
+    const double tol2 = (double)tol * (double)tol;
+    bool above = false, second = false;
+    {
+        int i = i0, j = j0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i < n && i != j) {
+                const bool up = i < j;
+                const double gij = mv[u], a = dg[up ? i : j], b = dg[up ? j : i];
+                const double g2d = gij * gij, nn = a * b;
+                above |= g2d > tol2 * nn;
+                // the sweep's tangent (single precision): t = 2 g / (|d| + sqrt(d^2 + 4 g^2)) with the sign of d = b - a
+                const float gf = (float)gij, df = (float)(b - a);
+                const float g2 = gf + gf;
+                const float hh = fmaf(df, df, g2 * g2);
+                const float den = fabsf(df) + hh * rsqrt_approx(hh);
+                float tf = g2 * rcp_approx(den);
+                tf = __int_as_float(__float_as_int(tf) ^ (__float_as_int(df) & 0x80000000));
+                if (!(g2d > 1e-30 * nn)) tf = 0.0f;
+                if (fabsf(tf) > (float)QX_POLISH_TBIG) {
+                    if (up) {
+                        const int idx = atomicAdd(cnt, 1);
+                        if (idx < QX_POLISH_CAP) list[idx] = (i << 16) | j;
+                    }
+                    tf = 0.0f;
+                }
+                second |= fabsf(tf) > (float)QX_POLISH_T2;
+                // row min gets -t row max, row max gets +t row min: the sweep's rotation to first order
+                Mg[(size_t)i * ld + j] = up ? -(double)tf : (double)tf;
+            }
+            i += di; j += dj;
+            if (j >= n) { j -= n; ++i; }
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += QX_NT) Mg[(size_t)i * ld + i] = 0.0;
+    if (__syncthreads_or(above ? 1 : 0)) { QX_PSUB(9); QX_PCOUNT(14); return false; }
+    QX_PSUB(9);
+    const int nbig = *cnt;
+    if (nbig > QX_POLISH_CAP) return false;
+    if (!__syncthreads_or(second ? 1 : 0) && nbig == 0) {
+        tc_polish_apply<NT8, 2>(n, Mg, G, G, G, ld);   // all angles below QX_POLISH_T2: G += Theta G is exact to 1e-12
+        QX_PSUB(10); QX_PCOUNT(15);
+        return true;
+    }
+    for (int t = threadIdx.x; t < nfull; t += QX_NT) park[t] = X[t];
+    __syncthreads();
+    QX_PSUB(11);
+    tc_polish_apply<NT8, 0>(n, Mg, G, G, X, ld);   // X = G + Theta G / 2
+    tc_polish_apply<NT8, 1>(n, Mg, X, G, G, ld);   // G += Theta X
+    QX_PSUB(12);
+    if (nbig > 0 && threadIdx.x < 32) {            // exact rotations of the near-degenerate pairs, one after the other
+        const int lane = threadIdx.x;
+        for (int e = 0; e < nbig; ++e) {
+            const int i = list[e] >> 16, j = list[e] & 0xffff;
+            double a = 0.0, b = 0.0, c = 0.0;
+            for (int k = lane; k < n; k += 32) { const double x = G[(size_t)i * ld + k], y = G[(size_t)j * ld + k]; a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+            if (c * c > 1e-30 * a * b) {
+                const double d = b - a;
+                double tt = 2.0 * c / (fabs(d) + sqrt(fma(d, d, 4.0 * c * c)));
+                if (d < 0.0) tt = -tt;
+                const double cs = 1.0 / sqrt(fma(tt, tt, 1.0)), sn = tt * cs;
+                for (int k = lane; k < n; k += 32) {
+                    const double x = G[(size_t)i * ld + k], y = G[(size_t)j * ld + k];
+                    G[(size_t)i * ld + k] = cs * x - sn * y;
+                    G[(size_t)j * ld + k] = sn * x + cs * y;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    for (int t = threadIdx.x; t < nfull; t += QX_NT) X[t] = __ldcg(park + t);
+    __syncthreads();
+    QX_PSUB(13);
+    return true;
+}
+
 // (2) the sweeps
 template <bool SH>
-__device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *red, double *jw, double *jblk = nullptr, int jblock = 0) {
+__device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *red, double *jw, double *jblk = nullptr, int jblock = 0,
+                                             double *Xc = nullptr, double *gpol = nullptr) {
     const float tol = 1e-7f;  // pre-rotation ratio of the last sweep; its rotations leave O(tol^2) couplings
     const int npair = (n + 1) >> 1;
     int sweeps;
     if (npair * 8 <= QX_NT && (ld & 1) == 0 && n <= 80) {
         const float tolr = QX_JACOBI_TOL;
-        switch ((n + 15) >> 4) {
-            case 1: sweeps = QX_JROWS<1>(n, G, ld, tolr, jw); break;
-            case 2: sweeps = QX_JROWS<2>(n, G, ld, tolr, jw); break;
-            case 3: sweeps = QX_JROWS<3>(n, G, ld, tolr, jw); break;
-            case 4: sweeps = QX_JROWS<4>(n, G, ld, tolr, jw); break;
-            default: sweeps = QX_JROWS<5>(n, G, ld, tolr, jw); break;   // 8 lanes per pair and QX_NT threads: n <= 72
+        // Xc / gpol given (strip-GEMM sizes only): the verification sweep is replaced by jacobi_polish
+        const int npad = tc_padded_dim(n);
+        const float gate = SH && Xc && gpol && n >= 16 && npad != 0 && npad / 8 <= QX_NT / 32 ? QX_POLISH_GATE : 0.0f;   // (n >= 16: the pair list lives in jw)
+        sweeps = 0;
+        for (;;) {
+            int r;
+            switch ((n + 15) >> 4) {
+                case 1: r = QX_JROWS<1>(n, G, ld, tolr, jw, gate); break;
+                case 2: r = QX_JROWS<2>(n, G, ld, tolr, jw, gate); break;
+                case 3: r = QX_JROWS<3>(n, G, ld, tolr, jw, gate); break;
+                case 4: r = QX_JROWS<4>(n, G, ld, tolr, jw, gate); break;
+                default: r = QX_JROWS<5>(n, G, ld, tolr, jw, gate); break;   // 8 lanes per pair and QX_NT threads: n <= 72
+            }
+            if (r >= 0) { sweeps += r; break; }
+            sweeps -= r;
+            const bool done = npad == 32 ? jacobi_polish<4>(n, G, Xc, ld, gpol, jw, tolr)
+                                         : (npad == 64 ? jacobi_polish<8>(n, G, Xc, ld, gpol, jw, tolr) : jacobi_polish<9>(n, G, Xc, ld, gpol, jw, tolr));
+            if (done) break;   // (not yet: another sweep, then the check again)
         }
     } else if ((ld & 1) == 0 && n <= 112 && SH) {   // matrices in shared memory, more pairs than 8-lane groups: several passes per round
         switch ((n + 15) >> 4) {   // R = ceil(n / 16): every chunk but the last is in range for all lanes
@@ -1938,9 +2166,10 @@ static __device__ __noinline__ void jacobi_finish(int n, double *G, int ld, doub
 
 // Eigen-decomposition of the symmetric A' held in G (n x n, ld).  Returns the number of sweeps.
 template <bool SH>
-__device__ __forceinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *emo, double *red, double *jw, double *jblk = nullptr, int jblock = 0) {
+__device__ __forceinline__ int jacobi_eigh_rows(int n, double *G, int ld, double *emo, double *red, double *jw, double *jblk = nullptr, int jblock = 0,
+                                                double *Xc = nullptr, double *gpol = nullptr) {
     jacobi_shift<SH>(n, G, ld, red);
-    const int sweeps = jacobi_sweeps<SH>(n, G, ld, red, jw, jblk, jblock);
+    const int sweeps = jacobi_sweeps<SH>(n, G, ld, red, jw, jblk, jblock, Xc, gpol);
     jacobi_finish<SH>(n, G, ld, emo, red);
     return sweeps;
 }

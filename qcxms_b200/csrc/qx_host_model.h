@@ -329,7 +329,7 @@ inline ScratchLayout make_layout(const HostModel &h) {
     auto take = [&](size_t n) { size_t o = off; off += (n + 1) & ~size_t(1); return o; };
     L.S = take(n2); L.H0 = take(n2); L.Dt = take(3 * n2); L.Qt = take(6 * n2);
     L.T = take(std::max(n2, (size_t)(7 * nat + 11 * h.nao)));
-    L.P = take(0); L.W = take(0);
+    L.P = take(h.dev.polish ? 2 * (size_t)h.rows8 * h.ld : 0); L.W = take(0);   // P: Gram matrix / rotation and the parked C^T of jacobi_polish
     L.matA = take(h.dev.mat_in_global ? 2 * (size_t)h.rows8 * h.ld + 4 : 0); L.matC = L.matA;
     L.gamma = take((size_t)h.nsh * h.nsh);
     L.dcnp = take(nat * nat); L.dcnp4 = take(nat * nat); L.edisp = take(nat * nat); L.c6 = take(nat * nat); L.dc6 = take(nat * nat);

@@ -22,6 +22,7 @@ struct DevModel {
     double oa_stop;                       // convergence threshold of the refinement (max |E_ij| of the last pass)
     int oa;                               // 1: GEMM-based eigenpair refinement (qx_oa.cuh) with three more shared-memory matrices (wide-CTA kernels)
     int method;                           // 2: GFN2-xTB, 1: GFN1-xTB (exp CN, D3(BJ), halogen bond, atomic third order, no multipoles)
+    int polish;                           // 1: the last Jacobi sweep of a decomposition runs as three DMMA products (jacobi_polish; scratch at ScratchLayout::P)
     int jblock;                           // global-slab mode: rows per block of the shared-memory blocked Jacobi (0: none)
     int extras_off;                       // offset (doubles) of the MD/CID kernels' per-trajectory vectors in the CTA's shared memory
     int mat_in_global;                    // 1: the two SCC matrices do not fit shared memory and live in the per-CTA global slab

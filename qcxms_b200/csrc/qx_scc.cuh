@@ -11,7 +11,7 @@ namespace qx {
 // optional per-phase cycle accounting (profiling builds only: -DQX_PROFILE_PHASES)
 #ifdef QX_PROFILE_PHASES
 static __device__ unsigned long long g_phase_cycles[16];
-static __device__ unsigned long long g_sub_cycles[16];   // finer marks inside a phase (thread 0's clock, no extra barrier)
+// (g_sub_cycles: finer marks inside a phase, thread 0's clock, no extra barrier -- declared in qx_device.cuh, jacobi_polish uses it too)
 #define QX_SUB_BEGIN() long long sub_t0_ = clock64()
 #define QX_SUB(idx) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_sub_cycles[idx], (unsigned long long)(t_ - sub_t0_)); sub_t0_ = t_; } } while (0)
 static __device__ unsigned long long g_sweep_hist[64];  // [iteration index (<32)] -> sweeps, [32+..] -> count
@@ -782,7 +782,7 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         }
         QX_PH(7);
         if (!refined) {
-            int sw_ = m.mat_in_global ? jacobi_eigh_rows<false>(nao, s.A, ld, s.emo, s.red, s.jw, s.jblk, m.jblock) : jacobi_eigh_rows<true>(nao, s.A, ld, s.emo, s.red, s.jw);
+            int sw_ = m.mat_in_global ? jacobi_eigh_rows<false>(nao, s.A, ld, s.emo, s.red, s.jw, s.jblk, m.jblock) : jacobi_eigh_rows<true>(nao, s.A, ld, s.emo, s.red, s.jw, nullptr, 0, s.C, m.polish ? scratch + L.P : nullptr);
             out.sweeps += sw_;
 #ifdef QX_PROFILE_PHASES
             if (threadIdx.x == 0 && iscf <= 32) { atomicAdd(&g_sweep_hist[iscf - 1], (unsigned long long)sw_); atomicAdd(&g_sweep_hist[32 + iscf - 1], 1ull); }
