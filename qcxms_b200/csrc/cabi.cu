@@ -142,10 +142,9 @@ static int context_init(Context &c, int nat, const int32_t *num, const double *m
         }
     } else
         c.hm.dev.extras_off = (int)(smem_doubles(c.hm.nat, c.hm.nsh, c.hm.nao, c.hm.ld, c.hm.rows8, 0, c.hm.ntype) + 8);
-    {   // the last Jacobi sweep as three DMMA products (shared-memory-resident strip-GEMM sizes); QCXMS_B200_POLISH=0: classical sweeps only
+    {   // the last Jacobi sweep as DMMA products (jacobi_polish / jacobi_polish_gen); QCXMS_B200_POLISH=0: classical sweeps only
         const char *pol = getenv("QCXMS_B200_POLISH");
-        const int npad = tc_padded_dim(c.hm.nao);
-        c.hm.dev.polish = !c.hm.dev.mat_in_global && c.hm.nao >= 16 && npad != 0 && c.hm.rows8 == npad && !(pol && atoi(pol) == 0);
+        c.hm.dev.polish = c.hm.nao >= 16 && !(pol && atoi(pol) == 0);
     }
     c.L = make_layout(c.hm);
     // the device maximum, not this composition's size: host threads set up different compositions concurrently

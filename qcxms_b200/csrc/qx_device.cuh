@@ -1430,7 +1430,7 @@ static __device__ __noinline__ int jacobi_rows_lp8r(int n, double *G, int ld, fl
 // (~110 AOs, one CTA per SM): the ceil(n/2) pairs of a round are worked off in passes of QX_NT/8 groups.  Same rotation as
 // jacobi_rows_lp8t; no kept row (a group would have to keep one per pass).
 template <int R>
-static __device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, float tol, double *jw) {
+static __device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, float tol, double *jw, float gate = 0.0f) {   // gate: as jacobi_rows_lp8r
     QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(jw);
     const int mm = (n + 1) & ~1, npair = mm >> 1, m1 = mm - 1;
     const int nslot = QX_NT / 8, slot = threadIdx.x >> 3, lsub = threadIdx.x & 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1441,8 +1441,9 @@ static __device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, fl
     __syncthreads();
     const bool tail_ok = 2 * lsub + 16 * (R - 1) < n;
     double *Gl = G + 2 * lsub;
-    const double tol2 = (double)tol * (double)tol;
+    const double tol2 = (double)tol * (double)tol, gate2 = (double)gate * (double)gate;
     int sweep = 0;
+    bool early = false;
     for (; sweep < 60; ++sweep) {
         for (int r = warp; r < n; r += QX_NT / 32) {
             const double d = dd[r].x;
@@ -1454,7 +1455,7 @@ static __device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, fl
             if (lane == 0) { nrm2[r] = acc; dd[r] = make_double2(1.0, 1.0); }
         }
         __syncthreads();
-        bool big = false;
+        bool big = false, mid = false;
         for (int round = 0; round < m1; ++round) {
             for (int pass = 0; pass < npass; ++pass) {
                 if ((warp << 2) + pass * nslot >= npair) continue;   // warp-uniform
@@ -1488,6 +1489,7 @@ static __device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, fl
                 gs += __shfl_xor_sync(0xffffffffu, gs, 1);
                 const double ga = (sp.x * sq.x) * gs, ga2 = ga * ga, nn = al * be;
                 big |= valid && ga2 > tol2 * nn;
+                mid |= valid && ga2 > gate2 * nn;
                 const bool rot = valid && ga2 > 1e-30 * nn;
                 const float gf = (float)ga, df = (float)(be - al);
                 const float g2 = gf + gf;
@@ -1524,13 +1526,14 @@ static __device__ __noinline__ int jacobi_rows_lp8m(int n, double *G, int ld, fl
             __syncthreads();
         }
         if (!__syncthreads_or(big ? 1 : 0)) { ++sweep; break; }
+        if (gate > 0.0f && !__syncthreads_or(mid ? 1 : 0)) { ++sweep; early = true; break; }
     }
     for (int r = warp; r < n; r += QX_NT / 32) {
         const double d = dd[r].x;
         for (int i = lane; i < n; i += 32) G[(size_t)r * ld + i] *= d;
     }
     __syncthreads();
-    return sweep;
+    return early ? -sweep : sweep;
 }
 
 // ---- large bases (matrices in the CTA's global slab, L2-resident): LP = 16 or 32 lanes per row pair, 128-bit coalesced row
@@ -1661,7 +1664,7 @@ static __device__ __noinline__ int jacobi_rows_glob(int n, double *G, int ld, fl
 // rotates every pair of rows exactly once.  L2 traffic per outer sweep: (nb - 1) reads and writes of G instead of n - 1.
 // Columns n <= 32 R.
 template <int R>
-static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float tol, double *jw, double *B, int bmax) {
+static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld, float tol, double *jw, double *B, int bmax, float gate = 0.0f) {
     QX_ASSUME_SHARED(jw); QX_ASSUME_SHARED(B);
     // 512-thread CTAs have 128 registers per thread: the row pair stays in registers between dot product and rotation (two passes
     // over shared memory per rotation instead of three; at 96 registers this spills and is slower: 486 vs 672 peptide single points/s)
@@ -1674,10 +1677,11 @@ static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld,
     double2 *dd = reinterpret_cast<double2 *>(jw + ((2 * b + 1) & ~1));
     double *Bl = B + 2 * lsub;
     const bool tail_ok = 2 * lsub + 2 * LP * (R - 1) < n;
-    const double tol2 = (double)tol * (double)tol;
+    const double tol2 = (double)tol * (double)tol, gate2 = (double)gate * (double)gate;
     int sweep = 0;
+    bool early = false;
     for (; sweep < 60; ++sweep) {
-        bool big = false;
+        bool big = false, mid = false;
         for (int bround = 0; bround < bm1; ++bround) {
             for (int bk = 0; bk < (nbe >> 1); ++bk) {
                 int I = bround + bk, J = bround - bk;
@@ -1752,6 +1756,7 @@ static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld,
                         for (int o = LP >> 1; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
                         const double ga = (sp.x * sq.x) * gs, ga2 = ga * ga, nn = al * be;
                         big |= valid && ga2 > tol2 * nn;
+                        mid |= valid && ga2 > gate2 * nn;
                         const bool rot = valid && ga2 > 1e-30 * nn;
                         const float gf = (float)ga, df = (float)(be - al);
                         const float g2 = gf + gf;
@@ -1801,8 +1806,9 @@ static __device__ __noinline__ int jacobi_rows_blocked(int n, double *G, int ld,
             }
         }
         if (!__syncthreads_or(big ? 1 : 0)) { ++sweep; break; }
+        if (gate > 0.0f && !__syncthreads_or(mid ? 1 : 0)) { ++sweep; early = true; break; }
     }
-    return sweep;
+    return early ? -sweep : sweep;
 }
 
 // generic fallback (any n): LP lanes per pair, scalar accesses
@@ -1897,7 +1903,7 @@ static __device__ unsigned long long g_sub_cycles[16];
 #define QX_POLISH_GATE 1e-3f   // try the Gram check after a sweep whose couplings all stayed below this
 #endif
 #define QX_POLISH_TBIG 1e-4    // tangents above this are rotated exactly, one after the other
-#define QX_POLISH_CAP 32       // at most this many of them (otherwise: back to the sweeps)
+#define QX_POLISH_CAP 64       // at most this many of them (otherwise: back to the sweeps)
 #define QX_POLISH_T2 1e-6      // all tangents below this: the second-order term (<= 1e-12) is dropped, one product instead of two
 
 // Mg (global, row stride ld) = G G^T
@@ -1984,7 +1990,7 @@ static __device__ __noinline__ bool jacobi_polish(int n, double *G, double *X, i
     const int nfull = 8 * NT8 * ld;
     double *Mg = gs, *park = gs + nfull;
     int *cnt = reinterpret_cast<int *>(jw), *list = cnt + 2;
-    double *dg = jw + 18;                                      // diagonal of M (jw: 3 n + 8 doubles, n >= 16)
+    double *dg = jw + 2 + QX_POLISH_CAP / 2;                   // diagonal of M (jw: 3 n + 8 doubles, n >= 16)
     if (threadIdx.x == 0) *cnt = 0;
     QX_PSUB_BEGIN();
     tc_gram<NT8>(n, G, Mg, ld);   // (ends with a barrier)
@@ -2082,6 +2088,101 @@ static __device__ __noinline__ bool jacobi_polish(int n, double *G, double *X, i
     return true;
 }
 
+// The same for bases that do not run the strip GEMMs (medium: G in shared memory; large: G in the CTA's global slab): the three
+// products go through gemm_tc (staged through `stage` when given), M / Theta and Y = Theta G live in gs (2 n^2 doubles, row stride n).
+template <bool SH>
+static __device__ __noinline__ bool jacobi_polish_gen(int n, double *G, int ld, double *gs, double *jw, float tol, double *stage, int stage_doubles) {
+    if (SH) QX_ASSUME_SHARED(G);
+    QX_ASSUME_SHARED(jw);
+    double *Mg = gs, *Yg = gs + (size_t)n * n;
+    int *cnt = reinterpret_cast<int *>(jw), *list = cnt + 2;
+    double *dg = jw + 2 + QX_POLISH_CAP / 2;
+    if (threadIdx.x == 0) *cnt = 0;
+    {
+        const double *Gc = G;
+        gemm_tc(n, [=](int i, int k) { return Gc[(size_t)i * ld + k]; }, [=](int k, int j) { return Gc[(size_t)j * ld + k]; },
+                [=](int i, int j, double v) { Mg[(size_t)i * n + j] = v; }, stage, stage_doubles);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += QX_NT) dg[i] = __ldcg(Mg + (size_t)i * n + i);
+    __syncthreads();
+    const double tol2 = (double)tol * (double)tol;
+    bool above = false, second = false;
+    for (int t0 = threadIdx.x; t0 < n * n; t0 += 4 * QX_NT) {   // four couplings in flight per thread
+        double mv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int t = t0 + u * QX_NT; mv[u] = t < n * n ? __ldcg(Mg + t) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * QX_NT, i = t / n, j = t - i * n;
+            if (t < n * n && i != j) {
+                const bool up = i < j;
+                const double gij = mv[u], a = dg[up ? i : j], b = dg[up ? j : i];
+                const double g2d = gij * gij, nn = a * b;
+                above |= g2d > tol2 * nn;
+                const float gf = (float)gij, df = (float)(b - a);
+                const float g2 = gf + gf;
+                const float hh = fmaf(df, df, g2 * g2);
+                const float den = fabsf(df) + hh * rsqrt_approx(hh);
+                float tf = g2 * rcp_approx(den);
+                tf = __int_as_float(__float_as_int(tf) ^ (__float_as_int(df) & 0x80000000));
+                if (!(g2d > 1e-30 * nn)) tf = 0.0f;
+                if (fabsf(tf) > (float)QX_POLISH_TBIG) {
+                    if (up) {
+                        const int idx = atomicAdd(cnt, 1);
+                        if (idx < QX_POLISH_CAP) list[idx] = (i << 16) | j;
+                    }
+                    tf = 0.0f;
+                }
+                second |= fabsf(tf) > (float)QX_POLISH_T2;
+                Mg[t] = up ? -(double)tf : (double)tf;
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += QX_NT) Mg[(size_t)i * n + i] = 0.0;
+    if (__syncthreads_or(above ? 1 : 0)) return false;
+    const int nbig = *cnt;
+    if (nbig > QX_POLISH_CAP) return false;
+    const bool need2 = __syncthreads_or(second ? 1 : 0) != 0;
+    {
+        const double *Gc = G;
+        gemm_tc(n, [=](int i, int k) { return __ldcg(Mg + (size_t)i * n + k); }, [=](int k, int j) { return Gc[(size_t)k * ld + j]; },
+                [=](int i, int j, double v) { Yg[(size_t)i * n + j] = v; }, stage, stage_doubles);
+    }
+    __syncthreads();
+    if (!need2) {
+        for (int t = threadIdx.x; t < n * n; t += QX_NT) { const int i = t / n, j = t - i * n; G[(size_t)i * ld + j] += __ldcg(Yg + t); }
+    } else {   // G += Y + Theta Y / 2 (the product reads Theta and Y only)
+        gemm_tc(n, [=](int i, int k) { return __ldcg(Mg + (size_t)i * n + k); }, [=](int k, int j) { return __ldcg(Yg + (size_t)k * n + j); },
+                [=](int i, int j, double v) { G[(size_t)i * ld + j] += __ldcg(Yg + (size_t)i * n + j) + 0.5 * v; }, stage, stage_doubles);
+    }
+    __syncthreads();
+    if (nbig > 0 && threadIdx.x < 32) {   // exact rotations of the near-degenerate pairs, one after the other
+        const int lane = threadIdx.x;
+        for (int e = 0; e < nbig; ++e) {
+            const int i = list[e] >> 16, j = list[e] & 0xffff;
+            double a = 0.0, b = 0.0, c = 0.0;
+            for (int k = lane; k < n; k += 32) { const double x = G[(size_t)i * ld + k], y = G[(size_t)j * ld + k]; a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+            if (c * c > 1e-30 * a * b) {
+                const double d = b - a;
+                double tt = 2.0 * c / (fabs(d) + sqrt(fma(d, d, 4.0 * c * c)));
+                if (d < 0.0) tt = -tt;
+                const double cs = 1.0 / sqrt(fma(tt, tt, 1.0)), sn = tt * cs;
+                for (int k = lane; k < n; k += 32) {
+                    const double x = G[(size_t)i * ld + k], y = G[(size_t)j * ld + k];
+                    G[(size_t)i * ld + k] = cs * x - sn * y;
+                    G[(size_t)j * ld + k] = sn * x + cs * y;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 // (2) the sweeps
 template <bool SH>
 __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *red, double *jw, double *jblk = nullptr, int jblock = 0,
@@ -2111,23 +2212,41 @@ __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *r
             if (done) break;   // (not yet: another sweep, then the check again)
         }
     } else if ((ld & 1) == 0 && n <= 112 && SH) {   // matrices in shared memory, more pairs than 8-lane groups: several passes per round
-        switch ((n + 15) >> 4) {   // R = ceil(n / 16): every chunk but the last is in range for all lanes
-            case 5: sweeps = jacobi_rows_lp8m<5>(n, G, ld, QX_JACOBI_TOL, jw); break;
-            case 6: sweeps = jacobi_rows_lp8m<6>(n, G, ld, QX_JACOBI_TOL, jw); break;
-            default: sweeps = jacobi_rows_lp8m<7>(n, G, ld, QX_JACOBI_TOL, jw); break;
+        // (jacobi_polish_gen measured here: C14H30 -2 %, C17H36 -51 % -- the generic products with operands behind lambdas cost more
+        // than the sweep they save at these sizes; the gate stays closed)
+        const float gate = 0.0f;
+        sweeps = 0;
+        for (;;) {
+            int r;
+            switch ((n + 15) >> 4) {   // R = ceil(n / 16): every chunk but the last is in range for all lanes
+                case 5: r = jacobi_rows_lp8m<5>(n, G, ld, QX_JACOBI_TOL, jw, gate); break;
+                case 6: r = jacobi_rows_lp8m<6>(n, G, ld, QX_JACOBI_TOL, jw, gate); break;
+                default: r = jacobi_rows_lp8m<7>(n, G, ld, QX_JACOBI_TOL, jw, gate); break;
+            }
+            if (r >= 0) { sweeps += r; break; }
+            sweeps -= r;
+            if (jacobi_polish_gen<SH>(n, G, ld, gpol, jw, QX_JACOBI_TOL, nullptr, 0)) break;
         }
     } else if (!SH && jblock >= 8 && (ld & 1) == 0 && (reinterpret_cast<size_t>(G) & 15) == 0 && n <= 316) {   // global slab, blocked through shared memory
         if (n <= 96) return jacobi_rows_generic(n, G, ld, red, tol);
-        switch ((n + 2 * QX_JB_LANES - 1) / (2 * QX_JB_LANES)) {   // R = double2 chunks per lane and row
-            case 2: sweeps = jacobi_rows_blocked<2>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
-            case 3: sweeps = jacobi_rows_blocked<3>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
-            case 4: sweeps = jacobi_rows_blocked<4>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
-            case 5: sweeps = jacobi_rows_blocked<5>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
-            case 6: sweeps = jacobi_rows_blocked<6>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
-            case 7: sweeps = jacobi_rows_blocked<7>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
-            case 8: sweeps = jacobi_rows_blocked<8>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
-            case 9: sweeps = jacobi_rows_blocked<9>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;
-            default: sweeps = jacobi_rows_blocked<10>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock); break;   // n <= 316 (ld <= 320)
+        const float gate = gpol ? QX_POLISH_GATE : 0.0f;
+        sweeps = 0;
+        for (;;) {
+            int r;
+            switch ((n + 2 * QX_JB_LANES - 1) / (2 * QX_JB_LANES)) {   // R = double2 chunks per lane and row
+                case 2: r = jacobi_rows_blocked<2>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock, gate); break;
+                case 3: r = jacobi_rows_blocked<3>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock, gate); break;
+                case 4: r = jacobi_rows_blocked<4>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock, gate); break;
+                case 5: r = jacobi_rows_blocked<5>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock, gate); break;
+                case 6: r = jacobi_rows_blocked<6>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock, gate); break;
+                case 7: r = jacobi_rows_blocked<7>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock, gate); break;
+                case 8: r = jacobi_rows_blocked<8>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock, gate); break;
+                case 9: r = jacobi_rows_blocked<9>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock, gate); break;
+                default: r = jacobi_rows_blocked<10>(n, G, ld, QX_JACOBI_TOL, jw, jblk, jblock, gate); break;   // n <= 316 (ld <= 320)
+            }
+            if (r >= 0) { sweeps += r; break; }
+            sweeps -= r;
+            if (jacobi_polish_gen<SH>(n, G, ld, gpol, jw, QX_JACOBI_TOL, jblk, 2 * jblock * ld)) break;
         }
     } else if (!SH && (ld & 1) == 0 && (reinterpret_cast<size_t>(G) & 15) == 0 && n <= 320) {   // global slab
         if (n <= 96) return jacobi_rows_generic(n, G, ld, red, tol);   // (never in practice: the slab mode starts above ~110 AOs)

@@ -782,7 +782,9 @@ __device__ inline void egrad_cta(const DevModel &m, Sm &s, double *scratch, cons
         }
         QX_PH(7);
         if (!refined) {
-            int sw_ = m.mat_in_global ? jacobi_eigh_rows<false>(nao, s.A, ld, s.emo, s.red, s.jw, s.jblk, m.jblock) : jacobi_eigh_rows<true>(nao, s.A, ld, s.emo, s.red, s.jw, nullptr, 0, s.C, m.polish ? scratch + L.P : nullptr);
+            double *gpol = m.polish ? scratch + L.P : nullptr;
+            int sw_ = m.mat_in_global ? jacobi_eigh_rows<false>(nao, s.A, ld, s.emo, s.red, s.jw, s.jblk, m.jblock, nullptr, gpol)
+                                      : jacobi_eigh_rows<true>(nao, s.A, ld, s.emo, s.red, s.jw, nullptr, 0, s.C, gpol);
             out.sweeps += sw_;
 #ifdef QX_PROFILE_PHASES
             if (threadIdx.x == 0 && iscf <= 32) { atomicAdd(&g_sweep_hist[iscf - 1], (unsigned long long)sw_); atomicAdd(&g_sweep_hist[32 + iscf - 1], 1ull); }

@@ -15,7 +15,10 @@ import qcxms_b200 as qx
 rng = np.random.default_rng(0)
 res = {}
 dt = 0.0
-for name, nsys in (("caffeine", 592), ("dichlorobenzamide_h", 300), ("thf_h", 300), ("chloroethanol", 300)):
+CASES = [("caffeine", 592), ("dichlorobenzamide_h", 300), ("thf_h", 300), ("chloroethanol", 300)]
+if os.environ.get("QX_POLISH_BIG"):
+    CASES = [("alkane_c14", 296), ("alkane_c17", 296), ("alkane_c32", 148), ("peptide_cl", 148)]
+for name, nsys in CASES:
     num, xyz, _ = qx.load_molecule(name)
     geoms = xyz[None] + 0.05 * rng.standard_normal((nsys,) + xyz.shape)
     qx.egrad_batch(num, geoms[:4], 1, 2, qx.gfn2_xtb, 5000.0)
