@@ -240,6 +240,10 @@ static int egrad_batch_impl(int nsys, int nat, const int32_t *num, const double 
     std::lock_guard<std::mutex> lock(mtx);
     std::vector<int32_t> key(num, num + nat);
     key.push_back(charge); key.push_back(multiplicity); key.push_back(nsys > 1 ? 1 << 20 : 1); key.push_back(method_id);
+    for (const char *hook : {"QCXMS_B200_CTA", "QCXMS_B200_OA", "QCXMS_B200_POLISH", "QCXMS_B200_JBLOCK"}) {   // measurement hooks read by context_init
+        const char *v = getenv(hook);
+        key.push_back(v ? atoi(v) + 1 : 0);
+    }
     int dev = 0;
     cudaGetDevice(&dev);
     EgradSlot *sl = nullptr;
