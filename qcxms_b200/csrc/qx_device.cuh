@@ -1900,8 +1900,10 @@ static __device__ unsigned long long g_sub_cycles[16];
 #define QX_PCOUNT(idx) do {} while (0)
 #endif
 #ifndef QX_POLISH_GATE
-#define QX_POLISH_GATE 1e-3f   // try the Gram check after a sweep whose couplings all stayed below this
+#define QX_POLISH_GATE 1e-2f   // try the Gram check after a sweep whose couplings all stayed below this (what it leaves is ~ 1e-4)
 #endif
+#define QX_POLISH_APPLY 1e-3   // couplings all below this: the correction is applied even if they are not yet below the tolerance
+                               // (quadratic convergence: the next check finds ~ 1e-8) -- a polish iteration instead of a sweep
 #define QX_POLISH_TBIG 1e-4    // tangents above this are rotated exactly, one after the other
 #define QX_POLISH_CAP 64       // at most this many of them (otherwise: back to the sweeps)
 #define QX_POLISH_T2 1e-6      // all tangents below this: the second-order term (<= 1e-12) is dropped, one product instead of two
@@ -1984,7 +1986,7 @@ static __device__ __noinline__ void tc_polish_apply(int n, const double *Th, con
 // gs: 2 * rows8 * ld doubles of the CTA's global slab; jw: the sweep's (now idle) state vector.  Returns true if the rows are
 // orthogonal to tol afterwards (the job of the last sweep is done), false if the couplings are not yet below tol (G unchanged).
 template <int NT8>
-static __device__ __noinline__ bool jacobi_polish(int n, double *G, double *X, int ld, double *gs, double *jw, float tol) {
+static __device__ __noinline__ int jacobi_polish(int n, double *G, double *X, int ld, double *gs, double *jw, float tol) {
     QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(X); QX_ASSUME_SHARED(jw);
     constexpr int U = (64 * NT8 * NT8 + QX_NT - 1) / QX_NT;   // elements of M per thread
     const int nfull = 8 * NT8 * ld;
@@ -2011,7 +2013,7 @@ static __device__ __noinline__ bool jacobi_polish(int n, double *G, double *X, i
     }
     __syncthreads();
     const double tol2 = (double)tol * (double)tol;
-    bool above = false, second = false;
+    bool above = false, second = false, far = false;
     {
         int i = i0, j = j0;
 #pragma unroll
@@ -2021,6 +2023,7 @@ static __device__ __noinline__ bool jacobi_polish(int n, double *G, double *X, i
                 const double gij = mv[u], a = dg[up ? i : j], b = dg[up ? j : i];
                 const double g2d = gij * gij, nn = a * b;
                 above |= g2d > tol2 * nn;
+                far |= g2d > (QX_POLISH_APPLY * QX_POLISH_APPLY) * nn;
                 // the sweep's tangent (single precision): t = 2 g / (|d| + sqrt(d^2 + 4 g^2)) with the sign of d = b - a
                 const float gf = (float)gij, df = (float)(b - a);
                 const float g2 = gf + gf;
@@ -2045,14 +2048,15 @@ static __device__ __noinline__ bool jacobi_polish(int n, double *G, double *X, i
         }
     }
     for (int i = threadIdx.x; i < n; i += QX_NT) Mg[(size_t)i * ld + i] = 0.0;
-    if (__syncthreads_or(above ? 1 : 0)) { QX_PSUB(9); QX_PCOUNT(14); return false; }
+    if (__syncthreads_or(far ? 1 : 0)) { QX_PSUB(9); QX_PCOUNT(14); return 0; }   // too far for a simultaneous correction: sweep
+    const int done = __syncthreads_or(above ? 1 : 0) ? 2 : 1;                      // 2: applied, to be checked again
     QX_PSUB(9);
     const int nbig = *cnt;
-    if (nbig > QX_POLISH_CAP) return false;
+    if (nbig > QX_POLISH_CAP) return 0;
     if (!__syncthreads_or(second ? 1 : 0) && nbig == 0) {
         tc_polish_apply<NT8, 2>(n, Mg, G, G, G, ld);   // all angles below QX_POLISH_T2: G += Theta G is exact to 1e-12
         QX_PSUB(10); QX_PCOUNT(15);
-        return true;
+        return done;
     }
     for (int t = threadIdx.x; t < nfull; t += QX_NT) park[t] = X[t];
     __syncthreads();
@@ -2062,8 +2066,15 @@ static __device__ __noinline__ bool jacobi_polish(int n, double *G, double *X, i
     QX_PSUB(12);
     if (nbig > 0 && threadIdx.x < 32) {            // exact rotations of the near-degenerate pairs, one after the other
         const int lane = threadIdx.x;
+        int last = -1;
         for (int e = 0; e < nbig; ++e) {
-            const int i = list[e] >> 16, j = list[e] & 0xffff;
+            // ascending (i, j): the list was filled through an atomic counter, its order is not reproducible -- the rotations' is
+            int best = 0x7fffffff;
+            for (int q = lane; q < nbig; q += 32) { const int kq = list[q]; if (kq > last && kq < best) best = kq; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const int other = __shfl_xor_sync(0xffffffffu, best, o); best = other < best ? other : best; }
+            last = best;
+            const int i = best >> 16, j = best & 0xffff;
             double a = 0.0, b = 0.0, c = 0.0;
             for (int k = lane; k < n; k += 32) { const double x = G[(size_t)i * ld + k], y = G[(size_t)j * ld + k]; a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c); }
 #pragma unroll
@@ -2085,13 +2096,13 @@ static __device__ __noinline__ bool jacobi_polish(int n, double *G, double *X, i
     for (int t = threadIdx.x; t < nfull; t += QX_NT) X[t] = __ldcg(park + t);
     __syncthreads();
     QX_PSUB(13);
-    return true;
+    return done;
 }
 
 // The same for bases that do not run the strip GEMMs (medium: G in shared memory; large: G in the CTA's global slab): the three
 // products go through gemm_tc (staged through `stage` when given), M / Theta and Y = Theta G live in gs (2 n^2 doubles, row stride n).
 template <bool SH>
-static __device__ __noinline__ bool jacobi_polish_gen(int n, double *G, int ld, double *gs, double *jw, float tol, double *stage, int stage_doubles) {
+static __device__ __noinline__ int jacobi_polish_gen(int n, double *G, int ld, double *gs, double *jw, float tol, double *stage, int stage_doubles) {
     if (SH) QX_ASSUME_SHARED(G);
     QX_ASSUME_SHARED(jw);
     double *Mg = gs, *Yg = gs + (size_t)n * n;
@@ -2107,7 +2118,7 @@ static __device__ __noinline__ bool jacobi_polish_gen(int n, double *G, int ld, 
     for (int i = threadIdx.x; i < n; i += QX_NT) dg[i] = __ldcg(Mg + (size_t)i * n + i);
     __syncthreads();
     const double tol2 = (double)tol * (double)tol;
-    bool above = false, second = false;
+    bool above = false, second = false, far = false;
     for (int t0 = threadIdx.x; t0 < n * n; t0 += 4 * QX_NT) {   // four couplings in flight per thread
         double mv[4];
 #pragma unroll
@@ -2120,6 +2131,7 @@ static __device__ __noinline__ bool jacobi_polish_gen(int n, double *G, int ld, 
                 const double gij = mv[u], a = dg[up ? i : j], b = dg[up ? j : i];
                 const double g2d = gij * gij, nn = a * b;
                 above |= g2d > tol2 * nn;
+                far |= g2d > (QX_POLISH_APPLY * QX_POLISH_APPLY) * nn;
                 const float gf = (float)gij, df = (float)(b - a);
                 const float g2 = gf + gf;
                 const float hh = fmaf(df, df, g2 * g2);
@@ -2140,9 +2152,10 @@ static __device__ __noinline__ bool jacobi_polish_gen(int n, double *G, int ld, 
         }
     }
     for (int i = threadIdx.x; i < n; i += QX_NT) Mg[(size_t)i * n + i] = 0.0;
-    if (__syncthreads_or(above ? 1 : 0)) return false;
+    if (__syncthreads_or(far ? 1 : 0)) return 0;                   // too far for a simultaneous correction: sweep
+    const int done = __syncthreads_or(above ? 1 : 0) ? 2 : 1;      // 2: applied, to be checked again
     const int nbig = *cnt;
-    if (nbig > QX_POLISH_CAP) return false;
+    if (nbig > QX_POLISH_CAP) return 0;
     const bool need2 = __syncthreads_or(second ? 1 : 0) != 0;
     {
         const double *Gc = G;
@@ -2159,8 +2172,15 @@ static __device__ __noinline__ bool jacobi_polish_gen(int n, double *G, int ld, 
     __syncthreads();
     if (nbig > 0 && threadIdx.x < 32) {   // exact rotations of the near-degenerate pairs, one after the other
         const int lane = threadIdx.x;
+        int last = -1;
         for (int e = 0; e < nbig; ++e) {
-            const int i = list[e] >> 16, j = list[e] & 0xffff;
+            // ascending (i, j): the list was filled through an atomic counter, its order is not reproducible -- the rotations' is
+            int best = 0x7fffffff;
+            for (int q = lane; q < nbig; q += 32) { const int kq = list[q]; if (kq > last && kq < best) best = kq; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const int other = __shfl_xor_sync(0xffffffffu, best, o); best = other < best ? other : best; }
+            last = best;
+            const int i = best >> 16, j = best & 0xffff;
             double a = 0.0, b = 0.0, c = 0.0;
             for (int k = lane; k < n; k += 32) { const double x = G[(size_t)i * ld + k], y = G[(size_t)j * ld + k]; a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c); }
 #pragma unroll
@@ -2180,7 +2200,7 @@ static __device__ __noinline__ bool jacobi_polish_gen(int n, double *G, int ld, 
         }
     }
     __syncthreads();
-    return true;
+    return done;
 }
 
 // (2) the sweeps
@@ -2207,9 +2227,11 @@ __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *r
             }
             if (r >= 0) { sweeps += r; break; }
             sweeps -= r;
-            const bool done = npad == 32 ? jacobi_polish<4>(n, G, Xc, ld, gpol, jw, tolr)
-                                         : (npad == 64 ? jacobi_polish<8>(n, G, Xc, ld, gpol, jw, tolr) : jacobi_polish<9>(n, G, Xc, ld, gpol, jw, tolr));
-            if (done) break;   // (not yet: another sweep, then the check again)
+            int st = 2;   // polish iterations: 0 = back to the sweeps, 1 = converged, 2 = corrected, check again
+            for (int it = 0; it < 4 && st == 2; ++it)
+                st = npad == 32 ? jacobi_polish<4>(n, G, Xc, ld, gpol, jw, tolr)
+                                : (npad == 64 ? jacobi_polish<8>(n, G, Xc, ld, gpol, jw, tolr) : jacobi_polish<9>(n, G, Xc, ld, gpol, jw, tolr));
+            if (st == 1) break;
         }
     } else if ((ld & 1) == 0 && n <= 112 && SH) {   // matrices in shared memory, more pairs than 8-lane groups: several passes per round
         // (jacobi_polish_gen measured here: C14H30 -2 %, C17H36 -51 % -- the generic products with operands behind lambdas cost more
@@ -2225,7 +2247,7 @@ __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *r
             }
             if (r >= 0) { sweeps += r; break; }
             sweeps -= r;
-            if (jacobi_polish_gen<SH>(n, G, ld, gpol, jw, QX_JACOBI_TOL, nullptr, 0)) break;
+            if (jacobi_polish_gen<SH>(n, G, ld, gpol, jw, QX_JACOBI_TOL, nullptr, 0) == 1) break;
         }
     } else if (!SH && jblock >= 8 && (ld & 1) == 0 && (reinterpret_cast<size_t>(G) & 15) == 0 && n <= 316) {   // global slab, blocked through shared memory
         if (n <= 96) return jacobi_rows_generic(n, G, ld, red, tol);
@@ -2246,7 +2268,9 @@ __device__ __forceinline__ int jacobi_sweeps(int n, double *G, int ld, double *r
             }
             if (r >= 0) { sweeps += r; break; }
             sweeps -= r;
-            if (jacobi_polish_gen<SH>(n, G, ld, gpol, jw, QX_JACOBI_TOL, jblk, 2 * jblock * ld)) break;
+            int st = 2;
+            for (int it = 0; it < 4 && st == 2; ++it) st = jacobi_polish_gen<SH>(n, G, ld, gpol, jw, QX_JACOBI_TOL, jblk, 2 * jblock * ld);
+            if (st == 1) break;
         }
     } else if (!SH && (ld & 1) == 0 && (reinterpret_cast<size_t>(G) & 15) == 0 && n <= 320) {   // global slab
         if (n <= 96) return jacobi_rows_generic(n, G, ld, red, tol);   // (never in practice: the slab mode starts above ~110 AOs)

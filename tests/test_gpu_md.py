@@ -93,6 +93,23 @@ def test_md_continue_in_chunks_equals_one_run(qx):
         assert np.array_equal(x["xyz"], y["xyz"]) and np.array_equal(x["velo"], y["velo"])   # bitwise reproducible
 
 
+@pytest.mark.parametrize("name,n,steps", [("caffeine", 320, 3), ("dichlorobenzamide_h", 96, 8)])
+def test_md_bitwise_reproducible_run_to_run(qx, name, n, steps):
+    """Same ensemble twice: every reduction on the path has a fixed order (the exact rotations of jacobi_polish are applied in
+    ascending pair order, not in the order an atomic counter handed them out), so positions and velocities agree bit for bit.
+    More trajectories than CTA slots for caffeine, so that the work queue hands them out in a different order as well."""
+    num, ic = _ic(qx, name, n, seed=5)
+    def run():
+        ens = qx.Ensemble(num, ic["mass"], n, mchrg=1, nmax=10 ** 6, exit_rules=False)
+        ens.set_all(ic["xyz"], ic["velo"], ic["velof"], ic["eimp"], ic["tadd"])
+        ens.run_md(max_steps=steps)
+        out = ens.results()
+        ens.close()
+        return out
+    a, b = run(), run()
+    assert np.array_equal(a["xyz"], b["xyz"]) and np.array_equal(a["velo"], b["velo"]) and np.array_equal(a["scc_iter_total"], b["scc_iter_total"])
+
+
 def test_histogram_counts_fragments(qx):
     num, ic = _ic(qx, "chloroethanol", 4)
     ens = qx.Ensemble(num, ic["mass"], 4, mchrg=1, nmax=3, exit_rules=True)
