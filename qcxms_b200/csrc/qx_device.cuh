@@ -1936,6 +1936,79 @@ static __device__ __noinline__ void tc_gram(int n, const double *G, double *Mg, 
     __syncthreads();
 }
 
+// The Gram product with the tangents taken straight from the accumulator fragments: lane (g, tg) of the warp that owns strip s holds
+// M[8 s + g][8 t + 2 tg + e]; the diagonal goes to shared memory (dg), then every lane turns its elements into Theta and stores them to
+// the global slab (row stride ld; padding and diagonal as zeros) -- M itself never leaves the registers.  flags: bit 0 a coupling above
+// tol, bit 1 above QX_POLISH_APPLY, bit 2 a tangent above QX_POLISH_T2 (this thread's elements; the caller combines them).
+template <int NT8>
+static __device__ __noinline__ int tc_gram_theta(int n, const double *G, double *Thg, int ld, double *dg, double tol2, int *cnt, int *list) {
+    constexpr int WPS = QX_WPS, TH = (NT8 + WPS - 1) / WPS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3, kmax = (n + 3) & ~3;
+    const int strip = warp / WPS, t0 = (warp % WPS) * TH;
+    const bool act = strip < NT8;
+    const unsigned gm = smem_addr(G), ld8 = 8u * (unsigned)ld;
+    double acc[TH][2];
+#pragma unroll
+    for (int t = 0; t < TH; ++t) acc[t][0] = acc[t][1] = 0.0;
+    if (act) {
+        const unsigned arow = gm + (unsigned)(strip * 8 + g) * ld8 + 8u * tg;   // A fragment: G[row][k0 + tg]
+        const unsigned brow = gm + (unsigned)(g + 8 * t0) * ld8 + 8u * tg;      // B fragment: G[8 t + g][k0 + tg]
+#pragma unroll 2
+        for (int k0 = 0; k0 < kmax; k0 += 4) {
+            const double a = lds_f64(arow + 8u * k0);
+#pragma unroll
+            for (int t = 0; t < TH; ++t) { const double b = t0 + t < NT8 ? lds_f64(brow + 8u * t * ld8 + 8u * k0) : 0.0; QX_DMMA(acc[t], a, b); }
+        }
+        // diagonal element (i, i), i = 8 strip + g: tile `strip`, held by the lane with 2 tg + e == g
+#pragma unroll
+        for (int t = 0; t < TH; ++t)
+            if (t0 + t == strip && tg == (g >> 1) && strip * 8 + g < n) dg[strip * 8 + g] = (g & 1) ? acc[t][1] : acc[t][0];
+    }
+    __syncthreads();
+    int flags = 0;
+    if (act) {
+        const int i = strip * 8 + g;
+        const double di = i < n ? dg[i] : 0.0;
+        double *orow = Thg + (size_t)i * ld + 2 * tg + 8 * t0;
+#pragma unroll
+        for (int t = 0; t < TH; ++t) {
+            double th[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = 8 * (t0 + t) + 2 * tg + e;
+                float tf = 0.0f;
+                if (t0 + t < NT8 && i < n && j < n && i != j) {
+                    const bool up = i < j;
+                    const double gij = acc[t][e], dj = dg[j], a = up ? di : dj, b = up ? dj : di;
+                    const double g2d = gij * gij, nn = a * b;
+                    flags |= g2d > tol2 * nn ? 1 : 0;
+                    flags |= g2d > (QX_POLISH_APPLY * QX_POLISH_APPLY) * nn ? 2 : 0;
+                    // the sweep's tangent (single precision): t = 2 g / (|d| + sqrt(d^2 + 4 g^2)) with the sign of d = b - a
+                    const float gf = (float)gij, df = (float)(b - a);
+                    const float g2 = gf + gf;
+                    const float hh = fmaf(df, df, g2 * g2);
+                    const float den = fabsf(df) + hh * rsqrt_approx(hh);
+                    tf = g2 * rcp_approx(den);
+                    tf = __int_as_float(__float_as_int(tf) ^ (__float_as_int(df) & 0x80000000));
+                    if (!(g2d > 1e-30 * nn)) tf = 0.0f;
+                    if (fabsf(tf) > (float)QX_POLISH_TBIG) {
+                        if (up) {
+                            const int idx = atomicAdd(cnt, 1);
+                            if (idx < QX_POLISH_CAP) list[idx] = (i << 16) | j;
+                        }
+                        tf = 0.0f;
+                    }
+                    flags |= fabsf(tf) > (float)QX_POLISH_T2 ? 4 : 0;
+                    if (up) tf = -tf;   // row min gets -t row max, row max gets +t row min: the sweep's rotation to first order
+                }
+                th[e] = (double)tf;
+            }
+            if (t0 + t < NT8 && 8 * (t0 + t) + 2 * tg + 1 < ld) *reinterpret_cast<double2 *>(orow + 8 * t) = make_double2(th[0], th[1]);
+        }
+    }
+    return flags;
+}
+
 // MODE 0: Out = G + (Th B) / 2 with B = G (Out: another matrix);  MODE 1: G += Th B with B = X;  MODE 2: G += Th G in place (first
 // order only: the products of all warps are complete before anybody stores).  Th: global, row stride ld.
 template <int NT8, int MODE>
@@ -1988,66 +2061,15 @@ static __device__ __noinline__ void tc_polish_apply(int n, const double *Th, con
 template <int NT8>
 static __device__ __noinline__ int jacobi_polish(int n, double *G, double *X, int ld, double *gs, double *jw, float tol) {
     QX_ASSUME_SHARED(G); QX_ASSUME_SHARED(X); QX_ASSUME_SHARED(jw);
-    constexpr int U = (64 * NT8 * NT8 + QX_NT - 1) / QX_NT;   // elements of M per thread
     const int nfull = 8 * NT8 * ld;
     double *Mg = gs, *park = gs + nfull;
     int *cnt = reinterpret_cast<int *>(jw), *list = cnt + 2;
     double *dg = jw + 2 + QX_POLISH_CAP / 2;                   // diagonal of M (jw: 3 n + 8 doubles, n >= 16)
-    if (threadIdx.x == 0) *cnt = 0;
+    if (threadIdx.x == 0) *cnt = 0;   // (tc_gram_theta has a barrier between its product and the tangents)
     QX_PSUB_BEGIN();
-    tc_gram<NT8>(n, G, Mg, ld);   // (ends with a barrier)
+    const int flags = tc_gram_theta<NT8>(n, G, Mg, ld, dg, (double)tol * (double)tol, cnt, list);   // Mg <- Theta
     QX_PSUB(8);
-    for (int i = threadIdx.x; i < n; i += QX_NT) dg[i] = __ldcg(Mg + (size_t)i * ld + i);
-    // Every element (i, j) of M is handled where it lies -- its thread derives the tangent of the pair (min, max) from M_ij and the two
-    // diagonal elements, and M_ij == M_ji bitwise (same products, same order) -- so all loads and stores are coalesced.
-    double mv[U];
-    const int i0 = threadIdx.x / n, j0 = threadIdx.x - i0 * n, di = QX_NT / n, dj = QX_NT - di * n;
-    {
-        int i = i0, j = j0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {   // all of this thread's couplings in flight at once: one L2 round trip
-            mv[u] = i < n && i != j ? __ldcg(Mg + (size_t)i * ld + j) : 0.0;
-            i += di; j += dj;
-            if (j >= n) { j -= n; ++i; }
-        }
-    }
-    __syncthreads();
-    const double tol2 = (double)tol * (double)tol;
-    bool above = false, second = false, far = false;
-    {
-        int i = i0, j = j0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (i < n && i != j) {
-                const bool up = i < j;
-                const double gij = mv[u], a = dg[up ? i : j], b = dg[up ? j : i];
-                const double g2d = gij * gij, nn = a * b;
-                above |= g2d > tol2 * nn;
-                far |= g2d > (QX_POLISH_APPLY * QX_POLISH_APPLY) * nn;
-                // the sweep's tangent (single precision): t = 2 g / (|d| + sqrt(d^2 + 4 g^2)) with the sign of d = b - a
-                const float gf = (float)gij, df = (float)(b - a);
-                const float g2 = gf + gf;
-                const float hh = fmaf(df, df, g2 * g2);
-                const float den = fabsf(df) + hh * rsqrt_approx(hh);
-                float tf = g2 * rcp_approx(den);
-                tf = __int_as_float(__float_as_int(tf) ^ (__float_as_int(df) & 0x80000000));
-                if (!(g2d > 1e-30 * nn)) tf = 0.0f;
-                if (fabsf(tf) > (float)QX_POLISH_TBIG) {
-                    if (up) {
-                        const int idx = atomicAdd(cnt, 1);
-                        if (idx < QX_POLISH_CAP) list[idx] = (i << 16) | j;
-                    }
-                    tf = 0.0f;
-                }
-                second |= fabsf(tf) > (float)QX_POLISH_T2;
-                // row min gets -t row max, row max gets +t row min: the sweep's rotation to first order
-                Mg[(size_t)i * ld + j] = up ? -(double)tf : (double)tf;
-            }
-            i += di; j += dj;
-            if (j >= n) { j -= n; ++i; }
-        }
-    }
-    for (int i = threadIdx.x; i < n; i += QX_NT) Mg[(size_t)i * ld + i] = 0.0;
+    const bool above = flags & 1, far = flags & 2, second = flags & 4;
     if (__syncthreads_or(far ? 1 : 0)) { QX_PSUB(9); QX_PCOUNT(14); return 0; }   // too far for a simultaneous correction: sweep
     const int done = __syncthreads_or(above ? 1 : 0) ? 2 : 1;                      // 2: applied, to be checked again
     QX_PSUB(9);
